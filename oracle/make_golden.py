@@ -1,0 +1,157 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference modules on CPU.
+
+Build-container only (needs /root/reference):  ``python -m oracle.make_golden``.
+Also checks the oracle restatement against the reference while it is at it and
+refuses to write fixtures if they disagree.
+
+Each fixture is small: inputs/targets/weights are regenerated from seeds by
+``oracle/synth.py``; only the reference *outputs* are stored.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shims, synth, unet_oracle, losses_oracle  # noqa: E402
+
+GOLDEN_DIR = os.path.join(ROOT, 'tests', 'golden')
+
+# (tag, depth, batch, size, weight seed, data seed)
+CASES = [
+    ('r18_b2_s64', 18, 2, 64, 0, 1234),
+    ('r34_b2_s64', 34, 2, 64, 1, 4321),
+    ('r18_b8_s128', 18, 8, 128, 0, 1234),     # BASELINE.json configs[0] shape
+]
+
+GRAD_KEYS = ['encoders.encoder.conv1.weight', 'encoders.encoder.layer1.0.conv1.weight',
+             'encoders.encoder.layer2.0.downsample.0.weight', 'encoders.encoder.layer4.1.bn2.weight',
+             'center.1.conv.weight', 'dec5.conv1.conv.weight', 'dec3.channel_se.fc.0.weight',
+             'dec2.spatial_se.fc.weight', 'dec1.conv1.conv.bias', 'final.0.conv.weight',
+             'final.0.batch_norm.bias', 'final.1.weight', 'final.1.bias']
+
+
+MAX_SAMPLES = 8192
+
+
+def sample(a, max_samples=MAX_SAMPLES):
+    """Deterministic strided subsample of a flattened array (keeps fixtures small)."""
+    flat = np.asarray(a).reshape(-1)
+    stride = max(1, -(-flat.size // max_samples))
+    return flat[::stride].copy()
+
+
+def _ref_losses():
+    ref_shims.install()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        from common_blocks import models as ref_models
+    return ref_models.lovasz_loss, ref_models.mixed_dice_bce_loss
+
+
+def run_case(tag, depth, batch, size, wseed, dseed):
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    sd_np = synth.synth_state_dict(depth, 2, wseed)
+    x = torch.from_numpy(synth.synth_inputs(batch, size, dseed))
+    t = torch.from_numpy(synth.synth_targets(batch, size, dseed))
+    lovasz_ref, bcedice_ref = _ref_losses()
+
+    out = {}
+    net = ref_shims.load_numpy_state(ref_shims.reference_unet(depth), sd_np, depth)
+
+    # ---- eval-mode forward (running statistics)
+    net.eval()
+    with torch.no_grad():
+        logits_eval = net(x)
+    out['logits_eval'] = logits_eval.numpy()
+    sd_t = unet_oracle.to_torch_state(sd_np)
+    with torch.no_grad():
+        mine = unet_oracle.unet_resnet_forward(sd_t, x, depth, train=False)
+    d = (mine - logits_eval).abs().max().item()
+    assert d <= 1e-5, 'oracle eval forward differs from reference: %g' % d
+
+    # ---- train-mode forward + both losses + backward (batch statistics)
+    for loss_name, loss_fn, mine_fn in (('lovasz', lovasz_ref, losses_oracle.lovasz_hinge_per_image),
+                                        ('bcedice', bcedice_ref, losses_oracle.bce_dice)):
+        net = ref_shims.load_numpy_state(ref_shims.reference_unet(depth), sd_np, depth)
+        net.train()
+        logits = net(x)
+        logits.retain_grad()
+        loss = loss_fn(logits, t.clone())
+        loss.backward()
+        out['logits_train'] = logits.detach().numpy()
+        out['loss_' + loss_name] = np.float32(loss.item())
+        out['dlogits_' + loss_name] = sample(logits.grad.numpy())
+        named = dict(net.named_parameters())
+        for k in GRAD_KEYS:
+            out['grad_%s_%s' % (loss_name, k)] = sample(named[k].grad.numpy())
+            out['gradl2_%s_%s' % (loss_name, k)] = np.float64(named[k].grad.double().norm().item())
+        gsq = {k: float((p.grad.double() ** 2).sum()) for k, p in named.items() if p.grad is not None}
+        out['gradnorm_' + loss_name] = np.float64(np.sqrt(sum(gsq.values())))
+        out['running_mean_stem_' + loss_name] = net.state_dict()['encoders.encoder.bn1.running_mean'].numpy()
+        out['running_var_final0_' + loss_name] = net.state_dict()['final.0.batch_norm.running_var'].numpy()
+
+        sd_t = unet_oracle.to_torch_state(sd_np, requires_grad=True)
+        lg = unet_oracle.unet_resnet_forward(sd_t, x, depth, train=True)
+        lg.retain_grad()
+        ls = mine_fn(lg, t)
+        ls.backward()
+        assert (lg.detach() - logits.detach()).abs().max().item() <= 1e-5, 'oracle train forward differs'
+        assert abs(ls.item() - loss.item()) <= 1e-5 * max(1.0, abs(loss.item())), \
+            'oracle %s loss differs: %r vs %r' % (loss_name, ls.item(), loss.item())
+        dd = (lg.grad - logits.grad).abs().max().item()
+        assert dd <= 1e-7 + 1e-4 * logits.grad.abs().max().item(), 'oracle dlogits differ: %g' % dd
+        for k in GRAD_KEYS:
+            a, b = sd_t[k].grad, named[k].grad
+            rel = (a - b).abs().max().item() / (b.abs().max().item() + 1e-12)
+            assert rel <= 2e-3, 'oracle grad %s differs rel %g' % (k, rel)
+        rm = sd_t['encoders.encoder.bn1.running_mean']
+        assert (rm - net.state_dict()['encoders.encoder.bn1.running_mean']).abs().max().item() <= 1e-6
+
+    # ---- post-processing (sigmoid, TTA h-flip mean, crop, binarize) through the reference functions
+    if size == 128:
+        ref_shims.install()
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            from common_blocks import postprocessing as ref_post
+            from common_blocks.utils import sigmoid as ref_sigmoid
+        net.eval()
+        with torch.no_grad():
+            lf = net(torch.flip(x, dims=[3])).numpy()
+        probs, masks = [], []
+        for i in range(batch):
+            p0 = ref_sigmoid(np.squeeze(out['logits_eval'][i]))
+            p1 = ref_sigmoid(np.squeeze(lf[i]))
+            p1 = np.stack([np.fliplr(ch) for ch in p1])            # augmentation.py:170-175
+            agg = np.mean(np.stack([p0, p1], axis=-1), axis=-1)    # loaders.py:751-760
+            probs.append(agg)
+            masks.append(ref_post.binarize(ref_post.crop_image(agg, (101, 101)), 0.5))
+        out['logits_eval_flip'] = lf
+        full_probs = np.stack(probs).astype(np.float32)
+        out['tta_probs'] = sample(full_probs)
+        out['tta_masks'] = np.stack(masks).astype(np.uint8)
+        p_mine, m_mine = losses_oracle.predict_masks(out['logits_eval'], lf, 101, 0.5)
+        assert np.abs(p_mine - full_probs).max() <= 1e-6
+        assert (m_mine == out['tta_masks']).all()
+
+    meta = dict(depth=depth, batch=batch, size=size, wseed=wseed, dseed=dseed)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, tag + '.npz'), **out,
+                        **{'meta_' + k: np.int64(v) for k, v in meta.items()})
+    print('wrote', tag, {k: getattr(v, 'shape', None) for k, v in out.items() if k.startswith('lo')})
+
+
+def main():
+    if not ref_shims.available():
+        sys.exit('reference tree not available; fixtures can only be regenerated in the build container')
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    for case in CASES:
+        run_case(*case)
+
+
+if __name__ == '__main__':
+    main()
