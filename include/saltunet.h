@@ -1,0 +1,121 @@
+/* libsaltunet - C ABI of the B200-native U-Net segmentation engine.
+ *
+ * Drop-in boundary for the hot path of neptune-ai/open-solution-salt-identification:
+ *   common_blocks/models.py:67-208  SegmentationModel (fit loop body, transform, load/persist)
+ * Every entry point below names the reference code it replaces.  All pointers are plain device pointers
+ * (CUDA, current device) unless said otherwise; no framework types cross this boundary.  `stream` is a
+ * cudaStream_t passed as void* (NULL = legacy default stream).  Functions return 0 on success, non-zero on
+ * error; salt_last_error() then returns a description (thread-local).
+ *
+ * Tensor layouts at the boundary are the reference's: images/logits/targets fp32 NCHW; parameters fp32 in
+ * the reference state_dict layout (conv weight [Cout][Cin][R][S]) inside one flat array whose table is
+ * given by salt_tensor_info().
+ */
+#ifndef SALTUNET_H
+#define SALTUNET_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct salt_engine salt_engine;
+
+enum { SALT_PREC_FP32 = 0, SALT_PREC_BF16 = 1 };
+enum { SALT_ARCH_UNET_RESNET = 0 };
+
+typedef struct salt_config {
+    int arch;            /* SALT_ARCH_UNET_RESNET  <- models.py:15-18 ARCHITECTURES['UNetResNet']                 */
+    int encoder_depth;   /* 18 or 34               <- architectures/unet.py:44-58                               */
+    int num_classes;     /* out_channels           <- models.py:182                                             */
+    int max_batch;       /* largest batch any call will pass                                                    */
+    int height, width;   /* network input size, multiples of 32 (128 for the 101x101 tiles, loaders.py)         */
+    int precision;       /* SALT_PREC_FP32: fp32 storage + fp32 FMA (parity mode); SALT_PREC_BF16: bf16 storage */
+    int use_tensor_cores;/* bf16 only: run eligible convolutions on the tcgen05 kernels                         */
+} salt_config;
+
+const char* salt_last_error(void);
+const char* salt_version(void);
+
+/* models.py:179-184 set_model(): build the network plan. */
+int salt_create(const salt_config* cfg, salt_engine** out);
+void salt_destroy(salt_engine* h);
+
+/* Sizes of the flat arrays the caller must provide to salt_bind(). */
+size_t salt_param_floats(const salt_engine* h);     /* trainable parameters (fp32)                      */
+size_t salt_buffer_floats(const salt_engine* h);    /* BatchNorm running_mean / running_var (fp32)      */
+size_t salt_workspace_bytes(const salt_engine* h);  /* activations, packed weights, scratch             */
+
+/* state_dict table (models.py:196-208 load / toolkit persist): entry i has the reference's key, shape, and
+ * its offset (in floats) inside the params (is_buffer=0) or buffers (is_buffer=1) array. */
+int salt_num_tensors(const salt_engine* h);
+int salt_tensor_info(const salt_engine* h, int i, char* name, int name_cap, int shape[4], int* ndim, size_t* offset,
+                     size_t* numel, int* is_buffer);
+
+/* Attach caller-owned device memory.  grads/adam_m/adam_v may be NULL for inference-only use. */
+int salt_bind(salt_engine* h, float* params, float* grads, float* adam_m, float* adam_v, float* buffers,
+              void* workspace, size_t workspace_bytes);
+/* Call after writing params from outside (load_state_dict, broadcast). */
+int salt_params_changed(salt_engine* h);
+
+/* unet.py:89-109 UNetResNet.forward: x [B,3,H,W] -> logits [B,num_classes,H,W].
+ * train=1: BatchNorm batch statistics (+ running-stat update) and activations kept for salt_backward;
+ * train=0: running statistics (model.eval(), models.py:150). */
+int salt_forward(salt_engine* h, const float* x_nchw, int batch, float* logits_nchw, int train, void* stream);
+
+/* models.py:326-328 lovasz_loss -> lovasz_losses.py:81-115 (per image, ELU variant).
+ * loss_out: 1 float; dlogits: d(mean loss)/d logits, same shape as logits. target: [B,C,H,W] fp32 of 0/1. */
+int salt_loss_lovasz(salt_engine* h, const float* logits, const float* target, int batch, float* loss_out,
+                     float* dlogits, void* stream);
+/* models.py:331-340 mixed_dice_bce_loss (dice 0.2 over the whole batch + BCE-with-logits 0.9), two stages so
+ * that data-parallel callers can all-reduce the 3*C+1 partial sums in between:
+ *   sums[3c+0]=sum(p*t) sums[3c+1]=sum(p) sums[3c+2]=sum(t)  sums[3C]=sum of element-wise BCE. */
+int salt_loss_bce_dice_reduce(salt_engine* h, const float* logits, const float* target, int batch, double* sums,
+                              void* stream);
+int salt_loss_bce_dice_finish(salt_engine* h, const float* logits, const float* target, int batch,
+                              const double* sums, double total_elements, float grad_scale, float* loss_out,
+                              float* dlogits, void* stream);
+
+/* models.py:133 batch_loss.backward(): fills the flat gradient array (zeroed first). */
+int salt_backward(salt_engine* h, const float* dlogits_nchw, void* stream);
+
+/* models.py:74-75,134,289-297: torch.optim.Adam step with L2 `grad += wd*p` on every parameter.
+ * grad_scale multiplies the stored gradients first (1/world after a SUM all-reduce). step counts from 1. */
+int salt_adam_step(salt_engine* h, float lr, float weight_decay, float beta1, float beta2, float eps, int step,
+                   float grad_scale, void* stream);
+
+/* utils.py:173-174 sigmoid, loaders.py:751-760 + augmentation.py:155-176 (mean over {orig, h-flip} of the
+ * un-flipped probabilities), postprocessing.py:24-43 crop_image + binarize.
+ * logits_flip may be NULL (no TTA). probs [B,C,S,S] and/or mask u8 [B,crop,crop] may be NULL. */
+int salt_predict(salt_engine* h, const float* logits, const float* logits_flip, int batch, int crop, float threshold,
+                 float* probs, uint8_t* mask, void* stream);
+
+/* Test/debug: copy a named internal activation ("stem","e2".."e5","center","d5".."d1","final_raw", "g_<name>")
+ * as fp32 NCHW into out (may be NULL to query the shape only). */
+int salt_get_activation(salt_engine* h, const char* name, float* out_nchw, int shape[4], void* stream);
+
+/* Number of CUDA kernels this library has launched so far in this process. */
+unsigned long long salt_launch_count(void);
+
+/* ---- single-operator entry points (unit tests; tensors NHWC in the given precision) ------------------ */
+typedef struct salt_conv_desc {
+    int batch, in_h, in_w, in_c;   /* physical input extent (borders included) */
+    int out_h, out_w, out_c;
+    int kernel, stride, pad;
+    int precision;
+    int use_tensor_cores;
+} salt_conv_desc;
+/* w: fp32 [out_c][in_c][k][k] (reference layout). stats may be NULL, else 2*out_c doubles (sum, sum of squares). */
+int salt_op_conv_forward(const salt_conv_desc* d, const void* in, const float* w, const float* bias, void* out,
+                         double* stats, void* stream);
+int salt_op_conv_dgrad(const salt_conv_desc* d, const void* gout, const float* w, void* gin, int accumulate,
+                       void* stream);
+int salt_op_conv_wgrad(const salt_conv_desc* d, const void* in, const void* gout, float* dw, void* stream);
+int salt_op_adam(float* p, const float* g, float* m, float* v, size_t n, float lr, float wd, float b1, float b2,
+                 float eps, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

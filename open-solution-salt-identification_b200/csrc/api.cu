@@ -1,0 +1,162 @@
+// extern "C" boundary of libsaltunet (declared in include/saltunet.h).
+#include "../../include/saltunet.h"
+#include "engine.h"
+#include <string>
+#include <cstring>
+#include <exception>
+
+struct salt_engine { Engine* e; };
+
+static thread_local std::string g_err;
+static int fail(const std::string& m) { g_err = m; return 1; }
+static int check_cuda(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string(what) + ": " + cudaGetErrorString(e));
+    return 0;
+}
+#define SALT_TRY(fn_name, ...)                                         \
+    try { __VA_ARGS__; } catch (const std::exception& ex) { return fail(std::string(fn_name) + ": " + ex.what()); } \
+    return check_cuda(fn_name);
+
+static int require_gpu() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); return fail("no CUDA device: libsaltunet has no CPU fallback"); }
+    return 0;
+}
+
+extern "C" {
+
+const char* salt_last_error(void) { return g_err.c_str(); }
+const char* salt_version(void) { return "saltunet-b200 0.1 (sm_100a)"; }
+
+int salt_create(const salt_config* cfg, salt_engine** out) {
+    if (!cfg || !out) return fail("salt_create: null argument");
+    if (cfg->arch != SALT_ARCH_UNET_RESNET) return fail("salt_create: unknown architecture (only UNetResNet is implemented)");
+    if (cfg->precision != SALT_PREC_FP32 && cfg->precision != SALT_PREC_BF16) return fail("salt_create: unknown precision");
+    try {
+        EngineConfig c;
+        c.depth = cfg->encoder_depth; c.num_classes = cfg->num_classes; c.max_batch = cfg->max_batch;
+        c.H = cfg->height; c.W = cfg->width; c.dt = cfg->precision == SALT_PREC_FP32 ? DT_F32 : DT_BF16;
+        c.use_tc = cfg->use_tensor_cores;
+        salt_engine* h = new salt_engine();
+        h->e = new Engine(c);
+        *out = h;
+    } catch (const std::exception& ex) { return fail(std::string("salt_create: ") + ex.what()); }
+    return 0;
+}
+void salt_destroy(salt_engine* h) { if (h) { delete h->e; delete h; } }
+
+size_t salt_param_floats(const salt_engine* h) { return h->e->param_floats(); }
+size_t salt_buffer_floats(const salt_engine* h) { return h->e->buffer_floats(); }
+size_t salt_workspace_bytes(const salt_engine* h) { return h->e->workspace_bytes(); }
+int salt_num_tensors(const salt_engine* h) { return (int)h->e->tensors().size(); }
+int salt_tensor_info(const salt_engine* h, int i, char* name, int name_cap, int shape[4], int* ndim, size_t* offset,
+                     size_t* numel, int* is_buffer) {
+    const auto& v = h->e->tensors();
+    if (i < 0 || i >= (int)v.size()) return fail("salt_tensor_info: index out of range");
+    const TensorInfo& t = v[i];
+    if (name && name_cap > 0) { strncpy(name, t.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    for (int k = 0; k < 4; ++k) shape[k] = t.shape[k];
+    *ndim = t.ndim; *offset = t.offset; *numel = t.numel; *is_buffer = t.is_buffer;
+    return 0;
+}
+int salt_bind(salt_engine* h, float* params, float* grads, float* adam_m, float* adam_v, float* buffers, void* workspace,
+              size_t workspace_bytes) {
+    if (!params || !buffers || !workspace) return fail("salt_bind: params, buffers and workspace are required");
+    if (require_gpu()) return 1;
+    SALT_TRY("salt_bind", h->e->bind(params, grads, adam_m, adam_v, buffers, workspace, workspace_bytes));
+}
+int salt_params_changed(salt_engine* h) { h->e->mark_params_dirty(); return 0; }
+
+int salt_forward(salt_engine* h, const float* x, int batch, float* logits, int train, void* stream) {
+    if (require_gpu()) return 1;
+    SALT_TRY("salt_forward", h->e->forward(x, batch, logits, train != 0, (cudaStream_t)stream));
+}
+int salt_loss_lovasz(salt_engine* h, const float* logits, const float* target, int batch, float* loss_out, float* dlogits,
+                     void* stream) {
+    const EngineConfig& c = h->e->config();
+    int P = c.num_classes * c.H * c.W;
+    if (P > 32768) return fail("salt_loss_lovasz: images with more than 32768 logits need the global-memory sort (not built yet)");
+    if (batch > c.max_batch) return fail("salt_loss_lovasz: batch exceeds max_batch");
+    SALT_TRY("salt_loss_lovasz", k_lovasz((cudaStream_t)stream, logits, target, batch, P, h->e->loss_scratch(), loss_out, dlogits));
+}
+int salt_loss_bce_dice_reduce(salt_engine* h, const float* logits, const float* target, int batch, double* sums, void* stream) {
+    const EngineConfig& c = h->e->config();
+    SALT_TRY("salt_loss_bce_dice_reduce", k_bce_dice_reduce((cudaStream_t)stream, logits, target, batch, c.num_classes, c.H * c.W, sums));
+}
+int salt_loss_bce_dice_finish(salt_engine* h, const float* logits, const float* target, int batch, const double* sums,
+                              double total_elements, float grad_scale, float* loss_out, float* dlogits, void* stream) {
+    const EngineConfig& c = h->e->config();
+    SALT_TRY("salt_loss_bce_dice_finish", k_bce_dice_finish((cudaStream_t)stream, logits, target, batch, c.num_classes, c.H * c.W, sums,
+                                                          total_elements, 0.2f, 0.9f, grad_scale, loss_out, dlogits));
+}
+int salt_backward(salt_engine* h, const float* dlogits, void* stream) {
+    SALT_TRY("salt_backward", h->e->backward(dlogits, (cudaStream_t)stream));
+}
+int salt_adam_step(salt_engine* h, float lr, float wd, float b1, float b2, float eps, int step, float grad_scale, void* stream) {
+    SALT_TRY("salt_adam_step", h->e->adam(lr, wd, b1, b2, eps, step, grad_scale, (cudaStream_t)stream));
+}
+int salt_predict(salt_engine* h, const float* logits, const float* logits_flip, int batch, int crop, float threshold,
+                 float* probs, uint8_t* mask, void* stream) {
+    const EngineConfig& c = h->e->config();
+    if (c.H != c.W) return fail("salt_predict: square inputs only");
+    if (crop > c.H) return fail("salt_predict: crop larger than the network input");
+    SALT_TRY("salt_predict", k_predict((cudaStream_t)stream, logits, logits_flip, batch, c.num_classes, c.H, crop, threshold, probs, mask));
+}
+int salt_get_activation(salt_engine* h, const char* name, float* out, int shape[4], void* stream) {
+    try {
+        if (!h->e->get_activation(name, out, shape, (cudaStream_t)stream)) return fail(std::string("salt_get_activation: unknown tensor ") + name);
+    } catch (const std::exception& ex) { return fail(ex.what()); }
+    return check_cuda("salt_get_activation");
+}
+unsigned long long salt_launch_count(void) { return g_salt_launches; }
+
+// ---------------------------------------------------------------------------------------- single operators
+static ConvGeom to_geom(const salt_conv_desc* d, int ci_mem) {
+    ConvGeom g;
+    g.B = d->batch; g.Hi = d->in_h; g.Wi = d->in_w; g.Ci = ci_mem; g.Ho = d->out_h; g.Wo = d->out_w; g.Co = d->out_c;
+    g.R = g.S = d->kernel; g.stride = d->stride; g.pad = d->pad;
+    return g;
+}
+struct PackedTmp {
+    void *wp = nullptr, *wpd = nullptr;
+    PackedTmp(const salt_conv_desc* d, const float* w, cudaStream_t st) {
+        DType dt = d->precision == SALT_PREC_FP32 ? DT_F32 : DT_BF16;
+        size_t bytes = (size_t)d->out_c * d->kernel * d->kernel * d->in_c * dtype_size(dt);
+        cudaMalloc(&wp, bytes); cudaMalloc(&wpd, bytes);
+        k_pack_weights(st, dt, w, wp, wpd, d->out_c, d->in_c, d->in_c, d->kernel, d->kernel);
+    }
+    ~PackedTmp() { cudaDeviceSynchronize(); cudaFree(wp); cudaFree(wpd); }
+};
+int salt_op_conv_forward(const salt_conv_desc* d, const void* in, const float* w, const float* bias, void* out, double* stats,
+                         void* stream) {
+    if (require_gpu()) return 1;
+    if (d->in_c % 4 || d->out_c % 4) return fail("salt_op_conv_forward: channel counts must be multiples of 4");
+    cudaStream_t st = (cudaStream_t)stream;
+    DType dt = d->precision == SALT_PREC_FP32 ? DT_F32 : DT_BF16;
+    PackedTmp pk(d, w, st);
+    k_conv_fwd_simt(st, dt, in, pk.wp, bias, out, stats, to_geom(d, d->in_c));
+    return check_cuda("salt_op_conv_forward");
+}
+int salt_op_conv_dgrad(const salt_conv_desc* d, const void* gout, const float* w, void* gin, int accumulate, void* stream) {
+    if (require_gpu()) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    DType dt = d->precision == SALT_PREC_FP32 ? DT_F32 : DT_BF16;
+    PackedTmp pk(d, w, st);
+    k_conv_dgrad_simt(st, dt, gout, pk.wpd, gin, accumulate != 0, to_geom(d, d->in_c));
+    return check_cuda("salt_op_conv_dgrad");
+}
+int salt_op_conv_wgrad(const salt_conv_desc* d, const void* in, const void* gout, float* dw, void* stream) {
+    if (require_gpu()) return 1;
+    DType dt = d->precision == SALT_PREC_FP32 ? DT_F32 : DT_BF16;
+    k_conv_wgrad_simt((cudaStream_t)stream, dt, in, gout, dw, d->in_c, to_geom(d, d->in_c));
+    return check_cuda("salt_op_conv_wgrad");
+}
+int salt_op_adam(float* p, const float* g, float* m, float* v, size_t n, float lr, float wd, float b1, float b2, float eps,
+                 int step, float grad_scale, void* stream) {
+    if (require_gpu()) return 1;
+    k_adam((cudaStream_t)stream, p, g, m, v, n, lr, wd, b1, b2, eps, step, grad_scale);
+    return check_cuda("salt_op_adam");
+}
+
+}  // extern "C"

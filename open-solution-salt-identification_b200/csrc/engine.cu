@@ -1,0 +1,488 @@
+#include "engine.h"
+#include <stdexcept>
+#include <cstring>
+#include <algorithm>
+
+unsigned long long g_salt_launches = 0;
+
+static const float BN_EPS = 1e-5f, BN_MOMENTUM = 0.1f;
+
+// ------------------------------------------------------------------------------------------------
+// plan construction
+// ------------------------------------------------------------------------------------------------
+Engine::Engine(const EngineConfig& cfg) : cfg_(cfg) {
+    if (cfg.depth != 18 && cfg.depth != 34) throw std::runtime_error("UNetResNet: only encoder_depth 18 and 34 are implemented in this engine");
+    if (cfg.H % 32 || cfg.W % 32) throw std::runtime_error("input height/width must be multiples of 32");
+    if (cfg.num_classes < 1 || cfg.num_classes > 4) throw std::runtime_error("num_classes must be 1..4");
+    counting_ = true;
+    build();            // pass 1: learns the BN-statistics arena and scratch sizes
+    build();            // pass 2: final layout
+    ws_bytes_ = ws_cursor_;
+}
+Engine::~Engine() {}
+
+size_t Engine::add_param(const std::string& name, std::vector<int> shape) {
+    TensorInfo ti; ti.name = name; ti.ndim = (int)shape.size(); ti.numel = 1; ti.is_buffer = 0;
+    for (int i = 0; i < 4; ++i) ti.shape[i] = i < ti.ndim ? shape[i] : 1;
+    for (int s : shape) ti.numel *= s;
+    ti.offset = n_params_;
+    n_params_ += (ti.numel + 3) / 4 * 4;      // keep every tensor 16-byte aligned
+    if (counting_) infos_.push_back(ti);
+    return ti.offset;
+}
+size_t Engine::add_buffer(const std::string& name, std::vector<int> shape) {
+    TensorInfo ti; ti.name = name; ti.ndim = (int)shape.size(); ti.numel = 1; ti.is_buffer = 1;
+    for (int i = 0; i < 4; ++i) ti.shape[i] = i < ti.ndim ? shape[i] : 1;
+    for (int s : shape) ti.numel *= s;
+    ti.offset = n_buffers_;
+    n_buffers_ += (ti.numel + 3) / 4 * 4;
+    if (counting_) infos_.push_back(ti);
+    return ti.offset;
+}
+void* Engine::ws_alloc(size_t bytes) {
+    size_t off = (ws_cursor_ + 255) / 256 * 256;
+    ws_cursor_ = off + bytes;
+    return counting_ ? nullptr : (void*)(ws_base_ + off);
+}
+Tensor Engine::make_tensor(int H, int W, int C, int pt, int pb, int pl, int pr) {
+    Tensor t; t.B = cfg_.max_batch; t.H = H; t.W = W; t.C = C; t.pt = pt; t.pb = pb; t.pl = pl; t.pr = pr; t.dt = cfg_.dt;
+    t.p = ws_alloc(t.bytes());
+    return t;
+}
+GradBuf* Engine::make_gradbuf(const Tensor& like) {
+    gradbufs_.emplace_back(new GradBuf());
+    GradBuf* g = gradbufs_.back().get();
+    g->g = make_tensor(like.H, like.W, like.C);
+    return g;
+}
+ConvLayer Engine::make_conv(const std::string& wname, const std::string& bname, int ci, int co, int k, int stride, int pad, int ci_mem) {
+    ConvLayer c; c.Ci_real = ci; c.Ci = ci_mem > 0 ? ci_mem : ci; c.Co = co; c.R = c.S = k; c.stride = stride; c.pad = pad;
+    c.o_w = add_param(wname, {co, ci, k, k});
+    c.o_b = bname.empty() ? -1 : (long long)add_param(bname, {co});
+    size_t wb = (size_t)co * k * k * c.Ci * dtype_size(cfg_.dt);
+    c.wp = ws_alloc(wb);
+    c.wpd = ws_alloc(wb);
+    return c;
+}
+BNLayer Engine::make_bn(const std::string& prefix, int c) {
+    BNLayer b; b.C = c;
+    b.o_gamma = add_param(prefix + ".weight", {c});
+    b.o_beta = add_param(prefix + ".bias", {c});
+    b.o_rm = add_buffer(prefix + ".running_mean", {c});
+    b.o_rv = add_buffer(prefix + ".running_var", {c});
+    b.sums = stats_arena_ + stats_cursor_; stats_cursor_ += 2 * c;
+    b.bsums = bstats_arena_ + bstats_cursor_; bstats_cursor_ += 2 * c;
+    float* f = (float*)ws_alloc(sizeof(float) * 6 * c);
+    b.scale = f; b.shift = f + c; b.mean = f + 2 * c; b.invstd = f + 3 * c; b.cb = f + 4 * c; b.cc = f + 5 * c;
+    return b;
+}
+void Engine::build_cbr(ConvBnRelu& u, const std::string& prefix, int ci, int co, int H, int W) {
+    // state_dict order of the reference: batch_norm.* then conv.* (base.py:24-27)
+    u.bn = make_bn(prefix + ".batch_norm", co);
+    u.c = make_conv(prefix + ".conv.weight", prefix + ".conv.bias", ci, co, 3, 1, 0);
+    u.P = make_tensor(H, W, ci, 2, 0, 0, 2);          // ReplicationPad2d((0,2,2,0)): 2 rows on top, 2 columns on the right
+    u.raw = make_tensor(H, W, co);
+    need_scratch(0, u.raw.bytes()); need_scratch(1, u.raw.bytes());
+    need_scratch(2, u.P.bytes());
+}
+void Engine::build_decoder(DecoderBlock& d, const std::string& name, std::vector<Source> srcs, int cm, int co, int H, int W) {
+    int ci = 0;
+    for (auto& s : srcs) ci += s.a->t.C;
+    d.srcs = srcs;
+    build_cbr(d.u1, name + ".conv1", ci, cm, H, W);
+    build_cbr(d.u2, name + ".conv2", cm, co, H, W);
+    d.se.C = co; d.se.Cr = co / 16;
+    d.se.o_w1 = add_param(name + ".channel_se.fc.0.weight", {co / 16, co});
+    d.se.o_b1 = add_param(name + ".channel_se.fc.0.bias", {co / 16});
+    d.se.o_w2 = add_param(name + ".channel_se.fc.2.weight", {co, co / 16});
+    d.se.o_b2 = add_param(name + ".channel_se.fc.2.bias", {co});
+    d.se.o_ws = add_param(name + ".spatial_se.fc.weight", {1, co, 1, 1});
+    d.se.o_bs = add_param(name + ".spatial_se.fc.bias", {1});
+    int B = cfg_.max_batch;
+    float* f = (float*)ws_alloc(sizeof(float) * B * (4 * co + d.se.Cr));
+    d.se.gap = f; d.se.cse = f + B * co; d.se.A = f + 2 * B * co; d.se.G = f + 3 * B * co; d.se.hid = f + 4 * B * co;
+    d.out.t = make_tensor(H, W, co);
+    d.out.gb = make_gradbuf(d.out.t);
+    for (auto& s : srcs)
+        if (s.f > 1) need_scratch(3, sizeof(float) * (size_t)B * (H + 2) * (W / s.f) * s.a->t.C);
+}
+size_t Engine::make_tensor_bytes(int H, int W, int C) const { return (size_t)cfg_.max_batch * H * W * C * dtype_size(cfg_.dt); }
+
+void Engine::build() {
+    n_params_ = n_buffers_ = 0; ws_cursor_ = 0; stats_cursor_ = bstats_cursor_ = 0;
+    blocks_.clear(); gradbufs_.clear();
+    if (counting_) infos_.clear();
+    const int B = cfg_.max_batch, H = cfg_.H, W = cfg_.W;
+    const int nblk18[4] = {2, 2, 2, 2}, nblk34[4] = {3, 4, 6, 3};
+    const int* nblk = cfg_.depth == 18 ? nblk18 : nblk34;
+    const int chans[4] = {64, 128, 256, 512};
+
+    // BN statistic arenas: sized on the counting pass
+    stats_arena_ = (double*)ws_alloc(sizeof(double) * std::max<size_t>(stats_doubles_, 1));
+    bstats_arena_ = (double*)ws_alloc(sizeof(double) * std::max<size_t>(bstats_doubles_, 1));
+
+    // ---- encoder (reference encoders.py:10-45, torchvision BasicBlock), parameter order = state_dict order
+    const std::string e = "encoders.encoder.";
+    x4_ = make_tensor(H, W, 4);
+    stem_ = make_conv(e + "conv1.weight", "", 3, 64, 7, 2, 3, 4);
+    stem_bn_ = make_bn(e + "bn1", 64);
+    stem_raw_ = make_tensor(H / 2, W / 2, 64);
+    stem_out_.t = make_tensor(H / 2, W / 2, 64);
+    stem_out_.gb = make_gradbuf(stem_out_.t);
+    need_scratch(1, stem_raw_.bytes());
+    Act* cur = &stem_out_;
+    int h = H / 2, w = W / 2, cin = 64;
+    for (int li = 0; li < 4; ++li) {
+        for (int bi = 0; bi < nblk[li]; ++bi) {
+            blocks_.emplace_back(new BasicBlock());
+            BasicBlock& b = *blocks_.back();
+            const std::string p = e + "layer" + std::to_string(li + 1) + "." + std::to_string(bi) + ".";
+            const int co = chans[li], stride = (bi == 0 && li > 0) ? 2 : 1;
+            b.down = (bi == 0 && li > 0);
+            b.x = cur;
+            b.c1 = make_conv(p + "conv1.weight", "", cin, co, 3, stride, 1);
+            b.b1 = make_bn(p + "bn1", co);
+            b.c2 = make_conv(p + "conv2.weight", "", co, co, 3, 1, 1);
+            b.b2 = make_bn(p + "bn2", co);
+            if (b.down) {
+                b.cd = make_conv(p + "downsample.0.weight", "", cin, co, 1, stride, 0);
+                b.bd = make_bn(p + "downsample.1", co);
+            }
+            h /= stride; w /= stride;
+            b.raw1 = make_tensor(h, w, co); b.a1 = make_tensor(h, w, co); b.raw2 = make_tensor(h, w, co);
+            if (b.down) b.rawd = make_tensor(h, w, co);
+            b.out.t = make_tensor(h, w, co);
+            b.out.gb = b.down ? make_gradbuf(b.out.t) : cur->gb;      // identity blocks pass the gradient buffer through
+            need_scratch(0, b.raw1.bytes()); need_scratch(1, b.raw1.bytes()); need_scratch(2, b.raw1.bytes());
+            cur = &b.out; cin = co;
+        }
+        enc_out_[li] = cur;
+    }
+    // ---- center (unet.py:60-63)
+    center_src_ = {{enc_out_[3], 1}};
+    build_cbr(center0_, "center.0", 512, 512, h, w);
+    build_cbr(center1_, "center.1", 512, 256, h, w);
+    center_out_.t = make_tensor(h / 2, w / 2, 256);
+    center_out_.gb = make_gradbuf(center_out_.t);
+    // ---- decoder (unet.py:65-79): dec5..dec1
+    build_decoder(dec_[0], "dec5", {{&center_out_, 2}, {enc_out_[3], 1}}, 512, 64, H / 16, W / 16);
+    build_decoder(dec_[1], "dec4", {{&dec_[0].out, 2}, {enc_out_[2], 1}}, 256, 64, H / 8, W / 8);
+    build_decoder(dec_[2], "dec3", {{&dec_[1].out, 2}, {enc_out_[1], 1}}, 128, 64, H / 4, W / 4);
+    build_decoder(dec_[3], "dec2", {{&dec_[2].out, 2}, {enc_out_[0], 1}}, 64, 64, H / 2, W / 2);
+    build_decoder(dec_[4], "dec1", {{&dec_[3].out, 2}}, 32, 64, H, W);
+    // ---- hypercolumn + final (unet.py:82-84, 101-109)
+    final_src_ = {{&dec_[4].out, 1}, {&dec_[3].out, 2}, {&dec_[2].out, 4}, {&dec_[1].out, 8}, {&dec_[0].out, 16}};
+    build_cbr(final0_, "final.0", 320, 64, H, W);
+    for (auto& s : final_src_)
+        if (s.f > 1) need_scratch(3, sizeof(float) * (size_t)B * (H + 2) * (W / s.f) * s.a->t.C);
+    o_final_w_ = add_param("final.1.weight", {cfg_.num_classes, 64, 1, 1});
+    o_final_b_ = add_param("final.1.bias", {cfg_.num_classes});
+
+    loss_scratch_ = (float*)ws_alloc(sizeof(float) * (B + 8));
+    loss_sums_ = (double*)ws_alloc(sizeof(double) * 16);
+    for (int i = 0; i < 4; ++i) scratch_[i] = ws_alloc(std::max<size_t>(scratch_bytes_[i], 256));
+    if (counting_) { stats_doubles_ = stats_cursor_; bstats_doubles_ = bstats_cursor_; }
+}
+
+void Engine::bind(float* params, float* grads, float* m, float* v, float* buffers, void* ws, size_t ws_bytes) {
+    if (ws_bytes < ws_bytes_) throw std::runtime_error("workspace too small");
+    params_ = params; grads_ = grads; adam_m_ = m; adam_v_ = v; buffers_ = buffers;
+    ws_base_ = (char*)ws;
+    counting_ = false;
+    build();
+    if (ws_cursor_ > ws_bytes_) throw std::runtime_error("internal error: workspace layout changed between passes");
+    packed_dirty_ = true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// run-time helpers
+// ------------------------------------------------------------------------------------------------
+BNRef Engine::bn_ref(const BNLayer& b) const {
+    BNRef r; r.C = b.C;
+    r.gamma = params_ + b.o_gamma; r.beta = params_ + b.o_beta;
+    r.rmean = buffers_ + b.o_rm; r.rvar = buffers_ + b.o_rv;
+    r.dgamma = grads_ ? grads_ + b.o_gamma : nullptr; r.dbeta = grads_ ? grads_ + b.o_beta : nullptr;
+    r.sums = b.sums; r.bsums = b.bsums; r.scale = b.scale; r.shift = b.shift; r.mean = b.mean; r.invstd = b.invstd;
+    r.cb = b.cb; r.cc = b.cc;
+    return r;
+}
+SERef Engine::se_ref(const SELayer& s) const {
+    SERef r; r.C = s.C; r.Cr = s.Cr;
+    r.w1 = params_ + s.o_w1; r.b1 = params_ + s.o_b1; r.w2 = params_ + s.o_w2; r.b2 = params_ + s.o_b2;
+    r.ws = params_ + s.o_ws; r.bs = params_ + s.o_bs;
+    float* g = grads_;
+    r.dw1 = g ? g + s.o_w1 : nullptr; r.db1 = g ? g + s.o_b1 : nullptr; r.dw2 = g ? g + s.o_w2 : nullptr;
+    r.db2 = g ? g + s.o_b2 : nullptr; r.dws = g ? g + s.o_ws : nullptr; r.dbs = g ? g + s.o_bs : nullptr;
+    r.gap = s.gap; r.hid = s.hid; r.cse = s.cse; r.A = s.A; r.G = s.G;
+    return r;
+}
+Tensor Engine::scratch(int i, int H, int W, int C, int pt, int pb, int pl, int pr) const {
+    Tensor t; t.p = scratch_[i]; t.B = B_; t.H = H; t.W = W; t.C = C; t.pt = pt; t.pb = pb; t.pl = pl; t.pr = pr; t.dt = cfg_.dt;
+    if (t.bytes() > scratch_bytes_[i]) throw std::runtime_error("internal error: scratch buffer too small");
+    return t;
+}
+ConvGeom Engine::geom(const ConvLayer& c, const Tensor& in, const Tensor& out) const {
+    ConvGeom g;
+    g.B = B_; g.Hi = in.Hp(); g.Wi = in.Wp(); g.Ci = c.Ci; g.Ho = out.H; g.Wo = out.W; g.Co = c.Co;
+    g.R = c.R; g.S = c.S; g.stride = c.stride; g.pad = c.pad;
+    return g;
+}
+void Engine::pack_all(cudaStream_t st) {
+    auto pack = [&](const ConvLayer& c) { k_pack_weights(st, cfg_.dt, params_ + c.o_w, c.wp, c.wpd, c.Co, c.Ci_real, c.Ci, c.R, c.S); };
+    pack(stem_);
+    for (auto& b : blocks_) { pack(b->c1); pack(b->c2); if (b->down) pack(b->cd); }
+    pack(center0_.c); pack(center1_.c);
+    for (auto& d : dec_) { pack(d.u1.c); pack(d.u2.c); }
+    pack(final0_.c);
+    packed_dirty_ = false;
+}
+void Engine::conv_fwd(const ConvLayer& c, const Tensor& in, const Tensor& out, BNLayer* bn, bool train, cudaStream_t st) {
+    ConvGeom g = geom(c, in, out);
+    const float* bias = c.o_b >= 0 ? params_ + c.o_b : nullptr;
+    k_conv_fwd_simt(st, cfg_.dt, in.p, c.wp, bias, out.p, (bn && train) ? bn->sums : nullptr, g);
+    if (bn) {
+        if (train) k_bn_finalize_train(st, bn_ref(*bn), (double)B_ * out.H * out.W, BN_MOMENTUM, BN_EPS);
+        else k_bn_finalize_eval(st, bn_ref(*bn), BN_EPS);
+    }
+}
+void Engine::conv_dgrad(const ConvLayer& c, const Tensor& gout, const Tensor& gin, bool accumulate, cudaStream_t st) {
+    ConvGeom g = geom(c, gin, gout);
+    k_conv_dgrad_simt(st, cfg_.dt, gout.p, c.wpd, gin.p, accumulate, g);
+}
+void Engine::conv_wgrad(const ConvLayer& c, const Tensor& in, const Tensor& gout, cudaStream_t st) {
+    ConvGeom g = geom(c, in, gout);
+    k_conv_wgrad_simt(st, cfg_.dt, in.p, gout.p, grads_ + c.o_w, c.Ci_real, g);
+}
+void Engine::gather_fwd(const std::vector<Source>& srcs, const Tensor& P, cudaStream_t st) {
+    GatherSrc gs[5];
+    for (size_t i = 0; i < srcs.size(); ++i) {
+        const Tensor& t = srcs[i].a->t;
+        gs[i].p = t.p; gs[i].H = t.H; gs[i].W = t.W; gs[i].C = t.C; gs[i].f = srcs[i].f;
+    }
+    k_gather_fwd(st, P, gs, (int)srcs.size());
+}
+void Engine::gather_bwd(const std::vector<Source>& srcs, const Tensor& gP, cudaStream_t st) {
+    int c0 = 0;
+    for (auto& s : srcs) {
+        GradBuf* gb = s.a->gb;
+        Tensor g = view(gb->g);
+        if (s.f == 1) k_fold_bwd(st, gP, c0, g, !gb->fresh);
+        else k_upsample_bwd(st, gP, c0, s.f, g, (float*)scratch_[3], !gb->fresh);
+        gb->fresh = false;
+        c0 += s.a->t.C;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+void Engine::block_fwd(BasicBlock& b, bool train, cudaStream_t st) {
+    Tensor x = view(b.x->t), raw1 = view(b.raw1), a1 = view(b.a1), raw2 = view(b.raw2), out = view(b.out.t);
+    conv_fwd(b.c1, x, raw1, &b.b1, train, st);
+    k_bn_apply(st, raw1, b.b1.scale, b.b1.shift, nullptr, nullptr, nullptr, true, a1);
+    conv_fwd(b.c2, a1, raw2, &b.b2, train, st);
+    if (b.down) {
+        Tensor rawd = view(b.rawd);
+        conv_fwd(b.cd, x, rawd, &b.bd, train, st);
+        k_bn_apply(st, raw2, b.b2.scale, b.b2.shift, &rawd, b.bd.scale, b.bd.shift, true, out);
+    } else {
+        k_bn_apply(st, raw2, b.b2.scale, b.b2.shift, &x, nullptr, nullptr, true, out);
+    }
+}
+void Engine::cbr_fwd(ConvBnRelu& u, bool train, cudaStream_t st) {
+    conv_fwd(u.c, view(u.P), view(u.raw), &u.bn, train, st);
+}
+void Engine::decoder_fwd(DecoderBlock& d, bool train, cudaStream_t st) {
+    gather_fwd(d.srcs, view(d.u1.P), st);
+    cbr_fwd(d.u1, train, st);
+    k_bn_apply(st, view(d.u1.raw), d.u1.bn.scale, d.u1.bn.shift, nullptr, nullptr, nullptr, true, view(d.u2.P));
+    cbr_fwd(d.u2, train, st);
+    k_scse_fwd(st, view(d.u2.raw), d.u2.bn.scale, d.u2.bn.shift, se_ref(d.se), view(d.out.t));
+}
+void Engine::forward(const float* x_nchw, int B, float* logits_nchw, bool train, cudaStream_t st) {
+    if (!params_) throw std::runtime_error("engine not bound");
+    if (B < 1 || B > cfg_.max_batch) throw std::runtime_error("batch size exceeds the engine's max_batch");
+    B_ = B;
+    if (packed_dirty_) pack_all(st);
+    if (train) k_zero(st, stats_arena_, sizeof(double) * stats_doubles_);
+    k_input_nchw_to_nhwc4(st, cfg_.dt, x_nchw, x4_.p, B, cfg_.H, cfg_.W);
+    Tensor x4 = view(x4_), sraw = view(stem_raw_);
+    conv_fwd(stem_, x4, sraw, &stem_bn_, train, st);
+    k_bn_apply(st, sraw, stem_bn_.scale, stem_bn_.shift, nullptr, nullptr, nullptr, true, view(stem_out_.t));
+    for (auto& b : blocks_) block_fwd(*b, train, st);
+    // center
+    gather_fwd(center_src_, view(center0_.P), st);
+    cbr_fwd(center0_, train, st);
+    k_bn_apply(st, view(center0_.raw), center0_.bn.scale, center0_.bn.shift, nullptr, nullptr, nullptr, true, view(center1_.P));
+    cbr_fwd(center1_, train, st);
+    k_bn_relu_avgpool(st, view(center1_.raw), center1_.bn.scale, center1_.bn.shift, view(center_out_.t));
+    for (auto& d : dec_) decoder_fwd(d, train, st);
+    gather_fwd(final_src_, view(final0_.P), st);
+    cbr_fwd(final0_, train, st);
+    k_final_fwd(st, view(final0_.raw), final0_.bn.scale, final0_.bn.shift, params_ + o_final_w_, params_ + o_final_b_,
+                cfg_.num_classes, logits_nchw);
+    trained_forward_ = train;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+void Engine::decoder_bwd(DecoderBlock& d, cudaStream_t st) {
+    const Tensor raw2 = view(d.u2.raw), raw1 = view(d.u1.raw), P2 = view(d.u2.P), P1 = view(d.u1.P);
+    const double cnt = (double)B_ * raw2.H * raw2.W;
+    BNRef bn2 = bn_ref(d.u2.bn), bn1 = bn_ref(d.u1.bn);
+    Tensor gbn2 = scratch(0, raw2.H, raw2.W, raw2.C), graw2 = scratch(1, raw2.H, raw2.W, raw2.C);
+    k_scse_bwd(st, view(d.out.gb->g), raw2, bn2, se_ref(d.se), gbn2);
+    k_bn_bwd_finalize(st, bn2, cnt);
+    k_bn_bwd_apply(st, gbn2, raw2, bn2, false, graw2);
+    conv_wgrad(d.u2.c, P2, graw2, st);
+    Tensor gP2 = scratch(2, P2.H, P2.W, P2.C, P2.pt, P2.pb, P2.pl, P2.pr);
+    conv_dgrad(d.u2.c, graw2, gP2, false, st);
+    Tensor ga1 = scratch(0, raw1.H, raw1.W, raw1.C), graw1 = scratch(1, raw1.H, raw1.W, raw1.C);
+    k_fold_bwd(st, gP2, 0, ga1, false);
+    k_bn_bwd_reduce(st, ga1, raw1, bn1, true);
+    k_bn_bwd_finalize(st, bn1, cnt);
+    k_bn_bwd_apply(st, ga1, raw1, bn1, true, graw1);
+    conv_wgrad(d.u1.c, P1, graw1, st);
+    Tensor gP1 = scratch(2, P1.H, P1.W, P1.C, P1.pt, P1.pb, P1.pl, P1.pr);
+    conv_dgrad(d.u1.c, graw1, gP1, false, st);
+    gather_bwd(d.srcs, gP1, st);
+}
+void Engine::block_bwd(BasicBlock& b, cudaStream_t st) {
+    Tensor x = view(b.x->t), raw1 = view(b.raw1), a1 = view(b.a1), raw2 = view(b.raw2), out = view(b.out.t);
+    Tensor G = view(b.out.gb->g);
+    const double cnt = (double)B_ * out.H * out.W;
+    BNRef bn1 = bn_ref(b.b1), bn2 = bn_ref(b.b2);
+    k_relu_mask_inplace(st, G, out);                               // gradient through the block's final ReLU
+    Tensor graw2 = scratch(0, out.H, out.W, out.C), ga1 = scratch(1, out.H, out.W, out.C);
+    k_bn_bwd_reduce(st, G, raw2, bn2, false);
+    k_bn_bwd_finalize(st, bn2, cnt);
+    k_bn_bwd_apply(st, G, raw2, bn2, false, graw2);
+    GradBuf* gxb = b.x->gb;
+    Tensor Gx = view(gxb->g);
+    if (b.down) {
+        Tensor rawd = view(b.rawd), grawd = scratch(2, out.H, out.W, out.C);
+        BNRef bnd = bn_ref(b.bd);
+        k_bn_bwd_reduce(st, G, rawd, bnd, false);
+        k_bn_bwd_finalize(st, bnd, cnt);
+        k_bn_bwd_apply(st, G, rawd, bnd, false, grawd);
+        conv_wgrad(b.cd, x, grawd, st);
+        conv_dgrad(b.cd, grawd, Gx, !gxb->fresh, st);
+        gxb->fresh = false;
+    }
+    conv_wgrad(b.c2, a1, graw2, st);
+    conv_dgrad(b.c2, graw2, ga1, false, st);
+    Tensor graw1 = scratch(0, out.H, out.W, out.C);
+    k_bn_bwd_reduce(st, ga1, raw1, bn1, true);
+    k_bn_bwd_finalize(st, bn1, cnt);
+    k_bn_bwd_apply(st, ga1, raw1, bn1, true, graw1);
+    conv_wgrad(b.c1, x, graw1, st);
+    // identity blocks: Gx aliases G and already holds the skip-path gradient -> accumulate
+    conv_dgrad(b.c1, graw1, Gx, b.down ? !gxb->fresh : true, st);
+    gxb->fresh = false;
+}
+void Engine::backward(const float* dlogits, cudaStream_t st) {
+    if (!grads_) throw std::runtime_error("engine bound without gradient buffers");
+    if (!trained_forward_) throw std::runtime_error("backward() requires a preceding forward(train=1)");
+    k_zero(st, grads_, sizeof(float) * n_params_);
+    k_zero(st, bstats_arena_, sizeof(double) * bstats_doubles_);
+    for (auto& g : gradbufs_) g->fresh = true;
+    // ---- final
+    {
+        const Tensor raw = view(final0_.raw), P = view(final0_.P);
+        BNRef bn = bn_ref(final0_.bn);
+        Tensor gbn = scratch(0, raw.H, raw.W, raw.C), graw = scratch(1, raw.H, raw.W, raw.C);
+        k_final_bwd(st, dlogits, raw, bn, params_ + o_final_w_, cfg_.num_classes, grads_ + o_final_w_, grads_ + o_final_b_, gbn);
+        k_bn_bwd_finalize(st, bn, (double)B_ * raw.H * raw.W);
+        k_bn_bwd_apply(st, gbn, raw, bn, false, graw);
+        conv_wgrad(final0_.c, P, graw, st);
+        Tensor gP = scratch(2, P.H, P.W, P.C, P.pt, P.pb, P.pl, P.pr);
+        conv_dgrad(final0_.c, graw, gP, false, st);
+        gather_bwd(final_src_, gP, st);
+    }
+    for (int i = 4; i >= 0; --i) decoder_bwd(dec_[i], st);
+    // ---- center
+    {
+        const Tensor raw1 = view(center1_.raw), raw0 = view(center0_.raw), P1 = view(center1_.P), P0 = view(center0_.P);
+        const double cnt = (double)B_ * raw1.H * raw1.W;
+        BNRef bn1 = bn_ref(center1_.bn), bn0 = bn_ref(center0_.bn);
+        Tensor gpost = scratch(0, raw1.H, raw1.W, raw1.C), graw1 = scratch(1, raw1.H, raw1.W, raw1.C);
+        k_avgpool_bwd(st, view(center_out_.gb->g), gpost);
+        k_bn_bwd_reduce(st, gpost, raw1, bn1, true);
+        k_bn_bwd_finalize(st, bn1, cnt);
+        k_bn_bwd_apply(st, gpost, raw1, bn1, true, graw1);
+        conv_wgrad(center1_.c, P1, graw1, st);
+        Tensor gP1 = scratch(2, P1.H, P1.W, P1.C, P1.pt, P1.pb, P1.pl, P1.pr);
+        conv_dgrad(center1_.c, graw1, gP1, false, st);
+        Tensor ga0 = scratch(0, raw0.H, raw0.W, raw0.C), graw0 = scratch(1, raw0.H, raw0.W, raw0.C);
+        k_fold_bwd(st, gP1, 0, ga0, false);
+        k_bn_bwd_reduce(st, ga0, raw0, bn0, true);
+        k_bn_bwd_finalize(st, bn0, cnt);
+        k_bn_bwd_apply(st, ga0, raw0, bn0, true, graw0);
+        conv_wgrad(center0_.c, P0, graw0, st);
+        Tensor gP0 = scratch(2, P0.H, P0.W, P0.C, P0.pt, P0.pb, P0.pl, P0.pr);
+        conv_dgrad(center0_.c, graw0, gP0, false, st);
+        gather_bwd(center_src_, gP0, st);
+    }
+    for (int i = (int)blocks_.size() - 1; i >= 0; --i) block_bwd(*blocks_[i], st);
+    // ---- stem (no input gradient)
+    {
+        const Tensor raw = view(stem_raw_);
+        BNRef bn = bn_ref(stem_bn_);
+        Tensor G = view(stem_out_.gb->g), graw = scratch(1, raw.H, raw.W, raw.C);
+        k_bn_bwd_reduce(st, G, raw, bn, true);
+        k_bn_bwd_finalize(st, bn, (double)B_ * raw.H * raw.W);
+        k_bn_bwd_apply(st, G, raw, bn, true, graw);
+        conv_wgrad(stem_, view(x4_), graw, st);
+    }
+}
+void Engine::adam(float lr, float wd, float b1, float b2, float eps, int step, float grad_scale, cudaStream_t st) {
+    if (!adam_m_ || !adam_v_ || !grads_) throw std::runtime_error("engine bound without optimiser state");
+    k_adam(st, params_, grads_, adam_m_, adam_v_, n_params_, lr, wd, b1, b2, eps, step, grad_scale);
+    packed_dirty_ = true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// debugging / test access to internal activations
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nhwc_to_nchw_f32_kernel(const T* __restrict__ src, float* __restrict__ dst, int B, int H, int W, int C, int pt,
+                                        int pl, int Hp, int Wp) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)B * C * H * W;
+    if (idx >= total) return;
+    int x = (int)(idx % W), y = (int)((idx / W) % H), c = (int)((idx / ((long long)W * H)) % C), n = (int)(idx / ((long long)W * H * C));
+    dst[idx] = ld1(src + (((size_t)n * Hp + y + pt) * Wp + x + pl) * C + c);
+}
+bool Engine::get_activation(const std::string& name, float* out, int* shape4, cudaStream_t st) {
+    const Tensor* t = nullptr;
+    auto dec_idx = [&](const std::string& n) { return n == "d5" ? 0 : n == "d4" ? 1 : n == "d3" ? 2 : n == "d2" ? 3 : n == "d1" ? 4 : -1; };
+    if (name == "stem") t = &stem_out_.t;
+    else if (name == "e2") t = &enc_out_[0]->t;
+    else if (name == "e3") t = &enc_out_[1]->t;
+    else if (name == "e4") t = &enc_out_[2]->t;
+    else if (name == "e5") t = &enc_out_[3]->t;
+    else if (name == "center") t = &center_out_.t;
+    else if (dec_idx(name) >= 0) t = &dec_[dec_idx(name)].out.t;
+    else if (name == "final_raw") t = &final0_.raw;
+    else if (name == "final_in") t = &final0_.P;
+    else if (name.rfind("g_", 0) == 0) {           // gradient buffers: g_e2.., g_d1.., g_center, g_stem
+        std::string n = name.substr(2);
+        if (n == "stem") t = &stem_out_.gb->g;
+        else if (n == "e2") t = &enc_out_[0]->gb->g;
+        else if (n == "e3") t = &enc_out_[1]->gb->g;
+        else if (n == "e4") t = &enc_out_[2]->gb->g;
+        else if (n == "e5") t = &enc_out_[3]->gb->g;
+        else if (n == "center") t = &center_out_.gb->g;
+        else if (dec_idx(n) >= 0) t = &dec_[dec_idx(n)].out.gb->g;
+    }
+    if (!t) return false;
+    Tensor v = view(*t);
+    shape4[0] = v.B; shape4[1] = v.C; shape4[2] = v.H; shape4[3] = v.W;
+    if (out) {
+        long long total = (long long)v.B * v.C * v.H * v.W;
+        SALT_DISPATCH(v.dt, T, (nhwc_to_nchw_f32_kernel<T><<<cdiv(total, 256), 256, 0, st>>>((const T*)v.p, out, v.B, v.H, v.W, v.C,
+                                                                                          v.pt, v.pl, v.Hp(), v.Wp())));
+    }
+    return true;
+}

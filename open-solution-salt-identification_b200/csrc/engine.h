@@ -1,0 +1,161 @@
+// U-Net (ResNet-18/34 encoder, scSE decoder, hypercolumn head) execution plan: static buffers, explicit
+// forward and backward passes built from the kernels in kernels.h.  Mirrors the computation of the reference
+// common_blocks/architectures/unet.py:44-109 (UNetResNet) - see DESIGN.md for the layer-by-layer mapping.
+#pragma once
+#include <string>
+#include <vector>
+#include <memory>
+#include "kernels.h"
+
+struct TensorInfo {            // one named entry of the reference state_dict
+    std::string name;
+    int shape[4];
+    int ndim;
+    size_t offset;             // in floats, inside the params (is_buffer=0) or buffers (is_buffer=1) flat array
+    size_t numel;
+    int is_buffer;
+};
+
+struct ConvLayer {
+    int Ci = 0, Ci_real = 0, Co = 0, R = 1, S = 1, stride = 1, pad = 0;
+    size_t o_w = 0;
+    long long o_b = -1;        // bias offset or -1
+    void* wp = nullptr;        // packed fwd weights   [Co][R*S][Ci]
+    void* wpd = nullptr;       // packed dgrad weights [Ci][R*S][Co]
+};
+struct BNLayer {
+    int C = 0;
+    size_t o_gamma = 0, o_beta = 0, o_rm = 0, o_rv = 0;
+    double *sums = nullptr, *bsums = nullptr;
+    float *scale = nullptr, *shift = nullptr, *mean = nullptr, *invstd = nullptr, *cb = nullptr, *cc = nullptr;
+};
+struct SELayer {
+    int C = 0, Cr = 0;
+    size_t o_w1 = 0, o_b1 = 0, o_w2 = 0, o_b2 = 0, o_ws = 0, o_bs = 0;
+    float *gap = nullptr, *hid = nullptr, *cse = nullptr, *A = nullptr, *G = nullptr;
+};
+struct GradBuf { Tensor g; bool fresh = true; };
+struct Act { Tensor t; GradBuf* gb = nullptr; };
+
+struct BasicBlock {
+    ConvLayer c1, c2, cd;
+    BNLayer b1, b2, bd;
+    bool down = false;
+    Act* x = nullptr;
+    Tensor raw1, a1, raw2, rawd;
+    Act out;
+};
+struct ConvBnRelu {            // reference base.py:7-37 on a replicate-bordered input
+    ConvLayer c;
+    BNLayer bn;
+    Tensor P, raw;
+};
+struct Source { Act* a; int f; };
+struct DecoderBlock {
+    ConvBnRelu u1, u2;
+    SELayer se;
+    std::vector<Source> srcs;
+    Act out;
+};
+
+struct EngineConfig {
+    int depth = 34, num_classes = 2, max_batch = 8, H = 128, W = 128;
+    DType dt = DT_F32;
+    int use_tc = 0;
+};
+
+class Engine {
+public:
+    explicit Engine(const EngineConfig& cfg);
+    ~Engine();
+
+    const std::vector<TensorInfo>& tensors() const { return infos_; }
+    size_t param_floats() const { return n_params_; }
+    size_t buffer_floats() const { return n_buffers_; }
+    size_t workspace_bytes() const { return ws_bytes_; }
+
+    void bind(float* params, float* grads, float* m, float* v, float* buffers, void* ws, size_t ws_bytes);
+    void forward(const float* x_nchw, int B, float* logits_nchw, bool train, cudaStream_t st);
+    void backward(const float* dlogits_nchw, cudaStream_t st);
+    void adam(float lr, float wd, float b1, float b2, float eps, int step, float grad_scale, cudaStream_t st);
+    void mark_params_dirty() { packed_dirty_ = true; }
+    // copy a named internal activation (NHWC T, border dropped) into fp32 NCHW; returns false if unknown
+    bool get_activation(const std::string& name, float* out_nchw, int* shape4, cudaStream_t st);
+
+    const EngineConfig& config() const { return cfg_; }
+    float* loss_scratch() { return loss_scratch_; }
+    double* loss_sums() { return loss_sums_; }
+
+private:
+    // ---- plan construction
+    size_t add_param(const std::string& name, std::vector<int> shape);
+    size_t add_buffer(const std::string& name, std::vector<int> shape);
+    ConvLayer make_conv(const std::string& wname, const std::string& bname, int ci, int co, int k, int stride, int pad, int ci_mem = -1);
+    BNLayer make_bn(const std::string& prefix, int c);
+    Tensor make_tensor(int H, int W, int C, int pt = 0, int pb = 0, int pl = 0, int pr = 0);
+    size_t make_tensor_bytes(int H, int W, int C) const;
+    GradBuf* make_gradbuf(const Tensor& like);
+    void* ws_alloc(size_t bytes);
+    void need_scratch(int i, size_t bytes) { if (bytes > scratch_bytes_[i]) scratch_bytes_[i] = bytes; }
+    void build();
+    void build_cbr(ConvBnRelu& u, const std::string& prefix, int ci, int co, int H, int W);
+    void build_decoder(DecoderBlock& d, const std::string& name, std::vector<Source> srcs, int cm, int co, int H, int W);
+
+    // ---- run time
+    BNRef bn_ref(const BNLayer& b) const;
+    SERef se_ref(const SELayer& s) const;
+    Tensor view(const Tensor& t) const { Tensor r = t; r.B = B_; return r; }
+    Tensor scratch(int i, int H, int W, int C, int pt = 0, int pb = 0, int pl = 0, int pr = 0) const;
+    ConvGeom geom(const ConvLayer& c, const Tensor& in, const Tensor& out) const;
+    void pack_all(cudaStream_t st);
+    void conv_fwd(const ConvLayer& c, const Tensor& in, const Tensor& out, BNLayer* bn, bool train, cudaStream_t st);
+    void conv_dgrad(const ConvLayer& c, const Tensor& gout, const Tensor& gin, bool accumulate, cudaStream_t st);
+    void conv_wgrad(const ConvLayer& c, const Tensor& in, const Tensor& gout, cudaStream_t st);
+    void gather_fwd(const std::vector<Source>& srcs, const Tensor& P, cudaStream_t st);
+    void gather_bwd(const std::vector<Source>& srcs, const Tensor& gP, cudaStream_t st);
+    void block_fwd(BasicBlock& b, bool train, cudaStream_t st);
+    void block_bwd(BasicBlock& b, cudaStream_t st);
+    void cbr_fwd(ConvBnRelu& u, bool train, cudaStream_t st);
+    void decoder_fwd(DecoderBlock& d, bool train, cudaStream_t st);
+    void decoder_bwd(DecoderBlock& d, cudaStream_t st);
+
+    EngineConfig cfg_;
+    std::vector<TensorInfo> infos_;
+    size_t n_params_ = 0, n_buffers_ = 0;
+    size_t ws_bytes_ = 0, ws_cursor_ = 0;
+    bool counting_ = true;
+    char* ws_base_ = nullptr;
+    float *params_ = nullptr, *grads_ = nullptr, *adam_m_ = nullptr, *adam_v_ = nullptr, *buffers_ = nullptr;
+    bool packed_dirty_ = true;
+    bool trained_forward_ = false;
+    int B_ = 0;
+
+    // network
+    Tensor x4_;
+    ConvLayer stem_;
+    BNLayer stem_bn_;
+    Tensor stem_raw_;
+    Act stem_out_;
+    std::vector<std::unique_ptr<BasicBlock>> blocks_;
+    Act* enc_out_[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<Source> center_src_;
+    ConvBnRelu center0_, center1_;
+    Act center_out_;
+    DecoderBlock dec_[5];            // dec5, dec4, dec3, dec2, dec1
+    std::vector<Source> final_src_;
+    ConvBnRelu final0_;
+    size_t o_final_w_ = 0, o_final_b_ = 0;
+    std::vector<std::unique_ptr<GradBuf>> gradbufs_;
+
+    // stats arenas (zeroed per pass)
+    double* stats_arena_ = nullptr; size_t stats_doubles_ = 0;
+    double* bstats_arena_ = nullptr; size_t bstats_doubles_ = 0;
+    size_t stats_cursor_ = 0, bstats_cursor_ = 0;
+    // scratch pool
+    void* scratch_[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes_[4] = {0, 0, 0, 0};
+    float* loss_scratch_ = nullptr;   // [max_batch + 8]
+    double* loss_sums_ = nullptr;     // [16]
+};
+
+extern unsigned long long g_salt_launches;

@@ -1,0 +1,166 @@
+"""Python handle on one engine instance: owns the device memory (torch tensors, used purely as
+allocations / views), exposes forward, losses, backward, optimiser step and prediction.
+
+PyTorch is plumbing here: it allocates HBM, provides the current CUDA stream and (in dist.py) the NCCL
+process group.  Every arithmetic operation runs in libsaltunet.so.
+"""
+import ctypes as C
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import SaltEngineError
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class UNetEngine:
+    """UNetResNet (reference architectures/unet.py:22-109) on the CUDA engine.
+
+    precision: 'fp32' (parity mode: fp32 storage, fp32 FMA) or 'bf16' (bf16 activations / weights copies,
+    fp32 accumulation, fp32 master weights and optimiser state).
+    """
+
+    def __init__(self, encoder_depth=34, num_classes=2, max_batch=8, size=128, precision='fp32',
+                 use_tensor_cores=True, training=True, device=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise SaltEngineError('UNetEngine needs a CUDA device (B200); there is no CPU fallback')
+        self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+        self.encoder_depth, self.num_classes, self.max_batch, self.size = encoder_depth, num_classes, max_batch, size
+        self.precision = precision
+        cfg = _lib.SaltConfig(_lib.ARCH_UNET_RESNET, encoder_depth, num_classes, max_batch, size, size,
+                              {'fp32': _lib.PREC_FP32, 'bf16': _lib.PREC_BF16}[precision], int(bool(use_tensor_cores)))
+        h = C.c_void_p()
+        _lib.check(self.lib.salt_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        n_p = self.lib.salt_param_floats(h)
+        n_b = self.lib.salt_buffer_floats(h)
+        ws = self.lib.salt_workspace_bytes(h)
+        with torch.cuda.device(self.device):
+            self.params = torch.zeros(n_p, dtype=torch.float32, device=self.device)
+            self.buffers = torch.zeros(n_b, dtype=torch.float32, device=self.device)
+            self.grads = torch.zeros(n_p, dtype=torch.float32, device=self.device) if training else None
+            self.adam_m = torch.zeros(n_p, dtype=torch.float32, device=self.device) if training else None
+            self.adam_v = torch.zeros(n_p, dtype=torch.float32, device=self.device) if training else None
+            self.workspace = torch.empty(ws, dtype=torch.uint8, device=self.device)
+            self._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+            self._sums = torch.zeros(16, dtype=torch.float64, device=self.device)
+        self.table = self._read_table()
+        _lib.check(self.lib.salt_bind(h, _ptr(self.params), _ptr(self.grads), _ptr(self.adam_m), _ptr(self.adam_v),
+                                      _ptr(self.buffers), _ptr(self.workspace), ws))
+        self.step_count = 0
+        self.num_batches_tracked = 0
+        self._init_buffers()
+
+    def __del__(self):
+        try:
+            if getattr(self, 'h', None):
+                self.lib.salt_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ parameters
+    def _read_table(self):
+        table = OrderedDict()
+        name = C.create_string_buffer(256)
+        shape = (C.c_int * 4)()
+        ndim, isbuf = C.c_int(), C.c_int()
+        off, numel = C.c_size_t(), C.c_size_t()
+        for i in range(self.lib.salt_num_tensors(self.h)):
+            _lib.check(self.lib.salt_tensor_info(self.h, i, name, 256, shape, C.byref(ndim), C.byref(off),
+                                                 C.byref(numel), C.byref(isbuf)))
+            table[name.value.decode()] = (tuple(shape[:ndim.value]), off.value, numel.value, bool(isbuf.value))
+        return table
+
+    def _init_buffers(self):
+        for k, (shape, off, numel, isbuf) in self.table.items():
+            if k.endswith('running_var'):
+                self.buffers[off:off + numel] = 1.0
+
+    def view(self, key, grad=False):
+        """Zero-copy torch view of one state_dict entry (or of its gradient)."""
+        shape, off, numel, isbuf = self.table[key]
+        flat = self.buffers if isbuf else (self.grads if grad else self.params)
+        return flat[off:off + numel].view(shape)
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def load_state(self, state):
+        """state: mapping of canonical reference keys -> array/tensor.  Unknown keys are ignored by the
+        caller (see models.EngineModule.load_state_dict)."""
+        for k, v in state.items():
+            if k in self.table:
+                t = torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v)
+                self.view(k).copy_(t.to(self.device, torch.float32).reshape(self.table[k][0]))
+        self.params_changed()
+
+    def params_changed(self):
+        _lib.check(self.lib.salt_params_changed(self.h))
+
+    # ------------------------------------------------------------------ compute
+    def forward(self, x, train=False, out=None):
+        """x: fp32 CUDA tensor [B,3,S,S] -> logits fp32 [B,num_classes,S,S]."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous(), 'x must be a contiguous fp32 CUDA tensor'
+        b = x.shape[0]
+        if tuple(x.shape[1:]) != (3, self.size, self.size):
+            raise SaltEngineError('input must be [B,3,%d,%d], got %s' % (self.size, self.size, tuple(x.shape)))
+        if out is None:
+            out = torch.empty((b, self.num_classes, self.size, self.size), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.salt_forward(self.h, _ptr(x), b, _ptr(out), int(train), self._stream()))
+        if train:
+            self.num_batches_tracked += 1
+        return out
+
+    def loss_lovasz(self, logits, target, dlogits=None):
+        if dlogits is None:
+            dlogits = torch.empty_like(logits)
+        _lib.check(self.lib.salt_loss_lovasz(self.h, _ptr(logits), _ptr(target), logits.shape[0], _ptr(self._loss),
+                                             _ptr(dlogits), self._stream()))
+        return self._loss, dlogits
+
+    def loss_bce_dice(self, logits, target, dlogits=None, group=None):
+        """0.2*dice + 0.9*bce; with a process group the Dice/BCE sums are all-reduced so that the loss is the
+        reference's whole-batch value."""
+        if dlogits is None:
+            dlogits = torch.empty_like(logits)
+        b = logits.shape[0]
+        _lib.check(self.lib.salt_loss_bce_dice_reduce(self.h, _ptr(logits), _ptr(target), b, _ptr(self._sums), self._stream()))
+        world = 1
+        if group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(group)
+            dist.all_reduce(self._sums, group=group)
+        total = float(logits.numel()) * world
+        _lib.check(self.lib.salt_loss_bce_dice_finish(self.h, _ptr(logits), _ptr(target), b, _ptr(self._sums), total,
+                                                      float(world), _ptr(self._loss), _ptr(dlogits), self._stream()))
+        return self._loss, dlogits
+
+    def backward(self, dlogits):
+        _lib.check(self.lib.salt_backward(self.h, _ptr(dlogits), self._stream()))
+
+    def adam_step(self, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+        self.step_count += 1
+        _lib.check(self.lib.salt_adam_step(self.h, lr, weight_decay, betas[0], betas[1], eps, self.step_count,
+                                           grad_scale, self._stream()))
+
+    def predict(self, logits, logits_flip=None, crop=101, threshold=0.5, want_probs=True, want_mask=True):
+        b = logits.shape[0]
+        probs = torch.empty_like(logits) if want_probs else None
+        mask = torch.empty((b, crop, crop), dtype=torch.uint8, device=self.device) if want_mask else None
+        _lib.check(self.lib.salt_predict(self.h, _ptr(logits), _ptr(logits_flip), b, crop, threshold, _ptr(probs),
+                                         _ptr(mask), self._stream()))
+        return probs, mask
+
+    def activation(self, name):
+        shape = (C.c_int * 4)()
+        _lib.check(self.lib.salt_get_activation(self.h, name.encode(), C.c_void_p(0), shape, self._stream()))
+        out = torch.empty(tuple(shape), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.salt_get_activation(self.h, name.encode(), _ptr(out), shape, self._stream()))
+        return out

@@ -83,7 +83,9 @@ def synth_state_dict(depth=34, num_classes=2, seed=0):
         elif kind == 'bias':
             a = rng.standard_normal(shape) * 0.1
         elif kind == 'bn_w':
-            a = rng.uniform(0.5, 1.5, shape)
+            # the last BN of a residual branch gets a small gain so that eval-mode activations (running
+            # statistics, no renormalisation) stay O(1) through 16 residual blocks
+            a = rng.uniform(0.1, 0.5, shape) if name.endswith('bn2.weight') else rng.uniform(0.5, 1.5, shape)
         elif kind == 'bn_b':
             a = rng.standard_normal(shape) * 0.1
         elif kind == 'bn_rm':
