@@ -1,0 +1,252 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: one training step of UNetResNet-34 (128x128 network input = one padded 101x101
+tile, bf16, 128 images per GPU, BCE+Dice) - BASELINE.json configs[1] - through the drop-in SegmentationModel.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                     (the reference algorithm's CPU path, oracle port)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'open-solution-salt-identification_b200')
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch        # noqa: E402
+
+DEPTH, SIZE, BATCH_PER_GPU, CLASSES = 34, 128, 128, 2
+WORKLOAD = 'UNetResNet-34 train step (fwd + BCE+Dice + bwd + Adam-L2), 3x128x128 inputs (padded 101x101 tiles), bf16, batch 128 per GPU'
+# algorithmic conv FLOPs of one training step per image: fwd + dgrad + wgrad
+TRAIN_GFLOP_PER_IMAGE = 58.42
+CPU_SAMPLE_BATCH = 8
+
+
+def _peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {'tflops': float(p.get('bf16_tflops_sustained', p.get('bf16_tflops'))), 'hbm_gbs': float(p['hbm_gbs']),
+                'source': 'MEASURED_PEAKS.json (bf16_tflops_sustained)'}
+    return {'tflops': 1400.0, 'hbm_gbs': 6650.0, 'source': 'fallback (B200_PROFILING.md: ~1.4 PFLOP/s sustained, 6.65 TB/s)'}
+
+
+# ------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix='.csv')
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [s.strip() for s in line.split(',')]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------- CPU arm
+def cpu_train_steps(steps, warmup, batch=CPU_SAMPLE_BATCH, threads=None):
+    """The reference algorithm's CPU path (oracle port, plain PyTorch fp32 on the host cores): `steps` timed training
+    steps on a bounded sample of `batch` images of the workload.  Returns (images_per_s, seconds_per_step, threads)."""
+    from oracle import synth, unet_oracle, losses_oracle
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sd = unet_oracle.to_torch_state(synth.synth_state_dict(DEPTH, CLASSES, 0), requires_grad=True)
+    params = {k: v for k, v in sd.items() if v.requires_grad}
+    m = {k: torch.zeros_like(v) for k, v in params.items()}
+    vv = {k: torch.zeros_like(v) for k, v in params.items()}
+    x = torch.from_numpy(synth.synth_inputs(batch, SIZE, 1234))
+    t = torch.from_numpy(synth.synth_targets(batch, SIZE, 1234))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for p in params.values():
+            p.grad = None
+        loss = losses_oracle.bce_dice(unet_oracle.unet_resnet_forward(sd, x, DEPTH, train=True), t)
+        loss.backward()
+        with torch.no_grad():
+            unet_oracle.adam_l2_step({k: v.data for k, v in params.items()}, {k: v.grad for k, v in params.items()}, m, vv, it + 1)
+        loss.item()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = float(np.sum(times))
+    return batch * steps / sec, sec / steps, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    ips, sec_step, threads = cpu_train_steps(args.steps, args.warmup)
+    sample = '%d-image sample of the 128-image batch per step, oracle port (PyTorch fp32 CPU), %d threads' % (CPU_SAMPLE_BATCH, threads)
+    line = {'impl': 'reference', 'metric': 'images/sec', 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': sec_step * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'sample': sample},
+            'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': threads, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------- our arm
+def make_model(precision, batch, loss):
+    from salt_b200.models import SegmentationModel
+    os.environ['SALT_ENGINE_PRECISION'] = precision
+    os.environ['SALT_ENGINE_MAX_BATCH'] = str(batch)
+    os.environ['SALT_ENGINE_SIZE'] = str(SIZE)
+    os.environ['SALT_ENGINE_LOSS'] = loss
+    arch = {'model_params': {'architecture': 'UNetResNet', 'encoder_depth': DEPTH, 'in_channels': 3, 'out_channels': CLASSES, 'activation': 'sigmoid'},
+            'optimizer_params': {'lr': 1e-4}, 'regularizer_params': {'regularize': True, 'weight_decay_conv2d': 1e-4},
+            'weights_init': {'function': 'he', 'pretrained': False}}
+    return SegmentationModel(arch, {'epochs': 1}, {})
+
+
+def run_ours(args):
+    from oracle import synth            # synthetic data / weight generators only (numpy); not on the timed path
+    from salt_b200 import _lib
+    model = make_model(args.precision, args.batch, args.loss)
+    ctx, eng = model.dp, model.engine
+    dev = eng.device
+    eng.load_state(synth.synth_state_dict(DEPTH, CLASSES, 0))
+    B = args.batch
+    x_h = torch.from_numpy(synth.synth_inputs(B, SIZE, 1234 + ctx.rank)).pin_memory()
+    t_h = torch.from_numpy(synth.synth_targets(B, SIZE, 1234 + ctx.rank)).pin_memory()
+    x_d, t_d = x_h.to(dev), t_h.to(dev)
+
+    def timed(fn, steps):
+        ctx.barrier(); torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev); ctx.barrier()
+        return ctx.max_over_ranks(e0.elapsed_time(e1))
+
+    def step_device():
+        return model.train_step_device(x_d, [t_d])
+
+    def step_e2e():
+        out = model._fit_loop([x_h, t_h])
+        return float(out['sum'].cpu()[0])       # D2H read of the step's loss
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(ctx.local_rank) if ctx.rank == 0 else None
+    l0 = _lib.launch_count()
+    ms = timed(step_device, args.steps)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    for _ in range(min(args.warmup, 3)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # per-kernel-class device time of the convolution kernels (CUDA events on the launch stream), 2 extra steps
+    eng.profile(True)
+    for _ in range(2):
+        step_device()
+    prof = eng.profile_read()
+    eng.profile(False)
+
+    if ctx.rank != 0:
+        return
+    peaks = _peaks()
+    n = ctx.world
+    value = B * n * args.steps / (ms / 1e3)
+    e2e = B * n * args.steps / (ms_e2e / 1e3)
+    kern = {k: {'ms_per_step': v[0] / 2, 'tflops': (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0), 'launches_per_step': v[2] // 2}
+            for k, v in prof.items()}
+    tot_ms = sum(v[0] for v in prof.values())
+    tot_fl = sum(v[1] for v in prof.values())
+    achieved = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get('traffic')
+    line = {
+        'metric': 'images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': n, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': args.precision, 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'global_batch': B * n, 'loss': args.loss, 'parallelism': 'dp%d' % n,
+                   'l2': 'per-step working set (saved activations of %d images, several GB) is far larger than the 126 MB L2; no explicit flush' % B},
+        'clocks': clocks,
+        'e2e': {'value': e2e, 'unit': 'images/s', 'ms_per_step': ms_e2e / args.steps,
+                'h2d_bytes_per_step': int(x_h.numel() * 4 + t_h.numel() * 4), 'd2h_bytes_per_step': 4,
+                'api': 'salt_b200.models.SegmentationModel._fit_loop (pinned host tensors in, loss read back)'},
+        'gpu_launches': int(launches),
+        'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
+                     'frac': achieved / peaks['tflops'], 'traffic': traffic, 'peak_source': peaks['source'],
+                     'kernel': 'implicit-GEMM convolution (forward + dgrad + wgrad launches of one step, algorithmic FLOPs / CUDA-event time)',
+                     'conv_share_of_step': (tot_ms / 2) / (ms / args.steps), 'per_class': kern,
+                     'step_tflops': value / n * TRAIN_GFLOP_PER_IMAGE / 1e3,
+                     'step_frac_of_peak': value / n * TRAIN_GFLOP_PER_IMAGE / 1e3 / peaks['tflops']},
+    }
+    if n == 1 and not args.no_cpu_baseline:
+        ips, sec_step, threads = cpu_train_steps(2, 1)
+        line['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
+                                'sample': '%d-image sample of the batch, 2 timed training steps of the oracle port (PyTorch fp32 CPU)' % CPU_SAMPLE_BATCH}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=BATCH_PER_GPU, help='images per GPU')
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--loss', default='bce_dice', choices=['bce_dice', 'lovasz'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

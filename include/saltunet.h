@@ -98,6 +98,12 @@ int salt_get_activation(salt_engine* h, const char* name, float* out_nchw, int s
 /* Number of CUDA kernels this library has launched so far in this process. */
 unsigned long long salt_launch_count(void);
 
+/* Measurement aid (bench.py roofline): bracket every convolution launch with CUDA events on its stream.
+ * kernel_class: 0 = conv forward, 1 = conv dgrad, 2 = conv wgrad.  salt_profile_read synchronises and returns the
+ * accumulated device milliseconds, algorithmic FLOPs (2*B*Ho*Wo*Cout*Cin*R*S per launch) and launch count. */
+int salt_profile_enable(salt_engine* h, int on);
+int salt_profile_read(salt_engine* h, int kernel_class, double* ms, double* flops, long long* launches);
+
 /* ---- single-operator entry points (unit tests; tensors NHWC in the given precision) ------------------ */
 typedef struct salt_conv_desc {
     int batch, in_h, in_w, in_c;   /* physical input extent (borders included) */

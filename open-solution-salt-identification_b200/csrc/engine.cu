@@ -99,8 +99,10 @@ void Engine::build_decoder(DecoderBlock& d, const std::string& name, std::vector
     d.se.o_ws = add_param(name + ".spatial_se.fc.weight", {1, co, 1, 1});
     d.se.o_bs = add_param(name + ".spatial_se.fc.bias", {1});
     int B = cfg_.max_batch;
-    float* f = (float*)ws_alloc(sizeof(float) * B * (4 * co + d.se.Cr));
-    d.se.gap = f; d.se.cse = f + B * co; d.se.A = f + 2 * B * co; d.se.G = f + 3 * B * co; d.se.hid = f + 4 * B * co;
+    d.se.chunks = std::max(1, std::min(64, (H * W) / 128));
+    float* f = (float*)ws_alloc(sizeof(float) * B * ((3 + d.se.chunks) * co + d.se.Cr));
+    d.se.gap = f; d.se.cse = f + B * co; d.se.G = f + 2 * B * co; d.se.part = f + 3 * B * co;
+    d.se.hid = f + (size_t)(3 + d.se.chunks) * B * co;
     d.out.t = make_tensor(H, W, co);
     d.out.gb = make_gradbuf(d.out.t);
     for (auto& s : srcs)
@@ -213,7 +215,7 @@ SERef Engine::se_ref(const SELayer& s) const {
     float* g = grads_;
     r.dw1 = g ? g + s.o_w1 : nullptr; r.db1 = g ? g + s.o_b1 : nullptr; r.dw2 = g ? g + s.o_w2 : nullptr;
     r.db2 = g ? g + s.o_b2 : nullptr; r.dws = g ? g + s.o_ws : nullptr; r.dbs = g ? g + s.o_bs : nullptr;
-    r.gap = s.gap; r.hid = s.hid; r.cse = s.cse; r.A = s.A; r.G = s.G;
+    r.gap = s.gap; r.hid = s.hid; r.cse = s.cse; r.part = s.part; r.G = s.G; r.chunks = s.chunks;
     return r;
 }
 Tensor Engine::scratch(int i, int H, int W, int C, int pt, int pb, int pl, int pr) const {
@@ -236,10 +238,41 @@ void Engine::pack_all(cudaStream_t st) {
     pack(final0_.c);
     packed_dirty_ = false;
 }
+static double conv_flops(const ConvGeom& g, int ci_real) {
+    return 2.0 * g.B * g.Ho * g.Wo * (double)g.Co * ci_real * g.R * g.S;
+}
+void Engine::profile_enable(bool on) {
+    for (auto& r : prof_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    prof_.clear();
+    prof_on_ = on;
+}
+void Engine::prof_begin(int cls, double flops, cudaStream_t st) {
+    if (!prof_on_) return;
+    ProfRec r; r.flops = flops; r.cls = cls;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    prof_.push_back(r);
+}
+void Engine::prof_end(cudaStream_t st) {
+    if (!prof_on_) return;
+    cudaEventRecord(prof_.back().b, st);
+}
+void Engine::profile_read(int cls, double* ms, double* flops, long long* launches) {
+    cudaDeviceSynchronize();
+    *ms = 0; *flops = 0; *launches = 0;
+    for (auto& r : prof_) {
+        if (r.cls != cls) continue;
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        *ms += t; *flops += r.flops; *launches += 1;
+    }
+}
 void Engine::conv_fwd(const ConvLayer& c, const Tensor& in, const Tensor& out, BNLayer* bn, bool train, cudaStream_t st) {
     ConvGeom g = geom(c, in, out);
     const float* bias = c.o_b >= 0 ? params_ + c.o_b : nullptr;
+    prof_begin(PROF_CONV_FWD, conv_flops(g, c.Ci_real), st);
     k_conv_fwd_simt(st, cfg_.dt, in.p, c.wp, bias, out.p, (bn && train) ? bn->sums : nullptr, g);
+    prof_end(st);
     if (bn) {
         if (train) k_bn_finalize_train(st, bn_ref(*bn), (double)B_ * out.H * out.W, BN_MOMENTUM, BN_EPS);
         else k_bn_finalize_eval(st, bn_ref(*bn), BN_EPS);
@@ -247,11 +280,15 @@ void Engine::conv_fwd(const ConvLayer& c, const Tensor& in, const Tensor& out, B
 }
 void Engine::conv_dgrad(const ConvLayer& c, const Tensor& gout, const Tensor& gin, bool accumulate, cudaStream_t st) {
     ConvGeom g = geom(c, gin, gout);
+    prof_begin(PROF_CONV_DGRAD, conv_flops(g, c.Ci_real), st);
     k_conv_dgrad_simt(st, cfg_.dt, gout.p, c.wpd, gin.p, accumulate, g);
+    prof_end(st);
 }
 void Engine::conv_wgrad(const ConvLayer& c, const Tensor& in, const Tensor& gout, cudaStream_t st) {
     ConvGeom g = geom(c, in, gout);
+    prof_begin(PROF_CONV_WGRAD, conv_flops(g, c.Ci_real), st);
     k_conv_wgrad_simt(st, cfg_.dt, in.p, gout.p, grads_ + c.o_w, c.Ci_real, g);
+    prof_end(st);
 }
 void Engine::gather_fwd(const std::vector<Source>& srcs, const Tensor& P, cudaStream_t st) {
     GatherSrc gs[5];

@@ -32,7 +32,8 @@ struct BNLayer {
 struct SELayer {
     int C = 0, Cr = 0;
     size_t o_w1 = 0, o_b1 = 0, o_w2 = 0, o_b2 = 0, o_ws = 0, o_bs = 0;
-    float *gap = nullptr, *hid = nullptr, *cse = nullptr, *A = nullptr, *G = nullptr;
+    float *gap = nullptr, *hid = nullptr, *cse = nullptr, *part = nullptr, *G = nullptr;
+    int chunks = 1;
 };
 struct GradBuf { Tensor g; bool fresh = true; };
 struct Act { Tensor t; GradBuf* gb = nullptr; };
@@ -81,6 +82,12 @@ public:
     void mark_params_dirty() { packed_dirty_ = true; }
     // copy a named internal activation (NHWC T, border dropped) into fp32 NCHW; returns false if unknown
     bool get_activation(const std::string& name, float* out_nchw, int* shape4, cudaStream_t st);
+
+    // ---- optional per-kernel-class timing with CUDA events on the launch stream (bench.py roofline)
+    enum ProfClass { PROF_CONV_FWD = 0, PROF_CONV_DGRAD = 1, PROF_CONV_WGRAD = 2, PROF_NCLASS = 3 };
+    void profile_enable(bool on);
+    // synchronises, then returns accumulated device time / algorithmic flops / launches since enable
+    void profile_read(int cls, double* ms, double* flops, long long* launches);
 
     const EngineConfig& config() const { return cfg_; }
     float* loss_scratch() { return loss_scratch_; }
@@ -154,6 +161,11 @@ private:
     // scratch pool
     void* scratch_[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes_[4] = {0, 0, 0, 0};
+    struct ProfRec { cudaEvent_t a, b; double flops; int cls; };
+    std::vector<ProfRec> prof_;
+    bool prof_on_ = false;
+    void prof_begin(int cls, double flops, cudaStream_t st);
+    void prof_end(cudaStream_t st);
     float* loss_scratch_ = nullptr;   // [max_batch + 8]
     double* loss_sums_ = nullptr;     // [16]
 };

@@ -63,7 +63,8 @@ struct SERef {
     const float *w1, *b1, *w2, *b2, *ws, *bs;   // fc.0 [Cr][C], fc.2 [C][Cr], spatial fc [C], [1]
     float *dw1, *db1, *dw2, *db2, *dws, *dbs;
     float *gap, *hid, *cse;                     // [B][C], [B][Cr], [B][C]   (saved by forward)
-    float *A, *G;                               // [B][C] backward scratch
+    float *part, *G;                            // [B][chunks][C] pooling partial sums, [B][C] backward scratch
+    int chunks;                                 // pixel chunks per image in the pooling kernels (depends on H*W only)
 };
 void k_scse_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const SERef& se,
                 const Tensor& out);

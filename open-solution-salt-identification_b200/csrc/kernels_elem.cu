@@ -348,7 +348,8 @@ void k_upsample_bwd(cudaStream_t st, const Tensor& gP, int c0, int f, const Tens
 // per-(n,c) sum over pixels of  [g *] relu(raw*scale+shift)
 template <typename T, bool WITH_G>
 __global__ void scse_pool_kernel(const T* __restrict__ raw, const T* __restrict__ g, const float* __restrict__ scale,
-                                 const float* __restrict__ shift, float* __restrict__ dst, int HW, int C) {
+                                 const float* __restrict__ shift, float* __restrict__ part, int HW, int C) {
+    // writes part[n][chunk][C]; the FC kernels add the chunks in a fixed order (deterministic, batch independent)
     __shared__ float4 red[EW_THREADS];
     const int cg = C >> 2, lanes = EW_THREADS / cg;
     const int cv = threadIdx.x % cg, lane = threadIdx.x / cg, n = blockIdx.y;
@@ -361,7 +362,13 @@ __global__ void scse_pool_kernel(const T* __restrict__ raw, const T* __restrict_
         if (WITH_G) z = f4_mul(z, ld4(g + o));
         acc = f4_add(acc, z);
     }
-    block_reduce_to_float(acc, cg, dst + (size_t)n * C, red);
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < cg) {
+        float4 s = red[threadIdx.x];
+        for (int t = threadIdx.x + cg; t < EW_THREADS; t += cg) s = f4_add(s, red[t]);
+        st4(part + ((size_t)n * gridDim.x + blockIdx.x) * C + threadIdx.x * 4, s);
+    }
 }
 // one block per image: squeeze -> fc(C->Cr) -> relu -> fc(Cr->C) -> sigmoid
 __global__ void scse_fc_kernel(SERef se, float inv_hw) {
@@ -369,7 +376,12 @@ __global__ void scse_fc_kernel(SERef se, float inv_hw) {
     float* gap = sm;               // [C]
     float* hid = sm + se.C;        // [Cr]
     const int n = blockIdx.x, c = threadIdx.x;
-    if (c < se.C) { gap[c] = se.gap[(size_t)n * se.C + c] * inv_hw; se.gap[(size_t)n * se.C + c] = gap[c]; }
+    if (c < se.C) {
+        float t = 0.f;
+        for (int k = 0; k < se.chunks; ++k) t += se.part[((size_t)n * se.chunks + k) * se.C + c];
+        gap[c] = t * inv_hw;
+        se.gap[(size_t)n * se.C + c] = gap[c];
+    }
     __syncthreads();
     if (c < se.Cr) {
         float a = se.b1[c];
@@ -411,11 +423,10 @@ __global__ void scse_apply_kernel(const T* __restrict__ raw, const float* __rest
 void k_scse_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const SERef& se, const Tensor& out) {
     SALT_COUNT(3);
     const int HW = raw.H * raw.W, C = raw.C, cg = C / 4;
-    cudaMemsetAsync(se.gap, 0, sizeof(float) * raw.B * C, st);
-    int chunks = max(1, min(cdiv(HW, (EW_THREADS / cg) * 8), cdiv(148 * 4, raw.B)));
+    const int chunks = se.chunks;
     long long npix = (long long)raw.B * HW;
     SALT_DISPATCH(raw.dt, T, {
-        scse_pool_kernel<T, false><<<dim3(chunks, raw.B), EW_THREADS, 0, st>>>((const T*)raw.p, nullptr, scale, shift, se.gap, HW, C);
+        scse_pool_kernel<T, false><<<dim3(chunks, raw.B), EW_THREADS, 0, st>>>((const T*)raw.p, nullptr, scale, shift, se.part, HW, C);
         scse_fc_kernel<<<raw.B, max(32, C), sizeof(float) * (C + se.Cr), st>>>(se, 1.0f / HW);
         scse_apply_kernel<T><<<cdiv(npix * cg, EW_THREADS), EW_THREADS, 0, st>>>((const T*)raw.p, scale, shift, se, (T*)out.p, npix, HW, C);
     });
@@ -429,7 +440,9 @@ __global__ void scse_fc_bwd_kernel(SERef se, float inv_hw) {
     const int n = blockIdx.x, c = threadIdx.x;
     if (c < se.C) {
         float cs = se.cse[(size_t)n * se.C + c];
-        float d = se.A[(size_t)n * se.C + c] * cs * (1.f - cs);
+        float t = 0.f;
+        for (int k = 0; k < se.chunks; ++k) t += se.part[((size_t)n * se.chunks + k) * se.C + c];
+        float d = t * cs * (1.f - cs);
         dpre2[c] = d;
         atomicAdd(se.db2 + c, d);
         for (int j = 0; j < se.Cr; ++j) atomicAdd(se.dw2 + c * se.Cr + j, d * se.hid[(size_t)n * se.Cr + j]);
@@ -503,11 +516,10 @@ __global__ void scse_bwd_apply_kernel(const T* __restrict__ gout, const T* __res
 void k_scse_bwd(cudaStream_t st, const Tensor& gout, const Tensor& raw, const BNRef& bn, const SERef& se, const Tensor& gbn) {
     SALT_COUNT(3);
     const int HW = raw.H * raw.W, C = raw.C, cg = C / 4;
-    cudaMemsetAsync(se.A, 0, sizeof(float) * raw.B * C, st);
-    int chunks = max(1, min(cdiv(HW, (EW_THREADS / cg) * 8), cdiv(148 * 4, raw.B)));
+    const int chunks = se.chunks;
     long long npix = (long long)raw.B * HW;
     SALT_DISPATCH(raw.dt, T, {
-        scse_pool_kernel<T, true><<<dim3(chunks, raw.B), EW_THREADS, 0, st>>>((const T*)raw.p, (const T*)gout.p, bn.scale, bn.shift, se.A, HW, C);
+        scse_pool_kernel<T, true><<<dim3(chunks, raw.B), EW_THREADS, 0, st>>>((const T*)raw.p, (const T*)gout.p, bn.scale, bn.shift, se.part, HW, C);
         scse_fc_bwd_kernel<<<raw.B, max(32, C), sizeof(float) * (C + se.Cr), st>>>(se, 1.0f / HW);
         scse_bwd_apply_kernel<T><<<reduce_blocks(npix, cg), EW_THREADS, 0, st>>>((const T*)gout.p, (const T*)raw.p, bn, se, (T*)gbn.p, npix, HW, C);
     });

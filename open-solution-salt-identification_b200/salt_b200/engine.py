@@ -158,6 +158,18 @@ class UNetEngine:
                                          _ptr(mask), self._stream()))
         return probs, mask
 
+    def profile(self, on):
+        _lib.check(self.lib.salt_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """{class: (ms, flops, launches)} for conv fwd / dgrad / wgrad since profile(True)."""
+        out = {}
+        for cls, name in enumerate(('conv_fwd', 'conv_dgrad', 'conv_wgrad')):
+            ms, fl, n = C.c_double(), C.c_double(), C.c_longlong()
+            _lib.check(self.lib.salt_profile_read(self.h, cls, C.byref(ms), C.byref(fl), C.byref(n)))
+            out[name] = (ms.value, fl.value, n.value)
+        return out
+
     def activation(self, name):
         shape = (C.c_int * 4)()
         _lib.check(self.lib.salt_get_activation(self.h, name.encode(), C.c_void_p(0), shape, self._stream()))

@@ -69,6 +69,8 @@ def run_case(tag, depth, batch, size, wseed, dseed):
     with torch.no_grad():
         logits_eval = net(x)
     out['logits_eval'] = logits_eval.numpy()
+    with torch.no_grad():
+        logits_eval_flip = net(torch.flip(x, dims=[3])).numpy()     # h-flip TTA copy, same (pristine) weights
     sd_t = unet_oracle.to_torch_state(sd_np)
     with torch.no_grad():
         mine = unet_oracle.unet_resnet_forward(sd_t, x, depth, train=False)
@@ -120,9 +122,7 @@ def run_case(tag, depth, batch, size, wseed, dseed):
             warnings.simplefilter('ignore')
             from common_blocks import postprocessing as ref_post
             from common_blocks.utils import sigmoid as ref_sigmoid
-        net.eval()
-        with torch.no_grad():
-            lf = net(torch.flip(x, dims=[3])).numpy()
+        lf = logits_eval_flip
         probs, masks = [], []
         for i in range(batch):
             p0 = ref_sigmoid(np.squeeze(out['logits_eval'][i]))
