@@ -141,7 +141,16 @@ int salt_op_conv_forward(const salt_conv_desc* d, const void* in, const float* w
     cudaStream_t st = (cudaStream_t)stream;
     DType dt = d->precision == SALT_PREC_FP32 ? DT_F32 : DT_BF16;
     PackedTmp pk(d, w, st);
-    k_conv_fwd_simt(st, dt, in, pk.wp, bias, out, stats, to_geom(d, d->in_c));
+    ConvGeom g = to_geom(d, d->in_c);
+    try {
+        if (d->use_tensor_cores) {
+            if (dt != DT_BF16 || !tc_conv_supported(g, false)) return fail("salt_op_conv_forward: geometry not supported by the tensor-core kernel");
+            k_conv_tc(st, in, g.B, g.Hi, g.Wi, g.Ci, pk.wp, g.Co, g.R, g.S, g.stride, g.pad, out, g.Ho, g.Wo, bias, stats, false);
+        } else {
+            k_conv_fwd_simt(st, dt, in, pk.wp, bias, out, stats, g);
+        }
+    } catch (const std::exception& ex) { return fail(std::string("salt_op_conv_forward: ") + ex.what()); }
+    cudaStreamSynchronize(st);
     return check_cuda("salt_op_conv_forward");
 }
 int salt_op_conv_dgrad(const salt_conv_desc* d, const void* gout, const float* w, void* gin, int accumulate, void* stream) {
@@ -149,7 +158,16 @@ int salt_op_conv_dgrad(const salt_conv_desc* d, const void* gout, const float* w
     cudaStream_t st = (cudaStream_t)stream;
     DType dt = d->precision == SALT_PREC_FP32 ? DT_F32 : DT_BF16;
     PackedTmp pk(d, w, st);
-    k_conv_dgrad_simt(st, dt, gout, pk.wpd, gin, accumulate != 0, to_geom(d, d->in_c));
+    ConvGeom g = to_geom(d, d->in_c);
+    try {
+        if (d->use_tensor_cores) {
+            if (dt != DT_BF16 || !tc_conv_supported(g, true)) return fail("salt_op_conv_dgrad: geometry not supported by the tensor-core kernel");
+            k_conv_tc(st, gout, g.B, g.Ho, g.Wo, g.Co, pk.wpd, g.Ci, g.R, g.S, 1, g.R - 1 - g.pad, gin, g.Hi, g.Wi, nullptr, nullptr, accumulate != 0);
+        } else {
+            k_conv_dgrad_simt(st, dt, gout, pk.wpd, gin, accumulate != 0, g);
+        }
+    } catch (const std::exception& ex) { return fail(std::string("salt_op_conv_dgrad: ") + ex.what()); }
+    cudaStreamSynchronize(st);
     return check_cuda("salt_op_conv_dgrad");
 }
 int salt_op_conv_wgrad(const salt_conv_desc* d, const void* in, const void* gout, float* dw, void* stream) {

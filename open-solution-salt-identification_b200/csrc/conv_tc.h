@@ -1,0 +1,11 @@
+// tcgen05 implicit-GEMM convolution (bf16 in, fp32 accumulate) - see conv_tc.cu
+#pragma once
+#include "kernels.h"
+
+// can the tensor-core kernel run this geometry (forward, or stride-1 dgrad)?
+bool tc_conv_supported(const ConvGeom& g, bool dgrad);
+
+// out[n,y,x,k] (+)= sum_{r,s,c} A[n, y*stride+r-pad, x*stride+s-pad, c] * Wp[k][(r*S+s)*Ca + c]   (zero outside A)
+// A: [B,Ha,Wa,Ca] bf16;  Wp: [Nout][R*S*Ca] bf16;  out: [B,Ho,Wo,Nout] bf16;  stats: 2*Nout doubles or NULL
+void k_conv_tc(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca, const void* Wp, int Nout, int R, int S, int stride,
+               int pad, void* out, int Ho, int Wo, const float* bias, double* stats, bool accumulate);

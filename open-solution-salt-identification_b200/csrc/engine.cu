@@ -271,7 +271,11 @@ void Engine::conv_fwd(const ConvLayer& c, const Tensor& in, const Tensor& out, B
     ConvGeom g = geom(c, in, out);
     const float* bias = c.o_b >= 0 ? params_ + c.o_b : nullptr;
     prof_begin(PROF_CONV_FWD, conv_flops(g, c.Ci_real), st);
-    k_conv_fwd_simt(st, cfg_.dt, in.p, c.wp, bias, out.p, (bn && train) ? bn->sums : nullptr, g);
+    double* stats = (bn && train) ? bn->sums : nullptr;
+    if (cfg_.dt == DT_BF16 && cfg_.use_tc && tc_conv_supported(g, false))
+        k_conv_tc(st, in.p, g.B, g.Hi, g.Wi, g.Ci, c.wp, g.Co, g.R, g.S, g.stride, g.pad, out.p, g.Ho, g.Wo, bias, stats, false);
+    else
+        k_conv_fwd_simt(st, cfg_.dt, in.p, c.wp, bias, out.p, stats, g);
     prof_end(st);
     if (bn) {
         if (train) k_bn_finalize_train(st, bn_ref(*bn), (double)B_ * out.H * out.W, BN_MOMENTUM, BN_EPS);
@@ -281,7 +285,11 @@ void Engine::conv_fwd(const ConvLayer& c, const Tensor& in, const Tensor& out, B
 void Engine::conv_dgrad(const ConvLayer& c, const Tensor& gout, const Tensor& gin, bool accumulate, cudaStream_t st) {
     ConvGeom g = geom(c, gin, gout);
     prof_begin(PROF_CONV_DGRAD, conv_flops(g, c.Ci_real), st);
-    k_conv_dgrad_simt(st, cfg_.dt, gout.p, c.wpd, gin.p, accumulate, g);
+    if (cfg_.dt == DT_BF16 && cfg_.use_tc && tc_conv_supported(g, true))
+        // dgrad = correlation of the output gradient with the tap-flipped, transposed weights, zero padding R-1-pad
+        k_conv_tc(st, gout.p, g.B, g.Ho, g.Wo, g.Co, c.wpd, g.Ci, g.R, g.S, 1, g.R - 1 - g.pad, gin.p, g.Hi, g.Wi, nullptr, nullptr, accumulate);
+    else
+        k_conv_dgrad_simt(st, cfg_.dt, gout.p, c.wpd, gin.p, accumulate, g);
     prof_end(st);
 }
 void Engine::conv_wgrad(const ConvLayer& c, const Tensor& in, const Tensor& gout, cudaStream_t st) {

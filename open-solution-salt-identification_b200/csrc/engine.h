@@ -6,6 +6,7 @@
 #include <vector>
 #include <memory>
 #include "kernels.h"
+#include "conv_tc.h"
 
 struct TensorInfo {            // one named entry of the reference state_dict
     std::string name;

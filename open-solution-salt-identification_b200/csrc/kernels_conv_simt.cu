@@ -27,7 +27,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, T* __restrict__
     int k = (int)(idx / ((long long)Ci * RS));
     float v = c < Ci_real ? w[((size_t)k * Ci_real + c) * RS + t] : 0.f;
     st1(wp + idx, v);
-    if (wpd) st1(wpd + ((size_t)c * RS + t) * Co + k, v);
+    // dgrad copy is stored with the taps FLIPPED (tap' = RS-1-tap), so that dgrad is a plain correlation of the output
+    // gradient with wpd (same kernel as forward): gin(y) = sum_{r'} gout(y - (R-1-pad) + r') * wpd[..][r'][..]
+    if (wpd) st1(wpd + ((size_t)c * RS + (RS - 1 - t)) * Co + k, v);
 }
 void k_pack_weights(cudaStream_t st, DType dt, const float* w, void* wp, void* wpd, int Co, int Ci_real, int Ci, int R, int S) {
     SALT_COUNT(1);
@@ -45,7 +47,7 @@ struct IGemmArgs {
     int Cred;                  // channels per tap in the reduction (FWD: Ci, DGRAD: Co)
     int Hs, Ws;                // source tensor spatial dims (FWD: Hi,Wi ; DGRAD: Ho,Wo)
     int Hd, Wd;                // destination spatial dims   (FWD: Ho,Wo ; DGRAD: Hi,Wi)
-    int S, stride, pad;
+    int R, S, stride, pad;
     int accumulate;
 };
 
@@ -78,7 +80,8 @@ __global__ void __launch_bounds__(256) conv_igemm_simt_kernel(const T* __restric
             sy = ay * a.stride + r - a.pad;
             sx = ax * a.stride + s - a.pad;
         } else {
-            int ty = ay + a.pad - r, tx = ax + a.pad - s;
+            // wpd holds flipped taps: reduction tap (r,s) multiplies W[..][R-1-r][S-1-s]
+            int ty = ay + a.pad - (a.R - 1 - r), tx = ax + a.pad - (a.S - 1 - s);
             if (ty < 0 || tx < 0) return f4_zero();
             if (a.stride > 1) {
                 if ((ty % a.stride) | (tx % a.stride)) return f4_zero();
@@ -165,7 +168,7 @@ void k_conv_fwd_simt(cudaStream_t st, DType dt, const void* in, const void* wp, 
     SALT_COUNT(1);
     IGemmArgs a;
     a.M = g.B * g.Ho * g.Wo; a.N = g.Co; a.Kred = g.R * g.S * g.Ci; a.Cred = g.Ci;
-    a.Hs = g.Hi; a.Ws = g.Wi; a.Hd = g.Ho; a.Wd = g.Wo; a.S = g.S; a.stride = g.stride; a.pad = g.pad; a.accumulate = 0;
+    a.Hs = g.Hi; a.Ws = g.Wi; a.Hd = g.Ho; a.Wd = g.Wo; a.R = g.R; a.S = g.S; a.stride = g.stride; a.pad = g.pad; a.accumulate = 0;
     dim3 grid(cdiv(a.M, TM), cdiv(a.N, TN));
     SALT_DISPATCH(dt, T, (conv_igemm_simt_kernel<T, false><<<grid, 256, 0, st>>>((const T*)in, (const T*)wp, bias, (T*)out, stats, a)));
 }
@@ -173,7 +176,7 @@ void k_conv_dgrad_simt(cudaStream_t st, DType dt, const void* gout, const void* 
     SALT_COUNT(1);
     IGemmArgs a;
     a.M = g.B * g.Hi * g.Wi; a.N = g.Ci; a.Kred = g.R * g.S * g.Co; a.Cred = g.Co;
-    a.Hs = g.Ho; a.Ws = g.Wo; a.Hd = g.Hi; a.Wd = g.Wi; a.S = g.S; a.stride = g.stride; a.pad = g.pad; a.accumulate = accumulate ? 1 : 0;
+    a.Hs = g.Ho; a.Ws = g.Wo; a.Hd = g.Hi; a.Wd = g.Wi; a.R = g.R; a.S = g.S; a.stride = g.stride; a.pad = g.pad; a.accumulate = accumulate ? 1 : 0;
     dim3 grid(cdiv(a.M, TM), cdiv(a.N, TN));
     SALT_DISPATCH(dt, T, (conv_igemm_simt_kernel<T, true><<<grid, 256, 0, st>>>((const T*)gout, (const T*)wpd, nullptr, (T*)gin, nullptr, a)));
 }

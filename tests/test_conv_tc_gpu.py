@@ -1,0 +1,59 @@
+"""GPU: the tcgen05 implicit-GEMM convolution (forward + stride-1 dgrad) against torch.nn.functional.conv2d
+(fp32, on bf16-rounded operands).  Tolerance: bf16 output rounding (2^-9 relative) + fp32 accumulation order:
+max-abs <= 2e-2 + 1e-2 * max|ref|.  BatchNorm statistics (fp32 accumulators, pre-rounding): 2e-3 relative."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from test_engine_gpu import report, _to_nhwc, _from_nhwc   # noqa: E402
+
+# (B, Cin, Cout, H, W, k, stride, pad)   H, W are the physical input dims
+TC_CASES = [
+    (2, 64, 64, 16, 16, 3, 1, 1),        # layer1-like, one tile per image pair
+    (4, 64, 64, 64, 64, 3, 1, 1),        # many tiles, persistent loop + double-buffered accumulators
+    (3, 64, 128, 32, 32, 3, 2, 1),       # stride 2 via TMA element strides, odd batch
+    (2, 64, 128, 32, 32, 1, 2, 0),       # 1x1 stride-2 downsample
+    (2, 128, 256, 16, 16, 3, 1, 1),      # BN = 256 -> or halved by the occupancy heuristic
+    (5, 512, 512, 8, 8, 3, 1, 1),        # 8x8 maps: two images per tile, odd batch, 2 channel tiles
+    (2, 96, 32, 18, 34, 3, 1, 0),        # valid conv on a bordered tensor, Cin = 96 (BK = 32), N = 32
+    (2, 32, 64, 34, 34, 3, 1, 0),        # dec1.conv2-like: Cin = 32
+    (2, 320, 64, 18, 18, 3, 1, 0),       # final.0-like: Cin = 320
+    (1, 768, 512, 10, 10, 3, 1, 0),      # dec5.conv1-like
+]
+
+
+@pytest.mark.parametrize('case', TC_CASES)
+def test_conv_tc_forward_and_dgrad(case):
+    from salt_b200 import _lib
+    lib = _lib.load()
+    B, Ci, Co, H, W, k, s, p = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = (torch.randn(B, Ci, H, W, generator=g)).bfloat16().float()
+    w = (torch.randn(Co, Ci, k, k, generator=g) * (2.0 / (Ci * k * k)) ** 0.5).bfloat16().float()
+    bias = torch.randn(Co, generator=g) * 0.1
+    y_ref = F.conv2d(x, w, bias, stride=s, padding=p)
+    Ho, Wo = y_ref.shape[2:]
+    d = _lib.SaltConvDesc(B, H, W, Ci, Ho, Wo, Co, k, s, p, 1, 1)
+    xd, wd, bd = _to_nhwc(x, 'bf16'), w.cuda().contiguous(), bias.cuda()
+    out = torch.full((B, Ho, Wo, Co), float('nan'), dtype=torch.bfloat16, device='cuda')
+    stats = torch.zeros(2 * Co, dtype=torch.float64, device='cuda')
+    _lib.check(lib.salt_op_conv_forward(C.byref(d), xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), out.data_ptr(), stats.data_ptr(), None))
+    torch.cuda.synchronize()
+    oks = [report('tc conv fwd %s' % (case,), _from_nhwc(out), y_ref, atol=2e-2, rtol=1e-2)[0]]
+    oks.append(report('tc conv stats sum', stats[:Co].cpu().float(), y_ref.sum((0, 2, 3)), atol=5e-2, rtol=2e-3)[0])
+    oks.append(report('tc conv stats sumsq', stats[Co:].cpu().float(), (y_ref ** 2).sum((0, 2, 3)), atol=5e-2, rtol=2e-3)[0])
+    if s == 1:
+        gy = torch.randn(B, Co, Ho, Wo, generator=g).bfloat16().float()
+        xr = x.clone().requires_grad_(True)
+        F.conv2d(xr, w, None, stride=s, padding=p).backward(gy)
+        gyd = _to_nhwc(gy, 'bf16')
+        gin = torch.full((B, H, W, Ci), float('nan'), dtype=torch.bfloat16, device='cuda')
+        _lib.check(lib.salt_op_conv_dgrad(C.byref(d), gyd.data_ptr(), wd.data_ptr(), gin.data_ptr(), 0, None))
+        oks.append(report('tc conv dgrad', _from_nhwc(gin), xr.grad, atol=2e-2, rtol=1e-2)[0])
+        _lib.check(lib.salt_op_conv_dgrad(C.byref(d), gyd.data_ptr(), wd.data_ptr(), gin.data_ptr(), 1, None))
+        oks.append(report('tc conv dgrad accumulate', _from_nhwc(gin), 2 * xr.grad, atol=4e-2, rtol=2e-2)[0])
+    assert all(oks)
