@@ -173,7 +173,16 @@ int salt_op_conv_dgrad(const salt_conv_desc* d, const void* gout, const float* w
 int salt_op_conv_wgrad(const salt_conv_desc* d, const void* in, const void* gout, float* dw, void* stream) {
     if (require_gpu()) return 1;
     DType dt = d->precision == SALT_PREC_FP32 ? DT_F32 : DT_BF16;
-    k_conv_wgrad_simt((cudaStream_t)stream, dt, in, gout, dw, d->in_c, to_geom(d, d->in_c));
+    ConvGeom g = to_geom(d, d->in_c);
+    try {
+        if (d->use_tensor_cores) {
+            if (dt != DT_BF16 || !tc_wgrad_supported(g)) return fail("salt_op_conv_wgrad: geometry not supported by the tensor-core kernel");
+            k_conv_wgrad_tc((cudaStream_t)stream, in, gout, dw, d->in_c, g);
+        } else {
+            k_conv_wgrad_simt((cudaStream_t)stream, dt, in, gout, dw, d->in_c, g);
+        }
+    } catch (const std::exception& ex) { return fail(std::string("salt_op_conv_wgrad: ") + ex.what()); }
+    cudaStreamSynchronize((cudaStream_t)stream);
     return check_cuda("salt_op_conv_wgrad");
 }
 int salt_op_adam(float* p, const float* g, float* m, float* v, size_t n, float lr, float wd, float b1, float b2, float eps,

@@ -9,3 +9,7 @@ bool tc_conv_supported(const ConvGeom& g, bool dgrad);
 // A: [B,Ha,Wa,Ca] bf16;  Wp: [Nout][R*S*Ca] bf16;  out: [B,Ho,Wo,Nout] bf16;  stats: 2*Nout doubles or NULL
 void k_conv_tc(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca, const void* Wp, int Nout, int R, int S, int stride,
                int pad, void* out, int Ho, int Wo, const float* bias, double* stats, bool accumulate);
+
+// tensor-core weight gradient (conv_wgrad_tc.cu): dw[k][c][r][s] += sum_pixels gout * in (fp32 accumulate, added into dw)
+bool tc_wgrad_supported(const ConvGeom& g);
+void k_conv_wgrad_tc(cudaStream_t st, const void* in, const void* gout, float* dw, int Ci_real, const ConvGeom& g);

@@ -1,0 +1,204 @@
+// tcgen05 weight-gradient convolution for sm_100a.
+//
+//   dw[k][c][r][s] += sum_{n,y,x} gout[n,y,x,k] * in[n, y*stride + r - pad, x*stride + s - pad, c]        (zero outside `in`)
+//
+// GEMM view per filter tap: D_tap[c][k] = X_tap^T (c x pixels) * G (pixels x k); the reduction runs over output pixels.
+// Both operands are "MN-major" for the tensor core (channels contiguous, the reduction index = pixel is the row index), which is
+// exactly what a TMA box load of an NHWC tensor produces: a [32 pixels][64 channels] 128B-swizzled tile.
+//   * M = 128 rows of D = two "slots" (slot = (tap, 64-channel block of the input)) stacked through the descriptor's
+//     leading-byte-offset, so 64-channel layers still issue full M=128 instructions;
+//   * N = NK output channels (64 or 128);  K = 32 pixels per pipeline stage (two K=16 instructions per slot pair);
+//   * one CTA owns up to 5 (NK=64) or 4 (NK=128) slot pairs -> that many fp32 accumulators live in TMEM for the whole pixel loop;
+//   * grid = (pixel splits, slot chunks, k tiles); partial results are added to the fp32 gradient with red.global.add.
+// Warp roles as in conv_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue.
+#include "tc_common.cuh"
+#include "conv_tc.h"
+
+using namespace tc;
+
+struct WgParams {
+    int B, Ho, Wo;
+    int Ci_real, Co;
+    int RS, S, stride, pad;
+    int cblks, total_slots, slots_per_cta;
+    int pw, ph, chunks_x, chunks_y, total_chunks, chunks_per_split;
+    float* dw;
+};
+
+constexpr int WG_THREADS = 192;
+constexpr int WG_TILE = 4096;                       // [32 pixels][64 channels] bf16
+template <int NK> struct WgCfg {
+    static constexpr int MAX_GROUPS = NK == 64 ? 5 : 4;
+    static constexpr int MAX_SLOTS = 2 * MAX_GROUPS;
+    static constexpr int G_TILES = NK / 64;
+    static constexpr int STAGE_BYTES = (MAX_SLOTS + G_TILES) * WG_TILE;
+    static constexpr int STAGES = 4;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int NK>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, const WgParams p) {
+    using Cfg = WgCfg<NK>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
+
+    // this CTA's work
+    const int slot0 = blockIdx.y * p.slots_per_cta;
+    const int nslots = min(p.slots_per_cta, p.total_slots - slot0);
+    const int ngroups = (nslots + 1) >> 1;
+    const int k0 = blockIdx.z * NK;
+    const int chunk_begin = blockIdx.x * p.chunks_per_split;
+    const int chunk_end = min(p.total_chunks, chunk_begin + p.chunks_per_split);
+    const int nchunks = chunk_end - chunk_begin;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_g) : "memory");
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (nchunks > 0 && nslots > 0) {
+        if (warp == 0) {
+            // ===================================================== TMA producer
+            if (elect_one()) {
+                int stage = 0; uint32_t phase = 0;
+                const uint32_t tx_bytes = (uint32_t)(nslots + Cfg::G_TILES) * WG_TILE;
+                for (int ck = chunk_begin; ck < chunk_end; ++ck) {
+                    const int cx = ck % p.chunks_x, cy = (ck / p.chunks_x) % p.chunks_y, n = ck / (p.chunks_x * p.chunks_y);
+                    const int x0 = cx * p.pw, y0 = cy * p.ph;
+                    uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(full0 + 8 * stage, tx_bytes);
+                    for (int i = 0; i < nslots; ++i) {
+                        const int slot = slot0 + i, tap = slot / p.cblks, cb = slot - tap * p.cblks;
+                        const int r = tap / p.S, s = tap - r * p.S;
+                        tma_load_4d(smem_u32(st + i * WG_TILE), &map_x, full0 + 8 * stage, cb * 64, x0 * p.stride + s - p.pad,
+                                    y0 * p.stride + r - p.pad, n);
+                    }
+                    for (int j = 0; j < Cfg::G_TILES; ++j)
+                        tma_load_4d(smem_u32(st + (Cfg::MAX_SLOTS + j) * WG_TILE), &map_g, full0 + 8 * stage, k0 + j * 64, x0, y0, n);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            // ===================================================== MMA issuer
+            const uint32_t idesc = instr_desc_bf16(NK, true, true);
+            int stage = 0; uint32_t phase = 0;
+            for (int it = 0; it < nchunks; ++it) {
+                mbar_wait(full0 + 8 * stage, phase);
+                fence_after();
+                if (elect_one()) {
+                    const uint32_t st = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint32_t gb = st + Cfg::MAX_SLOTS * WG_TILE;
+#pragma unroll 1
+                    for (int g = 0; g < ngroups; ++g) {
+                        const uint32_t lbo_a = (2 * g + 1 < nslots) ? WG_TILE : 0;     // odd tail: both halves read the same tile
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            // MN-major, 128B swizzle: 8-pixel groups 1024 B apart (SBO), 64-channel blocks LBO apart
+                            const uint64_t adesc = smem_desc(st + 2 * g * WG_TILE + kk * 2048, lbo_a, 1024, 2);
+                            const uint64_t bdesc = smem_desc(gb + kk * 2048, WG_TILE, 1024, 2);
+                            umma_bf16(tmem_base + g * NK, adesc, bdesc, idesc, (it | kk) != 0);
+                        }
+                    }
+                    umma_commit(empty0 + 8 * stage);
+                    if (it == nchunks - 1) umma_commit(tfull);
+                }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        } else {
+            // ===================================================== epilogue: TMEM -> red.global.add.f32
+            const int quarter = warp & 3;
+            const int m = quarter * 32 + lane;
+            mbar_wait(tfull, 0);
+            fence_after();
+            for (int g = 0; g < ngroups; ++g) {
+                const int slot = slot0 + 2 * g + (m >> 6);
+                const bool slot_ok = (2 * g + (m >> 6)) < nslots;
+                const int tap = slot / p.cblks, cb = slot - tap * p.cblks;
+                const int c = cb * 64 + (m & 63);
+                const bool row_ok = slot_ok && c < p.Ci_real;
+#pragma unroll 1
+                for (int ch = 0; ch < NK / 32; ++ch) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + g * NK + ch * 32, v);
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int k = k0 + ch * 32 + j;
+                            if (k < p.Co) atomicAdd(p.dw + ((size_t)k * p.Ci_real + c) * p.RS + tap, v[j]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) { fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+bool tc_wgrad_supported(const ConvGeom& g) {
+    if (g.Wo < 8 || g.Ho < 4) return false;
+    const int pw = g.Wo >= 16 ? 16 : 8, ph = 32 / pw;
+    if (g.Wo % pw || g.Ho % ph) return false;
+    if (g.Ci % 8 || g.Co % 8) return false;
+    if (g.stride != 1 && g.stride != 2) return false;
+    return true;
+}
+
+template <int NK>
+static void launch_wg(cudaStream_t st, const CUtensorMap& mx, const CUtensorMap& mg, const WgParams& p, dim3 grid) {
+    using Cfg = WgCfg<NK>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(conv_wgrad_tc_kernel<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        configured = true;
+    }
+    conv_wgrad_tc_kernel<NK><<<grid, WG_THREADS, Cfg::SMEM_BYTES, st>>>(mx, mg, p);
+}
+
+// in: [B,Hi,Wi,Ci] bf16 (physical dims); gout: [B,Ho,Wo,Co] bf16; dw: fp32 [Co][Ci_real][R][S], accumulated into
+void k_conv_wgrad_tc(cudaStream_t st, const void* in, const void* gout, float* dw, int Ci_real, const ConvGeom& g) {
+    SALT_COUNT(1);
+    WgParams p;
+    p.B = g.B; p.Ho = g.Ho; p.Wo = g.Wo; p.Ci_real = Ci_real; p.Co = g.Co;
+    p.RS = g.R * g.S; p.S = g.S; p.stride = g.stride; p.pad = g.pad;
+    p.cblks = cdiv(g.Ci, 64);
+    p.total_slots = p.RS * p.cblks;
+    const int NK = g.Co > 64 ? 128 : 64;
+    const int max_slots = NK == 64 ? 10 : 8;
+    int slot_chunks = cdiv(p.total_slots, max_slots);
+    p.slots_per_cta = cdiv(cdiv(p.total_slots, slot_chunks), 2) * 2;
+    slot_chunks = cdiv(p.total_slots, p.slots_per_cta);
+    p.pw = g.Wo >= 16 ? 16 : 8; p.ph = 32 / p.pw;
+    p.chunks_x = g.Wo / p.pw; p.chunks_y = g.Ho / p.ph;
+    p.total_chunks = g.B * p.chunks_x * p.chunks_y;
+    const int k_tiles = cdiv(g.Co, NK);
+    int splits = cdiv(2 * num_sms(), slot_chunks * k_tiles);
+    int max_splits = cdiv(p.total_chunks, 8);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.chunks_per_split = cdiv(p.total_chunks, splits);
+    splits = cdiv(p.total_chunks, p.chunks_per_split);
+    p.dw = dw;
+    CUtensorMap mx = make_map_nhwc(in, g.Ci, g.Wi, g.Hi, g.B, 64, p.pw, p.ph, 1, g.stride, CU_TENSOR_MAP_SWIZZLE_128B);
+    CUtensorMap mg = make_map_nhwc(gout, g.Co, g.Wo, g.Ho, g.B, 64, p.pw, p.ph, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+    dim3 grid(splits, slot_chunks, k_tiles);
+    if (NK == 64) launch_wg<64>(st, mx, mg, p, grid);
+    else launch_wg<128>(st, mx, mg, p, grid);
+}

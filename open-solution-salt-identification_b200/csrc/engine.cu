@@ -295,7 +295,10 @@ void Engine::conv_dgrad(const ConvLayer& c, const Tensor& gout, const Tensor& gi
 void Engine::conv_wgrad(const ConvLayer& c, const Tensor& in, const Tensor& gout, cudaStream_t st) {
     ConvGeom g = geom(c, in, gout);
     prof_begin(PROF_CONV_WGRAD, conv_flops(g, c.Ci_real), st);
-    k_conv_wgrad_simt(st, cfg_.dt, in.p, gout.p, grads_ + c.o_w, c.Ci_real, g);
+    if (cfg_.dt == DT_BF16 && cfg_.use_tc && tc_wgrad_supported(g))
+        k_conv_wgrad_tc(st, in.p, gout.p, grads_ + c.o_w, c.Ci_real, g);
+    else
+        k_conv_wgrad_simt(st, cfg_.dt, in.p, gout.p, grads_ + c.o_w, c.Ci_real, g);
     prof_end(st);
 }
 void Engine::gather_fwd(const std::vector<Source>& srcs, const Tensor& P, cudaStream_t st) {

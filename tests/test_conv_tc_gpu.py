@@ -57,3 +57,36 @@ def test_conv_tc_forward_and_dgrad(case):
         _lib.check(lib.salt_op_conv_dgrad(C.byref(d), gyd.data_ptr(), wd.data_ptr(), gin.data_ptr(), 1, None))
         oks.append(report('tc conv dgrad accumulate', _from_nhwc(gin), 2 * xr.grad, atol=4e-2, rtol=2e-2)[0])
     assert all(oks)
+
+
+WG_CASES = TC_CASES + [
+    (2, 64, 32, 34, 34, 3, 1, 0),        # dec1.conv1-like: Cout = 32 (zero-filled channel box)
+    (4, 64, 64, 128, 128, 3, 1, 1),      # many pixel chunks per CTA
+    (2, 256, 512, 16, 16, 3, 2, 1),      # layer4.0.conv1-like, stride 2
+]
+
+
+@pytest.mark.parametrize('case', WG_CASES)
+def test_conv_tc_wgrad(case):
+    """tcgen05 weight gradient (MN-major operands straight from NHWC TMA boxes, slot pairs stacked in M) vs autograd.
+    Tolerance: fp32 accumulation of bf16 products, different summation order: 1e-3 relative to the largest entry."""
+    from salt_b200 import _lib
+    lib = _lib.load()
+    B, Ci, Co, H, W, k, s, p = case
+    g = torch.Generator().manual_seed(sum(case) + 1)
+    x = torch.randn(B, Ci, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(Co, Ci, k, k, generator=g) * 0.05).requires_grad_(True)
+    y = F.conv2d(x, w, None, stride=s, padding=p)
+    Ho, Wo = y.shape[2:]
+    gy = torch.randn(B, Co, Ho, Wo, generator=g).bfloat16().float()
+    y.backward(gy)
+    d = _lib.SaltConvDesc(B, H, W, Ci, Ho, Wo, Co, k, s, p, 1, 1)
+    xd, gyd = _to_nhwc(x, 'bf16'), _to_nhwc(gy, 'bf16')
+    dw = torch.zeros((Co, Ci, k, k), dtype=torch.float32, device='cuda')
+    _lib.check(lib.salt_op_conv_wgrad(C.byref(d), xd.data_ptr(), gyd.data_ptr(), dw.data_ptr(), None))
+    torch.cuda.synchronize()
+    ok1 = report('tc wgrad %s' % (case,), dw.cpu(), w.grad, atol=1e-3, rtol=1e-3)[0]
+    _lib.check(lib.salt_op_conv_wgrad(C.byref(d), xd.data_ptr(), gyd.data_ptr(), dw.data_ptr(), None))
+    torch.cuda.synchronize()
+    ok2 = report('tc wgrad accumulates into dw', dw.cpu(), 2 * w.grad, atol=2e-3, rtol=1e-3)[0]
+    assert ok1 and ok2
