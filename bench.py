@@ -142,7 +142,7 @@ def make_model(precision, batch, loss):
 
 
 def run_ours(args):
-    from oracle import synth            # synthetic data / weight generators only (numpy); not on the timed path
+    from salt_b200 import synthetic as synth
     from salt_b200 import _lib
     model = make_model(args.precision, args.batch, args.loss)
     ctx, eng = model.dp, model.engine

@@ -162,7 +162,10 @@ int salt_op_conv_dgrad(const salt_conv_desc* d, const void* gout, const float* w
     try {
         if (d->use_tensor_cores) {
             if (dt != DT_BF16 || !tc_conv_supported(g, true)) return fail("salt_op_conv_dgrad: geometry not supported by the tensor-core kernel");
-            k_conv_tc(st, gout, g.B, g.Ho, g.Wo, g.Co, pk.wpd, g.Ci, g.R, g.S, 1, g.R - 1 - g.pad, gin, g.Hi, g.Wi, nullptr, nullptr, accumulate != 0);
+            if (g.stride == 1)
+                k_conv_tc(st, gout, g.B, g.Ho, g.Wo, g.Co, pk.wpd, g.Ci, g.R, g.S, 1, g.R - 1 - g.pad, gin, g.Hi, g.Wi, nullptr, nullptr, accumulate != 0);
+            else
+                k_conv_tc_dgrad_s2(st, gout, g.B, g.Ho, g.Wo, g.Co, pk.wpd, g.Ci, g.R, g.S, g.pad, gin, g.Hi, g.Wi, accumulate != 0);
         } else {
             k_conv_dgrad_simt(st, dt, gout, pk.wpd, gin, accumulate != 0, g);
         }

@@ -10,6 +10,10 @@ bool tc_conv_supported(const ConvGeom& g, bool dgrad);
 void k_conv_tc(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca, const void* Wp, int Nout, int R, int S, int stride,
                int pad, void* out, int Ho, int Wo, const float* bias, double* stats, bool accumulate);
 
+// stride-2 dgrad as four parity phases of the same kernel; wpd = flipped-tap packing [Ci][R*S*Co]
+void k_conv_tc_dgrad_s2(cudaStream_t st, const void* gout, int B, int Ho, int Wo, int Co, const void* wpd, int Ci, int R, int S,
+                        int pad, void* gin, int Hi, int Wi, bool accumulate);
+
 // tensor-core weight gradient (conv_wgrad_tc.cu): dw[k][c][r][s] += sum_pixels gout * in (fp32 accumulate, added into dw)
 bool tc_wgrad_supported(const ConvGeom& g);
 void k_conv_wgrad_tc(cudaStream_t st, const void* in, const void* gout, float* dw, int Ci_real, const ConvGeom& g);

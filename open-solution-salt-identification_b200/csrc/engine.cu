@@ -285,9 +285,12 @@ void Engine::conv_fwd(const ConvLayer& c, const Tensor& in, const Tensor& out, B
 void Engine::conv_dgrad(const ConvLayer& c, const Tensor& gout, const Tensor& gin, bool accumulate, cudaStream_t st) {
     ConvGeom g = geom(c, gin, gout);
     prof_begin(PROF_CONV_DGRAD, conv_flops(g, c.Ci_real), st);
-    if (cfg_.dt == DT_BF16 && cfg_.use_tc && tc_conv_supported(g, true))
+    const bool tc_ok = cfg_.dt == DT_BF16 && cfg_.use_tc && tc_conv_supported(g, true);
+    if (tc_ok && g.stride == 1)
         // dgrad = correlation of the output gradient with the tap-flipped, transposed weights, zero padding R-1-pad
         k_conv_tc(st, gout.p, g.B, g.Ho, g.Wo, g.Co, c.wpd, g.Ci, g.R, g.S, 1, g.R - 1 - g.pad, gin.p, g.Hi, g.Wi, nullptr, nullptr, accumulate);
+    else if (tc_ok && g.stride == 2 && (accumulate || g.R > 1))
+        k_conv_tc_dgrad_s2(st, gout.p, g.B, g.Ho, g.Wo, g.Co, c.wpd, g.Ci, g.R, g.S, g.pad, gin.p, g.Hi, g.Wi, accumulate);
     else
         k_conv_dgrad_simt(st, cfg_.dt, gout.p, c.wpd, gin.p, accumulate, g);
     prof_end(st);
@@ -408,15 +411,14 @@ void Engine::block_bwd(BasicBlock& b, cudaStream_t st) {
     k_bn_bwd_apply(st, G, raw2, bn2, false, graw2);
     GradBuf* gxb = b.x->gb;
     Tensor Gx = view(gxb->g);
+    Tensor grawd = scratch(2, out.H, out.W, out.C);
     if (b.down) {
-        Tensor rawd = view(b.rawd), grawd = scratch(2, out.H, out.W, out.C);
+        Tensor rawd = view(b.rawd);
         BNRef bnd = bn_ref(b.bd);
         k_bn_bwd_reduce(st, G, rawd, bnd, false);
         k_bn_bwd_finalize(st, bnd, cnt);
         k_bn_bwd_apply(st, G, rawd, bnd, false, grawd);
         conv_wgrad(b.cd, x, grawd, st);
-        conv_dgrad(b.cd, grawd, Gx, !gxb->fresh, st);
-        gxb->fresh = false;
     }
     conv_wgrad(b.c2, a1, graw2, st);
     conv_dgrad(b.c2, graw2, ga1, false, st);
@@ -428,6 +430,8 @@ void Engine::block_bwd(BasicBlock& b, cudaStream_t st) {
     // identity blocks: Gx aliases G and already holds the skip-path gradient -> accumulate
     conv_dgrad(b.c1, graw1, Gx, b.down ? !gxb->fresh : true, st);
     gxb->fresh = false;
+    // the 1x1 stride-2 shortcut only touches the even/even input positions: it accumulates after the 3x3 path wrote everything
+    if (b.down) conv_dgrad(b.cd, grawd, Gx, true, st);
 }
 void Engine::backward(const float* dlogits, cudaStream_t st) {
     if (!grads_) throw std::runtime_error("engine bound without gradient buffers");

@@ -46,16 +46,22 @@ def test_conv_tc_forward_and_dgrad(case):
     oks = [report('tc conv fwd %s' % (case,), _from_nhwc(out), y_ref, atol=2e-2, rtol=1e-2)[0]]
     oks.append(report('tc conv stats sum', stats[:Co].cpu().float(), y_ref.sum((0, 2, 3)), atol=5e-2, rtol=2e-3)[0])
     oks.append(report('tc conv stats sumsq', stats[Co:].cpu().float(), (y_ref ** 2).sum((0, 2, 3)), atol=5e-2, rtol=2e-3)[0])
-    if s == 1:
-        gy = torch.randn(B, Co, Ho, Wo, generator=g).bfloat16().float()
-        xr = x.clone().requires_grad_(True)
-        F.conv2d(xr, w, None, stride=s, padding=p).backward(gy)
-        gyd = _to_nhwc(gy, 'bf16')
+    gy = torch.randn(B, Co, Ho, Wo, generator=g).bfloat16().float()
+    xr = x.clone().requires_grad_(True)
+    F.conv2d(xr, w, None, stride=s, padding=p).backward(gy)
+    gyd = _to_nhwc(gy, 'bf16')
+    if s == 1 or k > 1:
         gin = torch.full((B, H, W, Ci), float('nan'), dtype=torch.bfloat16, device='cuda')
         _lib.check(lib.salt_op_conv_dgrad(C.byref(d), gyd.data_ptr(), wd.data_ptr(), gin.data_ptr(), 0, None))
-        oks.append(report('tc conv dgrad', _from_nhwc(gin), xr.grad, atol=2e-2, rtol=1e-2)[0])
+        oks.append(report('tc conv dgrad (stride %d)' % s, _from_nhwc(gin), xr.grad, atol=2e-2, rtol=1e-2)[0])
         _lib.check(lib.salt_op_conv_dgrad(C.byref(d), gyd.data_ptr(), wd.data_ptr(), gin.data_ptr(), 1, None))
         oks.append(report('tc conv dgrad accumulate', _from_nhwc(gin), 2 * xr.grad, atol=4e-2, rtol=2e-2)[0])
+    else:
+        # 1x1 stride-2: only the even/even lattice receives gradient -> the kernel is accumulate-only
+        base = torch.randn(B, Ci, H, W, generator=g).bfloat16().float()
+        gin = _to_nhwc(base, 'bf16').clone()
+        _lib.check(lib.salt_op_conv_dgrad(C.byref(d), gyd.data_ptr(), wd.data_ptr(), gin.data_ptr(), 1, None))
+        oks.append(report('tc conv dgrad 1x1 s2 accumulate', _from_nhwc(gin), base + xr.grad, atol=4e-2, rtol=2e-2)[0])
     assert all(oks)
 
 
