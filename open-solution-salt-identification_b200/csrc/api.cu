@@ -180,7 +180,14 @@ int salt_op_conv_wgrad(const salt_conv_desc* d, const void* in, const void* gout
     try {
         if (d->use_tensor_cores) {
             if (dt != DT_BF16 || !tc_wgrad_supported(g)) return fail("salt_op_conv_wgrad: geometry not supported by the tensor-core kernel");
-            k_conv_wgrad_tc((cudaStream_t)stream, in, gout, dw, d->in_c, g);
+            float* dwp = nullptr;
+            size_t nf = tc_wgrad_scratch_floats(g.Ci, g.Co, g.R * g.S);
+            cudaMalloc(&dwp, nf * sizeof(float));
+            cudaMemsetAsync(dwp, 0, nf * sizeof(float), (cudaStream_t)stream);
+            k_conv_wgrad_tc((cudaStream_t)stream, in, gout, dwp, g);
+            k_unpack_dw((cudaStream_t)stream, dwp, dw, g.Co, d->in_c, cdiv(g.Ci, 64) * 64, g.R * g.S, true);
+            cudaStreamSynchronize((cudaStream_t)stream);
+            cudaFree(dwp);
         } else {
             k_conv_wgrad_simt((cudaStream_t)stream, dt, in, gout, dw, d->in_c, g);
         }

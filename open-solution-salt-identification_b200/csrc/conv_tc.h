@@ -16,4 +16,8 @@ void k_conv_tc_dgrad_s2(cudaStream_t st, const void* gout, int B, int Ho, int Wo
 
 // tensor-core weight gradient (conv_wgrad_tc.cu): dw[k][c][r][s] += sum_pixels gout * in (fp32 accumulate, added into dw)
 bool tc_wgrad_supported(const ConvGeom& g);
-void k_conv_wgrad_tc(cudaStream_t st, const void* in, const void* gout, float* dw, int Ci_real, const ConvGeom& g);
+// dwp: zero-initialised fp32 scratch [R*S][ceil64(Ci)][Co] (k contiguous), partial sums are added with vector reductions
+size_t tc_wgrad_scratch_floats(int Ci, int Co, int RS);
+void k_conv_wgrad_tc(cudaStream_t st, const void* in, const void* gout, float* dwp, const ConvGeom& g);
+// dw[k][c][r][s] (+)= dwp[tap][c][k]
+void k_unpack_dw(cudaStream_t st, const float* dwp, float* dw, int Co, int Ci_real, int Ci_pad, int RS, bool accumulate);

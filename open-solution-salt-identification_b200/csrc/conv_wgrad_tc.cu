@@ -9,7 +9,9 @@
 //     leading-byte-offset, so 64-channel layers still issue full M=128 instructions;
 //   * N = NK output channels (64 or 128);  K = 32 pixels per pipeline stage (two K=16 instructions per slot pair);
 //   * one CTA owns up to 5 (NK=64) or 4 (NK=128) slot pairs -> that many fp32 accumulators live in TMEM for the whole pixel loop;
-//   * grid = (pixel splits, slot chunks, k tiles); partial results are added to the fp32 gradient with red.global.add.
+//   * grid = (pixel splits, slot chunks, k tiles); partial results are added with 16-byte vector reductions
+//     (red.global.add.v4.f32) into a k-contiguous fp32 scratch dwp[tap][c][k]; unpack_dw_kernel then transposes that
+//     into the reference layout dw[k][c][r][s] through shared memory (coalesced on both sides).
 // Warp roles as in conv_tc.cu: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue.
 #include "tc_common.cuh"
 #include "conv_tc.h"
@@ -18,11 +20,11 @@ using namespace tc;
 
 struct WgParams {
     int B, Ho, Wo;
-    int Ci_real, Co;
+    int Ci_pad, Co;
     int RS, S, stride, pad;
     int cblks, total_slots, slots_per_cta;
     int pw, ph, chunks_x, chunks_y, total_chunks, chunks_per_split;
-    float* dw;
+    float* dwp;                 // [RS][Ci_pad][Co] fp32, zero-initialised
 };
 
 constexpr int WG_THREADS = 192;
@@ -121,26 +123,27 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         } else {
-            // ===================================================== epilogue: TMEM -> red.global.add.f32
+            // ===================================================== epilogue: TMEM -> red.global.add.v4.f32
             const int quarter = warp & 3;
             const int m = quarter * 32 + lane;
             mbar_wait(tfull, 0);
             fence_after();
             for (int g = 0; g < ngroups; ++g) {
                 const int slot = slot0 + 2 * g + (m >> 6);
-                const bool slot_ok = (2 * g + (m >> 6)) < nslots;
+                const bool row_ok = (2 * g + (m >> 6)) < nslots;
                 const int tap = slot / p.cblks, cb = slot - tap * p.cblks;
                 const int c = cb * 64 + (m & 63);
-                const bool row_ok = slot_ok && c < p.Ci_real;
+                float* drow = p.dwp + ((size_t)tap * p.Ci_pad + c) * p.Co + k0;
 #pragma unroll 1
                 for (int ch = 0; ch < NK / 32; ++ch) {
                     float v[32];
                     tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + g * NK + ch * 32, v);
                     if (row_ok) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int k = k0 + ch * 32 + j;
-                            if (k < p.Co) atomicAdd(p.dw + ((size_t)k * p.Ci_real + c) * p.RS + tap, v[j]);
+                        for (int j = 0; j < 32; j += 4) {
+                            if (k0 + ch * 32 + j < p.Co)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + ch * 32 + j), "f"(v[j]),
+                                             "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
                         }
                     }
                 }
@@ -172,11 +175,38 @@ static void launch_wg(cudaStream_t st, const CUtensorMap& mx, const CUtensorMap&
     conv_wgrad_tc_kernel<NK><<<grid, WG_THREADS, Cfg::SMEM_BYTES, st>>>(mx, mg, p);
 }
 
-// in: [B,Hi,Wi,Ci] bf16 (physical dims); gout: [B,Ho,Wo,Co] bf16; dw: fp32 [Co][Ci_real][R][S], accumulated into
-void k_conv_wgrad_tc(cudaStream_t st, const void* in, const void* gout, float* dw, int Ci_real, const ConvGeom& g) {
+// dw[k][c][t] (+)= dwp[t][c][k]: 32(k) x 32(c) x RS tile transposed through shared memory
+__global__ void __launch_bounds__(256) unpack_dw_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int Co, int Ci_real,
+                                                        int Ci_pad, int RS, int accumulate) {
+    extern __shared__ float tile[];                  // [32 k][32 c * RS + 1]
+    const int k0 = blockIdx.x * 32, c0 = blockIdx.y * 32, pitch = 32 * RS + 1;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int t = 0; t < RS; ++t)
+        for (int c = ty; c < 32; c += 8) {
+            float v = 0.f;
+            if (k0 + tx < Co && c0 + c < Ci_pad) v = dwp[((size_t)t * Ci_pad + c0 + c) * Co + k0 + tx];
+            tile[tx * pitch + c * RS + t] = v;
+        }
+    __syncthreads();
+    const int ncols = min(32, Ci_real - c0) * RS;    // contiguous run in dw for one k
+    for (int k = ty; k < 32; k += 8) {
+        if (k0 + k >= Co) continue;
+        float* o = dw + ((size_t)(k0 + k) * Ci_real + c0) * RS;
+        for (int j = tx; j < ncols; j += 32) o[j] = (accumulate ? o[j] : 0.f) + tile[k * pitch + j];
+    }
+}
+void k_unpack_dw(cudaStream_t st, const float* dwp, float* dw, int Co, int Ci_real, int Ci_pad, int RS, bool accumulate) {
+    SALT_COUNT(1);
+    dim3 grid(cdiv(Co, 32), cdiv(Ci_real, 32));
+    unpack_dw_kernel<<<grid, 256, sizeof(float) * 32 * (32 * RS + 1), st>>>(dwp, dw, Co, Ci_real, Ci_pad, RS, accumulate ? 1 : 0);
+}
+size_t tc_wgrad_scratch_floats(int Ci, int Co, int RS) { return (size_t)RS * (cdiv(Ci, 64) * 64) * Co; }
+
+// in: [B,Hi,Wi,Ci] bf16 (physical dims); gout: [B,Ho,Wo,Co] bf16; dwp: zeroed fp32 scratch [RS][ceil64(Ci)][Co], accumulated into
+void k_conv_wgrad_tc(cudaStream_t st, const void* in, const void* gout, float* dwp, const ConvGeom& g) {
     SALT_COUNT(1);
     WgParams p;
-    p.B = g.B; p.Ho = g.Ho; p.Wo = g.Wo; p.Ci_real = Ci_real; p.Co = g.Co;
+    p.B = g.B; p.Ho = g.Ho; p.Wo = g.Wo; p.Ci_pad = cdiv(g.Ci, 64) * 64; p.Co = g.Co;
     p.RS = g.R * g.S; p.S = g.S; p.stride = g.stride; p.pad = g.pad;
     p.cblks = cdiv(g.Ci, 64);
     p.total_slots = p.RS * p.cblks;
@@ -189,13 +219,13 @@ void k_conv_wgrad_tc(cudaStream_t st, const void* in, const void* gout, float* d
     p.chunks_x = g.Wo / p.pw; p.chunks_y = g.Ho / p.ph;
     p.total_chunks = g.B * p.chunks_x * p.chunks_y;
     const int k_tiles = cdiv(g.Co, NK);
-    int splits = cdiv(2 * num_sms(), slot_chunks * k_tiles);
+    int splits = (num_sms() + slot_chunks * k_tiles / 2) / (slot_chunks * k_tiles);      // about one wave of CTAs
     int max_splits = cdiv(p.total_chunks, 8);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     p.chunks_per_split = cdiv(p.total_chunks, splits);
     splits = cdiv(p.total_chunks, p.chunks_per_split);
-    p.dw = dw;
+    p.dwp = dwp;
     CUtensorMap mx = make_map_nhwc(in, g.Ci, g.Wi, g.Hi, g.B, 64, p.pw, p.ph, 1, g.stride, CU_TENSOR_MAP_SWIZZLE_128B);
     CUtensorMap mg = make_map_nhwc(gout, g.Co, g.Wo, g.Ho, g.B, 64, p.pw, p.ph, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B);
     dim3 grid(splits, slot_chunks, k_tiles);

@@ -62,6 +62,8 @@ ConvLayer Engine::make_conv(const std::string& wname, const std::string& bname, 
     size_t wb = (size_t)co * k * k * c.Ci * dtype_size(cfg_.dt);
     c.wp = ws_alloc(wb);
     c.wpd = ws_alloc(wb);
+    c.dwp = dwp_arena_ + dwp_cursor_;
+    dwp_cursor_ += (tc_wgrad_scratch_floats(c.Ci, co, k * k) + 3) / 4 * 4;
     return c;
 }
 BNLayer Engine::make_bn(const std::string& prefix, int c) {
@@ -111,7 +113,7 @@ void Engine::build_decoder(DecoderBlock& d, const std::string& name, std::vector
 size_t Engine::make_tensor_bytes(int H, int W, int C) const { return (size_t)cfg_.max_batch * H * W * C * dtype_size(cfg_.dt); }
 
 void Engine::build() {
-    n_params_ = n_buffers_ = 0; ws_cursor_ = 0; stats_cursor_ = bstats_cursor_ = 0;
+    n_params_ = n_buffers_ = 0; ws_cursor_ = 0; stats_cursor_ = bstats_cursor_ = 0; dwp_cursor_ = 0;
     blocks_.clear(); gradbufs_.clear();
     if (counting_) infos_.clear();
     const int B = cfg_.max_batch, H = cfg_.H, W = cfg_.W;
@@ -122,6 +124,7 @@ void Engine::build() {
     // BN statistic arenas: sized on the counting pass
     stats_arena_ = (double*)ws_alloc(sizeof(double) * std::max<size_t>(stats_doubles_, 1));
     bstats_arena_ = (double*)ws_alloc(sizeof(double) * std::max<size_t>(bstats_doubles_, 1));
+    dwp_arena_ = (float*)ws_alloc(sizeof(float) * std::max<size_t>(cfg_.dt == DT_BF16 ? dwp_floats_ : 0, 4));
 
     // ---- encoder (reference encoders.py:10-45, torchvision BasicBlock), parameter order = state_dict order
     const std::string e = "encoders.encoder.";
@@ -183,7 +186,7 @@ void Engine::build() {
     loss_scratch_ = (float*)ws_alloc(sizeof(float) * (B + 8));
     loss_sums_ = (double*)ws_alloc(sizeof(double) * 16);
     for (int i = 0; i < 4; ++i) scratch_[i] = ws_alloc(std::max<size_t>(scratch_bytes_[i], 256));
-    if (counting_) { stats_doubles_ = stats_cursor_; bstats_doubles_ = bstats_cursor_; }
+    if (counting_) { stats_doubles_ = stats_cursor_; bstats_doubles_ = bstats_cursor_; dwp_floats_ = dwp_cursor_; }
 }
 
 void Engine::bind(float* params, float* grads, float* m, float* v, float* buffers, void* ws, size_t ws_bytes) {
@@ -298,9 +301,10 @@ void Engine::conv_dgrad(const ConvLayer& c, const Tensor& gout, const Tensor& gi
 void Engine::conv_wgrad(const ConvLayer& c, const Tensor& in, const Tensor& gout, cudaStream_t st) {
     ConvGeom g = geom(c, in, gout);
     prof_begin(PROF_CONV_WGRAD, conv_flops(g, c.Ci_real), st);
-    if (cfg_.dt == DT_BF16 && cfg_.use_tc && tc_wgrad_supported(g))
-        k_conv_wgrad_tc(st, in.p, gout.p, grads_ + c.o_w, c.Ci_real, g);
-    else
+    if (cfg_.dt == DT_BF16 && cfg_.use_tc && tc_wgrad_supported(g)) {
+        k_conv_wgrad_tc(st, in.p, gout.p, c.dwp, g);
+        k_unpack_dw(st, c.dwp, grads_ + c.o_w, c.Co, c.Ci_real, cdiv(c.Ci, 64) * 64, c.R * c.S, false);
+    } else
         k_conv_wgrad_simt(st, cfg_.dt, in.p, gout.p, grads_ + c.o_w, c.Ci_real, g);
     prof_end(st);
 }
@@ -438,6 +442,7 @@ void Engine::backward(const float* dlogits, cudaStream_t st) {
     if (!trained_forward_) throw std::runtime_error("backward() requires a preceding forward(train=1)");
     k_zero(st, grads_, sizeof(float) * n_params_);
     k_zero(st, bstats_arena_, sizeof(double) * bstats_doubles_);
+    if (cfg_.dt == DT_BF16 && cfg_.use_tc) k_zero(st, dwp_arena_, sizeof(float) * dwp_floats_);
     for (auto& g : gradbufs_) g->fresh = true;
     // ---- final
     {

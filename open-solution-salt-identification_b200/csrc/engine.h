@@ -23,6 +23,7 @@ struct ConvLayer {
     long long o_b = -1;        // bias offset or -1
     void* wp = nullptr;        // packed fwd weights   [Co][R*S][Ci]
     void* wpd = nullptr;       // packed dgrad weights [Ci][R*S][Co]
+    float* dwp = nullptr;      // tensor-core wgrad scratch [R*S][ceil64(Ci)][Co] fp32 (inside the zeroed-per-backward arena)
 };
 struct BNLayer {
     int C = 0;
@@ -159,6 +160,7 @@ private:
     double* stats_arena_ = nullptr; size_t stats_doubles_ = 0;
     double* bstats_arena_ = nullptr; size_t bstats_doubles_ = 0;
     size_t stats_cursor_ = 0, bstats_cursor_ = 0;
+    float* dwp_arena_ = nullptr; size_t dwp_floats_ = 0, dwp_cursor_ = 0;
     // scratch pool
     void* scratch_[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes_[4] = {0, 0, 0, 0};
