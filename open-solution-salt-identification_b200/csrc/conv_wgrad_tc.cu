@@ -78,42 +78,54 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             if (elect_one()) {
                 int stage = 0; uint32_t phase = 0;
                 const uint32_t tx_bytes = (uint32_t)(nslots + Cfg::G_TILES) * WG_TILE;
+                // per-slot constants (no divisions inside the pixel loop: this single thread must keep up with the tensor core)
+                int s_c[Cfg::MAX_SLOTS], s_dx[Cfg::MAX_SLOTS], s_dy[Cfg::MAX_SLOTS];
+#pragma unroll
+                for (int i = 0; i < Cfg::MAX_SLOTS; ++i) {
+                    const int slot = slot0 + (i < nslots ? i : 0), tap = slot / p.cblks, cb = slot - tap * p.cblks;
+                    const int r = tap / p.S, s = tap - r * p.S;
+                    s_c[i] = cb * 64; s_dx[i] = s - p.pad; s_dy[i] = r - p.pad;
+                }
+                int cx = chunk_begin % p.chunks_x, cy = (chunk_begin / p.chunks_x) % p.chunks_y, n = chunk_begin / (p.chunks_x * p.chunks_y);
                 for (int ck = chunk_begin; ck < chunk_end; ++ck) {
-                    const int cx = ck % p.chunks_x, cy = (ck / p.chunks_x) % p.chunks_y, n = ck / (p.chunks_x * p.chunks_y);
                     const int x0 = cx * p.pw, y0 = cy * p.ph;
-                    uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+                    const uint32_t st = smem_u32(smem + stage * Cfg::STAGE_BYTES), fb = full0 + 8 * stage;
                     mbar_wait(empty0 + 8 * stage, phase ^ 1);
-                    mbar_expect_tx(full0 + 8 * stage, tx_bytes);
-                    for (int i = 0; i < nslots; ++i) {
-                        const int slot = slot0 + i, tap = slot / p.cblks, cb = slot - tap * p.cblks;
-                        const int r = tap / p.S, s = tap - r * p.S;
-                        tma_load_4d(smem_u32(st + i * WG_TILE), &map_x, full0 + 8 * stage, cb * 64, x0 * p.stride + s - p.pad,
-                                    y0 * p.stride + r - p.pad, n);
-                    }
+                    mbar_expect_tx(fb, tx_bytes);
+#pragma unroll
+                    for (int i = 0; i < Cfg::MAX_SLOTS; ++i)
+                        if (i < nslots) tma_load_4d(st + i * WG_TILE, &map_x, fb, s_c[i], x0 * p.stride + s_dx[i], y0 * p.stride + s_dy[i], n);
+#pragma unroll
                     for (int j = 0; j < Cfg::G_TILES; ++j)
-                        tma_load_4d(smem_u32(st + (Cfg::MAX_SLOTS + j) * WG_TILE), &map_g, full0 + 8 * stage, k0 + j * 64, x0, y0, n);
+                        tma_load_4d(st + (Cfg::MAX_SLOTS + j) * WG_TILE, &map_g, fb, k0 + j * 64, x0, y0, n);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++cx == p.chunks_x) { cx = 0; if (++cy == p.chunks_y) { cy = 0; ++n; } }
                 }
             }
         } else if (warp == 1) {
             // ===================================================== MMA issuer
             const uint32_t idesc = instr_desc_bf16(NK, true, true);
+            // MN-major, 128B swizzle: 8-pixel groups 1024 B apart (SBO), 64-channel blocks LBO apart.  Descriptors are built once;
+            // per stage / K step only the 14-bit start-address field advances (16-byte units).
+            const uint32_t smem0 = smem_u32(smem);
+            uint64_t adesc0[Cfg::MAX_GROUPS];
+#pragma unroll
+            for (int g = 0; g < Cfg::MAX_GROUPS; ++g)      // odd tail: both halves read the same tile (LBO = 0)
+                adesc0[g] = smem_desc(smem0 + 2 * g * WG_TILE, (2 * g + 1 < nslots) ? WG_TILE : 0, 1024, 2);
+            const uint64_t bdesc0 = smem_desc(smem0 + Cfg::MAX_SLOTS * WG_TILE, WG_TILE, 1024, 2);
             int stage = 0; uint32_t phase = 0;
             for (int it = 0; it < nchunks; ++it) {
                 mbar_wait(full0 + 8 * stage, phase);
                 fence_after();
                 if (elect_one()) {
-                    const uint32_t st = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint32_t gb = st + Cfg::MAX_SLOTS * WG_TILE;
-#pragma unroll 1
-                    for (int g = 0; g < ngroups; ++g) {
-                        const uint32_t lbo_a = (2 * g + 1 < nslots) ? WG_TILE : 0;     // odd tail: both halves read the same tile
+                    const uint64_t soff = (uint64_t)((stage * Cfg::STAGE_BYTES) >> 4);
 #pragma unroll
-                        for (int kk = 0; kk < 2; ++kk) {
-                            // MN-major, 128B swizzle: 8-pixel groups 1024 B apart (SBO), 64-channel blocks LBO apart
-                            const uint64_t adesc = smem_desc(st + 2 * g * WG_TILE + kk * 2048, lbo_a, 1024, 2);
-                            const uint64_t bdesc = smem_desc(gb + kk * 2048, WG_TILE, 1024, 2);
-                            umma_bf16(tmem_base + g * NK, adesc, bdesc, idesc, (it | kk) != 0);
+                    for (int g = 0; g < Cfg::MAX_GROUPS; ++g) {
+                        if (g < ngroups) {
+#pragma unroll
+                            for (int kk = 0; kk < 2; ++kk)
+                                umma_bf16(tmem_base + g * NK, adesc0[g] + soff + (uint64_t)(kk * 128), bdesc0 + soff + (uint64_t)(kk * 128),
+                                          idesc, (it | kk) != 0);
                         }
                     }
                     umma_commit(empty0 + 8 * stage);

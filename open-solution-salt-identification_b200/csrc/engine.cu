@@ -183,6 +183,8 @@ void Engine::build() {
     o_final_w_ = add_param("final.1.weight", {cfg_.num_classes, 64, 1, 1});
     o_final_b_ = add_param("final.1.bias", {cfg_.num_classes});
 
+    d_pack_ = (PackDesc*)ws_alloc(sizeof(PackDesc) * 64); d_pack_start_ = (int*)ws_alloc(sizeof(int) * 65);
+    d_unpack_ = (UnpackDesc*)ws_alloc(sizeof(UnpackDesc) * 64); d_unpack_start_ = (int*)ws_alloc(sizeof(int) * 65);
     loss_scratch_ = (float*)ws_alloc(sizeof(float) * (B + 8));
     loss_sums_ = (double*)ws_alloc(sizeof(double) * 16);
     for (int i = 0; i < 4; ++i) scratch_[i] = ws_alloc(std::max<size_t>(scratch_bytes_[i], 256));
@@ -196,6 +198,8 @@ void Engine::bind(float* params, float* grads, float* m, float* v, float* buffer
     counting_ = false;
     build();
     if (ws_cursor_ > ws_bytes_) throw std::runtime_error("internal error: workspace layout changed between passes");
+    build_pack_table();
+    unpack_table_dirty_ = true;
     packed_dirty_ = true;
 }
 
@@ -232,14 +236,49 @@ ConvGeom Engine::geom(const ConvLayer& c, const Tensor& in, const Tensor& out) c
     g.R = c.R; g.S = c.S; g.stride = c.stride; g.pad = c.pad;
     return g;
 }
+std::vector<ConvLayer*> Engine::all_convs() {
+    std::vector<ConvLayer*> v;
+    v.push_back(&stem_);
+    for (auto& b : blocks_) { v.push_back(&b->c1); v.push_back(&b->c2); if (b->down) v.push_back(&b->cd); }
+    v.push_back(&center0_.c); v.push_back(&center1_.c);
+    for (auto& d : dec_) { v.push_back(&d.u1.c); v.push_back(&d.u2.c); }
+    v.push_back(&final0_.c);
+    return v;
+}
+void Engine::build_pack_table() {
+    std::vector<PackDesc> descs; std::vector<int> start(1, 0);
+    for (ConvLayer* c : all_convs()) {
+        PackDesc d; d.w = params_ + c->o_w; d.wp = c->wp; d.wpd = c->wpd; d.Co = c->Co; d.Ci_real = c->Ci_real; d.Ci = c->Ci; d.RS = c->R * c->S;
+        descs.push_back(d);
+        start.push_back(start.back() + cdiv((long long)c->Co * c->R * c->S * c->Ci, 256));
+    }
+    pack_layers_ = (int)descs.size(); pack_blocks_ = start.back();
+    cudaMemcpy(d_pack_, descs.data(), sizeof(PackDesc) * descs.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_pack_start_, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice);
+}
 void Engine::pack_all(cudaStream_t st) {
-    auto pack = [&](const ConvLayer& c) { k_pack_weights(st, cfg_.dt, params_ + c.o_w, c.wp, c.wpd, c.Co, c.Ci_real, c.Ci, c.R, c.S); };
-    pack(stem_);
-    for (auto& b : blocks_) { pack(b->c1); pack(b->c2); if (b->down) pack(b->cd); }
-    pack(center0_.c); pack(center1_.c);
-    for (auto& d : dec_) { pack(d.u1.c); pack(d.u2.c); }
-    pack(final0_.c);
+    k_pack_all(st, cfg_.dt, d_pack_, d_pack_start_, pack_layers_, pack_blocks_);
     packed_dirty_ = false;
+}
+// one launch: transpose every tensor-core wgrad scratch into the reference-layout gradient
+void Engine::unpack_all(cudaStream_t st) {
+    if (unpack_table_dirty_) {
+        std::vector<UnpackDesc> descs; std::vector<int> start(1, 0);
+        unpack_max_rs_ = 1;
+        for (ConvLayer* c : all_convs()) {
+            if (!c->in_unpack_table) continue;
+            UnpackDesc d; d.dwp = c->dwp; d.dw = grads_ + c->o_w; d.Co = c->Co; d.Ci_real = c->Ci_real; d.Ci_pad = cdiv(c->Ci, 64) * 64; d.RS = c->R * c->S;
+            descs.push_back(d);
+            start.push_back(start.back() + cdiv(c->Co, 32) * cdiv(c->Ci_real, 32));
+            unpack_max_rs_ = std::max(unpack_max_rs_, d.RS);
+        }
+        unpack_layers_ = (int)descs.size(); unpack_blocks_ = start.back();
+        cudaStreamSynchronize(st);
+        cudaMemcpy(d_unpack_, descs.data(), sizeof(UnpackDesc) * descs.size(), cudaMemcpyHostToDevice);
+        cudaMemcpy(d_unpack_start_, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice);
+        unpack_table_dirty_ = false;
+    }
+    if (unpack_layers_ > 0) k_unpack_all(st, d_unpack_, d_unpack_start_, unpack_layers_, unpack_blocks_, unpack_max_rs_);
 }
 static double conv_flops(const ConvGeom& g, int ci_real) {
     return 2.0 * g.B * g.Ho * g.Wo * (double)g.Co * ci_real * g.R * g.S;
@@ -298,12 +337,12 @@ void Engine::conv_dgrad(const ConvLayer& c, const Tensor& gout, const Tensor& gi
         k_conv_dgrad_simt(st, cfg_.dt, gout.p, c.wpd, gin.p, accumulate, g);
     prof_end(st);
 }
-void Engine::conv_wgrad(const ConvLayer& c, const Tensor& in, const Tensor& gout, cudaStream_t st) {
+void Engine::conv_wgrad(ConvLayer& c, const Tensor& in, const Tensor& gout, cudaStream_t st) {
     ConvGeom g = geom(c, in, gout);
     prof_begin(PROF_CONV_WGRAD, conv_flops(g, c.Ci_real), st);
     if (cfg_.dt == DT_BF16 && cfg_.use_tc && tc_wgrad_supported(g)) {
-        k_conv_wgrad_tc(st, in.p, gout.p, c.dwp, g);
-        k_unpack_dw(st, c.dwp, grads_ + c.o_w, c.Co, c.Ci_real, cdiv(c.Ci, 64) * 64, c.R * c.S, false);
+        k_conv_wgrad_tc(st, in.p, gout.p, c.dwp, g);      // partial sums land in c.dwp; unpack_all() transposes them at the end of backward()
+        if (!c.in_unpack_table) { c.in_unpack_table = true; unpack_table_dirty_ = true; }
     } else
         k_conv_wgrad_simt(st, cfg_.dt, in.p, gout.p, grads_ + c.o_w, c.Ci_real, g);
     prof_end(st);
@@ -492,6 +531,7 @@ void Engine::backward(const float* dlogits, cudaStream_t st) {
         k_bn_bwd_apply(st, G, raw, bn, true, graw);
         conv_wgrad(stem_, view(x4_), graw, st);
     }
+    unpack_all(st);
 }
 void Engine::adam(float lr, float wd, float b1, float b2, float eps, int step, float grad_scale, cudaStream_t st) {
     if (!adam_m_ || !adam_v_ || !grads_) throw std::runtime_error("engine bound without optimiser state");

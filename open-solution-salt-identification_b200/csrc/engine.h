@@ -7,6 +7,7 @@
 #include <memory>
 #include "kernels.h"
 #include "conv_tc.h"
+#include "kernels_batched.h"
 
 struct TensorInfo {            // one named entry of the reference state_dict
     std::string name;
@@ -23,6 +24,7 @@ struct ConvLayer {
     long long o_b = -1;        // bias offset or -1
     void* wp = nullptr;        // packed fwd weights   [Co][R*S][Ci]
     void* wpd = nullptr;       // packed dgrad weights [Ci][R*S][Co]
+    bool in_unpack_table = false;
     float* dwp = nullptr;      // tensor-core wgrad scratch [R*S][ceil64(Ci)][Co] fp32 (inside the zeroed-per-backward arena)
 };
 struct BNLayer {
@@ -119,7 +121,10 @@ private:
     void pack_all(cudaStream_t st);
     void conv_fwd(const ConvLayer& c, const Tensor& in, const Tensor& out, BNLayer* bn, bool train, cudaStream_t st);
     void conv_dgrad(const ConvLayer& c, const Tensor& gout, const Tensor& gin, bool accumulate, cudaStream_t st);
-    void conv_wgrad(const ConvLayer& c, const Tensor& in, const Tensor& gout, cudaStream_t st);
+    void conv_wgrad(ConvLayer& c, const Tensor& in, const Tensor& gout, cudaStream_t st);
+    std::vector<ConvLayer*> all_convs();
+    void build_pack_table();
+    void unpack_all(cudaStream_t st);
     void gather_fwd(const std::vector<Source>& srcs, const Tensor& P, cudaStream_t st);
     void gather_bwd(const std::vector<Source>& srcs, const Tensor& gP, cudaStream_t st);
     void block_fwd(BasicBlock& b, bool train, cudaStream_t st);
@@ -136,6 +141,10 @@ private:
     char* ws_base_ = nullptr;
     float *params_ = nullptr, *grads_ = nullptr, *adam_m_ = nullptr, *adam_v_ = nullptr, *buffers_ = nullptr;
     bool packed_dirty_ = true;
+    // batched pack / unpack tables (device copies live in the workspace)
+    PackDesc* d_pack_ = nullptr; int* d_pack_start_ = nullptr; int pack_layers_ = 0, pack_blocks_ = 0;
+    UnpackDesc* d_unpack_ = nullptr; int* d_unpack_start_ = nullptr; int unpack_layers_ = 0, unpack_blocks_ = 0, unpack_max_rs_ = 1;
+    bool unpack_table_dirty_ = false;
     bool trained_forward_ = false;
     int B_ = 0;
 

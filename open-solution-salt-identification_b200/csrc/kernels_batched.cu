@@ -1,0 +1,66 @@
+// Whole-network ("batched") versions of the small per-layer kernels: one launch covers every convolution layer, the layer
+// is found from a prefix table of block counts.  Removes ~100 tiny launches per training step.
+#include "kernels.h"
+#include "kernels_batched.h"
+
+__device__ __forceinline__ int find_layer(const int* __restrict__ blk_start, int n, int b) {
+    int lo = 0, hi = n - 1;                       // blk_start has n+1 entries; find l with blk_start[l] <= b < blk_start[l+1]
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (blk_start[mid] <= b) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------------ weight packing
+template <typename T>
+__global__ void pack_all_kernel(const PackDesc* __restrict__ descs, const int* __restrict__ blk_start, int nlayers) {
+    const int l = find_layer(blk_start, nlayers, blockIdx.x);
+    const PackDesc d = descs[l];
+    const int idx = (blockIdx.x - blk_start[l]) * 256 + threadIdx.x;
+    const int total = d.Co * d.RS * d.Ci;
+    if (idx >= total) return;
+    const int c = idx % d.Ci, t = (idx / d.Ci) % d.RS, k = idx / (d.Ci * d.RS);
+    const float v = c < d.Ci_real ? d.w[((size_t)k * d.Ci_real + c) * d.RS + t] : 0.f;
+    st1((T*)d.wp + idx, v);
+    st1((T*)d.wpd + ((size_t)c * d.RS + (d.RS - 1 - t)) * d.Co + k, v);       // flipped taps, see kernels_conv_simt.cu
+}
+void k_pack_all(cudaStream_t st, DType dt, const PackDesc* descs, const int* blk_start, int nlayers, int total_blocks) {
+    SALT_COUNT(1);
+    SALT_DISPATCH(dt, T, (pack_all_kernel<T><<<total_blocks, 256, 0, st>>>(descs, blk_start, nlayers)));
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad unpack
+// dw[k][c][t] = dwp[t][c][k]: 32(k) x 32(c) x RS tile transposed through shared memory (coalesced both sides)
+__global__ void __launch_bounds__(256) unpack_all_kernel(const UnpackDesc* __restrict__ descs, const int* __restrict__ blk_start, int nlayers) {
+    extern __shared__ float tile[];                  // [32 k][32 c * RS + 1]
+    const int l = find_layer(blk_start, nlayers, blockIdx.x);
+    const UnpackDesc d = descs[l];
+    const int b = blockIdx.x - blk_start[l];
+    const int ktiles = (d.Co + 31) >> 5;
+    const int k0 = (b % ktiles) * 32, c0 = (b / ktiles) * 32, RS = d.RS, pitch = 32 * RS + 1;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int t = 0; t < RS; ++t)
+        for (int c = ty; c < 32; c += 8) {
+            float v = 0.f;
+            if (k0 + tx < d.Co && c0 + c < d.Ci_pad) v = d.dwp[((size_t)t * d.Ci_pad + c0 + c) * d.Co + k0 + tx];
+            tile[tx * pitch + c * RS + t] = v;
+        }
+    __syncthreads();
+    const int ncols = min(32, d.Ci_real - c0) * RS;  // contiguous run in dw for one k
+    for (int k = ty; k < 32; k += 8) {
+        if (k0 + k >= d.Co) continue;
+        float* o = d.dw + ((size_t)(k0 + k) * d.Ci_real + c0) * RS;
+        for (int j = tx; j < ncols; j += 32) o[j] = tile[k * pitch + j];
+    }
+}
+void k_unpack_all(cudaStream_t st, const UnpackDesc* descs, const int* blk_start, int nlayers, int total_blocks, int max_rs) {
+    SALT_COUNT(1);
+    const size_t smem = sizeof(float) * 32 * (32 * max_rs + 1);
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaFuncSetAttribute(unpack_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = smem;
+    }
+    unpack_all_kernel<<<total_blocks, 256, smem, st>>>(descs, blk_start, nlayers);
+}

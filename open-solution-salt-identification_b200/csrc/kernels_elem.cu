@@ -111,7 +111,7 @@ __device__ __forceinline__ void block_reduce_add(const Vf<N>& v, int cg, D* dst,
 static inline int reduce_blocks(long long npix, int cg) {
     int lanes = EW_THREADS / cg;
     long long b = (npix + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
-    if (b > 148 * 8) b = 148 * 8;
+    if (b > 148 * 2) b = 148 * 2;      // few fat blocks: the final per-channel atomics hit the same 2*C addresses
     if (b < 1) b = 1;
     return (int)b;
 }
