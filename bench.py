@@ -21,6 +21,10 @@ for _p in (ROOT, PKG):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+# stdout must carry exactly one JSON line: keep NCCL's banner ("NCCL version ...") off it
+if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+    os.environ['NCCL_DEBUG'] = 'WARN'
+
 import numpy as np  # noqa: E402
 import torch        # noqa: E402
 

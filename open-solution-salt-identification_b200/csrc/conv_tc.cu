@@ -15,6 +15,7 @@
 // Two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1; an S-stage smem ring decouples TMA from MMA.
 #include "tc_common.cuh"
 #include "conv_tc.h"
+#include <cstdlib>
 
 using namespace tc;
 
@@ -299,9 +300,18 @@ static void run_tc(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca
     throw std::runtime_error("k_conv_tc: unsupported tile configuration");
 }
 
+static bool rows_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SALT_TC_ROWS"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
 // out[n,y,x,k] (+)= sum_{r,s,c} A[n, y*stride+r-pad, x*stride+s-pad, c] * Wp[k][(r*S+s)*Ca + c]
 void k_conv_tc(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca, const void* Wp, int Nout, int R, int S, int stride,
                int pad, void* out, int Ho, int Wo, const float* bias, double* stats, bool accumulate) {
+    if (rows_enabled() && tc_conv_rows_supported(Ca, Nout, R, S, stride, Ho, Wo)) {
+        k_conv_tc_rows(st, A, B, Ha, Wa, Ca, Wp, Nout, pad, out, Ho, Wo, bias, stats, accumulate);
+        return;
+    }
     SALT_COUNT(1);
     TcParams p;
     p.Ho = Ho; p.Wo = Wo; p.out_H = Ho; p.out_W = Wo; p.osy = p.osx = 1; p.a_stride = stride;
