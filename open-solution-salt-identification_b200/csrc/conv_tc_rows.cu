@@ -1,16 +1,18 @@
 // tcgen05 3x3 stride-1 convolution with shared-memory ROW-HALO reuse of the activation tile (forward and stride-1 dgrad).
 //
-// conv_tc.cu loads the A operand once per filter tap (9 TMA boxes per 64-channel block).  Its profile shows the kernel bound
-// by L2 -> shared-memory bandwidth, not by the tensor core.  Here the output tile is 16 rows x 8 columns and, per 64-channel
-// block, only THREE boxes are loaded - one per horizontal tap offset s - each 18 rows x 8 pixels (the 16 output rows plus the
-// vertical halo).  A pixel row of 8 pixels x 64 channels is exactly one 1024-byte swizzle atom, so the three vertical taps
-// r = 0,1,2 are the SAME buffer read at byte offsets r*1024: the UMMA descriptor start address stays 1024-byte aligned and the
-// canonical K-major 128B-swizzled layout is untouched.  A traffic drops from 9 x 16 KB to 3 x 18 KB per channel block.
-//
-// Pipeline: A ring (18 KB stages, one per (channel block, s)), B ring (weights [BN x 64], one per tap), warp 0 = TMA producer,
-// warp 1 = MMA issuer, warps 2-5 = epilogue (same epilogue as conv_tc.cu), two TMEM accumulators, persistent CTAs.
+// Measurements that shaped this kernel (profiles/r1_notes.md): conv_tc.cu issues 4 MMAs per pipeline stage; with every load and
+// store disabled it still ran at the same speed for N <= 128, i.e. it is bound by the single MMA-issuing thread's per-stage
+// overhead (mbarrier try_wait ~90 cycles + commit), not by memory.  So here one stage carries THREE filter taps:
+//   * the output tile is 16 rows x 8 columns; per 64-channel block and horizontal tap offset s one TMA box of 18 rows x 8 pixels
+//     (16 output rows + vertical halo) is loaded.  A pixel row of 8 pixels x 64 channels is exactly one 1024-byte swizzle atom,
+//     so the vertical taps r = 0,1,2 are the SAME buffer read at byte offsets r*1024 - the UMMA descriptor start address stays
+//     1024-byte aligned and the canonical K-major 128B-swizzled layout is untouched (A traffic: 3 x 18 KB instead of 9 x 16 KB);
+//   * the three weight slabs [BN x 64] of taps (0..2, s) arrive with ONE 4-D TMA box (c, n, r, s) in the same stage;
+//   * the issuer waits once and issues 12 MMAs (3 taps x 4 K-steps) per stage, then one tcgen05.commit frees the stage.
+// Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (as conv_tc.cu), two TMEM accumulators, persistent CTAs.
 #include "tc_common.cuh"
 #include "conv_tc.h"
+#include <cstdlib>
 
 using namespace tc;
 
@@ -36,118 +38,118 @@ struct RowsParams {
     int tiles_x, tiles_y, tiles_co, total_tiles;
     int B, Ho, Wo, Co, Ca, cblks, pad;
     int accumulate;
+    int debug;                 // timing experiments only (env SALT_TC_DEBUG): 1 = skip loads, 4 = skip stores+stats, 8 = skip stats, 16 = skip stores
     const float* bias;
     double* stats;
     bf16* out;
 };
 
-constexpr int RW_THREADS = 192;
+constexpr int RW_THREADS = 320;                              // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int RW_EPI_THREADS = 256;
 constexpr int RW_TH = 16, RW_TW = 8;
 constexpr int RW_A_BYTES = (RW_TH + 2) * RW_TW * 128;        // 18 pixel rows x 8 pixels x 64 channels bf16 = 18 KB
 template <int BN> struct RowsCfg {
-    static constexpr int B_BYTES = BN * 128;
-    static constexpr int A_STAGES = 4;
-    static constexpr int B_STAGES = BN == 256 ? 3 : (BN == 128 ? 6 : 8);
+    static constexpr int B_BYTES = BN * 128;                 // one tap: [BN][64] bf16
+    static constexpr int STAGE_BYTES = RW_A_BYTES + 3 * B_BYTES;
+    static constexpr int STAGES = BN == 128 ? 3 : (BN == 64 ? 4 : 6);
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-    static constexpr int BAR_OFF = A_STAGES * RW_A_BYTES + B_STAGES * B_BYTES;
-    static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256 + 2 * BN * 4;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256 + 8 * 2 * BN * 4;      // + per-epilogue-warp BN statistics
 };
 
 template <int BN>
 __global__ void __launch_bounds__(RW_THREADS, 1)
 conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const RowsParams p) {
     using Cfg = RowsCfg<BN>;
-    constexpr int SA = Cfg::A_STAGES, SB = Cfg::B_STAGES;
+    constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + SA * RW_A_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
-    // bars: a_full[SA], a_empty[SA], b_full[SB], b_empty[SB], tmem_full[2], tmem_empty[2]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 4);
+    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     float* s_stats = reinterpret_cast<float*>(smem + Cfg::BAR_OFF + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t afull0 = smem_u32(bars), aempty0 = afull0 + 8 * SA, bfull0 = aempty0 + 8 * SA, bempty0 = bfull0 + 8 * SB;
-    const uint32_t tfull0 = bempty0 + 8 * SB, tempty0 = tfull0 + 16;
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES, tfull0 = empty0 + 8 * STAGES, tempty0 = tfull0 + 16;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-        for (int i = 0; i < SA; ++i) { mbar_init(afull0 + 8 * i, 1); mbar_init(aempty0 + 8 * i, 1); }
-        for (int i = 0; i < SB; ++i) { mbar_init(bfull0 + 8 * i, 1); mbar_init(bempty0 + 8 * i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), Cfg::TMEM_COLS);
-    for (int i = threadIdx.x; i < 2 * BN; i += RW_THREADS) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < 8 * 2 * BN; i += RW_THREADS) s_stats[i] = 0.f;
     fence_before();
     __syncthreads();
     fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    const int stages_per_tile = p.cblks * 3;
 
     if (warp == 0) {
-        // ===================================================== TMA producer
+        // ===================================================== TMA producer: one A box + one 3-tap weight box per stage
         if (elect_one()) {
-            int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+            int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.tiles_co, mt = tile / p.tiles_co;
                 const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, n = mt / (p.tiles_x * p.tiles_y);
                 const int w0 = tx * RW_TW - p.pad, h0 = ty * RW_TH - p.pad;
                 for (int cb = 0; cb < p.cblks; ++cb) {
                     for (int s = 0; s < 3; ++s) {
-                        mbar_wait(aempty0 + 8 * sa, pa ^ 1);
-                        mbar_expect_tx(afull0 + 8 * sa, RW_A_BYTES);
-                        tma_load_4d(smem_u32(smem_a + sa * RW_A_BYTES), &map_a, afull0 + 8 * sa, cb * 64, w0 + s, h0, n);
-                        if (++sa == SA) { sa = 0; pa ^= 1; }
-                        for (int r = 0; r < 3; ++r) {
-                            mbar_wait(bempty0 + 8 * sb, pb ^ 1);
-                            mbar_expect_tx(bfull0 + 8 * sb, Cfg::B_BYTES);
-                            tma_load_2d(smem_u32(smem_b + sb * Cfg::B_BYTES), &map_b, bfull0 + 8 * sb, (r * 3 + s) * p.Ca + cb * 64, nt * BN);
-                            if (++sb == SB) { sb = 0; pb ^= 1; }
+                        const uint32_t st = smem0 + stage * Cfg::STAGE_BYTES, fb = full0 + 8 * stage;
+                        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                        if (p.debug & 1) mbar_arrive(fb);
+                        else {
+                            mbar_expect_tx(fb, Cfg::STAGE_BYTES);
+                            tma_load_4d(st, &map_a, fb, cb * 64, w0 + s, h0, n);
+                            tma_load_4d(st + RW_A_BYTES, &map_b, fb, cb * 64, nt * BN, 0, s);     // (c, n, r = 0..2, s)
                         }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================================================== MMA issuer
+        // ===================================================== MMA issuer: 12 MMAs per barrier wait
         const uint32_t idesc = instr_desc_bf16(BN, false, false);
-        const uint64_t adesc0 = smem_desc(smem_u32(smem_a), 16, 1024, 2);
-        const uint64_t bdesc0 = smem_desc(smem_u32(smem_b), 16, 1024, 2);
-        int sa = 0, sb = 0; uint32_t pa = 0, pb = 0;
+        const uint64_t adesc0 = smem_desc(smem0, 16, 1024, 2);
+        const uint64_t bdesc0 = smem_desc(smem0 + RW_A_BYTES, 16, 1024, 2);
+        int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
             fence_after();
             const uint32_t tmem_d = tmem_base + acc * BN;
-            const int num_a = p.cblks * 3;
-            for (int ia = 0; ia < num_a; ++ia) {
-                mbar_wait(afull0 + 8 * sa, pa);
-                for (int r = 0; r < 3; ++r) {
-                    mbar_wait(bfull0 + 8 * sb, pb);
-                    fence_after();
-                    if (elect_one()) {
+            for (int it = 0; it < stages_per_tile; ++it) {
+                mbar_wait(full0 + 8 * stage, phase);
+                fence_after();
+                if (elect_one()) {
+                    const uint64_t soff = (uint64_t)((stage * Cfg::STAGE_BYTES) >> 4);
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
                         // vertical tap r = the same A buffer, r pixel-rows (r * 1024 bytes) further down
-                        const uint64_t adesc = adesc0 + (uint64_t)((sa * RW_A_BYTES + r * 1024) >> 4);
-                        const uint64_t bdesc = bdesc0 + (uint64_t)((sb * Cfg::B_BYTES) >> 4);
+                        const uint64_t adesc = adesc0 + soff + (uint64_t)((r * 1024) >> 4);
+                        const uint64_t bdesc = bdesc0 + soff + (uint64_t)((r * Cfg::B_BYTES) >> 4);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (ia | r | k) != 0);
-                        umma_commit(bempty0 + 8 * sb);
-                        if (r == 2) umma_commit(aempty0 + 8 * sa);
-                        if (r == 2 && ia == num_a - 1) umma_commit(tfull0 + 8 * acc);
+                            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | r | k) != 0);
                     }
-                    __syncwarp();
-                    if (++sb == SB) { sb = 0; pb ^= 1; }
+                    umma_commit(empty0 + 8 * stage);
+                    if (it == stages_per_tile - 1) umma_commit(tfull0 + 8 * acc);
                 }
-                if (++sa == SA) { sa = 0; pa ^= 1; }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
-        // ===================================================== epilogue (warps 2..5 <-> TMEM lane quarters 2,3,0,1)
-        const int quarter = warp & 3;
+        // ===================================================== epilogue: 8 warps (2..9).  Warp w may touch TMEM lanes 32*(w%4)..+31;
+        // the two warps of a lane quarter split the 32-column chunks between them, so every scheduler has two epilogue warps
+        // to interleave (the shuffle/convert chains of a single warp left the issue slots idle - profiles/r1_notes.md).
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
+        float* my_stats = s_stats + (warp - 2) * (2 * BN);  // private per-warp accumulators: no shared-memory atomics
         const int m = quarter * 32 + lane;                  // row of the 128-position tile: 16 rows x 8 columns
         const int lx = m & (RW_TW - 1), ly = m >> 3;
         int acc = 0; uint32_t acc_phase = 0;
@@ -155,12 +157,12 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const int nt = tile % p.tiles_co, mt = tile / p.tiles_co;
             const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, n = mt / (p.tiles_x * p.tiles_y);
             const int x = tx * RW_TW + lx, y = ty * RW_TH + ly;
-            const bool valid = (y < p.Ho) && (x < p.Wo);
+            const bool valid = (y < p.Ho) && (x < p.Wo) && !(p.debug & (4 | 16));
             bf16* orow = p.out + (((size_t)n * p.Ho + y) * p.Wo + x) * p.Co + nt * BN;
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             fence_after();
 #pragma unroll 1
-            for (int ch = 0; ch < BN / 32; ++ch) {
+            for (int ch = half; ch < BN / 32; ch += 2) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + ch * 32, v);
                 if (p.bias) {
@@ -190,14 +192,14 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         o4[q] = pk;
                     }
                 }
-                if (p.stats) {
+                if (p.stats && !(p.debug & (4 | 8))) {
                     float sq[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i) { v[i] = valid ? v[i] : 0.f; sq[i] = v[i] * v[i]; }
                     float s1 = rows_butterfly_reduce32(v, lane);
                     float s2 = rows_butterfly_reduce32(sq, lane);
-                    atomicAdd(s_stats + ch * 32 + lane, s1);
-                    atomicAdd(s_stats + BN + ch * 32 + lane, s2);
+                    my_stats[ch * 32 + lane] += s1;
+                    my_stats[BN + ch * 32 + lane] += s2;
                 }
             }
             fence_before();
@@ -205,21 +207,26 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             if (p.stats && p.tiles_co > 1) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 const int tt = threadIdx.x - 64;
-                for (int i = tt; i < 2 * BN; i += 128) {
-                    float val = s_stats[i];
+                for (int i = tt; i < 2 * BN; i += RW_EPI_THREADS) {
+                    float val = 0.f;
+#pragma unroll
+                    for (int w8 = 0; w8 < 8; ++w8) { val += s_stats[w8 * 2 * BN + i]; s_stats[w8 * 2 * BN + i] = 0.f; }
                     if (val != 0.f) atomicAdd(p.stats + (i < BN ? nt * BN + i : p.Co + nt * BN + (i - BN)), (double)val);
-                    s_stats[i] = 0.f;
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
             }
         }
         if (p.stats && p.tiles_co == 1) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             const int tt = threadIdx.x - 64;
-            for (int i = tt; i < 2 * BN; i += 128)
-                atomicAdd(p.stats + (i < BN ? i : p.Co + (i - BN)), (double)s_stats[i]);
+            for (int i = tt; i < 2 * BN; i += RW_EPI_THREADS) {
+                float val = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) val += s_stats[w8 * 2 * BN + i];
+                atomicAdd(p.stats + (i < BN ? i : p.Co + (i - BN)), (double)val);
+            }
         }
     }
     fence_before();
@@ -249,26 +256,26 @@ void k_conv_tc_rows(cudaStream_t st, const void* A, int B, int Ha, int Wa, int C
     SALT_COUNT(1);
     RowsParams p;
     p.tiles_x = cdiv(Wo, RW_TW); p.tiles_y = cdiv(Ho, RW_TH);
-    int BN = Nout % 256 == 0 ? 256 : Nout % 128 == 0 ? 128 : Nout % 64 == 0 ? 64 : 32;
-    while (BN > 64 && (long long)p.tiles_x * p.tiles_y * B * (Nout / BN) < num_sms()) BN >>= 1;
+    const int BN = Nout % 128 == 0 ? 128 : Nout % 64 == 0 ? 64 : 32;
     p.tiles_co = Nout / BN;
     p.total_tiles = p.tiles_x * p.tiles_y * B * p.tiles_co;
     p.B = B; p.Ho = Ho; p.Wo = Wo; p.Co = Nout; p.Ca = Ca; p.cblks = Ca / 64; p.pad = pad;
     p.accumulate = accumulate ? 1 : 0; p.bias = bias; p.stats = stats; p.out = (bf16*)out;
+    { const char* e = getenv("SALT_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
     CUtensorMap ma = make_map_nhwc(A, Ca, Wa, Ha, B, 64, RW_TW, RW_TH + 2, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+    // weights Wp[n][(r*3+s)*Ca + c] viewed as a 4-D tensor (c, n, r, s): one box = [3 taps r][BN][64 c]
     CUtensorMap mb;
     {
-        cuuint64_t dims[2] = {(cuuint64_t)9 * Ca, (cuuint64_t)Nout};
-        cuuint64_t strides[1] = {(cuuint64_t)9 * Ca * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)BN};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = get_encode()(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(Wp), dims, strides, box, estr,
+        cuuint64_t dims[4] = {(cuuint64_t)Ca, (cuuint64_t)Nout, 3, 3};
+        cuuint64_t strides[3] = {(cuuint64_t)9 * Ca * 2, (cuuint64_t)3 * Ca * 2, (cuuint64_t)Ca * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)BN, 3, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = get_encode()(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(Wp), dims, strides, box, estr,
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(weights) failed with code " + std::to_string((int)r));
+        if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(weights 4d) failed with code " + std::to_string((int)r));
     }
-    if (BN == 256) launch_rows<256>(st, ma, mb, p);
-    else if (BN == 128) launch_rows<128>(st, ma, mb, p);
+    if (BN == 128) launch_rows<128>(st, ma, mb, p);
     else if (BN == 64) launch_rows<64>(st, ma, mb, p);
     else launch_rows<32>(st, ma, mb, p);
 }
