@@ -4,6 +4,7 @@
 // arithmetic fp32.  These are HBM-bound passes: every thread moves 16 bytes of storage (4 fp32 / 8 bf16
 // channels), rows map to blockIdx.x so that the index arithmetic is 32-bit and division-light.
 #include "kernels.h"
+#include <algorithm>
 
 #define EW_THREADS 256
 
@@ -35,6 +36,15 @@ __device__ __forceinline__ void stv(bf16* p, const Vf<8>& a) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(a.v[2 * i], a.v[2 * i + 1]);
     *reinterpret_cast<uint4*>(p) = u;
+}
+// streaming (evict-first) stores for write-once outputs that must not push re-used inputs out of L2
+__device__ __forceinline__ void stv_stream(float* p, const Vf<4>& a) { __stcs(reinterpret_cast<float4*>(p), make_float4(a.v[0], a.v[1], a.v[2], a.v[3])); }
+__device__ __forceinline__ void stv_stream(bf16* p, const Vf<8>& a) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(a.v[2 * i], a.v[2 * i + 1]);
+    __stcs(reinterpret_cast<uint4*>(p), u);
 }
 template <int N> __device__ __forceinline__ Vf<N> ldp(const float* p) {      // N fp32 per-channel parameters
     Vf<N> r;
@@ -194,31 +204,35 @@ template <typename T>
 __global__ void bn_apply_kernel(const T* __restrict__ raw, const float* __restrict__ scale, const float* __restrict__ shift,
                                 const T* __restrict__ res, const float* __restrict__ rscale, const float* __restrict__ rshift,
                                 int relu, T* __restrict__ out, int H, int W, int C, int pt, int pb, int pl, int pr) {
+    // one block per image row; a thread keeps ONE channel group (its scale/shift live in registers) and walks along x
     constexpr int N = VW<T>::N;
-    const int cg = C / N;
-    const int j = blockIdx.y * EW_THREADS + threadIdx.x;
-    if (j >= W * cg) return;
-    const int x = j / cg, c = (j - x * cg) * N;
+    const int cg = C / N, lanes = EW_THREADS / cg;
+    const int cv = threadIdx.x % cg, lane = threadIdx.x / cg, c = cv * N;
     const int row = blockIdx.x, n = row / H, y = row - n * H;
-    const size_t src = ((size_t)row * W + x) * C + c;
-    Vf<N> v = vfma(ldv(raw + src), ldp<N>(scale + c), ldp<N>(shift + c));
-    if (res) {
-        Vf<N> r = ldv(res + src);
-        if (rscale) r = vfma(r, ldp<N>(rscale + c), ldp<N>(rshift + c));
-        v = vadd(v, r);
-    }
-    if (relu) v = vrelu(v);
+    const Vf<N> sc = ldp<N>(scale + c), sh = ldp<N>(shift + c);
+    Vf<N> rsc = vzero<N>(), rsh = vzero<N>();
+    if (res && rscale) { rsc = ldp<N>(rscale + c); rsh = ldp<N>(rshift + c); }
     const int Hp = H + pt + pb, Wp = W + pl + pr;
     const int y0 = (y == 0) ? 0 : y + pt, y1 = (y == H - 1) ? Hp - 1 : y + pt;
-    const int x0 = (x == 0) ? 0 : x + pl, x1 = (x == W - 1) ? Wp - 1 : x + pl;
-    for (int yy = y0; yy <= y1; ++yy)
-        for (int xx = x0; xx <= x1; ++xx) stv(out + (((size_t)n * Hp + yy) * Wp + xx) * C + c, v);
+    for (int x = lane; x < W; x += lanes) {
+        const size_t src = ((size_t)row * W + x) * C + c;
+        Vf<N> v = vfma(ldv(raw + src), sc, sh);
+        if (res) {
+            Vf<N> r = ldv(res + src);
+            if (rscale) r = vfma(r, rsc, rsh);
+            v = vadd(v, r);
+        }
+        if (relu) v = vrelu(v);
+        const int x0 = (x == 0) ? 0 : x + pl, x1 = (x == W - 1) ? Wp - 1 : x + pl;
+        for (int yy = y0; yy <= y1; ++yy)
+            for (int xx = x0; xx <= x1; ++xx) stv(out + (((size_t)n * Hp + yy) * Wp + xx) * C + c, v);
+    }
 }
 void k_bn_apply(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const Tensor* res,
                 const float* rscale, const float* rshift, bool relu, const Tensor& out) {
     SALT_COUNT(1);
     SALT_DISPATCH(raw.dt, T, {
-        dim3 grid(raw.B * raw.H, cdiv(raw.W * (raw.C / VW<T>::N), EW_THREADS));
+        dim3 grid(raw.B * raw.H);
         bn_apply_kernel<T><<<grid, EW_THREADS, 0, st>>>((const T*)raw.p, scale, shift, res ? (const T*)res->p : nullptr, rscale,
                                                         rshift, relu ? 1 : 0, (T*)out.p, raw.H, raw.W, raw.C, out.pt, out.pb, out.pl, out.pr);
     });
@@ -309,7 +323,7 @@ __global__ void gather_fwd_kernel(T* __restrict__ out, GatherArgs a, int H, int 
             v.v[i] = top * wy0 + bot * ly;
         }
     }
-    stv(out + ((size_t)row * Wp + xp) * C + cv * N, v);
+    stv_stream(out + ((size_t)row * Wp + xp) * C + cv * N, v);
 }
 void k_gather_fwd(cudaStream_t st, const Tensor& out, const GatherSrc* srcs, int nsrc) {
     SALT_COUNT(1);
@@ -732,25 +746,29 @@ void k_bn_bwd_reduce(cudaStream_t st, const Tensor& g, const Tensor& raw, const 
 }
 template <typename T>
 __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict__ raw, BNRef bn, int self_mask,
-                                    T* __restrict__ graw, unsigned nvec, unsigned cg) {
+                                    T* __restrict__ graw, unsigned npix, int C) {
+    // a thread keeps ONE channel group (5 per-channel coefficient vectors in registers) and strides over pixels
     constexpr int N = VW<T>::N;
-    const unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
-    if (idx >= nvec) return;
-    const int c = (idx % cg) * N;
-    const Vf<N> x = ldv(raw + (size_t)idx * N), sc = ldp<N>(bn.scale + c);
-    Vf<N> gv = ldv(g + (size_t)idx * N);
-    if (self_mask) gv = vmaskpos(gv, vfma(x, sc, ldp<N>(bn.shift + c)));
-    const Vf<N> mu = ldp<N>(bn.mean + c), cb = ldp<N>(bn.cb + c), cc = ldp<N>(bn.cc + c);
-    Vf<N> r;
+    const int cg = C / N, lanes = EW_THREADS / cg;
+    const int cv = threadIdx.x % cg, lane = threadIdx.x / cg, c = cv * N;
+    const Vf<N> sc = ldp<N>(bn.scale + c), sh = ldp<N>(bn.shift + c), mu = ldp<N>(bn.mean + c), cb = ldp<N>(bn.cb + c),
+                cc = ldp<N>(bn.cc + c);
+    for (unsigned pix = blockIdx.x * lanes + lane; pix < npix; pix += gridDim.x * lanes) {
+        const Vf<N> x = ldv(raw + (size_t)pix * C + c);
+        Vf<N> gv = ldv(g + (size_t)pix * C + c);
+        if (self_mask) gv = vmaskpos(gv, vfma(x, sc, sh));
+        Vf<N> r;
 #pragma unroll
-    for (int i = 0; i < N; ++i) r.v[i] = sc.v[i] * (gv.v[i] - cb.v[i] - cc.v[i] * (x.v[i] - mu.v[i]));
-    stv(graw + (size_t)idx * N, r);
+        for (int i = 0; i < N; ++i) r.v[i] = sc.v[i] * (gv.v[i] - cb.v[i] - cc.v[i] * (x.v[i] - mu.v[i]));
+        stv(graw + (size_t)pix * C + c, r);
+    }
 }
 void k_bn_bwd_apply(cudaStream_t st, const Tensor& g, const Tensor& raw, const BNRef& bn, bool self_mask, const Tensor& graw) {
     SALT_COUNT(1);
     SALT_DISPATCH(raw.dt, T, {
-        const unsigned nvec = (unsigned)(raw.numel() / VW<T>::N);
-        bn_bwd_apply_kernel<T><<<cdiv(nvec, EW_THREADS), EW_THREADS, 0, st>>>((const T*)g.p, (const T*)raw.p, bn, self_mask ? 1 : 0,
-                                                                            (T*)graw.p, nvec, raw.C / VW<T>::N);
+        const unsigned npix = (unsigned)raw.B * raw.H * raw.W;
+        const int lanes = EW_THREADS / (raw.C / VW<T>::N);
+        const int blocks = (int)std::min<long long>(((long long)npix + lanes * 4 - 1) / (lanes * 4), 148 * 16);
+        bn_bwd_apply_kernel<T><<<blocks, EW_THREADS, 0, st>>>((const T*)g.p, (const T*)raw.p, bn, self_mask ? 1 : 0, (T*)graw.p, npix, raw.C);
     });
 }
