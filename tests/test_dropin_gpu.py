@@ -1,0 +1,128 @@
+"""GPU: the drop-in transformer surface (reference common_blocks/models.py:67-208) - constructor, fit, transform,
+fit_transform, persist/load with the reference's state_dict keys - on top of the CUDA engine, checked against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import synth, unet_oracle, losses_oracle       # noqa: E402
+
+ARCH = {'model_params': {'architecture': 'UNetResNet', 'encoder_depth': 18, 'in_channels': 3, 'out_channels': 2, 'activation': 'sigmoid'},
+        'optimizer_params': {'lr': 1e-4}, 'regularizer_params': {'regularize': True, 'weight_decay_conv2d': 1e-4},
+        'weights_init': {'function': 'he', 'pretrained': False}}
+S, B = 64, 4
+
+
+@pytest.fixture()
+def model(monkeypatch):
+    monkeypatch.setenv('SALT_ENGINE_PRECISION', 'fp32')
+    monkeypatch.setenv('SALT_ENGINE_MAX_BATCH', str(B))
+    monkeypatch.setenv('SALT_ENGINE_SIZE', str(S))
+    monkeypatch.setenv('SALT_ENGINE_LOSS', 'lovasz')
+    from salt_b200.models import SegmentationModel
+    m = SegmentationModel(ARCH, {'epochs': 1}, {})
+    m.engine.load_state(synth.synth_state_dict(18, 2, 0))
+    return m
+
+
+def _batches(n_batches, seed=1234):
+    xs = [torch.from_numpy(synth.synth_inputs(B, S, seed + i)) for i in range(n_batches)]
+    ts = [torch.from_numpy(synth.synth_targets(B, S, seed + i)) for i in range(n_batches)]
+    return xs, ts
+
+
+def _oracle_state(model):
+    sd = model.model.state_dict()
+    return {k[len('module.'):]: v.clone() for k, v in sd.items() if k.startswith('module.encoders.encoder.') or
+            not k.startswith('module.encoders.')}
+
+
+def test_surface_and_attributes(model):
+    assert model.output_names == ['mask']
+    name, fn, weight = model.loss_function[0]
+    assert name == 'mask' and weight == 1.0 and callable(fn)
+    assert model.optimizer.param_groups[0]['lr'] == 1e-4 and model.optimizer.state_dict()['param_groups'][0]['lr'] == 1e-4
+    assert model.validation_loss == {} and model.activation_func == 'sigmoid'
+    sd = model.model.state_dict()
+    assert all(k.startswith('module.') for k in sd)
+    for k in ('module.encoders.conv1.0.weight', 'module.encoders.encoder2.0.bn1.running_var', 'module.dec3.channel_se.fc.2.bias',
+              'module.final.1.weight', 'module.encoders.encoder.bn1.num_batches_tracked'):
+        assert k in sd, k
+    assert sd['module.encoders.conv1.0.weight'].shape == (64, 3, 7, 7)
+    with pytest.raises(NotImplementedError):
+        bad = dict(ARCH, model_params=dict(ARCH['model_params'], architecture='PSPNet'))
+        from salt_b200.models import SegmentationModel
+        SegmentationModel(bad, {'epochs': 1}, {})
+
+
+def test_fit_matches_oracle_training(model):
+    """fit() over 2 batches == 2 oracle steps (forward train-BN, Lovasz, backward, Adam+L2) on the same data."""
+    xs, ts = _batches(2)
+    sd = unet_oracle.to_torch_state(synth.synth_state_dict(18, 2, 0), requires_grad=True)
+    params = {k: v for k, v in sd.items() if v.requires_grad}
+    m = {k: torch.zeros_like(v) for k, v in params.items()}
+    vv = {k: torch.zeros_like(v) for k, v in params.items()}
+    ref_losses = []
+    for it, (x, t) in enumerate(zip(xs, ts)):
+        for p in params.values():
+            p.grad = None
+        loss = losses_oracle.lovasz_hinge_per_image(unet_oracle.unet_resnet_forward(sd, x, 18, train=True), t)
+        loss.backward()
+        ref_losses.append(loss.item())
+        with torch.no_grad():
+            unet_oracle.adam_l2_step({k: v.data for k, v in params.items()}, {k: v.grad for k, v in params.items()}, m, vv, it + 1)
+    losses = []
+    orig = model._fit_loop
+    model._fit_loop = lambda data: (lambda out: (losses.append(float(out['sum'].cpu()[0])), out)[1])(orig(data))
+    assert model.fit(datagen=(list(zip(xs, ts)), 2), validation_datagen=None, meta_valid=None) is model
+    print('fit losses', losses, 'oracle', ref_losses)
+    assert np.allclose(losses, ref_losses, rtol=2e-4, atol=1e-5)
+    # after two steps the parameters moved by ~2*lr; compare a few tensors with the oracle trajectory
+    for k in ('final.1.weight', 'dec1.conv2.conv.weight', 'encoders.encoder.layer1.0.conv1.weight', 'final.0.batch_norm.weight'):
+        got, ref = model.engine.view(k).cpu(), sd[k].detach()
+        moved = (ref - torch.from_numpy(synth.synth_state_dict(18, 2, 0)[k])).abs().max().item()
+        err = (got - ref).abs().max().item()
+        print('%-45s moved %.2e  err %.2e' % (k, moved, err))
+        assert moved > 1e-5 and err <= 0.3 * moved      # first Adam steps are ~ lr*sign(g): near-zero gradients may flip
+    assert model.engine.num_batches_tracked == 2
+
+
+def test_transform_persist_load_roundtrip(model, tmp_path):
+    xs, _ = _batches(2, seed=77)
+    out = model.transform(datagen=(xs, 2))
+    preds = out['mask_prediction']
+    assert isinstance(preds, list) and len(preds) == 2 * B
+    assert preds[0].shape == (2, S, S) and preds[0].dtype == np.float32
+    sd = unet_oracle.to_torch_state({k: v.numpy() for k, v in _oracle_state(model).items() if v.dtype == torch.float32})
+    with torch.no_grad():
+        ref = torch.sigmoid(unet_oracle.unet_resnet_forward(sd, torch.cat(xs), 18, train=False)).numpy()
+    err = np.abs(np.stack(preds) - ref).max()
+    print('transform: max-abs prob error vs oracle %.3e' % err)
+    assert err <= 1e-4
+    # batches given as [X] lists (loader with targets stripped) behave the same (models.py:155-158)
+    out2 = model.transform(datagen=([[x] for x in xs], 2))
+    assert np.array_equal(np.stack(out2['mask_prediction']), np.stack(preds))
+    # persist -> load into a fresh model -> identical predictions; unknown reference keys (resnet fc) survive a round trip
+    path = os.path.join(tmp_path, 'transformers', 'network')
+    model.model._extra['encoders.encoder.fc.weight'] = torch.ones(3, 5)
+    model.persist(path)
+    saved = torch.load(path, map_location='cpu')
+    assert 'module.encoders.encoder.fc.weight' in saved and 'module.encoders.encoder2.0.conv1.weight' in saved
+    from salt_b200.models import SegmentationModel
+    fresh = SegmentationModel(ARCH, {'epochs': 1}, {})
+    assert fresh.load(path) is fresh
+    out3 = fresh.transform(datagen=(xs, 2))
+    assert np.array_equal(np.stack(out3['mask_prediction']), np.stack(preds))
+    assert 'encoders.encoder.fc.weight' in fresh.model._extra
+
+
+def test_fit_transform_and_lr_mutation(model):
+    xs, ts = _batches(1)
+    model.optimizer.param_groups[0]['lr'] = 0.0          # what ReduceLROnPlateau does (callbacks.py:219-241)
+    before = model.engine.params.clone()
+    out = model.fit_transform(datagen=(list(zip(xs, ts)), 1), validation_datagen=None, meta_valid=None)
+    assert len(out['mask_prediction']) == B
+    assert torch.equal(before, model.engine.params)       # lr 0 -> Adam leaves the parameters untouched
