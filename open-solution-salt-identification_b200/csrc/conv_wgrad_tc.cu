@@ -231,7 +231,7 @@ void k_conv_wgrad_tc(cudaStream_t st, const void* in, const void* gout, float* d
     p.chunks_x = g.Wo / p.pw; p.chunks_y = g.Ho / p.ph;
     p.total_chunks = g.B * p.chunks_x * p.chunks_y;
     const int k_tiles = cdiv(g.Co, NK);
-    int splits = (num_sms() + slot_chunks * k_tiles / 2) / (slot_chunks * k_tiles);      // about one wave of CTAs
+    int splits = num_sms() / (slot_chunks * k_tiles);      // at most ONE wave of CTAs (1 CTA/SM): a few CTAs over would double the time
     int max_splits = cdiv(p.total_chunks, 8);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;

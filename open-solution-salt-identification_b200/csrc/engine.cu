@@ -128,8 +128,16 @@ void Engine::build() {
 
     // ---- encoder (reference encoders.py:10-45, torchvision BasicBlock), parameter order = state_dict order
     const std::string e = "encoders.encoder.";
-    x4_ = make_tensor(H, W, 4);
+    // the 7x7 stride-2 stem runs as a 1x1 convolution over im2col patches (160 channels, 147 real): see k_stem_im2col
+    x4_ = make_tensor(H / 2, W / 2, 160);
     stem_ = make_conv(e + "conv1.weight", "", 3, 64, 7, 2, 3, 4);
+    {
+        stem_.Ci = 160; stem_.Ci_real = 147; stem_.R = stem_.S = 1; stem_.stride = 1; stem_.pad = 0;
+        const size_t wb = (size_t)64 * 160 * dtype_size(cfg_.dt);
+        stem_.wp = ws_alloc(wb); stem_.wpd = ws_alloc(wb);
+        stem_.dwp = dwp_arena_ + dwp_cursor_;
+        dwp_cursor_ += (tc_wgrad_scratch_floats(160, 64, 1) + 3) / 4 * 4;
+    }
     stem_bn_ = make_bn(e + "bn1", 64);
     stem_raw_ = make_tensor(H / 2, W / 2, 64);
     stem_out_.t = make_tensor(H / 2, W / 2, 64);
@@ -399,7 +407,7 @@ void Engine::forward(const float* x_nchw, int B, float* logits_nchw, bool train,
     B_ = B;
     if (packed_dirty_) pack_all(st);
     if (train) k_zero(st, stats_arena_, sizeof(double) * stats_doubles_);
-    k_input_nchw_to_nhwc4(st, cfg_.dt, x_nchw, x4_.p, B, cfg_.H, cfg_.W);
+    k_stem_im2col(st, cfg_.dt, x_nchw, x4_.p, B, cfg_.H, cfg_.W);
     Tensor x4 = view(x4_), sraw = view(stem_raw_);
     conv_fwd(stem_, x4, sraw, &stem_bn_, train, st);
     k_bn_apply(st, sraw, stem_bn_.scale, stem_bn_.shift, nullptr, nullptr, nullptr, true, view(stem_out_.t));

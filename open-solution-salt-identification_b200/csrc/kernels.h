@@ -24,6 +24,10 @@ void k_conv_wgrad_simt(cudaStream_t st, DType dt, const void* in, const void* go
 
 // -------------------------------------------------------------------- input / elementwise
 void k_input_nchw_to_nhwc4(cudaStream_t st, DType dt, const float* x, void* out, int B, int H, int W);
+// stem input adapter: fp32 NCHW [B,3,H,W] -> im2col patches of the 7x7 stride-2 pad-3 stem convolution,
+// NHWC [B,H/2,W/2,160]: channel j = c*49 + r*7 + s (the reference weight layout [k][c][r][s] flattened), j >= 147 zero.
+// The stem then runs as a 1x1 convolution over 160 channels on the tensor cores (forward and wgrad).
+void k_stem_im2col(cudaStream_t st, DType dt, const float* x, void* patches, int B, int H, int W);
 void k_zero(cudaStream_t st, void* p, size_t bytes);
 
 struct BNRef {                 // device pointers describing one BatchNorm layer at run time

@@ -148,6 +148,38 @@ void k_input_nchw_to_nhwc4(cudaStream_t st, DType dt, const float* x, void* out,
 }
 void k_zero(cudaStream_t st, void* p, size_t bytes) { cudaMemsetAsync(p, 0, bytes, st); }
 
+#define STEM_PATCH_C 160
+template <typename T>
+__global__ void stem_im2col_kernel(const float* __restrict__ x, T* __restrict__ out, int H, int W) {
+    constexpr int N = VW<T>::N, CG = STEM_PATCH_C / N;
+    const int Ho = H / 2, Wo = W / 2;
+    const int j = blockIdx.y * EW_THREADS + threadIdx.x;
+    if (j >= Wo * CG) return;
+    const int xo = j / CG, cv = j - xo * CG;
+    const int row = blockIdx.x, n = row / Ho, yo = row - n * Ho;
+    const float* xn = x + (size_t)n * 3 * H * W;
+    Vf<N> v;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const int ch = cv * N + i;                       // c*49 + r*7 + s
+        float val = 0.f;
+        if (ch < 147) {
+            const int c = ch / 49, rs = ch - c * 49, r = rs / 7, s = rs - r * 7;
+            const int yi = 2 * yo + r - 3, xi = 2 * xo + s - 3;
+            if (yi >= 0 && yi < H && xi >= 0 && xi < W) val = __ldg(xn + ((size_t)c * H + yi) * W + xi);
+        }
+        v.v[i] = val;
+    }
+    stv(out + ((size_t)row * Wo + xo) * STEM_PATCH_C + cv * N, v);
+}
+void k_stem_im2col(cudaStream_t st, DType dt, const float* x, void* patches, int B, int H, int W) {
+    SALT_COUNT(1);
+    SALT_DISPATCH(dt, T, {
+        dim3 grid(B * (H / 2), cdiv((W / 2) * (STEM_PATCH_C / VW<T>::N), EW_THREADS));
+        stem_im2col_kernel<T><<<grid, EW_THREADS, 0, st>>>(x, (T*)patches, H, W);
+    });
+}
+
 // ------------------------------------------------------------------------------------------------
 // BatchNorm finalisation (nn.BatchNorm2d: eps 1e-5, momentum 0.1, biased var to normalise, unbiased to track)
 // ------------------------------------------------------------------------------------------------
