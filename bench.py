@@ -192,6 +192,30 @@ def run_ours(args):
     prof = eng.profile_read()
     eng.profile(False)
 
+    # ---- secondary measurements (not the headline): Lovasz-hinge training step (BASELINE configs[2] loss) and fused
+    #      sigmoid + h-flip TTA + crop + threshold inference (configs[4]) on the same engine
+    extra = {}
+    if not args.no_extra:
+        def step_lovasz():
+            logits = eng.forward(x_d, train=True)
+            _, dl = eng.loss_lovasz(logits, t_d)
+            eng.backward(dl)
+            eng.adam_step(grad_scale=ctx.allreduce_grads(eng.grads))
+        x_flip = torch.flip(x_d, dims=[3]).contiguous()
+
+        def infer_tta():
+            lo = eng.forward(x_d, train=False)
+            lf = eng.forward(x_flip, train=False)
+            return eng.predict(lo, lf, crop=101, threshold=0.5, want_probs=False)
+        for fn in (step_lovasz, infer_tta):
+            for _ in range(2):
+                fn()
+        ms_lv = timed(step_lovasz, 5)
+        ms_inf = timed(infer_tta, 5)
+        extra = {'lovasz_train_step': {'value': B * ctx.world * 5 / (ms_lv / 1e3), 'unit': 'images/s', 'ms_per_step': ms_lv / 5},
+                 'inference_tta_hflip': {'value': B * ctx.world * 5 / (ms_inf / 1e3), 'unit': 'tiles/s', 'ms_per_batch': ms_inf / 5,
+                                         'what': '%d tiles per GPU per pass = %d network inputs (orig + h-flip), fused sigmoid/un-flip/mean/crop/threshold -> u8 masks' % (B, 2 * B)}}
+
     if ctx.rank != 0:
         return
     peaks = _peaks()
@@ -225,6 +249,8 @@ def run_ours(args):
                      'step_tflops': value / n * TRAIN_GFLOP_PER_IMAGE / 1e3,
                      'step_frac_of_peak': value / n * TRAIN_GFLOP_PER_IMAGE / 1e3 / peaks['tflops']},
     }
+    if extra:
+        line['extra'] = extra
     if n == 1 and not args.no_cpu_baseline:
         ips, sec_step, threads = cpu_train_steps(2, 1)
         line['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
@@ -242,6 +268,7 @@ def main():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--loss', default='bce_dice', choices=['bce_dice', 'lovasz'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra', action='store_true', help='skip the secondary Lovasz / TTA-inference measurements')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':
