@@ -316,7 +316,6 @@ void k_avgpool_bwd(cudaStream_t st, const Tensor& gout, const Tensor& gin) {
 // gather: bordered conv input = concat_c( bilinear_upsample_f(src_i) ), replicate border
 //   bilinear: align_corners=False, src = max((d+0.5)/f - 0.5, 0)  (torch upsample_bilinear2d)
 // ------------------------------------------------------------------------------------------------
-struct GatherArgs { GatherSrc s[5]; int n; };
 
 __device__ __forceinline__ void bilin_coord(int d, int f, int nsrc, int& i0, int& i1, float& l) {
     float s = ((float)d + 0.5f) * (1.0f / (float)f) - 0.5f;
@@ -326,44 +325,69 @@ __device__ __forceinline__ void bilin_coord(int d, int f, int nsrc, int& i0, int
     l = s - (float)i0;
 }
 
+// One block per physical output row.  A work item = (source, run, channel vector); a run is the stretch of consecutive output
+// columns that interpolate between the SAME two source columns (f columns for an f-times upsampled source, the first / last
+// run also cover the replicated border), so the four source vectors are loaded once per run instead of once per output pixel
+// (the per-pixel version was L1/L2-throughput bound: profiles/r1_notes.md).
+struct GatherPlan { GatherSrc s[5]; int n; int item0[6]; int c0[5]; };
+
 template <typename T>
-__global__ void gather_fwd_kernel(T* __restrict__ out, GatherArgs a, int H, int W, int C, int pt, int pb, int pl, int pr) {
+__global__ void gather_fwd_kernel(T* __restrict__ out, GatherPlan a, int H, int W, int C, int pt, int pb, int pl, int pr) {
     constexpr int N = VW<T>::N;
-    const int cg = C / N, Hp = H + pt + pb, Wp = W + pl + pr;
-    const int j = blockIdx.y * EW_THREADS + threadIdx.x;
-    if (j >= Wp * cg) return;
-    const int xp = j / cg, cv = j - xp * cg;
+    const int Hp = H + pt + pb, Wp = W + pl + pr;
     const int row = blockIdx.x, n = row / Hp, yp = row - n * Hp;
-    const int y = min(max(yp - pt, 0), H - 1), x = min(max(xp - pl, 0), W - 1);
-    int c = cv * N, si = 0;
-    while (si < a.n - 1 && c >= a.s[si].C) { c -= a.s[si].C; ++si; }
-    const GatherSrc s = a.s[si];
-    const T* sp = (const T*)s.p + (size_t)n * s.H * s.W * s.C + c;
-    Vf<N> v;
-    if (s.f == 1) {
-        v = ldv(sp + ((size_t)y * s.W + x) * s.C);
-    } else {
-        int y0, y1, x0, x1; float ly, lx;
-        bilin_coord(y, s.f, s.H, y0, y1, ly);
-        bilin_coord(x, s.f, s.W, x0, x1, lx);
-        const Vf<N> v00 = ldv(sp + ((size_t)y0 * s.W + x0) * s.C), v01 = ldv(sp + ((size_t)y0 * s.W + x1) * s.C);
-        const Vf<N> v10 = ldv(sp + ((size_t)y1 * s.W + x0) * s.C), v11 = ldv(sp + ((size_t)y1 * s.W + x1) * s.C);
-        const float wy0 = 1.f - ly, wx0 = 1.f - lx;
+    const int y = min(max(yp - pt, 0), H - 1);
+    T* orow = out + (size_t)row * Wp * C;
+    for (int item = threadIdx.x; item < a.item0[a.n]; item += EW_THREADS) {
+        int si = 0;
+        while (si < a.n - 1 && item >= a.item0[si + 1]) ++si;
+        const GatherSrc s = a.s[si];
+        const int cg = s.C / N, local = item - a.item0[si];
+        const int run = local / cg, cv = local - run * cg;
+        const T* sp = (const T*)s.p + (size_t)n * s.H * s.W * s.C + cv * N;
+        T* o = orow + a.c0[si] + cv * N;
+        if (s.f == 1) {                                   // plain copy (+ replicate border): one run per physical column
+            const int x = min(max(run - pl, 0), W - 1);
+            stv_stream(o + (size_t)run * C, ldv(sp + ((size_t)y * s.W + x) * s.C));
+            continue;
+        }
+        // run r covers logical x in [r*f - f/2, r*f + f/2): all of them interpolate between source columns r-1 and r
+        const int f = s.f, xb = run * f - (f >> 1);
+        const int xlo = max(xb, 0), xhi = min(xb + f, W);   // logical range [xlo, xhi)
+        int y0, y1; float ly;
+        bilin_coord(y, f, s.H, y0, y1, ly);
+        const int j0 = max(run - 1, 0), j1 = min(run, s.W - 1);
+        const Vf<N> v00 = ldv(sp + ((size_t)y0 * s.W + j0) * s.C), v01 = ldv(sp + ((size_t)y0 * s.W + j1) * s.C);
+        const Vf<N> v10 = ldv(sp + ((size_t)y1 * s.W + j0) * s.C), v11 = ldv(sp + ((size_t)y1 * s.W + j1) * s.C);
+        const float wy0 = 1.f - ly;
+        // physical columns: logical x -> x + pl; the first run also fills the left border, the last run the right border
+        const int plo = (xlo == 0) ? 0 : xlo + pl, phi = (xhi == W) ? Wp : xhi + pl;
+        for (int xp = plo; xp < phi; ++xp) {
+            const int x = min(max(xp - pl, 0), W - 1);
+            int x0, x1; float lx;
+            bilin_coord(x, f, s.W, x0, x1, lx);           // x0 == j0, x1 == j1 by construction
+            const float wx0 = 1.f - lx;
+            Vf<N> v;
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            float top = v00.v[i] * wx0 + v01.v[i] * lx, bot = v10.v[i] * wx0 + v11.v[i] * lx;
-            v.v[i] = top * wy0 + bot * ly;
+            for (int i = 0; i < N; ++i) {
+                float top = v00.v[i] * wx0 + v01.v[i] * lx, bot = v10.v[i] * wx0 + v11.v[i] * lx;
+                v.v[i] = top * wy0 + bot * ly;
+            }
+            stv_stream(o + (size_t)xp * C, v);
         }
     }
-    stv_stream(out + ((size_t)row * Wp + xp) * C + cv * N, v);
 }
 void k_gather_fwd(cudaStream_t st, const Tensor& out, const GatherSrc* srcs, int nsrc) {
     SALT_COUNT(1);
-    GatherArgs a; a.n = nsrc;
-    for (int i = 0; i < nsrc; ++i) a.s[i] = srcs[i];
     SALT_DISPATCH(out.dt, T, {
-        dim3 grid(out.B * out.Hp(), cdiv(out.Wp() * (out.C / VW<T>::N), EW_THREADS));
-        gather_fwd_kernel<T><<<grid, EW_THREADS, 0, st>>>((T*)out.p, a, out.H, out.W, out.C, out.pt, out.pb, out.pl, out.pr);
+        GatherPlan a; a.n = nsrc; a.item0[0] = 0;
+        int c0 = 0;
+        for (int i = 0; i < nsrc; ++i) {
+            a.s[i] = srcs[i]; a.c0[i] = c0; c0 += srcs[i].C;
+            const int runs = srcs[i].f == 1 ? out.Wp() : out.W / srcs[i].f + 1;
+            a.item0[i + 1] = a.item0[i] + runs * (srcs[i].C / VW<T>::N);
+        }
+        gather_fwd_kernel<T><<<out.B * out.Hp(), EW_THREADS, 0, st>>>((T*)out.p, a, out.H, out.W, out.C, out.pt, out.pb, out.pl, out.pr);
     });
 }
 
