@@ -23,11 +23,12 @@ extern "C" {
 typedef struct salt_engine salt_engine;
 
 enum { SALT_PREC_FP32 = 0, SALT_PREC_BF16 = 1 };
-enum { SALT_ARCH_UNET_RESNET = 0 };
+enum { SALT_ARCH_UNET_RESNET = 0, SALT_ARCH_UNET_SERESNET = 1 };
 
 typedef struct salt_config {
-    int arch;            /* SALT_ARCH_UNET_RESNET  <- models.py:15-18 ARCHITECTURES['UNetResNet']                 */
-    int encoder_depth;   /* 18 or 34               <- architectures/unet.py:44-58                               */
+    int arch;            /* SALT_ARCH_UNET_RESNET   <- models.py:15-18 ARCHITECTURES['UNetResNet']   (unet.py:22-109)
+                            SALT_ARCH_UNET_SERESNET <- models.py:19-24 ARCHITECTURES['UNetSeResNet'] (unet.py:112-172)    */
+    int encoder_depth;   /* UNetResNet: 18 or 34 (encoders.py:10-13); UNetSeResNet: 50 (encoders.py:52-53)              */
     int num_classes;     /* out_channels           <- models.py:182                                             */
     int max_batch;       /* largest batch any call will pass                                                    */
     int height, width;   /* network input size, multiples of 32 (128 for the 101x101 tiles, loaders.py)         */

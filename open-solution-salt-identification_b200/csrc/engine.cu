@@ -6,12 +6,16 @@
 unsigned long long g_salt_launches = 0;
 
 static const float BN_EPS = 1e-5f, BN_MOMENTUM = 0.1f;
+static const int MAX_CONVS = 128;       // capacity of the batched pack / unpack descriptor tables
 
 // ------------------------------------------------------------------------------------------------
 // plan construction
 // ------------------------------------------------------------------------------------------------
 Engine::Engine(const EngineConfig& cfg) : cfg_(cfg) {
-    if (cfg.depth != 18 && cfg.depth != 34) throw std::runtime_error("UNetResNet: only encoder_depth 18 and 34 are implemented in this engine");
+    if (cfg.arch == 0 && cfg.depth != 18 && cfg.depth != 34)
+        throw std::runtime_error("UNetResNet: only encoder_depth 18 and 34 are implemented in this engine");
+    if (cfg.arch == 1 && cfg.depth != 50) throw std::runtime_error("UNetSeResNet: only encoder_depth 50 is implemented in this engine");
+    if (cfg.arch != 0 && cfg.arch != 1) throw std::runtime_error("unknown architecture id");
     if (cfg.H % 32 || cfg.W % 32) throw std::runtime_error("input height/width must be multiples of 32");
     if (cfg.num_classes < 1 || cfg.num_classes > 4) throw std::runtime_error("num_classes must be 1..4");
     counting_ = true;
@@ -87,38 +91,44 @@ void Engine::build_cbr(ConvBnRelu& u, const std::string& prefix, int ci, int co,
     need_scratch(0, u.raw.bytes()); need_scratch(1, u.raw.bytes());
     need_scratch(2, u.P.bytes());
 }
+SELayer Engine::make_se(const std::string& w1, const std::string& b1, const std::string& w2, const std::string& b2, int C, int HW,
+                        bool conv_shape) {
+    SELayer se; se.C = C; se.Cr = C / 16; se.spatial = !conv_shape;
+    const int Cr = se.Cr, B = cfg_.max_batch;
+    se.o_w1 = conv_shape ? add_param(w1, {Cr, C, 1, 1}) : add_param(w1, {Cr, C});
+    se.o_b1 = add_param(b1, {Cr});
+    se.o_w2 = conv_shape ? add_param(w2, {C, Cr, 1, 1}) : add_param(w2, {C, Cr});
+    se.o_b2 = add_param(b2, {C});
+    se.chunks = std::max(1, std::min(64, HW / 128));
+    float* f = (float*)ws_alloc(sizeof(float) * B * ((size_t)(3 + se.chunks) * C + 2 * Cr));
+    se.gap = f; se.cse = f + (size_t)B * C; se.G = f + (size_t)2 * B * C; se.part = f + (size_t)3 * B * C;
+    se.hid = f + (size_t)(3 + se.chunks) * B * C; se.dhid = se.hid + (size_t)B * Cr;
+    return se;
+}
 void Engine::build_decoder(DecoderBlock& d, const std::string& name, std::vector<Source> srcs, int cm, int co, int H, int W) {
     int ci = 0;
     for (auto& s : srcs) ci += s.a->t.C;
     d.srcs = srcs;
     build_cbr(d.u1, name + ".conv1", ci, cm, H, W);
     build_cbr(d.u2, name + ".conv2", cm, co, H, W);
-    d.se.C = co; d.se.Cr = co / 16;
-    d.se.o_w1 = add_param(name + ".channel_se.fc.0.weight", {co / 16, co});
-    d.se.o_b1 = add_param(name + ".channel_se.fc.0.bias", {co / 16});
-    d.se.o_w2 = add_param(name + ".channel_se.fc.2.weight", {co, co / 16});
-    d.se.o_b2 = add_param(name + ".channel_se.fc.2.bias", {co});
+    d.se = make_se(name + ".channel_se.fc.0.weight", name + ".channel_se.fc.0.bias", name + ".channel_se.fc.2.weight",
+                   name + ".channel_se.fc.2.bias", co, H * W, false);
     d.se.o_ws = add_param(name + ".spatial_se.fc.weight", {1, co, 1, 1});
     d.se.o_bs = add_param(name + ".spatial_se.fc.bias", {1});
-    int B = cfg_.max_batch;
-    d.se.chunks = std::max(1, std::min(64, (H * W) / 128));
-    float* f = (float*)ws_alloc(sizeof(float) * B * ((3 + d.se.chunks) * co + d.se.Cr));
-    d.se.gap = f; d.se.cse = f + B * co; d.se.G = f + 2 * B * co; d.se.part = f + 3 * B * co;
-    d.se.hid = f + (size_t)(3 + d.se.chunks) * B * co;
     d.out.t = make_tensor(H, W, co);
     d.out.gb = make_gradbuf(d.out.t);
     for (auto& s : srcs)
-        if (s.f > 1) need_scratch(3, sizeof(float) * (size_t)B * (H + 2) * (W / s.f) * s.a->t.C);
+        if (s.f > 1) need_scratch(3, sizeof(float) * (size_t)cfg_.max_batch * (H + 2) * (W / s.f) * s.a->t.C);
 }
 size_t Engine::make_tensor_bytes(int H, int W, int C) const { return (size_t)cfg_.max_batch * H * W * C * dtype_size(cfg_.dt); }
 
 void Engine::build() {
     n_params_ = n_buffers_ = 0; ws_cursor_ = 0; stats_cursor_ = bstats_cursor_ = 0; dwp_cursor_ = 0;
-    blocks_.clear(); gradbufs_.clear();
+    blocks_.clear(); bnecks_.clear(); gradbufs_.clear();
     if (counting_) infos_.clear();
     const int B = cfg_.max_batch, H = cfg_.H, W = cfg_.W;
     const int nblk18[4] = {2, 2, 2, 2}, nblk34[4] = {3, 4, 6, 3};
-    const int* nblk = cfg_.depth == 18 ? nblk18 : nblk34;
+    const int* nblk = cfg_.depth == 18 ? nblk18 : nblk34;      // SE-ResNet-50 shares [3,4,6,3]
     const int chans[4] = {64, 128, 256, 512};
 
     // BN statistic arenas: sized on the counting pass
@@ -126,11 +136,14 @@ void Engine::build() {
     bstats_arena_ = (double*)ws_alloc(sizeof(double) * std::max<size_t>(bstats_doubles_, 1));
     dwp_arena_ = (float*)ws_alloc(sizeof(float) * std::max<size_t>(cfg_.dt == DT_BF16 ? dwp_floats_ : 0, 4));
 
-    // ---- encoder (reference encoders.py:10-45, torchvision BasicBlock), parameter order = state_dict order
+    // ---- encoder, parameter order = state_dict order
+    //   arch 0: reference encoders.py:10-45, torchvision ResNet-18/34 (BasicBlock)
+    //   arch 1: reference encoders.py:48-83, pretrainedmodels se_resnet50 (layer0 = conv7x7/2 + BN + ReLU, SEResNetBottleneck x [3,4,6,3])
+    const bool se50 = cfg_.arch == 1;
     const std::string e = "encoders.encoder.";
     // the 7x7 stride-2 stem runs as a 1x1 convolution over im2col patches (160 channels, 147 real): see k_stem_im2col
     x4_ = make_tensor(H / 2, W / 2, 160);
-    stem_ = make_conv(e + "conv1.weight", "", 3, 64, 7, 2, 3, 4);
+    stem_ = make_conv(e + (se50 ? "layer0.conv1.weight" : "conv1.weight"), "", 3, 64, 7, 2, 3, 4);
     {
         stem_.Ci = 160; stem_.Ci_real = 147; stem_.R = stem_.S = 1; stem_.stride = 1; stem_.pad = 0;
         const size_t wb = (size_t)64 * 160 * dtype_size(cfg_.dt);
@@ -138,7 +151,7 @@ void Engine::build() {
         stem_.dwp = dwp_arena_ + dwp_cursor_;
         dwp_cursor_ += (tc_wgrad_scratch_floats(160, 64, 1) + 3) / 4 * 4;
     }
-    stem_bn_ = make_bn(e + "bn1", 64);
+    stem_bn_ = make_bn(e + (se50 ? "layer0.bn1" : "bn1"), 64);
     stem_raw_ = make_tensor(H / 2, W / 2, 64);
     stem_out_.t = make_tensor(H / 2, W / 2, 64);
     stem_out_.gb = make_gradbuf(stem_out_.t);
@@ -147,52 +160,83 @@ void Engine::build() {
     int h = H / 2, w = W / 2, cin = 64;
     for (int li = 0; li < 4; ++li) {
         for (int bi = 0; bi < nblk[li]; ++bi) {
-            blocks_.emplace_back(new BasicBlock());
-            BasicBlock& b = *blocks_.back();
             const std::string p = e + "layer" + std::to_string(li + 1) + "." + std::to_string(bi) + ".";
-            const int co = chans[li], stride = (bi == 0 && li > 0) ? 2 : 1;
-            b.down = (bi == 0 && li > 0);
-            b.x = cur;
-            b.c1 = make_conv(p + "conv1.weight", "", cin, co, 3, stride, 1);
-            b.b1 = make_bn(p + "bn1", co);
-            b.c2 = make_conv(p + "conv2.weight", "", co, co, 3, 1, 1);
-            b.b2 = make_bn(p + "bn2", co);
-            if (b.down) {
-                b.cd = make_conv(p + "downsample.0.weight", "", cin, co, 1, stride, 0);
-                b.bd = make_bn(p + "downsample.1", co);
+            const int stride = (bi == 0 && li > 0) ? 2 : 1;
+            if (!se50) {
+                blocks_.emplace_back(new BasicBlock());
+                BasicBlock& b = *blocks_.back();
+                const int co = chans[li];
+                b.down = (bi == 0 && li > 0);
+                b.x = cur;
+                b.c1 = make_conv(p + "conv1.weight", "", cin, co, 3, stride, 1);
+                b.b1 = make_bn(p + "bn1", co);
+                b.c2 = make_conv(p + "conv2.weight", "", co, co, 3, 1, 1);
+                b.b2 = make_bn(p + "bn2", co);
+                if (b.down) {
+                    b.cd = make_conv(p + "downsample.0.weight", "", cin, co, 1, stride, 0);
+                    b.bd = make_bn(p + "downsample.1", co);
+                }
+                h /= stride; w /= stride;
+                b.raw1 = make_tensor(h, w, co); b.a1 = make_tensor(h, w, co); b.raw2 = make_tensor(h, w, co);
+                if (b.down) b.rawd = make_tensor(h, w, co);
+                b.out.t = make_tensor(h, w, co);
+                b.out.gb = b.down ? make_gradbuf(b.out.t) : cur->gb;      // identity blocks pass the gradient buffer through
+                need_scratch(0, b.raw1.bytes()); need_scratch(1, b.raw1.bytes()); need_scratch(2, b.raw1.bytes());
+                cur = &b.out; cin = co;
+            } else {
+                bnecks_.emplace_back(new Bottleneck());
+                Bottleneck& b = *bnecks_.back();
+                const int pl = chans[li], co = 4 * pl;
+                b.down = (bi == 0);
+                b.x = cur;
+                b.c1 = make_conv(p + "conv1.weight", "", cin, pl, 1, stride, 0);      // Caffe-style: the stride sits on conv1
+                b.b1 = make_bn(p + "bn1", pl);
+                b.c2 = make_conv(p + "conv2.weight", "", pl, pl, 3, 1, 1);
+                b.b2 = make_bn(p + "bn2", pl);
+                b.c3 = make_conv(p + "conv3.weight", "", pl, co, 1, 1, 0);
+                b.b3 = make_bn(p + "bn3", co);
+                h /= stride; w /= stride;
+                b.se = make_se(p + "se_module.fc1.weight", p + "se_module.fc1.bias", p + "se_module.fc2.weight", p + "se_module.fc2.bias",
+                               co, h * w, true);
+                if (b.down) {
+                    b.cd = make_conv(p + "downsample.0.weight", "", cin, co, 1, stride, 0);
+                    b.bd = make_bn(p + "downsample.1", co);
+                }
+                b.raw1 = make_tensor(h, w, pl); b.a1 = make_tensor(h, w, pl);
+                b.raw2 = make_tensor(h, w, pl); b.a2 = make_tensor(h, w, pl);
+                b.raw3 = make_tensor(h, w, co);
+                if (b.down) b.rawd = make_tensor(h, w, co);
+                b.out.t = make_tensor(h, w, co);
+                b.out.gb = b.down ? make_gradbuf(b.out.t) : cur->gb;
+                need_scratch(0, b.raw3.bytes()); need_scratch(1, b.raw3.bytes()); need_scratch(2, b.raw3.bytes());
+                cur = &b.out; cin = co;
             }
-            h /= stride; w /= stride;
-            b.raw1 = make_tensor(h, w, co); b.a1 = make_tensor(h, w, co); b.raw2 = make_tensor(h, w, co);
-            if (b.down) b.rawd = make_tensor(h, w, co);
-            b.out.t = make_tensor(h, w, co);
-            b.out.gb = b.down ? make_gradbuf(b.out.t) : cur->gb;      // identity blocks pass the gradient buffer through
-            need_scratch(0, b.raw1.bytes()); need_scratch(1, b.raw1.bytes()); need_scratch(2, b.raw1.bytes());
-            cur = &b.out; cin = co;
         }
         enc_out_[li] = cur;
     }
-    // ---- center (unet.py:60-63)
+    // ---- center (unet.py:60-63 / :123-126); bc = bottom_channel_nr
+    const int bc = se50 ? 2048 : 512, dc = bc / 8;
     center_src_ = {{enc_out_[3], 1}};
-    build_cbr(center0_, "center.0", 512, 512, h, w);
-    build_cbr(center1_, "center.1", 512, 256, h, w);
-    center_out_.t = make_tensor(h / 2, w / 2, 256);
+    build_cbr(center0_, "center.0", bc, bc, h, w);
+    build_cbr(center1_, "center.1", bc, bc / 2, h, w);
+    center_out_.t = make_tensor(h / 2, w / 2, bc / 2);
     center_out_.gb = make_gradbuf(center_out_.t);
-    // ---- decoder (unet.py:65-79): dec5..dec1
-    build_decoder(dec_[0], "dec5", {{&center_out_, 2}, {enc_out_[3], 1}}, 512, 64, H / 16, W / 16);
-    build_decoder(dec_[1], "dec4", {{&dec_[0].out, 2}, {enc_out_[2], 1}}, 256, 64, H / 8, W / 8);
-    build_decoder(dec_[2], "dec3", {{&dec_[1].out, 2}, {enc_out_[1], 1}}, 128, 64, H / 4, W / 4);
-    build_decoder(dec_[3], "dec2", {{&dec_[2].out, 2}, {enc_out_[0], 1}}, 64, 64, H / 2, W / 2);
-    build_decoder(dec_[4], "dec1", {{&dec_[3].out, 2}}, 32, 64, H, W);
-    // ---- hypercolumn + final (unet.py:82-84, 101-109)
+    // ---- decoder (unet.py:65-79 / :128-143): dec5..dec1
+    build_decoder(dec_[0], "dec5", {{&center_out_, 2}, {enc_out_[3], 1}}, bc, dc, H / 16, W / 16);
+    build_decoder(dec_[1], "dec4", {{&dec_[0].out, 2}, {enc_out_[2], 1}}, bc / 2, dc, H / 8, W / 8);
+    build_decoder(dec_[2], "dec3", {{&dec_[1].out, 2}, {enc_out_[1], 1}}, bc / 4, dc, H / 4, W / 4);
+    build_decoder(dec_[3], "dec2", {{&dec_[2].out, 2}, {enc_out_[0], 1}}, bc / 8, dc, H / 2, W / 2);
+    build_decoder(dec_[4], "dec1", {{&dec_[3].out, 2}}, bc / 16, dc, H, W);
+    // ---- hypercolumn + final (unet.py:82-84, 101-109 / :145-172)
     final_src_ = {{&dec_[4].out, 1}, {&dec_[3].out, 2}, {&dec_[2].out, 4}, {&dec_[1].out, 8}, {&dec_[0].out, 16}};
-    build_cbr(final0_, "final.0", 320, 64, H, W);
+    build_cbr(final0_, "final.0", 5 * dc, dc, H, W);
     for (auto& s : final_src_)
         if (s.f > 1) need_scratch(3, sizeof(float) * (size_t)B * (H + 2) * (W / s.f) * s.a->t.C);
-    o_final_w_ = add_param("final.1.weight", {cfg_.num_classes, 64, 1, 1});
+    o_final_w_ = add_param("final.1.weight", {cfg_.num_classes, dc, 1, 1});
     o_final_b_ = add_param("final.1.bias", {cfg_.num_classes});
 
-    d_pack_ = (PackDesc*)ws_alloc(sizeof(PackDesc) * 64); d_pack_start_ = (int*)ws_alloc(sizeof(int) * 65);
-    d_unpack_ = (UnpackDesc*)ws_alloc(sizeof(UnpackDesc) * 64); d_unpack_start_ = (int*)ws_alloc(sizeof(int) * 65);
+    d_pack_ = (PackDesc*)ws_alloc(sizeof(PackDesc) * MAX_CONVS); d_pack_start_ = (int*)ws_alloc(sizeof(int) * (MAX_CONVS + 1));
+    d_unpack_ = (UnpackDesc*)ws_alloc(sizeof(UnpackDesc) * MAX_CONVS); d_unpack_start_ = (int*)ws_alloc(sizeof(int) * (MAX_CONVS + 1));
     loss_scratch_ = (float*)ws_alloc(sizeof(float) * (B + 8));
     loss_sums_ = (double*)ws_alloc(sizeof(double) * 16);
     for (int i = 0; i < 4; ++i) scratch_[i] = ws_alloc(std::max<size_t>(scratch_bytes_[i], 256));
@@ -230,7 +274,8 @@ SERef Engine::se_ref(const SELayer& s) const {
     float* g = grads_;
     r.dw1 = g ? g + s.o_w1 : nullptr; r.db1 = g ? g + s.o_b1 : nullptr; r.dw2 = g ? g + s.o_w2 : nullptr;
     r.db2 = g ? g + s.o_b2 : nullptr; r.dws = g ? g + s.o_ws : nullptr; r.dbs = g ? g + s.o_bs : nullptr;
-    r.gap = s.gap; r.hid = s.hid; r.cse = s.cse; r.part = s.part; r.G = s.G; r.chunks = s.chunks;
+    r.gap = s.gap; r.hid = s.hid; r.cse = s.cse; r.part = s.part; r.G = s.G; r.dhid = s.dhid; r.chunks = s.chunks;
+    if (!s.spatial) { r.ws = r.bs = nullptr; r.dws = r.dbs = nullptr; }
     return r;
 }
 Tensor Engine::scratch(int i, int H, int W, int C, int pt, int pb, int pl, int pr) const {
@@ -248,6 +293,8 @@ std::vector<ConvLayer*> Engine::all_convs() {
     std::vector<ConvLayer*> v;
     v.push_back(&stem_);
     for (auto& b : blocks_) { v.push_back(&b->c1); v.push_back(&b->c2); if (b->down) v.push_back(&b->cd); }
+    for (auto& b : bnecks_) { v.push_back(&b->c1); v.push_back(&b->c2); v.push_back(&b->c3); if (b->down) v.push_back(&b->cd); }
+    if ((int)v.size() + 13 > MAX_CONVS) throw std::runtime_error("internal error: MAX_CONVS too small");
     v.push_back(&center0_.c); v.push_back(&center1_.c);
     for (auto& d : dec_) { v.push_back(&d.u1.c); v.push_back(&d.u2.c); }
     v.push_back(&final0_.c);
@@ -391,6 +438,23 @@ void Engine::block_fwd(BasicBlock& b, bool train, cudaStream_t st) {
         k_bn_apply(st, raw2, b.b2.scale, b.b2.shift, &x, nullptr, nullptr, true, out);
     }
 }
+void Engine::bneck_fwd(Bottleneck& b, bool train, cudaStream_t st) {
+    Tensor x = view(b.x->t), raw1 = view(b.raw1), a1 = view(b.a1), raw2 = view(b.raw2), a2 = view(b.a2), raw3 = view(b.raw3),
+           out = view(b.out.t);
+    conv_fwd(b.c1, x, raw1, &b.b1, train, st);
+    k_bn_apply(st, raw1, b.b1.scale, b.b1.shift, nullptr, nullptr, nullptr, true, a1);
+    conv_fwd(b.c2, a1, raw2, &b.b2, train, st);
+    k_bn_apply(st, raw2, b.b2.scale, b.b2.shift, nullptr, nullptr, nullptr, true, a2);
+    conv_fwd(b.c3, a2, raw3, &b.b3, train, st);
+    k_se_gate_fwd(st, raw3, b.b3.scale, b.b3.shift, se_ref(b.se));
+    if (b.down) {
+        Tensor rawd = view(b.rawd);
+        conv_fwd(b.cd, x, rawd, &b.bd, train, st);
+        k_bn_apply(st, raw3, b.b3.scale, b.b3.shift, &rawd, b.bd.scale, b.bd.shift, true, out, b.se.cse);
+    } else {
+        k_bn_apply(st, raw3, b.b3.scale, b.b3.shift, &x, nullptr, nullptr, true, out, b.se.cse);
+    }
+}
 void Engine::cbr_fwd(ConvBnRelu& u, bool train, cudaStream_t st) {
     conv_fwd(u.c, view(u.P), view(u.raw), &u.bn, train, st);
 }
@@ -412,6 +476,7 @@ void Engine::forward(const float* x_nchw, int B, float* logits_nchw, bool train,
     conv_fwd(stem_, x4, sraw, &stem_bn_, train, st);
     k_bn_apply(st, sraw, stem_bn_.scale, stem_bn_.shift, nullptr, nullptr, nullptr, true, view(stem_out_.t));
     for (auto& b : blocks_) block_fwd(*b, train, st);
+    for (auto& b : bnecks_) bneck_fwd(*b, train, st);
     // center
     gather_fwd(center_src_, view(center0_.P), st);
     cbr_fwd(center0_, train, st);
@@ -484,6 +549,54 @@ void Engine::block_bwd(BasicBlock& b, cudaStream_t st) {
     // the 1x1 stride-2 shortcut only touches the even/even input positions: it accumulates after the 3x3 path wrote everything
     if (b.down) conv_dgrad(b.cd, grawd, Gx, true, st);
 }
+void Engine::bneck_bwd(Bottleneck& b, cudaStream_t st) {
+    Tensor x = view(b.x->t), raw1 = view(b.raw1), a1 = view(b.a1), raw2 = view(b.raw2), a2 = view(b.a2), raw3 = view(b.raw3),
+           out = view(b.out.t);
+    Tensor G = view(b.out.gb->g);
+    const double cnt = (double)B_ * out.H * out.W;
+    BNRef bn1 = bn_ref(b.b1), bn2 = bn_ref(b.b2), bn3 = bn_ref(b.b3);
+    SERef se = se_ref(b.se);
+    k_relu_mask_inplace(st, G, out);                               // gradient through the block's final ReLU
+    // out = u*cse + shortcut, u = bn3(raw3):  d/du = G*cse + (gap path, se.G);  shortcut gets G
+    k_se_gate_bwd(st, G, raw3, bn3.scale, bn3.shift, se);
+    Tensor graw3 = scratch(0, out.H, out.W, out.C);
+    k_bn_bwd_reduce(st, G, raw3, bn3, false, se.cse, se.G);
+    k_bn_bwd_finalize(st, bn3, cnt);
+    k_bn_bwd_apply(st, G, raw3, bn3, false, graw3, se.cse, se.G);
+    GradBuf* gxb = b.x->gb;
+    Tensor Gx = view(gxb->g);
+    Tensor grawd = scratch(2, out.H, out.W, out.C);
+    if (b.down) {
+        Tensor rawd = view(b.rawd);
+        BNRef bnd = bn_ref(b.bd);
+        k_bn_bwd_reduce(st, G, rawd, bnd, false);
+        k_bn_bwd_finalize(st, bnd, cnt);
+        k_bn_bwd_apply(st, G, rawd, bnd, false, grawd);
+        conv_wgrad(b.cd, x, grawd, st);
+    }
+    conv_wgrad(b.c3, a2, graw3, st);
+    Tensor ga2 = scratch(1, raw2.H, raw2.W, raw2.C);
+    conv_dgrad(b.c3, graw3, ga2, false, st);
+    Tensor graw2 = scratch(0, raw2.H, raw2.W, raw2.C);
+    k_bn_bwd_reduce(st, ga2, raw2, bn2, true);
+    k_bn_bwd_finalize(st, bn2, cnt);
+    k_bn_bwd_apply(st, ga2, raw2, bn2, true, graw2);
+    conv_wgrad(b.c2, a1, graw2, st);
+    Tensor ga1 = scratch(1, raw1.H, raw1.W, raw1.C);
+    conv_dgrad(b.c2, graw2, ga1, false, st);
+    Tensor graw1 = scratch(0, raw1.H, raw1.W, raw1.C);
+    k_bn_bwd_reduce(st, ga1, raw1, bn1, true);
+    k_bn_bwd_finalize(st, bn1, cnt);
+    k_bn_bwd_apply(st, ga1, raw1, bn1, true, graw1);
+    conv_wgrad(b.c1, x, graw1, st);
+    // identity blocks: Gx aliases G and already holds the shortcut gradient -> accumulate.  A stride-2 1x1 convolution only
+    // reaches the even/even input positions, so a fresh buffer is cleared first.
+    bool acc = b.down ? !gxb->fresh : true;
+    if (!acc && b.c1.stride == 2) { k_zero(st, Gx.p, Gx.bytes()); acc = true; }
+    conv_dgrad(b.c1, graw1, Gx, acc, st);
+    gxb->fresh = false;
+    if (b.down) conv_dgrad(b.cd, grawd, Gx, true, st);
+}
 void Engine::backward(const float* dlogits, cudaStream_t st) {
     if (!grads_) throw std::runtime_error("engine bound without gradient buffers");
     if (!trained_forward_) throw std::runtime_error("backward() requires a preceding forward(train=1)");
@@ -529,6 +642,7 @@ void Engine::backward(const float* dlogits, cudaStream_t st) {
         gather_bwd(center_src_, gP0, st);
     }
     for (int i = (int)blocks_.size() - 1; i >= 0; --i) block_bwd(*blocks_[i], st);
+    for (int i = (int)bnecks_.size() - 1; i >= 0; --i) bneck_bwd(*bnecks_[i], st);
     // ---- stem (no input gradient)
     {
         const Tensor raw = view(stem_raw_);

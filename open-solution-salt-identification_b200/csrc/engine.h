@@ -1,6 +1,6 @@
-// U-Net (ResNet-18/34 encoder, scSE decoder, hypercolumn head) execution plan: static buffers, explicit
+// U-Net (ResNet-18/34 or SE-ResNet-50 encoder, scSE decoder, hypercolumn head) execution plan: static buffers, explicit
 // forward and backward passes built from the kernels in kernels.h.  Mirrors the computation of the reference
-// common_blocks/architectures/unet.py:44-109 (UNetResNet) - see DESIGN.md for the layer-by-layer mapping.
+// common_blocks/architectures/unet.py:44-109 (UNetResNet) and :112-172 (UNetSeResNet) - see DESIGN.md for the layer mapping.
 #pragma once
 #include <string>
 #include <vector>
@@ -36,8 +36,9 @@ struct BNLayer {
 struct SELayer {
     int C = 0, Cr = 0;
     size_t o_w1 = 0, o_b1 = 0, o_w2 = 0, o_b2 = 0, o_ws = 0, o_bs = 0;
-    float *gap = nullptr, *hid = nullptr, *cse = nullptr, *part = nullptr, *G = nullptr;
+    float *gap = nullptr, *hid = nullptr, *cse = nullptr, *part = nullptr, *G = nullptr, *dhid = nullptr;
     int chunks = 1;
+    bool spatial = true;       // decoder scSE has the spatial branch, the encoder SE module does not
 };
 struct GradBuf { Tensor g; bool fresh = true; };
 struct Act { Tensor t; GradBuf* gb = nullptr; };
@@ -48,6 +49,17 @@ struct BasicBlock {
     bool down = false;
     Act* x = nullptr;
     Tensor raw1, a1, raw2, rawd;
+    Act out;
+};
+// SE-ResNet bottleneck (pretrainedmodels senet.py SEResNetBottleneck; restated in oracle/senet_restated.py):
+// 1x1 (stride here) -> 3x3 -> 1x1 (x4), each + BN, SE gate on the last BN output, + shortcut, ReLU
+struct Bottleneck {
+    ConvLayer c1, c2, c3, cd;
+    BNLayer b1, b2, b3, bd;
+    SELayer se;
+    bool down = false;
+    Act* x = nullptr;
+    Tensor raw1, a1, raw2, a2, raw3, rawd;
     Act out;
 };
 struct ConvBnRelu {            // reference base.py:7-37 on a replicate-bordered input
@@ -65,6 +77,7 @@ struct DecoderBlock {
 
 struct EngineConfig {
     int depth = 34, num_classes = 2, max_batch = 8, H = 128, W = 128;
+    int arch = 0;              // 0 = UNetResNet (depth 18/34), 1 = UNetSeResNet (depth 50)
     DType dt = DT_F32;
     int use_tc = 0;
 };
@@ -129,6 +142,9 @@ private:
     void gather_bwd(const std::vector<Source>& srcs, const Tensor& gP, cudaStream_t st);
     void block_fwd(BasicBlock& b, bool train, cudaStream_t st);
     void block_bwd(BasicBlock& b, cudaStream_t st);
+    void bneck_fwd(Bottleneck& b, bool train, cudaStream_t st);
+    void bneck_bwd(Bottleneck& b, cudaStream_t st);
+    SELayer make_se(const std::string& w1, const std::string& b1, const std::string& w2, const std::string& b2, int C, int HW, bool conv_shape);
     void cbr_fwd(ConvBnRelu& u, bool train, cudaStream_t st);
     void decoder_fwd(DecoderBlock& d, bool train, cudaStream_t st);
     void decoder_bwd(DecoderBlock& d, cudaStream_t st);
@@ -155,6 +171,7 @@ private:
     Tensor stem_raw_;
     Act stem_out_;
     std::vector<std::unique_ptr<BasicBlock>> blocks_;
+    std::vector<std::unique_ptr<Bottleneck>> bnecks_;
     Act* enc_out_[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<Source> center_src_;
     ConvBnRelu center0_, center1_;

@@ -46,9 +46,9 @@ void k_bn_finalize_train(cudaStream_t st, const BNRef& bn, double count, float m
 void k_bn_finalize_eval(cudaStream_t st, const BNRef& bn, float eps);
 void k_bn_bwd_finalize(cudaStream_t st, const BNRef& bn, double count);
 
-// out = [relu]( raw*scale+shift  [+ res | + res*rscale+rshift] ), out may carry a replicate border
+// out = [relu]( (raw*scale+shift) [* gate[n][c]]  [+ res | + res*rscale+rshift] ), out may carry a replicate border
 void k_bn_apply(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const Tensor* res,
-                const float* rscale, const float* rshift, bool relu, const Tensor& out);
+                const float* rscale, const float* rshift, bool relu, const Tensor& out, const float* gate = nullptr);
 // out[B,H/2,W/2,C] = avgpool2( relu(raw*scale+shift) )
 void k_bn_relu_avgpool(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const Tensor& out);
 void k_avgpool_bwd(cudaStream_t st, const Tensor& gout /*[B,h,w,C]*/, const Tensor& gin /*[B,2h,2w,C]*/);
@@ -68,6 +68,7 @@ struct SERef {
     float *dw1, *db1, *dw2, *db2, *dws, *dbs;
     float *gap, *hid, *cse;                     // [B][C], [B][Cr], [B][C]   (saved by forward)
     float *part, *G;                            // [B][chunks][C] pooling partial sums, [B][C] backward scratch
+    float *dhid;                                // [B][Cr] backward scratch
     int chunks;                                 // pixel chunks per image in the pooling kernels (depends on H*W only)
 };
 void k_scse_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const SERef& se,
@@ -75,6 +76,12 @@ void k_scse_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const fl
 // g_out -> g_bn (gradient w.r.t. the BN output feeding the block's last ReLU), accumulates bn.bsums and SE grads
 void k_scse_bwd(cudaStream_t st, const Tensor& gout, const Tensor& raw, const BNRef& bn, const SERef& se,
                 const Tensor& gbn);
+
+// encoder SE module (SE-ResNet bottleneck): gates se.cse[n][c] = sigmoid(fc2(relu(fc1(mean_pix(raw*scale+shift)))));
+// the product with the gate is fused into k_bn_apply / k_bn_bwd_* (their `gate` arguments)
+void k_se_gate_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const SERef& se);
+// g = d loss / d (u*cse) with u = raw*scale+shift; accumulates the FC weight gradients, leaves se.G[n][c] (see k_bn_bwd_reduce)
+void k_se_gate_bwd(cudaStream_t st, const Tensor& g, const Tensor& raw, const float* scale, const float* shift, const SERef& se);
 
 // -------------------------------------------------------------------- final 1x1 conv (unet.py:84)
 void k_final_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const float* w,
@@ -85,11 +92,13 @@ void k_final_bwd(cudaStream_t st, const float* dlogits_nchw, const Tensor& raw, 
 // -------------------------------------------------------------------- BN / ReLU backward
 // g <- g * [mask > 0]   (in place)
 void k_relu_mask_inplace(cudaStream_t st, const Tensor& g, const Tensor& mask);
-// bsums += per-channel { sum(gm), sum(gm*xhat) },  gm = g * [raw*scale+shift > 0] if self_mask else g
-void k_bn_bwd_reduce(cudaStream_t st, const Tensor& g, const Tensor& raw, const BNRef& bn, bool self_mask);
+// bsums += per-channel { sum(gm), sum(gm*xhat) },  gm = g' * [raw*scale+shift > 0] if self_mask else g',
+// g' = g*gate[n][c] + addc[n][c] when gate != NULL (encoder SE), else g
+void k_bn_bwd_reduce(cudaStream_t st, const Tensor& g, const Tensor& raw, const BNRef& bn, bool self_mask,
+                     const float* gate = nullptr, const float* addc = nullptr);
 // graw = scale*(gm - cb - cc*(raw-mean))
 void k_bn_bwd_apply(cudaStream_t st, const Tensor& g, const Tensor& raw, const BNRef& bn, bool self_mask,
-                    const Tensor& graw);
+                    const Tensor& graw, const float* gate = nullptr, const float* addc = nullptr);
 
 // -------------------------------------------------------------------- losses / prediction / optimiser
 // Lovasz hinge with ELU (lovasz_losses.py:97-115): loss_out[0] = mean_b loss_b; dlogits = d loss / d logits

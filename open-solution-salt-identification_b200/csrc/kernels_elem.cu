@@ -5,6 +5,7 @@
 // channels), rows map to blockIdx.x so that the index arithmetic is 32-bit and division-light.
 #include "kernels.h"
 #include <algorithm>
+#include <stdexcept>
 
 #define EW_THREADS 256
 
@@ -45,6 +46,19 @@ __device__ __forceinline__ void stv_stream(bf16* p, const Vf<8>& a) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(a.v[2 * i], a.v[2 * i + 1]);
     __stcs(reinterpret_cast<uint4*>(p), u);
+}
+// The per-pixel kernels (scSE, final 1x1) reduce over the channel groups of ONE pixel with warp shuffles (<= 32 lanes); they use
+// 8-channel vectors for both storage types so that C <= 256 fits a warp.
+__device__ __forceinline__ Vf<8> ldv8(const bf16* p) { return ldv(p); }
+__device__ __forceinline__ Vf<8> ldv8(const float* p) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    Vf<8> r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void stv8(bf16* p, const Vf<8>& a) { stv(p, a); }
+__device__ __forceinline__ void stv8(float* p, const Vf<8>& a) {
+    *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(a.v[4], a.v[5], a.v[6], a.v[7]);
 }
 template <int N> __device__ __forceinline__ Vf<N> ldp(const float* p) {      // N fp32 per-channel parameters
     Vf<N> r;
@@ -234,21 +248,27 @@ void k_bn_bwd_finalize(cudaStream_t st, const BNRef& bn, double count) {
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void bn_apply_kernel(const T* __restrict__ raw, const float* __restrict__ scale, const float* __restrict__ shift,
-                                const T* __restrict__ res, const float* __restrict__ rscale, const float* __restrict__ rshift,
-                                int relu, T* __restrict__ out, int H, int W, int C, int pt, int pb, int pl, int pr) {
-    // one block per image row; a thread keeps ONE channel group (its scale/shift live in registers) and walks along x
+                                const float* __restrict__ gate, const T* __restrict__ res, const float* __restrict__ rscale,
+                                const float* __restrict__ rshift, int relu, T* __restrict__ out, int H, int W, int C, int pt, int pb,
+                                int pl, int pr) {
+    // one block per image row (and per slab of EW_THREADS channel groups when C is very wide); a thread keeps ONE channel
+    // group (its scale/shift live in registers) and walks along x
     constexpr int N = VW<T>::N;
-    const int cg = C / N, lanes = EW_THREADS / cg;
-    const int cv = threadIdx.x % cg, lane = threadIdx.x / cg, c = cv * N;
+    const int cg = min(C / N, EW_THREADS), lanes = EW_THREADS / cg;
+    const int cv = blockIdx.y * cg + threadIdx.x % cg, lane = threadIdx.x / cg, c = cv * N;
     const int row = blockIdx.x, n = row / H, y = row - n * H;
-    const Vf<N> sc = ldp<N>(scale + c), sh = ldp<N>(shift + c);
+    Vf<N> sc = ldp<N>(scale + c);
+    const Vf<N> sh = ldp<N>(shift + c);
     Vf<N> rsc = vzero<N>(), rsh = vzero<N>();
     if (res && rscale) { rsc = ldp<N>(rscale + c); rsh = ldp<N>(rshift + c); }
+    Vf<N> gt = vzero<N>();
+    if (gate) gt = ldp<N>(gate + (size_t)n * C + c);          // per-(image, channel) SE gate: (raw*scale+shift)*gate
     const int Hp = H + pt + pb, Wp = W + pl + pr;
     const int y0 = (y == 0) ? 0 : y + pt, y1 = (y == H - 1) ? Hp - 1 : y + pt;
     for (int x = lane; x < W; x += lanes) {
         const size_t src = ((size_t)row * W + x) * C + c;
         Vf<N> v = vfma(ldv(raw + src), sc, sh);
+        if (gate) v = vmul(v, gt);
         if (res) {
             Vf<N> r = ldv(res + src);
             if (rscale) r = vfma(r, rsc, rsh);
@@ -261,11 +281,11 @@ __global__ void bn_apply_kernel(const T* __restrict__ raw, const float* __restri
     }
 }
 void k_bn_apply(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const Tensor* res,
-                const float* rscale, const float* rshift, bool relu, const Tensor& out) {
+                const float* rscale, const float* rshift, bool relu, const Tensor& out, const float* gate) {
     SALT_COUNT(1);
     SALT_DISPATCH(raw.dt, T, {
-        dim3 grid(raw.B * raw.H);
-        bn_apply_kernel<T><<<grid, EW_THREADS, 0, st>>>((const T*)raw.p, scale, shift, res ? (const T*)res->p : nullptr, rscale,
+        dim3 grid(raw.B * raw.H, cdiv(raw.C / VW<T>::N, EW_THREADS));
+        bn_apply_kernel<T><<<grid, EW_THREADS, 0, st>>>((const T*)raw.p, scale, shift, gate, res ? (const T*)res->p : nullptr, rscale,
                                                         rshift, relu ? 1 : 0, (T*)out.p, raw.H, raw.W, raw.C, out.pt, out.pb, out.pl, out.pr);
     });
 }
@@ -485,24 +505,28 @@ void k_upsample_bwd(cudaStream_t st, const Tensor& gP, int c0, int f, const Tens
 }
 
 // ------------------------------------------------------------------------------------------------
-// scSE (base.py:82-117).  z = relu(bn(raw));  out = relu(z*cse[n,c] + z*sse[n,y,x]) = z*(cse+sse)
+// squeeze-and-excitation
+//   decoder scSE (base.py:82-117): z = relu(bn(raw));  out = relu(z*cse[n,c] + z*sse[n,y,x]) = z*(cse+sse)
+//   encoder SE   (pretrainedmodels senet.py SEModule, restated in oracle/senet_restated.py): u = bn(raw);
+//                out = relu(u*cse[n,c] + residual)  - the gate is applied by bn_apply / bn_bwd_* through their `gate` arguments
 // ------------------------------------------------------------------------------------------------
-// per-(n,c) sum over a pixel chunk of  [g *] relu(raw*scale+shift)  ->  part[n][chunk][C]
-// (the FC kernels add the chunks in a fixed order: deterministic and batch independent)
-template <typename T, bool WITH_G>
-__global__ void scse_pool_kernel(const T* __restrict__ raw, const T* __restrict__ g, const float* __restrict__ scale,
-                                 const float* __restrict__ shift, float* __restrict__ part, int HW, int C) {
+// per-(n,c) sum over a pixel chunk of  [g *] [relu](raw*scale+shift)  ->  part[n][chunk][C]
+// (the FC kernels add the chunks in a fixed order: deterministic and batch independent).  grid = (chunks, B, channel slabs)
+template <typename T, bool WITH_G, bool RELU>
+__global__ void se_pool_kernel(const T* __restrict__ raw, const T* __restrict__ g, const float* __restrict__ scale,
+                               const float* __restrict__ shift, float* __restrict__ part, int HW, int C) {
     constexpr int N = VW<T>::N;
     __shared__ float red[N * EW_THREADS];
-    const int cg = C / N, lanes = EW_THREADS / cg;
-    const int cv = threadIdx.x % cg, lane = threadIdx.x / cg, n = blockIdx.y;
+    const int cg = min(C / N, EW_THREADS), lanes = EW_THREADS / cg;
+    const int cv = blockIdx.z * cg + threadIdx.x % cg, lane = threadIdx.x / cg, n = blockIdx.y;
     const int chunk = (HW + gridDim.x - 1) / gridDim.x;
     const int p0 = blockIdx.x * chunk, p1 = min(HW, p0 + chunk);
     const Vf<N> sc = ldp<N>(scale + cv * N), sh = ldp<N>(shift + cv * N);
     Vf<N> acc = vzero<N>();
     for (int p = p0 + lane; p < p1; p += lanes) {
         const size_t o = ((size_t)n * HW + p) * C + cv * N;
-        Vf<N> z = vrelu(vfma(ldv(raw + o), sc, sh));
+        Vf<N> z = vfma(ldv(raw + o), sc, sh);
+        if (RELU) z = vrelu(z);
         if (WITH_G) z = vmul(z, ldv(g + o));
         acc = vadd(acc, z);
     }
@@ -510,7 +534,7 @@ __global__ void scse_pool_kernel(const T* __restrict__ raw, const T* __restrict_
     for (int i = 0; i < N; ++i) red[i * EW_THREADS + threadIdx.x] = acc.v[i];
     __syncthreads();
     if (threadIdx.x < cg) {
-        float* o = part + ((size_t)n * gridDim.x + blockIdx.x) * C + threadIdx.x * N;
+        float* o = part + ((size_t)n * gridDim.x + blockIdx.x) * C + (blockIdx.z * cg + threadIdx.x) * N;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             float s = 0.f;
@@ -519,37 +543,128 @@ __global__ void scse_pool_kernel(const T* __restrict__ raw, const T* __restrict_
         }
     }
 }
-// one block per image: squeeze -> fc(C->Cr) -> relu -> fc(Cr->C) -> sigmoid
-__global__ void scse_fc_kernel(SERef se, float inv_hw) {
+template <typename T, bool WITH_G, bool RELU>
+static void launch_se_pool(cudaStream_t st, const Tensor& raw, const void* g, const float* scale, const float* shift, const SERef& se) {
+    dim3 grid(se.chunks, raw.B, cdiv(raw.C / VW<T>::N, EW_THREADS));
+    se_pool_kernel<T, WITH_G, RELU><<<grid, EW_THREADS, 0, st>>>((const T*)raw.p, (const T*)g, scale, shift, se.part, raw.H * raw.W, raw.C);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// one block per image: squeeze -> fc(C->Cr) -> relu -> fc(Cr->C) -> sigmoid   (any C, Cr)
+__global__ void se_fc_kernel(SERef se, float inv_hw) {
     extern __shared__ float sm[];
     float* gap = sm;               // [C]
     float* hid = sm + se.C;        // [Cr]
-    const int n = blockIdx.x, c = threadIdx.x;
-    if (c < se.C) {
+    const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    for (int c = tid; c < se.C; c += blockDim.x) {
         float t = 0.f;
         for (int k = 0; k < se.chunks; ++k) t += se.part[((size_t)n * se.chunks + k) * se.C + c];
         gap[c] = t * inv_hw;
         se.gap[(size_t)n * se.C + c] = gap[c];
     }
     __syncthreads();
-    if (c < se.Cr) {
-        float a = se.b1[c];
-        for (int i = 0; i < se.C; ++i) a = fmaf(se.w1[c * se.C + i], gap[i], a);
-        a = fmaxf(a, 0.f);
-        hid[c] = a;
-        se.hid[(size_t)n * se.Cr + c] = a;
+    for (int j = warp; j < se.Cr; j += nwarps) {
+        float a = 0.f;
+        for (int i = lane; i < se.C; i += 32) a = fmaf(se.w1[(size_t)j * se.C + i], gap[i], a);
+        a = warp_sum(a);
+        if (lane == 0) {
+            a = fmaxf(a + se.b1[j], 0.f);
+            hid[j] = a;
+            se.hid[(size_t)n * se.Cr + j] = a;
+        }
     }
     __syncthreads();
-    if (c < se.C) {
+    for (int c = tid; c < se.C; c += blockDim.x) {
         float a = se.b2[c];
-        for (int j = 0; j < se.Cr; ++j) a = fmaf(se.w2[c * se.Cr + j], hid[j], a);
+        for (int j = 0; j < se.Cr; ++j) a = fmaf(se.w2[(size_t)c * se.Cr + j], hid[j], a);
         se.cse[(size_t)n * se.C + c] = 1.f / (1.f + expf(-a));
     }
 }
+// backward of the two FCs.  Stage 1, one block per image: part[n][*][c] = sum_pix g*z  ->  dpre2 (saved over part[n][0][c]),
+// dhid, and G[n][c] = d loss / d gap / HW.  Stage 2, one thread per weight: batch reduction of the outer products (no atomics).
+__global__ void se_fc_bwd_kernel(SERef se, float inv_hw) {
+    extern __shared__ float sm[];
+    float* dpre2 = sm;             // [C]
+    float* dhid = sm + se.C;       // [Cr]
+    const int n = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    for (int c = tid; c < se.C; c += blockDim.x) {
+        const float cs = se.cse[(size_t)n * se.C + c];
+        float t = 0.f;
+        for (int k = 0; k < se.chunks; ++k) t += se.part[((size_t)n * se.chunks + k) * se.C + c];
+        const float d = t * cs * (1.f - cs);
+        dpre2[c] = d;
+        se.part[(size_t)n * se.chunks * se.C + c] = d;
+    }
+    __syncthreads();
+    for (int j = warp; j < se.Cr; j += nwarps) {
+        float a = 0.f;
+        for (int i = lane; i < se.C; i += 32) a = fmaf(se.w2[(size_t)i * se.Cr + j], dpre2[i], a);
+        a = warp_sum(a);
+        if (lane == 0) {
+            a = se.hid[(size_t)n * se.Cr + j] > 0.f ? a : 0.f;
+            dhid[j] = a;
+            se.dhid[(size_t)n * se.Cr + j] = a;
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < se.C; c += blockDim.x) {
+        float gsum = 0.f;
+        for (int j = 0; j < se.Cr; ++j) gsum = fmaf(se.w1[(size_t)j * se.C + c], dhid[j], gsum);
+        se.G[(size_t)n * se.C + c] = gsum * inv_hw;
+    }
+}
+__global__ void se_fc_wgrad_kernel(SERef se, int B) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int C = se.C, Cr = se.Cr;
+    const size_t pstride = (size_t)se.chunks * C;          // dpre2[n][c] lives in part[n][0][c]
+    if (idx < C * Cr) {
+        { const int c = idx / Cr, j = idx - c * Cr;        // dw2[c][j] = sum_n dpre2[n][c] * hid[n][j]
+          float a = 0.f;
+          for (int n = 0; n < B; ++n) a = fmaf(se.part[n * pstride + c], se.hid[(size_t)n * Cr + j], a);
+          se.dw2[idx] += a; }
+        { const int j = idx / C, c = idx - j * C;          // dw1[j][c] = sum_n dhid[n][j] * gap[n][c]
+          float a = 0.f;
+          for (int n = 0; n < B; ++n) a = fmaf(se.dhid[(size_t)n * Cr + j], se.gap[(size_t)n * C + c], a);
+          se.dw1[idx] += a; }
+    }
+    if (idx < C) {
+        float a = 0.f;
+        for (int n = 0; n < B; ++n) a += se.part[n * pstride + idx];
+        se.db2[idx] += a;
+    }
+    if (idx < Cr) {
+        float a = 0.f;
+        for (int n = 0; n < B; ++n) a += se.dhid[(size_t)n * Cr + idx];
+        se.db1[idx] += a;
+    }
+}
+static void launch_se_fc(cudaStream_t st, const SERef& se, int B, int HW) {
+    se_fc_kernel<<<B, 256, sizeof(float) * (se.C + se.Cr), st>>>(se, 1.0f / HW);
+}
+static void launch_se_fc_bwd(cudaStream_t st, const SERef& se, int B, int HW) {
+    se_fc_bwd_kernel<<<B, 256, sizeof(float) * (se.C + se.Cr), st>>>(se, 1.0f / HW);
+    se_fc_wgrad_kernel<<<cdiv(se.C * se.Cr, 256), 256, 0, st>>>(se, B);
+}
+// encoder SE: squeeze bn(raw) (no ReLU) and compute the channel gates se.cse[n][c]
+void k_se_gate_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const SERef& se) {
+    SALT_COUNT(2);
+    SALT_DISPATCH(raw.dt, T, (launch_se_pool<T, false, false>(st, raw, nullptr, scale, shift, se)));
+    launch_se_fc(st, se, raw.B, raw.H * raw.W);
+}
+// encoder SE backward: g = gradient w.r.t. u*cse (already ReLU-masked); accumulates the FC gradients and leaves
+// se.G[n][c] = the per-(image, channel) term that the gap path adds to d loss / d u
+void k_se_gate_bwd(cudaStream_t st, const Tensor& g, const Tensor& raw, const float* scale, const float* shift, const SERef& se) {
+    SALT_COUNT(3);
+    SALT_DISPATCH(raw.dt, T, (launch_se_pool<T, true, false>(st, raw, g.p, scale, shift, se)));
+    launch_se_fc_bwd(st, se, raw.B, raw.H * raw.W);
+}
+
 template <typename T>
 __global__ void scse_apply_kernel(const T* __restrict__ raw, const float* __restrict__ scale, const float* __restrict__ shift,
                                   SERef se, T* __restrict__ out, unsigned npix, int HW, int C) {
-    constexpr int N = VW<T>::N;
+    constexpr int N = 8;
     const unsigned cg = C / N;
     const unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
     unsigned pix = idx / cg;
@@ -557,63 +672,30 @@ __global__ void scse_apply_kernel(const T* __restrict__ raw, const float* __rest
     const bool ok = pix < npix;
     if (!ok) pix = npix - 1;
     const int n = pix / HW;
-    const Vf<N> z = vrelu(vfma(ldv(raw + (size_t)pix * C + c), ldp<N>(scale + c), ldp<N>(shift + c)));
+    const Vf<N> z = vrelu(vfma(ldv8(raw + (size_t)pix * C + c), ldp<N>(scale + c), ldp<N>(shift + c)));
     const float dot = group_sum(vdot(z, ldp<N>(se.ws + c)), cg);
     const float s = 1.f / (1.f + expf(-(dot + se.bs[0])));
     Vf<N> gate = ldp<N>(se.cse + (size_t)n * C + c);
 #pragma unroll
     for (int i = 0; i < N; ++i) gate.v[i] += s;
-    if (ok) stv(out + (size_t)pix * C + c, vrelu(vmul(z, gate)));
+    if (ok) stv8(out + (size_t)pix * C + c, vrelu(vmul(z, gate)));
 }
 void k_scse_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const SERef& se, const Tensor& out) {
     SALT_COUNT(3);
     const int HW = raw.H * raw.W, C = raw.C;
     const unsigned npix = (unsigned)raw.B * HW;
+    if (C % 8 || C / 8 > 32 || ((C / 8) & (C / 8 - 1))) throw std::runtime_error("scSE: channel count must be 8 * 2^k <= 256");
     SALT_DISPATCH(raw.dt, T, {
-        const int cg = C / VW<T>::N;
-        scse_pool_kernel<T, false><<<dim3(se.chunks, raw.B), EW_THREADS, 0, st>>>((const T*)raw.p, nullptr, scale, shift, se.part, HW, C);
-        scse_fc_kernel<<<raw.B, max(32, C), sizeof(float) * (C + se.Cr), st>>>(se, 1.0f / HW);
-        scse_apply_kernel<T><<<cdiv((long long)npix * cg, EW_THREADS), EW_THREADS, 0, st>>>((const T*)raw.p, scale, shift, se, (T*)out.p, npix, HW, C);
+        launch_se_pool<T, false, true>(st, raw, nullptr, scale, shift, se);
+        launch_se_fc(st, se, raw.B, HW);
+        scse_apply_kernel<T><<<cdiv((long long)npix * (C / 8), EW_THREADS), EW_THREADS, 0, st>>>((const T*)raw.p, scale, shift, se, (T*)out.p, npix, HW, C);
     });
 }
 
-// backward of the two tiny FCs, one block per image
-__global__ void scse_fc_bwd_kernel(SERef se, float inv_hw) {
-    extern __shared__ float sm[];
-    float* dpre2 = sm;             // [C]
-    float* dhid = sm + se.C;       // [Cr]
-    const int n = blockIdx.x, c = threadIdx.x;
-    if (c < se.C) {
-        float cs = se.cse[(size_t)n * se.C + c];
-        float t = 0.f;
-        for (int k = 0; k < se.chunks; ++k) t += se.part[((size_t)n * se.chunks + k) * se.C + c];
-        float d = t * cs * (1.f - cs);
-        dpre2[c] = d;
-        atomicAdd(se.db2 + c, d);
-        for (int j = 0; j < se.Cr; ++j) atomicAdd(se.dw2 + c * se.Cr + j, d * se.hid[(size_t)n * se.Cr + j]);
-    }
-    __syncthreads();
-    if (c < se.Cr) {
-        float a = 0.f;
-        for (int i = 0; i < se.C; ++i) a = fmaf(se.w2[i * se.Cr + c], dpre2[i], a);
-        a = se.hid[(size_t)n * se.Cr + c] > 0.f ? a : 0.f;
-        dhid[c] = a;
-        atomicAdd(se.db1 + c, a);
-    }
-    __syncthreads();
-    if (c < se.C) {
-        float gsum = 0.f, gp = se.gap[(size_t)n * se.C + c];
-        for (int j = 0; j < se.Cr; ++j) {
-            atomicAdd(se.dw1 + j * se.C + c, dhid[j] * gp);
-            gsum = fmaf(se.w1[j * se.C + c], dhid[j], gsum);
-        }
-        se.G[(size_t)n * se.C + c] = gsum * inv_hw;
-    }
-}
 template <typename T>
 __global__ void scse_bwd_apply_kernel(const T* __restrict__ gout, const T* __restrict__ raw, BNRef bn, SERef se,
                                       T* __restrict__ gbn, unsigned npix, int HW, int C) {
-    constexpr int N = VW<T>::N;
+    constexpr int N = 8;
     __shared__ float red[N * EW_THREADS];
     const int cg = C / N, lanes = EW_THREADS / cg;
     const int cv = threadIdx.x % cg, lane = threadIdx.x / cg, c = cv * N;
@@ -628,9 +710,9 @@ __global__ void scse_bwd_apply_kernel(const T* __restrict__ gout, const T* __res
         const bool ok = pix < npix;
         if (!ok) pix = npix - 1;
         const int n = pix / HW;
-        const Vf<N> x = ldv(raw + (size_t)pix * C + c);
+        const Vf<N> x = ldv8(raw + (size_t)pix * C + c);
         const Vf<N> z = vrelu(vfma(x, sc, sh));
-        const Vf<N> g = ldv(gout + (size_t)pix * C + c);
+        const Vf<N> g = ldv8(gout + (size_t)pix * C + c);
         const float dot = group_sum(vdot(z, w), cg);
         const float s = 1.f / (1.f + expf(-(dot + bs)));
         const float D = group_sum(vdot(g, z), cg);
@@ -640,7 +722,7 @@ __global__ void scse_bwd_apply_kernel(const T* __restrict__ gout, const T* __res
 #pragma unroll
         for (int i = 0; i < N; ++i) dz.v[i] = z.v[i] > 0.f ? g.v[i] * (cse.v[i] + s) + dsp * w.v[i] + G.v[i] : 0.f;
         if (ok) {
-            stv(gbn + (size_t)pix * C + c, dz);
+            stv8(gbn + (size_t)pix * C + c, dz);
             sg = vadd(sg, dz);
             sgx = vfma(dz, vxhat(x, mu, is), sgx);
             sws = vaxpy(z, dsp, sws);
@@ -659,14 +741,13 @@ __global__ void scse_bwd_apply_kernel(const T* __restrict__ gout, const T* __res
     }
 }
 void k_scse_bwd(cudaStream_t st, const Tensor& gout, const Tensor& raw, const BNRef& bn, const SERef& se, const Tensor& gbn) {
-    SALT_COUNT(3);
+    SALT_COUNT(4);
     const int HW = raw.H * raw.W, C = raw.C;
     const unsigned npix = (unsigned)raw.B * HW;
     SALT_DISPATCH(raw.dt, T, {
-        const int cg = C / VW<T>::N;
-        scse_pool_kernel<T, true><<<dim3(se.chunks, raw.B), EW_THREADS, 0, st>>>((const T*)raw.p, (const T*)gout.p, bn.scale, bn.shift, se.part, HW, C);
-        scse_fc_bwd_kernel<<<raw.B, max(32, C), sizeof(float) * (C + se.Cr), st>>>(se, 1.0f / HW);
-        scse_bwd_apply_kernel<T><<<reduce_blocks(npix, cg), EW_THREADS, 0, st>>>((const T*)gout.p, (const T*)raw.p, bn, se, (T*)gbn.p, npix, HW, C);
+        launch_se_pool<T, true, true>(st, raw, gout.p, bn.scale, bn.shift, se);
+        launch_se_fc_bwd(st, se, raw.B, HW);
+        scse_bwd_apply_kernel<T><<<reduce_blocks(npix, C / 8), EW_THREADS, 0, st>>>((const T*)gout.p, (const T*)raw.p, bn, se, (T*)gbn.p, npix, HW, C);
     });
 }
 
@@ -677,14 +758,14 @@ template <typename T>
 __global__ void final_fwd_kernel(const T* __restrict__ raw, const float* __restrict__ scale, const float* __restrict__ shift,
                                  const float* __restrict__ w, const float* __restrict__ b, int K, float* __restrict__ logits,
                                  unsigned npix, int HW, int C) {
-    constexpr int N = VW<T>::N;
+    constexpr int N = 8;
     const unsigned cg = C / N;
     const unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
     unsigned pix = idx / cg;
     const int cv = idx - pix * cg, c = cv * N;
     const bool ok = pix < npix;
     if (!ok) pix = npix - 1;
-    const Vf<N> z = vrelu(vfma(ldv(raw + (size_t)pix * C + c), ldp<N>(scale + c), ldp<N>(shift + c)));
+    const Vf<N> z = vrelu(vfma(ldv8(raw + (size_t)pix * C + c), ldp<N>(scale + c), ldp<N>(shift + c)));
     const int n = pix / HW, p = pix - n * HW;
     for (int k = 0; k < K; ++k) {
         const float d = group_sum(vdot(z, ldp<N>(w + k * C + c)), cg);
@@ -695,8 +776,9 @@ void k_final_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const f
                  int K, float* logits) {
     SALT_COUNT(1);
     const unsigned npix = (unsigned)raw.B * raw.H * raw.W;
+    const int cg = raw.C / 8;
+    if (raw.C % 8 || cg > 32 || (cg & (cg - 1))) throw std::runtime_error("final 1x1 conv: channel count must be 8 * 2^k <= 256");
     SALT_DISPATCH(raw.dt, T, {
-        const int cg = raw.C / VW<T>::N;
         final_fwd_kernel<T><<<cdiv((long long)npix * cg, EW_THREADS), EW_THREADS, 0, st>>>((const T*)raw.p, scale, shift, w, b, K, logits,
                                                                                        npix, raw.H * raw.W, raw.C);
     });
@@ -705,7 +787,7 @@ template <typename T, int K>
 __global__ void final_bwd_kernel(const float* __restrict__ dlogits, const T* __restrict__ raw, BNRef bn,
                                  const float* __restrict__ w, float* __restrict__ dw, float* __restrict__ db,
                                  T* __restrict__ gbn, unsigned npix, int HW, int C) {
-    constexpr int N = VW<T>::N;
+    constexpr int N = 8;
     __shared__ float red[N * EW_THREADS];
     const int cg = C / N, lanes = EW_THREADS / cg;
     const int cv = threadIdx.x % cg, lane = threadIdx.x / cg, c = cv * N;
@@ -716,7 +798,7 @@ __global__ void final_bwd_kernel(const float* __restrict__ dlogits, const T* __r
     Vf<N> sg = vzero<N>(), sgx = vzero<N>();
     for (unsigned pix = blockIdx.x * lanes + lane; pix < npix; pix += gridDim.x * lanes) {
         const int n = pix / HW, p = pix - n * HW;
-        const Vf<N> x = ldv(raw + (size_t)pix * C + c);
+        const Vf<N> x = ldv8(raw + (size_t)pix * C + c);
         const Vf<N> z = vrelu(vfma(x, sc, sh));
         Vf<N> gz = vzero<N>();
 #pragma unroll
@@ -727,7 +809,7 @@ __global__ void final_bwd_kernel(const float* __restrict__ dlogits, const T* __r
             if (cv == 0) sdb[k] += dl;
         }
         gz = vmaskpos(gz, z);
-        stv(gbn + (size_t)pix * C + c, gz);
+        stv8(gbn + (size_t)pix * C + c, gz);
         sg = vadd(sg, gz);
         sgx = vfma(gz, vxhat(x, mu, is), sgx);
     }
@@ -752,7 +834,7 @@ void k_final_bwd(cudaStream_t st, const float* dlogits, const Tensor& raw, const
     const int HW = raw.H * raw.W;
 #define LAUNCH_FB(KK) final_bwd_kernel<T, KK><<<blocks, EW_THREADS, 0, st>>>(dlogits, (const T*)raw.p, bn, w, dw, db, (T*)gbn.p, npix, HW, raw.C)
     SALT_DISPATCH(raw.dt, T, {
-        const int blocks = reduce_blocks(npix, raw.C / VW<T>::N);
+        const int blocks = reduce_blocks(npix, raw.C / 8);
         if (K == 1) LAUNCH_FB(1); else if (K == 2) LAUNCH_FB(2); else if (K == 3) LAUNCH_FB(3); else LAUNCH_FB(4);
     });
 #undef LAUNCH_FB
@@ -775,43 +857,60 @@ void k_relu_mask_inplace(cudaStream_t st, const Tensor& g, const Tensor& mask) {
         relu_mask_inplace_kernel<T><<<cdiv(nvec, EW_THREADS), EW_THREADS, 0, st>>>((T*)g.p, (const T*)mask.p, nvec);
     });
 }
+// upstream gradient seen by a BN layer: g, optionally gated per (image, channel): g*gate[n][c] + addc[n][c] (encoder SE),
+// optionally masked by the layer's own ReLU.  grid = (pixel blocks, channel slabs)
 template <typename T>
 __global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ raw, BNRef bn, int self_mask,
-                                     unsigned npix, int C) {
+                                     const float* __restrict__ gate, const float* __restrict__ addc, unsigned npix, int HW, int C) {
     constexpr int N = VW<T>::N;
     __shared__ float red[N * EW_THREADS];
-    const int cg = C / N, lanes = EW_THREADS / cg;
-    const int cv = threadIdx.x % cg, lane = threadIdx.x / cg, c = cv * N;
+    const int cg = min(C / N, EW_THREADS), lanes = EW_THREADS / cg;
+    const int cv = blockIdx.y * cg + threadIdx.x % cg, lane = threadIdx.x / cg, c = cv * N;
     const Vf<N> sc = ldp<N>(bn.scale + c), sh = ldp<N>(bn.shift + c), mu = ldp<N>(bn.mean + c), is = ldp<N>(bn.invstd + c);
     Vf<N> sg = vzero<N>(), sgx = vzero<N>();
     for (unsigned pix = blockIdx.x * lanes + lane; pix < npix; pix += gridDim.x * lanes) {
         const Vf<N> x = ldv(raw + (size_t)pix * C + c);
         Vf<N> gv = ldv(g + (size_t)pix * C + c);
+        if (gate) {
+            const size_t o = (size_t)(pix / HW) * C + c;
+            gv = vfma(gv, ldp<N>(gate + o), ldp<N>(addc + o));
+        }
         if (self_mask) gv = vmaskpos(gv, vfma(x, sc, sh));
         sg = vadd(sg, gv);
         sgx = vfma(gv, vxhat(x, mu, is), sgx);
     }
-    block_reduce_add<N, double>(sg, cg, bn.bsums, red);
-    block_reduce_add<N, double>(sgx, cg, bn.bsums + C, red);
+    const int coff = blockIdx.y * cg * N;
+    block_reduce_add<N, double>(sg, cg, bn.bsums + coff, red);
+    block_reduce_add<N, double>(sgx, cg, bn.bsums + C + coff, red);
 }
-void k_bn_bwd_reduce(cudaStream_t st, const Tensor& g, const Tensor& raw, const BNRef& bn, bool self_mask) {
+void k_bn_bwd_reduce(cudaStream_t st, const Tensor& g, const Tensor& raw, const BNRef& bn, bool self_mask, const float* gate,
+                     const float* addc) {
     SALT_COUNT(1);
     const unsigned npix = (unsigned)raw.B * raw.H * raw.W;
-    SALT_DISPATCH(raw.dt, T, (bn_bwd_reduce_kernel<T><<<reduce_blocks(npix, raw.C / VW<T>::N), EW_THREADS, 0, st>>>(
-        (const T*)g.p, (const T*)raw.p, bn, self_mask ? 1 : 0, npix, raw.C)));
+    SALT_DISPATCH(raw.dt, T, {
+        const int cgt = raw.C / VW<T>::N, cg = std::min(cgt, EW_THREADS);
+        dim3 grid(reduce_blocks(npix, cg), cgt / cg);
+        bn_bwd_reduce_kernel<T><<<grid, EW_THREADS, 0, st>>>((const T*)g.p, (const T*)raw.p, bn, self_mask ? 1 : 0, gate, addc, npix,
+                                                             raw.H * raw.W, raw.C);
+    });
 }
 template <typename T>
 __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict__ raw, BNRef bn, int self_mask,
-                                    T* __restrict__ graw, unsigned npix, int C) {
+                                    const float* __restrict__ gate, const float* __restrict__ addc, T* __restrict__ graw,
+                                    unsigned npix, int HW, int C) {
     // a thread keeps ONE channel group (5 per-channel coefficient vectors in registers) and strides over pixels
     constexpr int N = VW<T>::N;
-    const int cg = C / N, lanes = EW_THREADS / cg;
-    const int cv = threadIdx.x % cg, lane = threadIdx.x / cg, c = cv * N;
+    const int cg = min(C / N, EW_THREADS), lanes = EW_THREADS / cg;
+    const int cv = blockIdx.y * cg + threadIdx.x % cg, lane = threadIdx.x / cg, c = cv * N;
     const Vf<N> sc = ldp<N>(bn.scale + c), sh = ldp<N>(bn.shift + c), mu = ldp<N>(bn.mean + c), cb = ldp<N>(bn.cb + c),
                 cc = ldp<N>(bn.cc + c);
     for (unsigned pix = blockIdx.x * lanes + lane; pix < npix; pix += gridDim.x * lanes) {
         const Vf<N> x = ldv(raw + (size_t)pix * C + c);
         Vf<N> gv = ldv(g + (size_t)pix * C + c);
+        if (gate) {
+            const size_t o = (size_t)(pix / HW) * C + c;
+            gv = vfma(gv, ldp<N>(gate + o), ldp<N>(addc + o));
+        }
         if (self_mask) gv = vmaskpos(gv, vfma(x, sc, sh));
         Vf<N> r;
 #pragma unroll
@@ -819,12 +918,14 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict
         stv(graw + (size_t)pix * C + c, r);
     }
 }
-void k_bn_bwd_apply(cudaStream_t st, const Tensor& g, const Tensor& raw, const BNRef& bn, bool self_mask, const Tensor& graw) {
+void k_bn_bwd_apply(cudaStream_t st, const Tensor& g, const Tensor& raw, const BNRef& bn, bool self_mask, const Tensor& graw,
+                    const float* gate, const float* addc) {
     SALT_COUNT(1);
     SALT_DISPATCH(raw.dt, T, {
         const unsigned npix = (unsigned)raw.B * raw.H * raw.W;
-        const int lanes = EW_THREADS / (raw.C / VW<T>::N);
+        const int cgt = raw.C / VW<T>::N, cg = std::min(cgt, EW_THREADS), lanes = EW_THREADS / cg;
         const int blocks = (int)std::min<long long>(((long long)npix + lanes * 4 - 1) / (lanes * 4), 148 * 16);
-        bn_bwd_apply_kernel<T><<<blocks, EW_THREADS, 0, st>>>((const T*)g.p, (const T*)raw.p, bn, self_mask ? 1 : 0, (T*)graw.p, npix, raw.C);
+        bn_bwd_apply_kernel<T><<<dim3(blocks, cgt / cg), EW_THREADS, 0, st>>>((const T*)g.p, (const T*)raw.p, bn, self_mask ? 1 : 0, gate,
+                                                                             addc, (T*)graw.p, npix, raw.H * raw.W, raw.C);
     });
 }

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libsaltunet.so')
 
 PREC_FP32, PREC_BF16 = 0, 1
 ARCH_UNET_RESNET = 0
+ARCH_UNET_SERESNET = 1
 
 
 class SaltEngineError(RuntimeError):

@@ -19,21 +19,26 @@ def _ptr(t):
 
 
 class UNetEngine:
-    """UNetResNet (reference architectures/unet.py:22-109) on the CUDA engine.
+    """UNetResNet (reference architectures/unet.py:22-109; encoder_depth 18/34) or UNetSeResNet (unet.py:112-172;
+    encoder_depth 50, architecture='UNetSeResNet') on the CUDA engine.
 
     precision: 'fp32' (parity mode: fp32 storage, fp32 FMA) or 'bf16' (bf16 activations / weights copies,
     fp32 accumulation, fp32 master weights and optimiser state).
     """
 
     def __init__(self, encoder_depth=34, num_classes=2, max_batch=8, size=128, precision='fp32',
-                 use_tensor_cores=True, training=True, device=None):
+                 use_tensor_cores=True, training=True, device=None, architecture=None):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise SaltEngineError('UNetEngine needs a CUDA device (B200); there is no CPU fallback')
         self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
         self.encoder_depth, self.num_classes, self.max_batch, self.size = encoder_depth, num_classes, max_batch, size
         self.precision = precision
-        cfg = _lib.SaltConfig(_lib.ARCH_UNET_RESNET, encoder_depth, num_classes, max_batch, size, size,
+        if architecture is None:
+            architecture = 'UNetSeResNet' if encoder_depth == 50 else 'UNetResNet'
+        self.architecture = architecture
+        arch_id = {'UNetResNet': _lib.ARCH_UNET_RESNET, 'UNetSeResNet': _lib.ARCH_UNET_SERESNET}[architecture]
+        cfg = _lib.SaltConfig(arch_id, encoder_depth, num_classes, max_batch, size, size,
                               {'fp32': _lib.PREC_FP32, 'bf16': _lib.PREC_BF16}[precision], int(bool(use_tensor_cores)))
         h = C.c_void_p()
         _lib.check(self.lib.salt_create(C.byref(cfg), C.byref(h)))

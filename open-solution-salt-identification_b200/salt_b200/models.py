@@ -23,17 +23,22 @@ from .engine import UNetEngine
 # reference models.py:15-24 - the entries this engine implements
 ARCHITECTURES = {'UNetResNet': {'model_config': {'encoder_depth': 34, 'use_hypercolumn': True, 'dropout_2d': 0.0,
                                                  'pretrained': True, 'pool0': False},
-                                'init_weights': False}}
+                                'init_weights': False},
+                 'UNetSeResNet': {'model_config': {'encoder_depth': 50, 'use_hypercolumn': True, 'dropout_2d': 0.0,
+                                                   'pretrained': 'imagenet', 'pool0': False},
+                                  'init_weights': False}}
 
 
 def _alias_map(table):
-    """alias key -> canonical key for the duplicated registrations of reference encoders.py:21-36."""
+    """alias key -> canonical key for the duplicated registrations of reference encoders.py:21-36 (ResNet) and
+    :59-74 (SE-ResNet: the stem lives in ``encoder.layer0``)."""
     amap = {}
+    stems = (('encoders.encoder.conv1.', 'encoders.conv1.0.'), ('encoders.encoder.bn1.', 'encoders.conv1.1.'),
+             ('encoders.encoder.layer0.conv1.', 'encoders.conv1.0.'), ('encoders.encoder.layer0.bn1.', 'encoders.conv1.1.'))
     for k in table:
-        if k.startswith('encoders.encoder.conv1.'):
-            amap['encoders.conv1.0.' + k[len('encoders.encoder.conv1.'):]] = k
-        elif k.startswith('encoders.encoder.bn1.'):
-            amap['encoders.conv1.1.' + k[len('encoders.encoder.bn1.'):]] = k
+        stem = [(a, b) for a, b in stems if k.startswith(a)]
+        if stem:
+            amap[stem[0][1] + k[len(stem[0][0]):]] = k
         else:
             for li in (1, 2, 3, 4):
                 pre = 'encoders.encoder.layer%d.' % li
@@ -220,7 +225,7 @@ class SegmentationModel(Model):
             raise NotImplementedError('architecture %r is not implemented by the B200 engine (have: %s)'
                                       % (architecture, sorted(ARCHITECTURES)))
         cfg = ARCHITECTURES[architecture]['model_config']
-        self.engine = UNetEngine(encoder_depth=mp.get('encoder_depth', cfg['encoder_depth']),
+        self.engine = UNetEngine(architecture=architecture, encoder_depth=mp.get('encoder_depth', cfg['encoder_depth']),
                                  num_classes=mp['out_channels'],
                                  max_batch=int(os.environ.get('SALT_ENGINE_MAX_BATCH', mp.get('max_batch', 128))),
                                  size=int(os.environ.get('SALT_ENGINE_SIZE', mp.get('size', 128))),

@@ -10,16 +10,17 @@ STD = (0.229, 0.224, 0.225)    # reference main.py:56
 
 
 def resnet_block_counts(depth):
-    return {18: (2, 2, 2, 2), 34: (3, 4, 6, 3)}[depth]
+    return {18: (2, 2, 2, 2), 34: (3, 4, 6, 3), 50: (3, 4, 6, 3)}[depth]
 
 
 def param_specs(depth=34, num_classes=2):
-    """Canonical (name, shape, kind) list of every tensor UNetResNet owns.
+    """Canonical (name, shape, kind) list of every tensor the network owns.
 
-    Names are the reference's ``state_dict`` keys under ``encoders.encoder.*``
-    (the aliases ``encoders.conv1.*`` / ``encoders.encoderN.*`` share storage,
-    reference encoders.py:21-36).  kind in {conv_w, bias, bn_w, bn_b, bn_rm,
-    bn_rv, lin_w}.
+    depth 18/34 -> UNetResNet (unet.py:22-109), depth 50 -> UNetSeResNet
+    (unet.py:112-172, SE-ResNet-50 encoder).  Names are the reference's
+    ``state_dict`` keys under ``encoders.encoder.*`` (the aliases
+    ``encoders.conv1.*`` / ``encoders.encoderN.*`` share storage, reference
+    encoders.py:21-36 / :59-74).  kind in {conv_w, bias, bn_w, bn_b, bn_rm, bn_rv, lin_w}.
     """
     specs = []
 
@@ -30,12 +31,30 @@ def param_specs(depth=34, num_classes=2):
         specs.append((prefix + '.running_var', (c,), 'bn_rv'))
 
     e = 'encoders.encoder.'
-    specs.append((e + 'conv1.weight', (64, 3, 7, 7), 'conv_w'))
-    bn(e + 'bn1', 64)
+    se50 = depth == 50
+    specs.append((e + ('layer0.conv1.weight' if se50 else 'conv1.weight'), (64, 3, 7, 7), 'conv_w'))
+    bn(e + ('layer0.bn1' if se50 else 'bn1'), 64)
     cin = 64
     for li, (nblk, cout) in enumerate(zip(resnet_block_counts(depth), (64, 128, 256, 512)), start=1):
         for b in range(nblk):
             p = '%slayer%d.%d.' % (e, li, b)
+            if se50:        # pretrainedmodels SEResNetBottleneck: registration order conv1..bn3, se_module, downsample
+                co = 4 * cout
+                specs.append((p + 'conv1.weight', (cout, cin, 1, 1), 'conv_w'))
+                bn(p + 'bn1', cout)
+                specs.append((p + 'conv2.weight', (cout, cout, 3, 3), 'conv_w'))
+                bn(p + 'bn2', cout)
+                specs.append((p + 'conv3.weight', (co, cout, 1, 1), 'conv_w'))
+                bn(p + 'bn3', co)
+                specs.append((p + 'se_module.fc1.weight', (co // 16, co, 1, 1), 'conv_w'))
+                specs.append((p + 'se_module.fc1.bias', (co // 16,), 'bias'))
+                specs.append((p + 'se_module.fc2.weight', (co, co // 16, 1, 1), 'conv_w'))
+                specs.append((p + 'se_module.fc2.bias', (co,), 'bias'))
+                if b == 0:
+                    specs.append((p + 'downsample.0.weight', (co, cin, 1, 1), 'conv_w'))
+                    bn(p + 'downsample.1', co)
+                cin = co
+                continue
             specs.append((p + 'conv1.weight', (cout, cin, 3, 3), 'conv_w'))
             bn(p + 'bn1', cout)
             specs.append((p + 'conv2.weight', (cout, cout, 3, 3), 'conv_w'))
@@ -50,7 +69,7 @@ def param_specs(depth=34, num_classes=2):
         specs.append((prefix + '.conv.weight', (co, ci, 3, 3), 'conv_w'))
         specs.append((prefix + '.conv.bias', (co,), 'bias'))
 
-    bc = 512
+    bc = 2048 if se50 else 512
     cbr('center.0', bc, bc)
     cbr('center.1', bc, bc // 2)
     dec = {'dec5': (bc + bc // 2, bc, bc // 8), 'dec4': (bc // 2 + bc // 8, bc // 2, bc // 8),
@@ -85,7 +104,8 @@ def synth_state_dict(depth=34, num_classes=2, seed=0):
         elif kind == 'bn_w':
             # the last BN of a residual branch gets a small gain so that eval-mode activations (running
             # statistics, no renormalisation) stay O(1) through 16 residual blocks
-            a = rng.uniform(0.1, 0.5, shape) if name.endswith('bn2.weight') else rng.uniform(0.5, 1.5, shape)
+            last = 'bn3.weight' if depth == 50 else 'bn2.weight'
+            a = rng.uniform(0.1, 0.5, shape) if name.endswith(last) else rng.uniform(0.5, 1.5, shape)
         elif kind == 'bn_b':
             a = rng.standard_normal(shape) * 0.1
         elif kind == 'bn_rm':

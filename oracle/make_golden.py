@@ -26,6 +26,9 @@ CASES = [
     ('r18_b2_s64', 18, 2, 64, 0, 1234),
     ('r34_b2_s64', 34, 2, 64, 1, 4321),
     ('r18_b8_s128', 18, 8, 128, 0, 1234),     # BASELINE.json configs[0] shape
+    # UNetSeResNet-50 (BASELINE.json configs[3] architecture): the reference's own UNetSeResNet / SeResNetEncoders classes
+    # on top of oracle/senet_restated.py (pretrainedmodels is absent - see that file's header)
+    ('se50_b2_s64', 50, 2, 64, 2, 777),
 ]
 
 GRAD_KEYS = ['encoders.encoder.conv1.weight', 'encoders.encoder.layer1.0.conv1.weight',
@@ -33,6 +36,24 @@ GRAD_KEYS = ['encoders.encoder.conv1.weight', 'encoders.encoder.layer1.0.conv1.w
              'center.1.conv.weight', 'dec5.conv1.conv.weight', 'dec3.channel_se.fc.0.weight',
              'dec2.spatial_se.fc.weight', 'dec1.conv1.conv.bias', 'final.0.conv.weight',
              'final.0.batch_norm.bias', 'final.1.weight', 'final.1.bias']
+
+
+GRAD_KEYS_SE50 = ['encoders.encoder.layer0.conv1.weight', 'encoders.encoder.layer1.0.conv1.weight',
+                  'encoders.encoder.layer1.0.downsample.0.weight', 'encoders.encoder.layer2.0.conv1.weight',
+                  'encoders.encoder.layer2.0.downsample.0.weight', 'encoders.encoder.layer2.1.se_module.fc2.bias',
+                  'encoders.encoder.layer3.2.se_module.fc1.weight', 'encoders.encoder.layer3.5.conv2.weight',
+                  'encoders.encoder.layer4.1.bn3.weight', 'encoders.encoder.layer4.2.conv3.weight',
+                  'center.1.conv.weight', 'dec5.conv1.conv.weight', 'dec3.channel_se.fc.0.weight',
+                  'dec2.spatial_se.fc.weight', 'dec1.conv1.conv.bias', 'final.0.conv.weight',
+                  'final.0.batch_norm.bias', 'final.1.weight', 'final.1.bias']
+
+
+def grad_keys(depth):
+    return GRAD_KEYS_SE50 if depth == 50 else GRAD_KEYS
+
+
+def stem_bn(depth):
+    return 'encoders.encoder.layer0.bn1' if depth == 50 else 'encoders.encoder.bn1'
 
 
 MAX_SAMPLES = 8192
@@ -90,12 +111,12 @@ def run_case(tag, depth, batch, size, wseed, dseed):
         out['loss_' + loss_name] = np.float32(loss.item())
         out['dlogits_' + loss_name] = sample(logits.grad.numpy())
         named = dict(net.named_parameters())
-        for k in GRAD_KEYS:
+        for k in grad_keys(depth):
             out['grad_%s_%s' % (loss_name, k)] = sample(named[k].grad.numpy())
             out['gradl2_%s_%s' % (loss_name, k)] = np.float64(named[k].grad.double().norm().item())
         gsq = {k: float((p.grad.double() ** 2).sum()) for k, p in named.items() if p.grad is not None}
         out['gradnorm_' + loss_name] = np.float64(np.sqrt(sum(gsq.values())))
-        out['running_mean_stem_' + loss_name] = net.state_dict()['encoders.encoder.bn1.running_mean'].numpy()
+        out['running_mean_stem_' + loss_name] = net.state_dict()[stem_bn(depth) + '.running_mean'].numpy()
         out['running_var_final0_' + loss_name] = net.state_dict()['final.0.batch_norm.running_var'].numpy()
 
         sd_t = unet_oracle.to_torch_state(sd_np, requires_grad=True)
@@ -108,12 +129,12 @@ def run_case(tag, depth, batch, size, wseed, dseed):
             'oracle %s loss differs: %r vs %r' % (loss_name, ls.item(), loss.item())
         dd = (lg.grad - logits.grad).abs().max().item()
         assert dd <= 1e-7 + 1e-4 * logits.grad.abs().max().item(), 'oracle dlogits differ: %g' % dd
-        for k in GRAD_KEYS:
+        for k in grad_keys(depth):
             a, b = sd_t[k].grad, named[k].grad
             rel = (a - b).abs().max().item() / (b.abs().max().item() + 1e-12)
             assert rel <= 2e-3, 'oracle grad %s differs rel %g' % (k, rel)
-        rm = sd_t['encoders.encoder.bn1.running_mean']
-        assert (rm - net.state_dict()['encoders.encoder.bn1.running_mean']).abs().max().item() <= 1e-6
+        rm = sd_t[stem_bn(depth) + '.running_mean']
+        assert (rm - net.state_dict()[stem_bn(depth) + '.running_mean']).abs().max().item() <= 1e-6
 
     # ---- post-processing (sigmoid, TTA h-flip mean, crop, binarize) through the reference functions
     if size == 128:
@@ -149,8 +170,10 @@ def main():
     if not ref_shims.available():
         sys.exit('reference tree not available; fixtures can only be regenerated in the build container')
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    only = set(sys.argv[1:])                   # optional: tags to (re)generate
     for case in CASES:
-        run_case(*case)
+        if not only or case[0] in only:
+            run_case(*case)
 
 
 if __name__ == '__main__':

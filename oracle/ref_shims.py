@@ -130,6 +130,10 @@ def install():
             __import__(name)
         except Exception:
             _stub(name)
+    if isinstance(sys.modules['pretrainedmodels'], _StubModule):
+        # encoders.py:52-53 looks the constructor up in the package __dict__; the package is absent, use the restatement
+        from . import senet_restated
+        sys.modules['pretrainedmodels'].__dict__['se_resnet50'] = senet_restated.se_resnet50
     sys.modules['steppy.base'].BaseTransformer = BaseTransformer
     sys.modules['toolkit.pytorch_transformers.models'].Model = Model
     import joblib
@@ -144,12 +148,16 @@ def install():
 
 
 def reference_unet(depth, num_classes=2):
-    """common_blocks.architectures.unet.UNetResNet(pretrained=False, hypercolumn, pool0=False)."""
+    """common_blocks.architectures.unet.UNetResNet(pretrained=False, hypercolumn, pool0=False); depth 50 builds
+    unet.UNetSeResNet on top of oracle/senet_restated.py (the reference's own wrapper classes, unmodified)."""
     install()
     import warnings
     from common_blocks.architectures import unet
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
+        if depth == 50:
+            return unet.UNetSeResNet(encoder_depth=50, num_classes=num_classes, dropout_2d=0.0, pretrained=None,
+                                     use_hypercolumn=True, pool0=False)
         return unet.UNetResNet(encoder_depth=depth, num_classes=num_classes, dropout_2d=0.0,
                                pretrained=False, use_hypercolumn=True, pool0=False)
 

@@ -1,4 +1,4 @@
-"""Functional CPU restatement of the reference UNetResNet forward (fp32, PyTorch).
+"""Functional CPU restatement of the reference UNetResNet / UNetSeResNet forward (fp32, PyTorch).
 
 TEST INFRASTRUCTURE (see oracle/__init__.py).  The network is expressed as pure
 functions over a ``state_dict`` (canonical ``encoders.encoder.*`` keys), so the
@@ -10,6 +10,8 @@ Reference followed:
   common_blocks/architectures/base.py:65-117     DecoderBlock, ChannelSELayer, SpatialSELayer
   common_blocks/architectures/encoders.py:6-45   ResNetEncoders (pool0=False)
   torchvision/models/resnet.py:59-105            BasicBlock
+  common_blocks/architectures/unet.py:112-172    UNetSeResNet (depth 50; bottom_channel_nr 2048)
+  common_blocks/architectures/encoders.py:48-83  SeResNetEncoders (pretrainedmodels se_resnet50, see senet_restated.py)
 """
 import numpy as np
 import torch
@@ -36,10 +38,11 @@ def alias_keys(depth=34):
     """alias key -> canonical key, for the duplicated registrations the reference
     creates in ResNetEncoders (encoders.py:21-36)."""
     amap = {}
+    stem = 'encoders.encoder.layer0.' if depth == 50 else 'encoders.encoder.'       # encoders.py:59-66 vs :21-28
     for s in ('weight',):
-        amap['encoders.conv1.0.' + s] = 'encoders.encoder.conv1.' + s
+        amap['encoders.conv1.0.' + s] = stem + 'conv1.' + s
     for s in ('weight', 'bias', 'running_mean', 'running_var', 'num_batches_tracked'):
-        amap['encoders.conv1.1.' + s] = 'encoders.encoder.bn1.' + s
+        amap['encoders.conv1.1.' + s] = stem + 'bn1.' + s
     for name, _, _ in param_specs(depth):
         for li in (1, 2, 3, 4):
             pre = 'encoders.encoder.layer%d.' % li
@@ -70,16 +73,37 @@ def _basic_block(sd, p, x, stride, train):
     return F.relu(out + idn)
 
 
+def _se_bottleneck(sd, p, x, stride, train):
+    # pretrainedmodels senet.py SEResNetBottleneck / SEModule (restated: oracle/senet_restated.py): stride on conv1
+    out = F.conv2d(x, sd[p + 'conv1.weight'], None, stride=stride)
+    out = F.relu(_bn(sd, p + 'bn1', out, train))
+    out = F.conv2d(out, sd[p + 'conv2.weight'], None, stride=1, padding=1)
+    out = F.relu(_bn(sd, p + 'bn2', out, train))
+    out = F.conv2d(out, sd[p + 'conv3.weight'], None)
+    out = _bn(sd, p + 'bn3', out, train)
+    if (p + 'downsample.0.weight') in sd:
+        idn = F.conv2d(x, sd[p + 'downsample.0.weight'], None, stride=stride)
+        idn = _bn(sd, p + 'downsample.1', idn, train)
+    else:
+        idn = x
+    g = out.mean(dim=(2, 3), keepdim=True)
+    g = F.relu(F.conv2d(g, sd[p + 'se_module.fc1.weight'], sd[p + 'se_module.fc1.bias']))
+    g = torch.sigmoid(F.conv2d(g, sd[p + 'se_module.fc2.weight'], sd[p + 'se_module.fc2.bias']))
+    return F.relu(out * g + idn)
+
+
 def encoder_forward(sd, x, depth, train):
-    # encoders.py:38-45 with pool0=False (no maxpool)
+    # encoders.py:38-45 / :76-83 with pool0=False (no maxpool)
     e = 'encoders.encoder.'
-    y = F.conv2d(x, sd[e + 'conv1.weight'], None, stride=2, padding=3)
-    y = F.relu(_bn(sd, e + 'bn1', y, train))
+    stem = e + ('layer0.' if depth == 50 else '')
+    block = _se_bottleneck if depth == 50 else _basic_block
+    y = F.conv2d(x, sd[stem + 'conv1.weight'], None, stride=2, padding=3)
+    y = F.relu(_bn(sd, stem + 'bn1', y, train))
     feats = []
     for li, nblk in enumerate(resnet_block_counts(depth), start=1):
         for b in range(nblk):
             stride = 2 if (b == 0 and li > 1) else 1
-            y = _basic_block(sd, '%slayer%d.%d.' % (e, li, b), y, stride, train)
+            y = block(sd, '%slayer%d.%d.' % (e, li, b), y, stride, train)
         feats.append(y)
     return feats  # encoder2..encoder5
 
@@ -115,7 +139,8 @@ def decoder_block(sd, name, x, skip, train):
 
 def unet_resnet_forward(sd, x, depth=34, train=False, return_stages=False):
     """[B,3,H,W] fp32 -> logits [B,num_classes,H,W] (unet.py:89-109, hypercolumn on,
-    dropout_2d p=0 is the identity)."""
+    dropout_2d p=0 is the identity).  depth 50 = UNetSeResNet (unet.py:152-172): same graph, SE-ResNet-50 encoder,
+    decoder widths derived from the state (bottom_channel_nr 2048)."""
     e2, e3, e4, e5 = encoder_forward(sd, x, depth, train)
     c = conv_bn_relu(sd, 'center.0', e5, train)
     c = conv_bn_relu(sd, 'center.1', c, train)

@@ -15,7 +15,7 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 from oracle import synth, unet_oracle, losses_oracle            # noqa: E402
-from oracle.make_golden import sample, GRAD_KEYS                 # noqa: E402
+from oracle.make_golden import sample, GRAD_KEYS, grad_keys                 # noqa: E402
 
 
 def _engine(*a, **k):
@@ -214,7 +214,7 @@ def test_train_step_fp32(depth, b, s, loss_name):
     assert worst <= 1e-6
 
 
-@pytest.mark.parametrize('tag', ['r18_b2_s64', 'r34_b2_s64', 'r18_b8_s128'])
+@pytest.mark.parametrize('tag', ['r18_b2_s64', 'r34_b2_s64', 'r18_b8_s128', 'se50_b2_s64'])
 def test_golden_fixtures_fp32(golden_dir, tag):
     """Engine vs vectors produced by the unmodified reference modules (tests/golden, oracle/make_golden.py)."""
     g = np.load(os.path.join(golden_dir, tag + '.npz'))
@@ -242,14 +242,14 @@ def test_golden_fixtures_fp32(golden_dir, tag):
         oks.append(report('golden train logits', logits, g['logits_train'], atol=1e-3)[0])
         oks.append(report('golden loss ' + loss_name, loss.cpu()[0], float(g['loss_' + loss_name]), atol=1e-5, rtol=1e-4)[0])
         oks.append(report('golden dlogits ' + loss_name, sample(dlogits.cpu().numpy()), g['dlogits_' + loss_name], atol=1e-9, rtol=2e-3)[0])
-        for k in GRAD_KEYS:
+        for k in grad_keys(m['depth']):
             if k.endswith('.conv.bias'):
                 continue
             oks.append(report('golden grad %s' % k, sample(eng.view(k, grad=True).cpu().numpy()), g['grad_%s_%s' % (loss_name, k)], atol=1e-7, rtol=5e-3)[0])
     assert all(oks)
 
 
-@pytest.mark.parametrize('depth,b,s', [(18, 8, 128), (34, 4, 128)])
+@pytest.mark.parametrize('depth,b,s', [(18, 8, 128), (34, 4, 128), (50, 4, 128)])
 def test_bf16_mode(depth, b, s):
     """bf16 precision mode (configs 2-5): bounded deviation from the fp32 oracle.  bf16 storage rounds every
     activation to 8 mantissa bits (2^-9 relative) ~50 times along the deepest path, so the stated tolerances are:
@@ -288,7 +288,7 @@ def test_bf16_mode(depth, b, s):
     torch.cuda.synchronize()
     assert report('bf16 train logits', lt, ref, atol=0.05 + 0.08 * ref.abs().max().item())[0]
     assert report('bf16 lovasz loss', loss.cpu()[0], loss_ref, rtol=0.02)[0]
-    for k in GRAD_KEYS:
+    for k in grad_keys(depth):
         if k.endswith('.conv.bias'):
             continue
         a, r = eng.view(k, grad=True).cpu().flatten(), sd[k].grad.flatten()

@@ -7,9 +7,9 @@ import pytest
 import torch
 
 from oracle import synth, unet_oracle, losses_oracle
-from oracle.make_golden import sample, GRAD_KEYS
+from oracle.make_golden import sample, grad_keys, stem_bn
 
-CASES = ['r18_b2_s64', 'r34_b2_s64']
+CASES = ['r18_b2_s64', 'r34_b2_s64', 'se50_b2_s64']
 
 
 def _load(golden_dir, tag):
@@ -44,12 +44,12 @@ def test_train_step_matches_reference(golden_dir, tag, loss_name):
     assert abs(loss.item() - float(g['loss_' + loss_name])) <= 1e-5 * max(1.0, abs(loss.item()))
     ref = g['dlogits_' + loss_name]
     assert np.abs(sample(logits.grad.numpy()) - ref).max() <= 1e-7 + 1e-4 * np.abs(ref).max()
-    for k in GRAD_KEYS:
+    for k in grad_keys(m['depth']):
         ref = g['grad_%s_%s' % (loss_name, k)]
         got = sample(sd[k].grad.numpy())
         assert np.abs(got - ref).max() <= 2e-3 * (np.abs(ref).max() + 1e-12), k
     # BatchNorm running statistics were updated like the reference's
-    assert np.abs(sd['encoders.encoder.bn1.running_mean'].numpy() - g['running_mean_stem_' + loss_name]).max() <= 1e-6
+    assert np.abs(sd[stem_bn(m['depth']) + '.running_mean'].numpy() - g['running_mean_stem_' + loss_name]).max() <= 1e-6
     assert np.abs(sd['final.0.batch_norm.running_var'].numpy() - g['running_var_final0_' + loss_name]).max() <= 1e-5
 
 
