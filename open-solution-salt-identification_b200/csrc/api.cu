@@ -78,9 +78,9 @@ int salt_loss_lovasz(salt_engine* h, const float* logits, const float* target, i
                      void* stream) {
     const EngineConfig& c = h->e->config();
     int P = c.num_classes * c.H * c.W;
-    if (P > 32768) return fail("salt_loss_lovasz: images with more than 32768 logits need the global-memory sort (not built yet)");
     if (batch > c.max_batch) return fail("salt_loss_lovasz: batch exceeds max_batch");
-    SALT_TRY("salt_loss_lovasz", k_lovasz((cudaStream_t)stream, logits, target, batch, P, h->e->loss_scratch(), loss_out, dlogits));
+    SALT_TRY("salt_loss_lovasz", k_lovasz((cudaStream_t)stream, logits, target, batch, P, h->e->loss_scratch(), loss_out, dlogits,
+                                          h->e->lovasz_sort_scratch()));
 }
 int salt_loss_bce_dice_reduce(salt_engine* h, const float* logits, const float* target, int batch, double* sums, void* stream) {
     const EngineConfig& c = h->e->config();

@@ -238,6 +238,10 @@ void Engine::build() {
     d_pack_ = (PackDesc*)ws_alloc(sizeof(PackDesc) * MAX_CONVS); d_pack_start_ = (int*)ws_alloc(sizeof(int) * (MAX_CONVS + 1));
     d_unpack_ = (UnpackDesc*)ws_alloc(sizeof(UnpackDesc) * MAX_CONVS); d_unpack_start_ = (int*)ws_alloc(sizeof(int) * (MAX_CONVS + 1));
     loss_scratch_ = (float*)ws_alloc(sizeof(float) * (B + 8));
+    {
+        const size_t sb = lovasz_sort_scratch_bytes(B, cfg_.num_classes * H * W);
+        lovasz_sort_ = sb ? ws_alloc(sb) : nullptr;
+    }
     loss_sums_ = (double*)ws_alloc(sizeof(double) * 16);
     for (int i = 0; i < 4; ++i) scratch_[i] = ws_alloc(std::max<size_t>(scratch_bytes_[i], 256));
     if (counting_) { stats_doubles_ = stats_cursor_; bstats_doubles_ = bstats_cursor_; dwp_floats_ = dwp_cursor_; }

@@ -108,6 +108,7 @@ public:
 
     const EngineConfig& config() const { return cfg_; }
     float* loss_scratch() { return loss_scratch_; }
+    void* lovasz_sort_scratch() { return lovasz_sort_; }
     double* loss_sums() { return loss_sums_; }
 
 private:
@@ -196,6 +197,7 @@ private:
     void prof_begin(int cls, double flops, cudaStream_t st);
     void prof_end(cudaStream_t st);
     float* loss_scratch_ = nullptr;   // [max_batch + 8]
+    void* lovasz_sort_ = nullptr;     // global-memory sort buffers of the Lovasz loss for images with > 32768 logits
     double* loss_sums_ = nullptr;     // [16]
 };
 

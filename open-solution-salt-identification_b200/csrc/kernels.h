@@ -102,8 +102,11 @@ void k_bn_bwd_apply(cudaStream_t st, const Tensor& g, const Tensor& raw, const B
 
 // -------------------------------------------------------------------- losses / prediction / optimiser
 // Lovasz hinge with ELU (lovasz_losses.py:97-115): loss_out[0] = mean_b loss_b; dlogits = d loss / d logits
+// P <= 32768 logits per image: one CTA sorts them in shared memory.  Larger images: sort_scratch (lovasz_sort_scratch_bytes)
+// holds the keys / payloads of a global-memory bitonic sort.
+size_t lovasz_sort_scratch_bytes(int B, int P);
 void k_lovasz(cudaStream_t st, const float* logits, const float* target, int B, int P, float* per_image,
-              float* loss_out, float* dlogits);
+              float* loss_out, float* dlogits, void* sort_scratch = nullptr);
 // 0.2*dice + 0.9*bce (models.py:331-340).  sums: scratch [3K+1] doubles.  If allreduce is wanted the caller
 // reduces `sums` between the two stages.
 void k_bce_dice_reduce(cudaStream_t st, const float* logits, const float* target, int B, int K, int HW, double* sums);

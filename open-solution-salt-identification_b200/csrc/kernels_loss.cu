@@ -7,6 +7,7 @@
 //   * Adam with L2 (models.py:74-75,289-297), fused over the flat parameter buffer.
 #include "kernels.h"
 #include <math_constants.h>
+#include <stdexcept>
 
 // ------------------------------------------------------------------------------------------------
 // Lovasz hinge
@@ -114,8 +115,166 @@ __global__ void mean_kernel(const float* __restrict__ v, int n, float* __restric
         out[0] = t / (float)n;
     }
 }
+// ---- images with more than 32768 logits (256x256 inputs, BASELINE config 4): the same algorithm with the sort in global memory.
+// Keys / payloads (pixel index | label << 31) live in a [B][Ppad] scratch; chunks of LVB_CH elements are sorted in shared
+// memory, the bitonic merge levels above the chunk size run their wide strides as global passes and their tail in shared memory.
+#define LVB_CH 16384
+#define LVB_SMEM (LVB_CH * 8)
+__device__ __forceinline__ bool lvb_before(float ka, unsigned ia, float kb, unsigned ib) {
+    return (ka > kb) || (ka == kb && (ia & 0x7fffffffu) < (ib & 0x7fffffffu));
+}
+// in-smem bitonic stages j = j0 .. 1 of merge level k on one chunk whose first element has global index g0
+__device__ __forceinline__ void lvb_smem_stages(float* key, unsigned* pay, int g0, int k, int j0) {
+    for (int j = j0; j > 0; j >>= 1) {
+        for (int t = threadIdx.x; t < (LVB_CH >> 1); t += LV_THREADS) {
+            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+            const bool up = ((g0 + i) & k) == 0;
+            const float ka = key[i], kb = key[l];
+            const unsigned ia = pay[i], ib = pay[l];
+            if (lvb_before(ka, ia, kb, ib) != up) { key[i] = kb; key[l] = ka; pay[i] = ib; pay[l] = ia; }
+        }
+        __syncthreads();
+    }
+}
+// grid (Ppad / LVB_CH, B): hinge errors -> keys, then every merge level up to the chunk size
+__global__ void __launch_bounds__(LV_THREADS) lvb_init_kernel(const float* __restrict__ logits, const float* __restrict__ target,
+                                                              int P, int Ppad, float* __restrict__ gkey, unsigned* __restrict__ gpay) {
+    extern __shared__ __align__(16) unsigned char lv_smem[];
+    float* key = reinterpret_cast<float*>(lv_smem);
+    unsigned* pay = reinterpret_cast<unsigned*>(lv_smem + sizeof(float) * LVB_CH);
+    const int b = blockIdx.y, g0 = blockIdx.x * LVB_CH;
+    const float* lg = logits + (size_t)b * P;
+    const float* tg = target + (size_t)b * P;
+    for (int i = threadIdx.x; i < LVB_CH; i += LV_THREADS) {
+        const int g = g0 + i;
+        if (g < P) {
+            const unsigned lab = ((long long)tg[g]) != 0 ? 1u : 0u;
+            key[i] = 1.f - lg[g] * (lab ? 1.f : -1.f);
+            pay[i] = (unsigned)g | (lab << 31);
+        } else {
+            key[i] = -CUDART_INF_F;
+            pay[i] = 0x7fffffffu;
+        }
+    }
+    __syncthreads();
+    for (int k = 2; k <= LVB_CH; k <<= 1) lvb_smem_stages(key, pay, g0, k, k >> 1);
+    for (int i = threadIdx.x; i < LVB_CH; i += LV_THREADS) {
+        gkey[(size_t)b * Ppad + g0 + i] = key[i];
+        gpay[(size_t)b * Ppad + g0 + i] = pay[i];
+    }
+}
+// one compare-exchange pass with stride j >= LVB_CH of merge level k.  grid (Ppad / 2 / 256, B)
+__global__ void lvb_global_pass_kernel(float* __restrict__ gkey, unsigned* __restrict__ gpay, int Ppad, int k, int j) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (Ppad >> 1)) return;
+    float* key = gkey + (size_t)blockIdx.y * Ppad;
+    unsigned* pay = gpay + (size_t)blockIdx.y * Ppad;
+    const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+    const bool up = (i & k) == 0;
+    const float ka = key[i], kb = key[l];
+    const unsigned ia = pay[i], ib = pay[l];
+    if (lvb_before(ka, ia, kb, ib) != up) { key[i] = kb; key[l] = ka; pay[i] = ib; pay[l] = ia; }
+}
+// strides LVB_CH/2 .. 1 of merge level k, one chunk per CTA.  grid (Ppad / LVB_CH, B)
+__global__ void __launch_bounds__(LV_THREADS) lvb_tail_kernel(float* __restrict__ gkey, unsigned* __restrict__ gpay, int Ppad, int k) {
+    extern __shared__ __align__(16) unsigned char lv_smem[];
+    float* key = reinterpret_cast<float*>(lv_smem);
+    unsigned* pay = reinterpret_cast<unsigned*>(lv_smem + sizeof(float) * LVB_CH);
+    const int g0 = blockIdx.x * LVB_CH;
+    const size_t base = (size_t)blockIdx.y * Ppad + g0;
+    for (int i = threadIdx.x; i < LVB_CH; i += LV_THREADS) { key[i] = gkey[base + i]; pay[i] = gpay[base + i]; }
+    __syncthreads();
+    lvb_smem_stages(key, pay, g0, k, LVB_CH >> 1);
+    for (int i = threadIdx.x; i < LVB_CH; i += LV_THREADS) { gkey[base + i] = key[i]; gpay[base + i] = pay[i]; }
+}
+// one CTA per image over the sorted errors: label scan -> Jaccard gradient -> loss and d/dlogit (same arithmetic as lovasz_kernel)
+__global__ void __launch_bounds__(LV_THREADS) lvb_scan_kernel(const float* __restrict__ gkey, const unsigned* __restrict__ gpay, int P,
+                                                              int Ppad, float inv_b, float* __restrict__ per_image,
+                                                              float* __restrict__ dlogits) {
+    __shared__ float warp_tot[32];
+    __shared__ float warp_loss[32];
+    const int tid = threadIdx.x, b = blockIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float* key = gkey + (size_t)b * Ppad;
+    const unsigned* pay = gpay + (size_t)b * Ppad;
+    const int chunk = Ppad / 32, c0 = warp * chunk;
+    float tot = 0.f;
+    for (int i = c0 + lane; i < c0 + chunk; i += 32) tot += (float)(pay[i] >> 31);
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0) warp_tot[warp] = tot;
+    __syncthreads();
+    float G = 0.f, carry = 0.f;
+    for (int w = 0; w < 32; ++w) { float t = warp_tot[w]; G += t; if (w < warp) carry += t; }
+    float loss = 0.f;
+    for (int base = c0; base < c0 + chunk; base += 32) {
+        const int i = base + lane;
+        const unsigned pv = pay[i];
+        const float gt = (float)(pv >> 31);
+        float inc = gt;
+        for (int o = 1; o < 32; o <<= 1) {
+            float n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        const float cs = carry + inc;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+        if (i < P) {
+            const float inter = G - cs, uni = G + ((float)(i + 1) - cs);
+            const float jac = 1.f - inter / uni;
+            float grad = jac;
+            if (i > 0) {
+                const float csp = cs - gt;
+                const float interp = G - csp, unip = G + ((float)i - csp);
+                grad = jac - (1.f - interp / unip);
+            }
+            const float e = key[i];
+            const float elu = e > 0.f ? e : expm1f(e);
+            const float delu = e > 0.f ? 1.f : expf(e);
+            loss = fmaf(elu, grad, loss);
+            const float sign = (pv >> 31) ? 1.f : -1.f;
+            dlogits[(size_t)b * P + (pv & 0x7fffffffu)] = -sign * delu * grad * inv_b;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    if (lane == 0) warp_loss[warp] = loss;
+    __syncthreads();
+    if (tid == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 32; ++w) t += warp_loss[w];
+        per_image[b] = t;
+    }
+}
+size_t lovasz_sort_scratch_bytes(int B, int P) {
+    if (P <= 32768) return 0;
+    size_t Ppad = LVB_CH;
+    while (Ppad < (size_t)P) Ppad <<= 1;
+    return (size_t)B * Ppad * 8;
+}
 void k_lovasz(cudaStream_t st, const float* logits, const float* target, int B, int P, float* per_image, float* loss_out,
-              float* dlogits) {
+              float* dlogits, void* sort_scratch) {
+    if (P > 32768) {
+        if (!sort_scratch) throw std::runtime_error("k_lovasz: images with more than 32768 logits need the sort scratch buffer");
+        int Ppad = LVB_CH;
+        while (Ppad < P) Ppad <<= 1;
+        float* gkey = (float*)sort_scratch;
+        unsigned* gpay = (unsigned*)(gkey + (size_t)B * Ppad);
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(lvb_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LVB_SMEM);
+            cudaFuncSetAttribute(lvb_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LVB_SMEM);
+            configured = true;
+        }
+        const dim3 gc(Ppad / LVB_CH, B), gp(cdiv(Ppad / 2, 256), B);
+        int launches = 1;
+        lvb_init_kernel<<<gc, LV_THREADS, LVB_SMEM, st>>>(logits, target, P, Ppad, gkey, gpay);
+        for (int k = 2 * LVB_CH; k <= Ppad; k <<= 1) {
+            for (int j = k >> 1; j >= LVB_CH; j >>= 1) { lvb_global_pass_kernel<<<gp, 256, 0, st>>>(gkey, gpay, Ppad, k, j); ++launches; }
+            lvb_tail_kernel<<<gc, LV_THREADS, LVB_SMEM, st>>>(gkey, gpay, Ppad, k);
+            ++launches;
+        }
+        lvb_scan_kernel<<<B, LV_THREADS, 0, st>>>(gkey, gpay, P, Ppad, 1.0f / B, per_image, dlogits);
+        mean_kernel<<<1, 32, 0, st>>>(per_image, B, loss_out);
+        SALT_COUNT(launches + 2);
+        return;
+    }
     SALT_COUNT(2);
     int Ppad = 1024;
     while (Ppad < P) Ppad <<= 1;
