@@ -145,6 +145,40 @@ def make_model(precision, batch, loss):
     return SegmentationModel(arch, {'epochs': 1}, {})
 
 
+def se50_train_step(ctx, timed, batch=64, size=256):
+    """BASELINE configs[3]: UNetSeResNet-50, 202x202 tiles padded to a 256x256 network input, bf16, 64 images per GPU, full
+    training step (forward, Lovasz hinge with the global-memory sort, backward, gradient all-reduce, Adam).  Secondary number."""
+    from salt_b200 import synthetic as synth
+    from salt_b200.engine import UNetEngine
+    eng = UNetEngine(architecture='UNetSeResNet', encoder_depth=50, num_classes=CLASSES, max_batch=batch, size=size,
+                     precision='bf16', device=ctx.device)
+    eng.load_state(synth.synth_state_dict(50, CLASSES, 0))
+    x = torch.from_numpy(synth.synth_inputs(batch, size, 99 + ctx.rank)).to(eng.device)
+    t = torch.from_numpy(synth.synth_targets(batch, size, 99 + ctx.rank)).to(eng.device)
+
+    def step():
+        logits = eng.forward(x, train=True)
+        _, dl = eng.loss_lovasz(logits, t)
+        eng.backward(dl)
+        eng.adam_step(grad_scale=ctx.allreduce_grads(eng.grads))
+    for _ in range(2):
+        step()
+    ms = timed(step, 3) / 3
+    eng.profile(True)
+    step()
+    prof = eng.profile_read()
+    eng.profile(False)
+    tot_ms = sum(v[0] for v in prof.values())
+    tot_fl = sum(v[1] for v in prof.values())
+    out = {'value': batch * ctx.world / (ms / 1e3), 'unit': 'images/s', 'ms_per_step': ms,
+           'what': 'UNetSeResNet-50, %dx%d input, bf16, %d images/GPU, Lovasz hinge, full training step' % (size, size, batch),
+           'conv_tflops': tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0, 'conv_ms_per_step': tot_ms,
+           'train_gflop_per_image': tot_fl / batch / 1e9}
+    del eng, x, t
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     from salt_b200 import synthetic as synth
     from salt_b200 import _lib
@@ -212,9 +246,15 @@ def run_ours(args):
                 fn()
         ms_lv = timed(step_lovasz, 5)
         ms_inf = timed(infer_tta, 5)
+        se50 = None
+        if not args.no_se50:
+            se50 = se50_train_step(ctx, timed)
         extra = {'lovasz_train_step': {'value': B * ctx.world * 5 / (ms_lv / 1e3), 'unit': 'images/s', 'ms_per_step': ms_lv / 5},
                  'inference_tta_hflip': {'value': B * ctx.world * 5 / (ms_inf / 1e3), 'unit': 'tiles/s', 'ms_per_batch': ms_inf / 5,
                                          'what': '%d tiles per GPU per pass = %d network inputs (orig + h-flip), fused sigmoid/un-flip/mean/crop/threshold -> u8 masks' % (B, 2 * B)}}
+
+        if se50:
+            extra['seresnet50_256_train_step'] = se50
 
     if ctx.rank != 0:
         return
@@ -268,6 +308,7 @@ def main():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--loss', default='bce_dice', choices=['bce_dice', 'lovasz'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-se50', action='store_true', help='skip the secondary UNetSeResNet-50 256x256 training-step measurement')
     ap.add_argument('--no-extra', action='store_true', help='skip the secondary Lovasz / TTA-inference measurements')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup

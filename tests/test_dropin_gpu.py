@@ -128,3 +128,36 @@ def test_fit_transform_and_lr_mutation(model):
     out = model.fit_transform(datagen=(list(zip(xs, ts)), 1), validation_datagen=None, meta_valid=None)
     assert len(out['mask_prediction']) == B
     assert torch.equal(before, model.engine.params)       # lr 0 -> Adam leaves the parameters untouched
+
+
+def test_unet_seresnet_dropin(monkeypatch, tmp_path):
+    """ARCHITECTURES['UNetSeResNet'] (models.py:19-24, unet.py:112-172): constructor, state_dict keys of the reference
+    (SE-ResNet-50 encoder registered under encoders.encoder.layer0..4 + the encoders.conv1 / encoderN aliases), transform vs oracle,
+    persist / load round trip."""
+    monkeypatch.setenv('SALT_ENGINE_PRECISION', 'fp32')
+    monkeypatch.setenv('SALT_ENGINE_MAX_BATCH', '2')
+    monkeypatch.setenv('SALT_ENGINE_SIZE', str(S))
+    from salt_b200.models import SegmentationModel
+    arch = dict(ARCH, model_params=dict(ARCH['model_params'], architecture='UNetSeResNet', encoder_depth=50))
+    m = SegmentationModel(arch, {'epochs': 1}, {})
+    sd_np = synth.synth_state_dict(50, 2, 3)
+    m.engine.load_state(sd_np)
+    sd = m.model.state_dict()
+    for k in ('module.encoders.encoder.layer0.conv1.weight', 'module.encoders.conv1.0.weight', 'module.encoders.conv1.1.running_mean',
+              'module.encoders.encoder3.0.se_module.fc1.weight', 'module.encoders.encoder.layer4.2.conv3.weight',
+              'module.encoders.encoder5.0.downsample.1.num_batches_tracked', 'module.dec5.conv1.conv.weight'):
+        assert k in sd, k
+    assert sd['module.encoders.encoder3.0.se_module.fc1.weight'].shape == (32, 512, 1, 1)
+    assert sd['module.dec5.conv1.conv.weight'].shape == (2048, 3072, 3, 3)
+    xs = [torch.from_numpy(synth.synth_inputs(2, S, 5))]
+    preds = np.stack(m.transform(datagen=(xs, 1))['mask_prediction'])
+    with torch.no_grad():
+        ref = torch.sigmoid(unet_oracle.unet_resnet_forward(unet_oracle.to_torch_state(sd_np), xs[0], 50, train=False)).numpy()
+    err = np.abs(preds - ref).max()
+    print('UNetSeResNet transform: max-abs prob error vs oracle %.3e' % err)
+    assert err <= 1e-4
+    path = os.path.join(tmp_path, 'network')
+    m.persist(path)
+    fresh = SegmentationModel(arch, {'epochs': 1}, {})
+    fresh.load(path)
+    assert np.array_equal(np.stack(fresh.transform(datagen=(xs, 1))['mask_prediction']), preds)
