@@ -92,6 +92,33 @@ int salt_adam_step(salt_engine* h, float lr, float weight_decay, float beta1, fl
 int salt_predict(salt_engine* h, const float* logits, const float* logits_flip, int batch, int crop, float threshold,
                  float* probs, uint8_t* mask, void* stream);
 
+/* ---- data formats either side of the network ------------------------------- */
+
+/* loaders.py:607-612 (Grayscale(3) + ToTensor + Normalize + AddDepthChannels, utils.py:494-500) after
+ * augmentation.py:247-281 InferencePad('edge') with the pad split of utils.py:308-313: raw u8 tiles [B,tile_h,tile_w]
+ * -> fp32 NCHW [B,3,size,size]. Only channel 0's mean/std matter (channels 1, 2 are overwritten by the depth
+ * channels). hflip: np.fliplr of the raw tile first (augmentation.py:143-147, TTA). Bit-exact with the reference. */
+int salt_adapt_tiles(const uint8_t* tiles, int batch, int tile_h, int tile_w, int size, float mean0, float std0, int hflip,
+                     float* x_nchw, void* stream);
+/* salt_forward with that adapter fused into the stem: u8 tiles in (12x fewer input bytes than fp32 [B,3,S,S]). */
+int salt_forward_tiles(salt_engine* h, const uint8_t* tiles, int batch, int tile_h, int tile_w, float mean0, float std0,
+                       int hflip, float* logits_nchw, int train, void* stream);
+
+/* utils.py:99-111 run_length_encoding (called from utils.py:68-75 create_submission / :78-79 encode_rle): masks u8
+ * [B,height,width] -> runs int32 [B,cap_runs,2] = (start, length), pixels numbered from 1 in column-major order;
+ * nruns[b] = number of runs of image b (may exceed cap_runs: then only the first cap_runs are stored). */
+int salt_rle_encode(const uint8_t* mask, int batch, int height, int width, int cap_runs, int32_t* runs, int32_t* nruns,
+                    void* stream);
+
+/* callbacks.py:499-527 ValidationMonitor._get_validation_loss inner loop (callbacks.py:832-866 crop_image + binarize at
+ * each threshold, metrics.py:8-64 on single-object masks): for image b and threshold k
+ *   pred = sigmoid(logits[b,1]) (mean with the un-flipped logits_flip if given) cropped to crop x crop, > thresholds[k]
+ *   inter[b,k] = |pred & gt[b]|, pred[b,k] = |pred|, gtsum[b] = |gt[b]|      (gt: u8 [B,crop,crop], nthr <= 32).
+ * thresholds: HOST pointer to float64 values (np.linspace(0.5, 0.3, 21) in the reference). */
+int salt_validation_counts(const float* logits, const float* logits_flip, int batch, int classes, int size, int crop,
+                           const uint8_t* gt, const double* thresholds, int nthr, int32_t* inter, int32_t* pred,
+                           int32_t* gtsum, void* stream);
+
 /* Test/debug: copy a named internal activation ("stem","e2".."e5","center","d5".."d1","final_raw", "g_<name>")
  * as fp32 NCHW into out (may be NULL to query the shape only). */
 int salt_get_activation(salt_engine* h, const char* name, float* out_nchw, int shape[4], void* stream);

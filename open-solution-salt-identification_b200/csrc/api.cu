@@ -105,6 +105,42 @@ int salt_predict(salt_engine* h, const float* logits, const float* logits_flip, 
     if (crop > c.H) return fail("salt_predict: crop larger than the network input");
     SALT_TRY("salt_predict", k_predict((cudaStream_t)stream, logits, logits_flip, batch, c.num_classes, c.H, crop, threshold, probs, mask));
 }
+int salt_adapt_tiles(const uint8_t* tiles, int batch, int tile_h, int tile_w, int size, float mean0, float std0, int hflip,
+                     float* x_nchw, void* stream) {
+    if (require_gpu()) return 1;
+    if (batch < 0 || tile_h < 1 || tile_w < 1 || size < 2 || tile_h > size || tile_w > size)
+        return fail("salt_adapt_tiles: tile must be non-empty and fit into the padded size");
+    if (batch == 0) return 0;
+    if (!tiles || !x_nchw) return fail("salt_adapt_tiles: null argument");
+    SALT_TRY("salt_adapt_tiles", k_adapt_tiles((cudaStream_t)stream, tiles, batch, make_tile_geom(tile_h, tile_w, size, mean0, std0, hflip != 0), x_nchw));
+}
+int salt_forward_tiles(salt_engine* h, const uint8_t* tiles, int batch, int tile_h, int tile_w, float mean0, float std0, int hflip,
+                       float* logits, int train, void* stream) {
+    if (require_gpu()) return 1;
+    if (!tiles || !logits) return fail("salt_forward_tiles: null argument");
+    SALT_TRY("salt_forward_tiles", h->e->forward_tiles(tiles, batch, make_tile_geom(tile_h, tile_w, h->e->config().H, mean0, std0, hflip != 0),
+                                                       logits, train != 0, (cudaStream_t)stream));
+}
+int salt_rle_encode(const uint8_t* mask, int batch, int height, int width, int cap_runs, int32_t* runs, int32_t* nruns, void* stream) {
+    if (require_gpu()) return 1;
+    if (batch < 0 || height < 1 || width < 1 || cap_runs < 1) return fail("salt_rle_encode: bad shape");
+    if (batch == 0) return 0;
+    if (!mask || !runs || !nruns) return fail("salt_rle_encode: null argument");
+    SALT_TRY("salt_rle_encode", k_rle_encode((cudaStream_t)stream, mask, batch, height, width, cap_runs, runs, nruns));
+}
+int salt_validation_counts(const float* logits, const float* logits_flip, int batch, int classes, int size, int crop,
+                           const uint8_t* gt, const double* thresholds, int nthr, int32_t* inter, int32_t* pred, int32_t* gtsum,
+                           void* stream) {
+    if (require_gpu()) return 1;
+    if (batch == 0) return 0;
+    if (!logits || !gt || !thresholds || !inter || !pred || !gtsum) return fail("salt_validation_counts: null argument");
+    if (classes < 2) return fail("salt_validation_counts: the salt map is class 1, needs >= 2 classes (postprocessing.py:41-43)");
+    if (nthr < 1 || nthr > 32) return fail("salt_validation_counts: 1..32 thresholds");
+    if (crop < 1 || crop > size) return fail("salt_validation_counts: crop larger than the network output");
+    if (batch == 0) return 0;
+    SALT_TRY("salt_validation_counts", k_validation_counts((cudaStream_t)stream, logits, logits_flip, batch, classes, size, crop, gt,
+                                                           thresholds, nthr, inter, pred, gtsum));
+}
 int salt_get_activation(salt_engine* h, const char* name, float* out, int shape[4], void* stream) {
     try {
         if (!h->e->get_activation(name, out, shape, (cudaStream_t)stream)) return fail(std::string("salt_get_activation: unknown tensor ") + name);

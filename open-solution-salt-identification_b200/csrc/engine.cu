@@ -473,9 +473,21 @@ void Engine::forward(const float* x_nchw, int B, float* logits_nchw, bool train,
     if (!params_) throw std::runtime_error("engine not bound");
     if (B < 1 || B > cfg_.max_batch) throw std::runtime_error("batch size exceeds the engine's max_batch");
     B_ = B;
+    k_stem_im2col(st, cfg_.dt, x_nchw, x4_.p, B, cfg_.H, cfg_.W);
+    forward_body(B, logits_nchw, train, st);
+}
+void Engine::forward_tiles(const uint8_t* tiles, int B, const TileGeom& g, float* logits_nchw, bool train, cudaStream_t st) {
+    if (!params_) throw std::runtime_error("engine not bound");
+    if (B < 1 || B > cfg_.max_batch) throw std::runtime_error("batch size exceeds the engine's max_batch");
+    if (cfg_.H != cfg_.W || g.S != cfg_.H) throw std::runtime_error("tile adapter: network input must be square and equal to the padded size");
+    if (g.th < 1 || g.tw < 1 || g.th > g.S || g.tw > g.S) throw std::runtime_error("tile adapter: tile larger than the network input");
+    B_ = B;
+    k_stem_im2col_tiles(st, cfg_.dt, tiles, x4_.p, B, g);
+    forward_body(B, logits_nchw, train, st);
+}
+void Engine::forward_body(int B, float* logits_nchw, bool train, cudaStream_t st) {
     if (packed_dirty_) pack_all(st);
     if (train) k_zero(st, stats_arena_, sizeof(double) * stats_doubles_);
-    k_stem_im2col(st, cfg_.dt, x_nchw, x4_.p, B, cfg_.H, cfg_.W);
     Tensor x4 = view(x4_), sraw = view(stem_raw_);
     conv_fwd(stem_, x4, sraw, &stem_bn_, train, st);
     k_bn_apply(st, sraw, stem_bn_.scale, stem_bn_.shift, nullptr, nullptr, nullptr, true, view(stem_out_.t));

@@ -94,6 +94,9 @@ public:
 
     void bind(float* params, float* grads, float* m, float* v, float* buffers, void* ws, size_t ws_bytes);
     void forward(const float* x_nchw, int B, float* logits_nchw, bool train, cudaStream_t st);
+    // same network, input given as raw u8 tiles [B][th][tw]: the loader's pad / normalise / depth-channel adapter is fused
+    // into the stem's im2col
+    void forward_tiles(const uint8_t* tiles, int B, const TileGeom& g, float* logits_nchw, bool train, cudaStream_t st);
     void backward(const float* dlogits_nchw, cudaStream_t st);
     void adam(float lr, float wd, float b1, float b2, float eps, int step, float grad_scale, cudaStream_t st);
     void mark_params_dirty() { packed_dirty_ = true; }
@@ -163,6 +166,7 @@ private:
     UnpackDesc* d_unpack_ = nullptr; int* d_unpack_start_ = nullptr; int unpack_layers_ = 0, unpack_blocks_ = 0, unpack_max_rs_ = 1;
     bool unpack_table_dirty_ = false;
     bool trained_forward_ = false;
+    void forward_body(int B, float* logits_nchw, bool train, cudaStream_t st);
     int B_ = 0;
 
     // network

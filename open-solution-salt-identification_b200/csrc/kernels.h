@@ -30,6 +30,29 @@ void k_input_nchw_to_nhwc4(cudaStream_t st, DType dt, const float* x, void* out,
 void k_stem_im2col(cudaStream_t st, DType dt, const float* x, void* patches, int B, int H, int W);
 void k_zero(cudaStream_t st, void* p, size_t bytes);
 
+// -------------------------------------------------------------------- data formats either side of the network (kernels_io.cu)
+// raw u8 tile [th][tw] -> network input [3][S][S]: edge pad (top/left offsets as utils.py:308-313), /255, normalise, depth channels
+struct TileGeom {
+    int th, tw, S, top, left, hflip;
+    float mean0, std0;         // only channel 0 survives AddDepthChannels (utils.py:494-500)
+    double lin_step;           // 1/(S-1), the float64 step of np.linspace(0, 1, S)
+};
+static inline TileGeom make_tile_geom(int th, int tw, int S, float mean0, float std0, bool hflip) {
+    TileGeom g;
+    g.th = th; g.tw = tw; g.S = S; g.hflip = hflip ? 1 : 0; g.mean0 = mean0; g.std0 = std0;
+    g.top = (S - th) / 2;                      // get_crop_pad_sequence: top = int(v/2)
+    g.left = (S - tw) - (S - tw) / 2;          //                        left = h - int(h/2)
+    g.lin_step = 1.0 / (double)(S - 1);
+    return g;
+}
+void k_adapt_tiles(cudaStream_t st, const uint8_t* tiles, int B, const TileGeom& g, float* x_nchw);
+void k_stem_im2col_tiles(cudaStream_t st, DType dt, const uint8_t* tiles, void* patches, int B, const TileGeom& g);
+// column-major run-length encoding of u8 masks [B][H][W] (utils.py:99-111); runs int32 [B][cap][2] = (start from 1, length)
+void k_rle_encode(cudaStream_t st, const uint8_t* mask, int B, int H, int W, int cap, int* runs, int* nruns);
+// per image and threshold: |pred & gt|, |pred| (pred = sigmoid(logit[1]) cropped to T x T > thr), and |gt|; nthr <= 32
+void k_validation_counts(cudaStream_t st, const float* logits, const float* logits_flip, int B, int K, int S, int T,
+                         const uint8_t* gt, const double* thresholds, int nthr, int* inter, int* pred, int* gtsum);
+
 struct BNRef {                 // device pointers describing one BatchNorm layer at run time
     int C;
     const float *gamma, *beta;

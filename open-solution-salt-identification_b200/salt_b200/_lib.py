@@ -53,6 +53,10 @@ PROTOTYPES = {
     'salt_backward': (_i, [_vp, _fp, _vp]),
     'salt_adam_step': (_i, [_vp, _f, _f, _f, _f, _f, _i, _f, _vp]),
     'salt_predict': (_i, [_vp, _fp, _fp, _i, _i, _f, _fp, _vp, _vp]),
+    'salt_adapt_tiles': (_i, [_vp, _i, _i, _i, _i, _f, _f, _i, _fp, _vp]),
+    'salt_forward_tiles': (_i, [_vp, _vp, _i, _i, _i, _f, _f, _i, _fp, _i, _vp]),
+    'salt_rle_encode': (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    'salt_validation_counts': (_i, [_fp, _fp, _i, _i, _i, _i, _vp, C.POINTER(C.c_double), _i, _vp, _vp, _vp, _vp]),
     'salt_get_activation': (_i, [_vp, C.c_char_p, _fp, C.POINTER(_i), _vp]),
     'salt_launch_count': (C.c_ulonglong, []),
     'salt_profile_enable': (_i, [_vp, _i]),

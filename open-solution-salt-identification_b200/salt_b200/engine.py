@@ -123,6 +123,20 @@ class UNetEngine:
             self.num_batches_tracked += 1
         return out
 
+    def forward_tiles(self, tiles, train=False, out=None, hflip=False, mean0=0.485, std0=0.229):
+        """tiles: uint8 CUDA tensor [B,h,w] (raw grey tiles) -> logits fp32 [B,num_classes,S,S].  The reference loader's
+        pad / normalise / depth-channel adapter (loaders.py:607-612, utils.py:494-500, augmentation.py:247-281) runs fused
+        into the stem's im2col kernel; mean0/std0 default to reference main.py:55-56."""
+        assert tiles.is_cuda and tiles.dtype == torch.uint8 and tiles.is_contiguous() and tiles.dim() == 3
+        b, th, tw = tiles.shape
+        if out is None:
+            out = torch.empty((b, self.num_classes, self.size, self.size), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.salt_forward_tiles(self.h, _ptr(tiles), b, th, tw, mean0, std0, int(hflip), _ptr(out), int(train),
+                                               self._stream()))
+        if train:
+            self.num_batches_tracked += 1
+        return out
+
     def loss_lovasz(self, logits, target, dlogits=None):
         if dlogits is None:
             dlogits = torch.empty_like(logits)

@@ -166,6 +166,113 @@ def run_case(tag, depth, batch, size, wseed, dseed):
     print('wrote', tag, {k: getattr(v, 'shape', None) for k, v in out.items() if k.startswith('lo')})
 
 
+def io_inputs():
+    """Seeded inputs of the I/O fixture (regenerated by the tests; only reference OUTPUTS are stored)."""
+    rng = np.random.default_rng(2024)
+    tiles = synth.synth_tiles_u8(3, 101, 77)                                   # the competition's tile size -> 128
+    tiles_odd = rng.integers(0, 256, (2, 50, 37), dtype=np.uint8)              # ragged tile -> 64 (odd pads both ways)
+    masks = []
+    for kind in range(8):
+        m = np.zeros((101, 101), np.uint8)
+        if kind == 1:
+            m[:] = 1                                                           # full: one run of 10201
+        elif kind == 2:
+            m[100, 3] = 1; m[0, 4] = 1                                         # run crossing a column boundary
+        elif kind == 3:
+            m[::2, :] = 1                                                      # many runs; (101*101+1)/2 = 5101 of length 1
+            m = (np.arange(101 * 101).reshape(101, 101).T % 2 == 0).astype(np.uint8)
+        elif kind == 4:
+            m[0, 0] = 1; m[100, 100] = 1                                       # first and last pixel
+        elif kind >= 5:
+            m = (rng.random((101, 101)) < (0.1, 0.5, 0.9)[kind - 5]).astype(np.uint8)
+        masks.append(m)
+    masks = np.stack(masks)
+    logits = (rng.standard_normal((6, 2, 128, 128)) * 1.5).astype(np.float32)
+    logits[:, 1] += np.linspace(-2, 2, 128, dtype=np.float32)[None, None, :]   # a salt/no-salt edge
+    logits[4, 1] = -9.0                                                        # empty prediction
+    y_true = np.zeros((6, 101, 101), np.uint8)
+    y_true[:, :, 55:] = 1
+    y_true[1] = (rng.random((101, 101)) < 0.5)
+    y_true[3] = 0                                                              # empty truth, non-empty prediction
+    y_true[4] = 0                                                              # both empty
+    y_true[5, :, :] = 1
+    return dict(tiles=tiles, tiles_odd=tiles_odd, masks=masks, logits=logits, y_true=y_true)
+
+
+def make_io_golden():
+    """tests/golden/io_cases.npz: outputs of the UNMODIFIED reference functions for SURVEY.md 8(f) N1-N3."""
+    from PIL import Image
+    from torchvision import transforms
+    from oracle import io_oracle
+    ref_shims.install()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        from common_blocks import utils as ref_utils
+        from common_blocks import metrics as ref_metrics
+        from common_blocks import postprocessing as ref_post
+    inp = io_inputs()
+    out = {}
+
+    # ---- N2 tile adapter: torchvision transforms of loaders.py:607-612 + the reference AddDepthChannels / pad split
+    tf = transforms.Compose([transforms.Grayscale(num_output_channels=3), transforms.ToTensor(),
+                             transforms.Normalize(mean=synth.MEAN, std=synth.STD), ref_utils.AddDepthChannels()])
+
+    def ref_adapt(tiles, size, flip):
+        res = []
+        for tile in tiles:
+            if flip:
+                tile = np.fliplr(tile)                                         # augmentation.py:146-147
+            top, right, bottom, left = ref_utils.get_crop_pad_sequence(size - tile.shape[0], size - tile.shape[1])
+            padded = np.pad(tile, ((top, bottom), (left, right)), mode='edge')  # imgaug iaa.Pad(px=(t,r,b,l), pad_mode='edge')
+            res.append(tf(Image.fromarray(padded)).numpy())
+        return np.stack(res)
+    for key, tiles, size in (('adapt', inp['tiles'], 128), ('adapt_odd', inp['tiles_odd'], 64)):
+        for flip in (0, 1):
+            ref = ref_adapt(tiles, size, flip)
+            mine = io_oracle.adapt_tiles_hflip(tiles, size) if flip else io_oracle.adapt_tiles(tiles, size)
+            assert mine.dtype == ref.dtype and (mine == ref).all(), 'tile adapter restatement is not bit-exact (%s flip %d)' % (key, flip)
+            out['%s_flip%d' % (key, flip)] = ref
+
+    # ---- N3 run-length encoding (utils.py:99-111) and its inverse (utils.py:114-132)
+    flat, lens = [], []
+    for m in inp['masks']:
+        ref = ref_utils.run_length_encoding(m)
+        assert ref == io_oracle.run_length_encoding(m)
+        if ref:
+            back = ref_utils.run_length_decoding(' '.join(str(v) for v in ref), m.shape)
+            assert (back == m).all()
+        flat.extend(ref); lens.append(len(ref))
+    out['rle_flat'] = np.asarray(flat, np.int64)
+    out['rle_lens'] = np.asarray(lens, np.int64)
+
+    # ---- N1 validation sweep: callbacks.py:499-527 replayed with the reference's sigmoid / crop_image / binarize / metrics
+    probs = [ref_utils.sigmoid(np.squeeze(m)) for m in inp['logits']]
+    y_true = list(inp['y_true'])
+    iout_best, threshold_best, seen = 0.0, 0.5, []
+    all_iout = []
+    for thr in np.linspace(0.5, 0.3, 21):
+        y_pred = [ref_post.binarize(ref_post.crop_image(p, (101, 101)), thr) for p in probs]
+        all_iout.append(ref_metrics.intersection_over_union_thresholds(y_true, y_pred))
+    for thr, sc in zip(np.linspace(0.5, 0.3, 21), all_iout):
+        seen.append(sc)
+        if sc > iout_best:
+            iout_best, threshold_best = sc, thr
+        else:
+            break
+    y_pred = [ref_post.binarize(ref_post.crop_image(p, (101, 101)), threshold_best) for p in probs]
+    out['val_threshold'] = np.float64(threshold_best)
+    out['val_iout'] = np.float64(ref_metrics.intersection_over_union_thresholds(y_true, y_pred))
+    out['val_iou'] = np.float64(ref_metrics.intersection_over_union(y_true, y_pred))
+    out['val_iout_all'] = np.asarray(all_iout, np.float64)
+    out['val_pred_best'] = np.stack(y_pred).astype(np.uint8)
+    mine = io_oracle.validation_sweep(inp['logits'], y_true)
+    assert mine['threshold'] == float(threshold_best) and abs(mine['iout'] - out['val_iout']) < 1e-12 \
+        and abs(mine['iou'] - out['val_iou']) < 1e-12, (mine, threshold_best, out['val_iout'], out['val_iou'])
+    assert np.allclose(mine['iouts_seen'], seen, atol=1e-12)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, 'io_cases.npz'), **out)
+    print('wrote io_cases', {k: getattr(v, 'shape', None) for k, v in out.items()})
+
+
 def main():
     if not ref_shims.available():
         sys.exit('reference tree not available; fixtures can only be regenerated in the build container')
@@ -174,6 +281,8 @@ def main():
     for case in CASES:
         if not only or case[0] in only:
             run_case(*case)
+    if not only or 'io_cases' in only:
+        make_io_golden()
 
 
 if __name__ == '__main__':

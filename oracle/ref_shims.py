@@ -102,6 +102,39 @@ class Model(BaseTransformer):
         torch.save(self.model.state_dict(), filepath)
 
 
+def _install_cocomask_stub():
+    """pycocotools.mask as used by utils.py:292-305 / metrics.py:21-35 (package absent): `encode` of a dense uint8 mask and
+    `iou` of two lists of such encodings with iscrowd = 0, i.e. |a & b| / |a | b|.  Dense bytes stand in for the RLE string."""
+    import numpy as np
+    m = sys.modules['pycocotools.mask']
+    if not isinstance(m, _StubModule):
+        return
+
+    def encode(mask):
+        mask = np.asarray(mask)
+        return {'size': list(mask.shape), 'counts': bytes(np.ascontiguousarray(mask).astype(np.uint8).tobytes())}
+
+    def _dense(seg):
+        c = seg['counts']
+        c = c.encode('UTF-8') if isinstance(c, str) else c
+        return np.frombuffer(c, dtype=np.uint8).reshape(seg['size']) != 0
+
+    def iou(dt, gt, iscrowd):
+        # cocoapi maskApi.c rleIou: rows follow the first list, columns the second
+        if len(dt) == 0 or len(gt) == 0:
+            return []
+        out = np.zeros((len(dt), len(gt)))
+        for i, a in enumerate(dt):
+            for j, b in enumerate(gt):
+                a_, b_ = _dense(a), _dense(b)
+                u = np.logical_or(a_, b_).sum()
+                out[i, j] = np.logical_and(a_, b_).sum() / u if u else 0.0
+        return out
+
+    m.__dict__['encode'] = encode
+    m.__dict__['iou'] = iou
+
+
 def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, 'common_blocks'))
 
@@ -134,6 +167,7 @@ def install():
         # encoders.py:52-53 looks the constructor up in the package __dict__; the package is absent, use the restatement
         from . import senet_restated
         sys.modules['pretrainedmodels'].__dict__['se_resnet50'] = senet_restated.se_resnet50
+    _install_cocomask_stub()
     sys.modules['steppy.base'].BaseTransformer = BaseTransformer
     sys.modules['toolkit.pytorch_transformers.models'].Model = Model
     import joblib
