@@ -241,11 +241,34 @@ def run_ours(args):
             lo = eng.forward(x_d, train=False)
             lf = eng.forward(x_flip, train=False)
             return eng.predict(lo, lf, crop=101, threshold=0.5, want_probs=False)
-        for fn in (step_lovasz, infer_tta):
+        # SURVEY.md 8(f) N2 + N3 end to end: raw u8 101x101 tiles in pinned host memory -> H2D (1.3 MB instead of 25 MB) ->
+        # adapter fused into the stem (orig + h-flipped tile) -> fused sigmoid/un-flip/mean/crop/threshold -> column-major RLE
+        # on the device -> D2H of the run table; and N1: the 21-threshold validation sweep counts for the same batch
+        from salt_b200 import io_ops, validation
+        tiles_h = torch.from_numpy(synth.synth_tiles_u8(B, 101, 4321 + ctx.rank)).pin_memory()
+        gt_d = (t_d[:, 1, 13:114, 14:115] > 0.5).to(torch.uint8).contiguous()
+        d2h = {}
+
+        def infer_tiles_rle():
+            tl = tiles_h.to(dev, non_blocking=True)
+            lo = eng.forward_tiles(tl, train=False)
+            lf = eng.forward_tiles(tl, train=False, hflip=True)
+            _, mask = eng.predict(lo, lf, crop=101, threshold=0.5, want_probs=False)
+            runs, nruns = io_ops.rle_encode_device(mask, cap_runs=256)
+            r, n = runs.cpu(), nruns.cpu()
+            d2h['bytes'] = r.numel() * 4 + n.numel() * 4
+            return r, n
+
+        def validation_sweep():
+            lo = eng.forward(x_d, train=False)
+            return validation.select_threshold(*[a.cpu().numpy() for a in validation.validation_counts(lo, gt_d)])
+        for fn in (step_lovasz, infer_tta, infer_tiles_rle, validation_sweep):
             for _ in range(2):
                 fn()
         ms_lv = timed(step_lovasz, 5)
         ms_inf = timed(infer_tta, 5)
+        ms_rle = timed(infer_tiles_rle, 5)
+        ms_val = timed(validation_sweep, 5)
         se50 = None
         if not args.no_se50:
             se50 = se50_train_step(ctx, timed)
@@ -253,6 +276,13 @@ def run_ours(args):
                  'inference_tta_hflip': {'value': B * ctx.world * 5 / (ms_inf / 1e3), 'unit': 'tiles/s', 'ms_per_batch': ms_inf / 5,
                                          'what': '%d tiles per GPU per pass = %d network inputs (orig + h-flip), fused sigmoid/un-flip/mean/crop/threshold -> u8 masks' % (B, 2 * B)}}
 
+        extra['inference_u8_tiles_to_rle_e2e'] = {
+            'value': B * ctx.world * 5 / (ms_rle / 1e3), 'unit': 'tiles/s', 'ms_per_batch': ms_rle / 5,
+            'h2d_bytes_per_batch': int(tiles_h.numel()), 'd2h_bytes_per_batch': int(d2h.get('bytes', 0)),
+            'what': 'pinned u8 101x101 tiles -> fused adapter+stem (orig + h-flip) -> TTA mean/crop/threshold -> device RLE -> host run table'}
+        extra['validation_sweep'] = {
+            'value': B * ctx.world * 5 / (ms_val / 1e3), 'unit': 'tiles/s', 'ms_per_batch': ms_val / 5,
+            'what': 'eval forward + 21-threshold intersection/prediction counts in one kernel + host IoU/IoUT selection (callbacks.py:499-527)'}
         if se50:
             extra['seresnet50_256_train_step'] = se50
 
@@ -276,6 +306,7 @@ def run_ours(args):
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': args.precision, 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'global_batch': B * n, 'loss': args.loss, 'parallelism': 'dp%d' % n,
+                   'cuda_graphs': os.environ.get('SALT_ENGINE_GRAPH', '1') != '0',
                    'l2': 'per-step working set (saved activations of %d images, several GB) is far larger than the 126 MB L2; no explicit flush' % B},
         'clocks': clocks,
         'e2e': {'value': e2e, 'unit': 'images/s', 'ms_per_step': ms_e2e / args.steps,

@@ -38,7 +38,8 @@ struct RowsParams {
     int tiles_x, tiles_y, tiles_co, total_tiles;
     int B, Ho, Wo, Co, Ca, cblks, pad;
     int accumulate;
-    int debug;                 // timing experiments only (env SALT_TC_DEBUG): 1 = skip loads, 4 = skip stores+stats, 8 = skip stats, 16 = skip stores
+    int debug;                 // timing experiments only (env SALT_TC_DEBUG): 1 = skip loads, 4 = skip stores+stats, 8 = skip stats, 16 = skip stores,
+                               // 32 = per-tile butterflies for the BatchNorm sums also on narrow layers (the pre-round-1b epilogue)
     const float* bias;
     double* stats;
     bf16* out;
@@ -56,6 +57,122 @@ template <int BN> struct RowsCfg {
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
     static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256 + 8 * 2 * BN * 4;      // + per-epilogue-warp BN statistics
 };
+
+template <int BN, bool NARROW>
+__device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int warp, const int lane, const uint32_t tmem_base,
+                                      const uint32_t tfull0, const uint32_t tempty0, float* s_stats) {
+    // Epilogue, 8 warps (2..9).  Warp w may touch TMEM lanes 32*(w%4)..+31;
+    // the two warps of a lane quarter split the 32-column chunks between them, so every scheduler has two epilogue warps
+    // to interleave (the shuffle/convert chains of a single warp left the issue slots idle - profiles/r1_notes.md).
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    float* my_stats = s_stats + (warp - 2) * (2 * BN);  // private per-warp accumulators: no shared-memory atomics
+    const int m = quarter * 32 + lane;                  // row of the 128-position tile: 16 rows x 8 columns
+    const int lx = m & (RW_TW - 1), ly = m >> 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    // Narrow layers (BN <= 64, one channel tile): every epilogue warp owns ONE fixed 32-column chunk for the whole kernel, so
+    // its bias lives in registers and the BatchNorm sums are accumulated per THREAD (one pixel row each) across all tiles of
+    // the CTA; the cross-lane butterfly runs once per kernel instead of once per tile.  For K = 576 layers the per-tile
+    // butterflies (62 shuffles per chunk) made the epilogue longer than the MMA phase (profiles/r1_notes.md).
+    const bool own_chunk = half < BN / 32;
+    float rs1[32], rs2[32], rbias[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { rs1[i] = 0.f; rs2[i] = 0.f; rbias[i] = 0.f; }
+    if (NARROW && own_chunk && p.bias) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rbias[i] = __ldg(p.bias + half * 32 + i);
+    }
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_co, mt = tile / p.tiles_co;
+        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, n = mt / (p.tiles_x * p.tiles_y);
+        const int x = tx * RW_TW + lx, y = ty * RW_TH + ly;
+        const bool valid = (y < p.Ho) && (x < p.Wo) && !(p.debug & (4 | 16));
+        bf16* orow = p.out + (((size_t)n * p.Ho + y) * p.Wo + x) * p.Co + nt * BN;
+        mbar_wait(tfull0 + 8 * acc, acc_phase);
+        fence_after();
+#pragma unroll 1
+        for (int ch = half; ch < BN / 32; ch += 2) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + ch * 32, v);
+            if constexpr (NARROW) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += rbias[i];
+            } else if (p.bias) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + nt * BN + ch * 32 + i);
+            }
+            if (valid) {
+                uint4* o4 = reinterpret_cast<uint4*>(orow + ch * 32);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (p.accumulate) {
+                        uint4 old = o4[q];
+                        const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float2 f = __bfloat1622float2(ob[j]);
+                            v[q * 8 + 2 * j] += f.x; v[q * 8 + 2 * j + 1] += f.y;
+                        }
+                    }
+                    uint4 pk;
+                    __nv_bfloat162 b0 = __floats2bfloat162_rn(v[q * 8 + 0], v[q * 8 + 1]);
+                    __nv_bfloat162 b1 = __floats2bfloat162_rn(v[q * 8 + 2], v[q * 8 + 3]);
+                    __nv_bfloat162 b2 = __floats2bfloat162_rn(v[q * 8 + 4], v[q * 8 + 5]);
+                    __nv_bfloat162 b3 = __floats2bfloat162_rn(v[q * 8 + 6], v[q * 8 + 7]);
+                    pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+                    o4[q] = pk;
+                }
+            }
+            if (p.stats && !(p.debug & (4 | 8))) {
+                if constexpr (NARROW) {
+                    if (valid) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { rs1[i] += v[i]; rs2[i] = fmaf(v[i], v[i], rs2[i]); }
+                    }
+                } else {
+                    float sq[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { v[i] = valid ? v[i] : 0.f; sq[i] = v[i] * v[i]; }
+                    float s1 = rows_butterfly_reduce32(v, lane);
+                    float s2 = rows_butterfly_reduce32(sq, lane);
+                    my_stats[ch * 32 + lane] += s1;
+                    my_stats[BN + ch * 32 + lane] += s2;
+                }
+            }
+        }
+        fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (p.stats && p.tiles_co > 1) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int tt = threadIdx.x - 64;
+            for (int i = tt; i < 2 * BN; i += RW_EPI_THREADS) {
+                float val = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) { val += s_stats[w8 * 2 * BN + i]; s_stats[w8 * 2 * BN + i] = 0.f; }
+                if (val != 0.f) atomicAdd(p.stats + (i < BN ? nt * BN + i : p.Co + nt * BN + (i - BN)), (double)val);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+    }
+    if (NARROW && p.stats && own_chunk) {
+        const float s1 = rows_butterfly_reduce32(rs1, lane);
+        const float s2 = rows_butterfly_reduce32(rs2, lane);
+        my_stats[half * 32 + lane] += s1;
+        my_stats[BN + half * 32 + lane] += s2;
+    }
+    if (p.stats && p.tiles_co == 1) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int tt = threadIdx.x - 64;
+        for (int i = tt; i < 2 * BN; i += RW_EPI_THREADS) {
+            float val = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) val += s_stats[w8 * 2 * BN + i];
+            atomicAdd(p.stats + (i < BN ? i : p.Co + (i - BN)), (double)val);
+        }
+    }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(RW_THREADS, 1)
@@ -145,89 +262,13 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
-        // ===================================================== epilogue: 8 warps (2..9).  Warp w may touch TMEM lanes 32*(w%4)..+31;
-        // the two warps of a lane quarter split the 32-column chunks between them, so every scheduler has two epilogue warps
-        // to interleave (the shuffle/convert chains of a single warp left the issue slots idle - profiles/r1_notes.md).
-        const int quarter = warp & 3, half = (warp - 2) >> 2;
-        float* my_stats = s_stats + (warp - 2) * (2 * BN);  // private per-warp accumulators: no shared-memory atomics
-        const int m = quarter * 32 + lane;                  // row of the 128-position tile: 16 rows x 8 columns
-        const int lx = m & (RW_TW - 1), ly = m >> 3;
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const int nt = tile % p.tiles_co, mt = tile / p.tiles_co;
-            const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, n = mt / (p.tiles_x * p.tiles_y);
-            const int x = tx * RW_TW + lx, y = ty * RW_TH + ly;
-            const bool valid = (y < p.Ho) && (x < p.Wo) && !(p.debug & (4 | 16));
-            bf16* orow = p.out + (((size_t)n * p.Ho + y) * p.Wo + x) * p.Co + nt * BN;
-            mbar_wait(tfull0 + 8 * acc, acc_phase);
-            fence_after();
-#pragma unroll 1
-            for (int ch = half; ch < BN / 32; ch += 2) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + ch * 32, v);
-                if (p.bias) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + nt * BN + ch * 32 + i);
-                }
-                if (valid) {
-                    uint4* o4 = reinterpret_cast<uint4*>(orow + ch * 32);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (p.accumulate) {
-                            uint4 old = o4[q];
-                            const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float2 f = __bfloat1622float2(ob[j]);
-                                v[q * 8 + 2 * j] += f.x; v[q * 8 + 2 * j + 1] += f.y;
-                            }
-                        }
-                        uint4 pk;
-                        __nv_bfloat162 b0 = __floats2bfloat162_rn(v[q * 8 + 0], v[q * 8 + 1]);
-                        __nv_bfloat162 b1 = __floats2bfloat162_rn(v[q * 8 + 2], v[q * 8 + 3]);
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(v[q * 8 + 4], v[q * 8 + 5]);
-                        __nv_bfloat162 b3 = __floats2bfloat162_rn(v[q * 8 + 6], v[q * 8 + 7]);
-                        pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
-                        pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
-                        o4[q] = pk;
-                    }
-                }
-                if (p.stats && !(p.debug & (4 | 8))) {
-                    float sq[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) { v[i] = valid ? v[i] : 0.f; sq[i] = v[i] * v[i]; }
-                    float s1 = rows_butterfly_reduce32(v, lane);
-                    float s2 = rows_butterfly_reduce32(sq, lane);
-                    my_stats[ch * 32 + lane] += s1;
-                    my_stats[BN + ch * 32 + lane] += s2;
-                }
-            }
-            fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-            if (p.stats && p.tiles_co > 1) {
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                const int tt = threadIdx.x - 64;
-                for (int i = tt; i < 2 * BN; i += RW_EPI_THREADS) {
-                    float val = 0.f;
-#pragma unroll
-                    for (int w8 = 0; w8 < 8; ++w8) { val += s_stats[w8 * 2 * BN + i]; s_stats[w8 * 2 * BN + i] = 0.f; }
-                    if (val != 0.f) atomicAdd(p.stats + (i < BN ? nt * BN + i : p.Co + nt * BN + (i - BN)), (double)val);
-                }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-            }
+        // ===================================================== epilogue: 8 warps (2..9)
+        bool narrow = false;
+        if constexpr (BN <= 64) narrow = p.tiles_co == 1 && !(p.debug & 32);
+        if constexpr (BN <= 64) {
+            if (narrow) rows_epilogue<BN, true>(p, warp, lane, tmem_base, tfull0, tempty0, s_stats);
         }
-        if (p.stats && p.tiles_co == 1) {
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const int tt = threadIdx.x - 64;
-            for (int i = tt; i < 2 * BN; i += RW_EPI_THREADS) {
-                float val = 0.f;
-#pragma unroll
-                for (int w8 = 0; w8 < 8; ++w8) val += s_stats[w8 * 2 * BN + i];
-                atomicAdd(p.stats + (i < BN ? i : p.Co + (i - BN)), (double)val);
-            }
-        }
+        if (!narrow) rows_epilogue<BN, false>(p, warp, lane, tmem_base, tfull0, tempty0, s_stats);
     }
     fence_before();
     __syncthreads();

@@ -92,5 +92,14 @@ def check(status):
         raise SaltEngineError(load().salt_last_error().decode())
 
 
+_replayed = 0
+
+
+def count_replayed(n):
+    """Kernel launches executed by CUDA-graph replays (the library counter only sees launches issued through its host code)."""
+    global _replayed
+    _replayed += int(n)
+
+
 def launch_count():
-    return int(load().salt_launch_count())
+    return int(load().salt_launch_count()) + _replayed

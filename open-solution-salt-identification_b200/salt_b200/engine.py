@@ -59,6 +59,7 @@ class UNetEngine:
         _lib.check(self.lib.salt_bind(h, _ptr(self.params), _ptr(self.grads), _ptr(self.adam_m), _ptr(self.adam_v),
                                       _ptr(self.buffers), _ptr(self.workspace), ws))
         self.step_count = 0
+        self.profiling = False
         self.num_batches_tracked = 0
         self._init_buffers()
 
@@ -178,6 +179,7 @@ class UNetEngine:
         return probs, mask
 
     def profile(self, on):
+        self.profiling = bool(on)
         _lib.check(self.lib.salt_profile_enable(self.h, int(on)))
 
     def profile_read(self):
