@@ -61,6 +61,17 @@ class DataParallelContext:
         dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=self.group)
         return 1.0 / self.world
 
+    def gather_rows(self, *arrays):
+        """Concatenate per-rank numpy arrays along axis 0 in rank order on every rank (validation counts: the images of a
+        validation epoch are sharded across ranks, the threshold sweep needs all of them; a few KB, once per epoch)."""
+        if self.world == 1:
+            return arrays
+        import numpy as np
+        import torch.distributed as dist
+        parts = [None] * self.world
+        dist.all_gather_object(parts, arrays, group=self.group)
+        return tuple(np.concatenate([p[i] for p in parts], axis=0) for i in range(len(arrays)))
+
     def max_over_ranks(self, value):
         if self.world == 1:
             return float(value)

@@ -278,9 +278,16 @@ class SegmentationModel(Model):
         b = int(data[0].shape[0])
         if self._graph_enabled() and len(data) == 2 and b in self._graph_state()['graphs']:
             st = self._graph_state()               # host -> static device buffers, no intermediate tensor
+            cur = torch.cuda.current_stream(dev)
+            if 'copy_stream' not in st:
+                st['copy_stream'], st['t_ready'] = torch.cuda.Stream(dev), torch.cuda.Event()
+            # the target is not needed before the loss: its H2D copy runs on a side stream under the forward pass
+            st['copy_stream'].wait_stream(cur)     # the previous step's loss kernels have finished reading st['t']
+            with torch.cuda.stream(st['copy_stream']):
+                st['t'][:b].copy_(torch.as_tensor(data[1]), non_blocking=True)
+                st['t_ready'].record()
             st['x'][:b].copy_(torch.as_tensor(data[0]), non_blocking=True)
-            st['t'][:b].copy_(torch.as_tensor(data[1]), non_blocking=True)
-            return self.train_step_device(st['x'][:b], [st['t'][:b]])
+            return self._train_step_graph(b, wait=st['t_ready'])
         X = torch.as_tensor(data[0]).to(dev, torch.float32, non_blocking=True).contiguous()
         targets = [torch.as_tensor(t).to(dev, torch.float32, non_blocking=True).contiguous() for t in data[1:]]
         return self.train_step_device(X, targets)
@@ -322,13 +329,16 @@ class SegmentationModel(Model):
         eng.num_batches_tracked -= 1              # capture does not execute
         st['graphs'][b] = (gf, gb, n1 - n0, n2 - n1)
 
-    def _train_step_graph(self, b):
+    def _train_step_graph(self, b, wait=None):
         from . import _lib
         eng, st = self.engine, self._graph_state()
         gf, gb, nf, nb = st['graphs'][b]
         (name, loss_function, weight) = self.loss_function[0]
+        self.model.train()
         gf.replay()
         eng.num_batches_tracked += 1
+        if wait is not None:
+            torch.cuda.current_stream(eng.device).wait_event(wait)
         loss_function.dlogits = st['dlogits'][:b]
         batch_loss = loss_function(st['logits'][:b], st['t'][:b])
         if weight != 1.0:

@@ -68,8 +68,9 @@ class ValidationScorer:
     best-threshold selection: thresholds walk from 0.5 down to 0.3 and stop at the first one that does not improve IoUT
     (callbacks.py:502-512)."""
 
-    def __init__(self, thresholds=SWEEP_THRESHOLDS):
+    def __init__(self, thresholds=SWEEP_THRESHOLDS, dp=None):
         self.thresholds = np.asarray(thresholds, dtype=np.float64)
+        self.dp = dp                 # salt_b200.dist.DataParallelContext: ranks score disjoint shards of the validation set
         self._parts = []
 
     def update(self, logits, gt, logits_flip=None):
@@ -79,6 +80,8 @@ class ValidationScorer:
         inter = torch.cat([p[0] for p in self._parts]).cpu().numpy()
         pred = torch.cat([p[1] for p in self._parts]).cpu().numpy()
         gts = torch.cat([p[2] for p in self._parts]).cpu().numpy()
+        if self.dp is not None and self.dp.world > 1:
+            inter, pred, gts = self.dp.gather_rows(inter, pred, gts)
         return inter, pred, gts
 
     def result(self):

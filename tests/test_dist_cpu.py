@@ -28,10 +28,22 @@ WORKER = textwrap.dedent('''
         bad = False
     except ValueError:
         bad = True
+    # validation epoch sharded over the ranks: each scores its half, the sweep sees all images (rank order)
+    import numpy as np
+    from salt_b200 import validation
+    sys.path.insert(0, %r)
+    from oracle import io_oracle
+    from oracle.make_golden import io_inputs
+    inp = io_inputs()
+    lo6, hi6 = ctx.shard(6)
+    counts = io_oracle.validation_counts(inp['logits'][lo6:hi6], inp['y_true'][lo6:hi6])
+    sc = validation.ValidationScorer(dp=ctx)
+    sc._parts.append(tuple(torch.from_numpy(np.ascontiguousarray(c)) for c in counts))
+    res = sc.result()
     print(json.dumps(dict(rank=ctx.rank, shard=[lo, hi], gsum=float(grads[0]), gmean=float(grads[0] * scale),
-                          p1=float(params[1]), mx=mx, bad=bad)))
+                          p1=float(params[1]), mx=mx, bad=bad, thr=res['threshold'], iout=res['iout'], iou=res['iou'])))
     torch.distributed.destroy_process_group()
-''') % ROOT
+''') % (ROOT, ROOT)
 
 
 def _free_port():
@@ -63,6 +75,11 @@ def test_data_parallel_context_gloo_world2(tmp_path):
         assert d['p1'] == 1.0                                 # rank 0's parameters everywhere
         assert d['mx'] == 11.0                                # max over ranks (timing reduction)
         assert d['bad']                                       # uneven global batches are rejected
+    import numpy as np
+    gold = np.load(os.path.join(ROOT, 'tests', 'golden', 'io_cases.npz'))
+    for d in outs:                                            # both ranks select the reference's threshold / scores
+        assert d['thr'] == float(gold['val_threshold'])
+        assert abs(d['iout'] - float(gold['val_iout'])) < 1e-12 and abs(d['iou'] - float(gold['val_iou'])) < 1e-12
 
 
 def test_single_process_context_is_identity():
