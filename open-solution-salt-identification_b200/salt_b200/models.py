@@ -260,7 +260,7 @@ class SegmentationModel(Model):
         batch_gen, steps = datagen
         for epoch_id in range(self.training_config['epochs']):
             self.callbacks.on_epoch_begin()
-            for batch_id, data in enumerate(batch_gen):
+            for batch_id, data in enumerate(self._prefetch(batch_gen)):
                 self.callbacks.on_batch_begin()
                 metrics = self._fit_loop(data)
                 self.callbacks.on_batch_end(metrics=metrics)
@@ -272,8 +272,61 @@ class SegmentationModel(Model):
         self.callbacks.on_train_end()
         return self
 
+    # ------------------------------------------------------------------ input prefetch (fit only)
+    # models.py:106-117 copies every batch to the GPU at the top of the step.  Here the copy of batch i+1 is issued on a side
+    # stream, into one of two staging buffers, BEFORE step i is launched, so it runs under step i's kernels; step i+1 then
+    # starts with a device-to-device copy of X into the graph's static input (25 MB, ~10 us) and reads its target in place.
+    class _Staged:
+        __slots__ = ('b', 'slot', 'ready')
+
+    def _stage(self, data):
+        if data is None or not self._graph_enabled() or not isinstance(data, (list, tuple)) or len(data) != 2:
+            return data
+        x, t = data
+        if not (torch.is_tensor(x) and torch.is_tensor(t)) or x.is_cuda or x.dtype != torch.float32 or t.dtype != torch.float32:
+            return data
+        st, b = self._graph_state(), int(x.shape[0])
+        if b not in st['graphs']:
+            return data
+        dev = self.engine.device
+        if 'stage' not in st:
+            st['stage'] = [{'x': torch.empty_like(st['x']), 't': torch.empty_like(st['t']), 'free': None} for _ in range(2)]
+            st['stage_stream'], st['stage_next'] = torch.cuda.Stream(dev), 0
+        slot = st['stage_next']
+        st['stage_next'] ^= 1
+        buf = st['stage'][slot]
+        if buf['free'] is not None:
+            st['stage_stream'].wait_event(buf['free'])        # the step that last read this slot has finished
+        s = self._Staged()
+        s.b, s.slot, s.ready = b, slot, torch.cuda.Event()
+        with torch.cuda.stream(st['stage_stream']):
+            buf['x'][:b].copy_(x, non_blocking=True)
+            buf['t'][:b].copy_(t, non_blocking=True)
+            s.ready.record()
+        return s
+
+    def _prefetch(self, batch_gen):
+        it = iter(batch_gen)
+        cur = self._stage(next(it, None))
+        while cur is not None:
+            nxt = self._stage(next(it, None))
+            yield cur
+            cur = nxt
+
+    def _fit_staged(self, s):
+        st, dev = self._graph_state(), self.engine.device
+        buf, cur = st['stage'][s.slot], torch.cuda.current_stream(dev)
+        cur.wait_event(s.ready)
+        st['x'][:s.b].copy_(buf['x'][:s.b], non_blocking=True)
+        out = self._train_step_graph(s.b, target=buf['t'][:s.b])
+        buf['free'] = torch.cuda.Event()
+        buf['free'].record(cur)
+        return out
+
     # models.py:105-136
     def _fit_loop(self, data):
+        if isinstance(data, self._Staged):
+            return self._fit_staged(data)
         dev = self.engine.device
         b = int(data[0].shape[0])
         if self._graph_enabled() and len(data) == 2 and b in self._graph_state()['graphs']:
@@ -329,7 +382,7 @@ class SegmentationModel(Model):
         eng.num_batches_tracked -= 1              # capture does not execute
         st['graphs'][b] = (gf, gb, n1 - n0, n2 - n1)
 
-    def _train_step_graph(self, b, wait=None):
+    def _train_step_graph(self, b, wait=None, target=None):
         from . import _lib
         eng, st = self.engine, self._graph_state()
         gf, gb, nf, nb = st['graphs'][b]
@@ -340,7 +393,7 @@ class SegmentationModel(Model):
         if wait is not None:
             torch.cuda.current_stream(eng.device).wait_event(wait)
         loss_function.dlogits = st['dlogits'][:b]
-        batch_loss = loss_function(st['logits'][:b], st['t'][:b])
+        batch_loss = loss_function(st['logits'][:b], st['t'][:b] if target is None else target)
         if weight != 1.0:
             batch_loss = batch_loss * weight
             st['dlogits'][:b].mul_(weight)
