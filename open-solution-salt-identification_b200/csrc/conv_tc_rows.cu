@@ -13,6 +13,7 @@
 #include "tc_common.cuh"
 #include "conv_tc.h"
 #include <cstdlib>
+#include <algorithm>
 
 using namespace tc;
 
@@ -36,6 +37,7 @@ __device__ __forceinline__ float rows_butterfly_reduce32(float* v, int lane) {
 
 struct RowsParams {
     int tiles_x, tiles_y, tiles_co, total_tiles;
+    int m_tiles, total_groups;  // cluster mode: a group = CL consecutive pixel tiles of one channel tile (one per CTA of the cluster)
     int B, Ho, Wo, Co, Ca, cblks, pad;
     int accumulate;
     int debug;                 // timing experiments only (env SALT_TC_DEBUG): 1 = skip loads, 4 = skip stores+stats, 8 = skip stats, 16 = skip stores,
@@ -58,9 +60,50 @@ template <int BN> struct RowsCfg {
     static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256 + 8 * 2 * BN * 4;      // + per-epilogue-warp BN statistics
 };
 
-template <int BN, bool NARROW>
+// ---- thread-block-cluster helpers (weight multicast)
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA box delivered to the same shared-memory offset of every CTA in `mask`, completing bytes on the mbarrier at the same offset
+__device__ __forceinline__ void tma_load_4d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3,
+                                               uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+                 " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(mask) : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+// Work item k of this CTA.  CL == 1: tile = blockIdx.x + k*gridDim.x, channel tile fastest.  CL > 1: the CL CTAs of a cluster take
+// CL consecutive pixel tiles of ONE channel tile, so they consume identical weight stages in lockstep; a cluster whose last group
+// is short gives the surplus CTAs a clamped tile whose results are dropped (`live` = false).
+template <int CL>
+struct RowsTile { int nt, tx, ty, n; bool live; };
+template <int CL>
+__device__ __forceinline__ bool rows_tile(const RowsParams& p, int k, uint32_t rank, RowsTile<CL>& t) {
+    int mt;
+    if constexpr (CL == 1) {
+        const int tile = blockIdx.x + k * gridDim.x;
+        if (tile >= p.total_tiles) return false;
+        t.nt = tile % p.tiles_co; mt = tile / p.tiles_co; t.live = true;
+    } else {
+        const int g = blockIdx.x / CL + k * (gridDim.x / CL);
+        if (g >= p.total_groups) return false;
+        t.nt = g % p.tiles_co; mt = (g / p.tiles_co) * CL + (int)rank;
+        t.live = mt < p.m_tiles;
+        if (!t.live) mt = p.m_tiles - 1;
+    }
+    t.tx = mt % p.tiles_x; t.ty = (mt / p.tiles_x) % p.tiles_y; t.n = mt / (p.tiles_x * p.tiles_y);
+    return true;
+}
+
+template <int BN, bool NARROW, int CL>
 __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int warp, const int lane, const uint32_t tmem_base,
-                                      const uint32_t tfull0, const uint32_t tempty0, float* s_stats) {
+                                      const uint32_t tfull0, const uint32_t tempty0, float* s_stats, const uint32_t rank) {
     // Epilogue, 8 warps (2..9).  Warp w may touch TMEM lanes 32*(w%4)..+31;
     // the two warps of a lane quarter split the 32-column chunks between them, so every scheduler has two epilogue warps
     // to interleave (the shuffle/convert chains of a single warp left the issue slots idle - profiles/r1_notes.md).
@@ -81,17 +124,31 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
 #pragma unroll
         for (int i = 0; i < 32; ++i) rbias[i] = __ldg(p.bias + half * 32 + i);
     }
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int nt = tile % p.tiles_co, mt = tile / p.tiles_co;
-        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, n = mt / (p.tiles_x * p.tiles_y);
-        const int x = tx * RW_TW + lx, y = ty * RW_TH + ly;
-        const bool valid = (y < p.Ho) && (x < p.Wo) && !(p.debug & (4 | 16));
+    RowsTile<CL> t;
+    for (int k = 0; rows_tile<CL>(p, k, rank, t); ++k) {
+        const int nt = t.nt, n = t.n;
+        const int x = t.tx * RW_TW + lx, y = t.ty * RW_TH + ly;
+        const bool valid = t.live && (y < p.Ho) && (x < p.Wo) && !(p.debug & (4 | 16));
         bf16* orow = p.out + (((size_t)n * p.Ho + y) * p.Wo + x) * p.Co + nt * BN;
+        // accumulate mode (dgrad into an existing gradient): the old values of the first chunk are fetched BEFORE waiting for the
+        // accumulator, so their DRAM latency hides behind the MMA phase instead of serialising the epilogue
+        uint4 old[4];
+        const bool accum = !NARROW && p.accumulate;
+        if (accum && valid && half < BN / 32) {
+            const uint4* o4 = reinterpret_cast<const uint4*>(orow + half * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) old[q] = o4[q];
+        }
         mbar_wait(tfull0 + 8 * acc, acc_phase);
         fence_after();
 #pragma unroll 1
         for (int ch = half; ch < BN / 32; ch += 2) {
             float v[32];
+            if (accum && valid && ch != half) {
+                const uint4* o4 = reinterpret_cast<const uint4*>(orow + ch * 32);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) old[q] = o4[q];
+            }
             tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + ch * 32, v);
             if constexpr (NARROW) {
 #pragma unroll
@@ -104,9 +161,8 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
                 uint4* o4 = reinterpret_cast<uint4*>(orow + ch * 32);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    if (p.accumulate) {
-                        uint4 old = o4[q];
-                        const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
+                    if (accum) {
+                        const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old[q]);
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             float2 f = __bfloat1622float2(ob[j]);
@@ -174,7 +230,12 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
     }
 }
 
-template <int BN>
+// CL = thread-block-cluster size.  CL > 1: the CL CTAs of a cluster work on CL different pixel tiles of the same channel tile and
+// share every weight stage: each CTA fetches 1/CL of the three weight slabs and TMA-multicasts it into the shared memory of all
+// CL CTAs (map_b then has a [64 c][BN/CL n] box).  Weights are 60-75 % of the bytes a stage pulls through L2, and the L2 -> SM
+// path (~42 B/clk/SM chip-wide), not the tensor pipe, bounds these kernels (profiles/r1_notes.md).  A stage may be overwritten only
+// when ALL CTAs of the cluster have consumed it: the MMA issuer's tcgen05.commit arrives on the `empty` barrier of every CTA.
+template <int BN, int CL>
 __global__ void __launch_bounds__(RW_THREADS, 1)
 conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const RowsParams p) {
     using Cfg = RowsCfg<BN>;
@@ -193,7 +254,7 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -201,18 +262,21 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     for (int i = threadIdx.x; i < 8 * 2 * BN; i += RW_THREADS) s_stats[i] = 0.f;
     fence_before();
     __syncthreads();
+    uint32_t rank = 0;
+    if constexpr (CL > 1) { rank = cluster_ctarank(); cluster_sync_all(); }      // every CTA's barriers exist before any multicast
     fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
     const int stages_per_tile = p.cblks * 3;
+    constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
 
     if (warp == 0) {
         // ===================================================== TMA producer: one A box + one 3-tap weight box per stage
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const int nt = tile % p.tiles_co, mt = tile / p.tiles_co;
-                const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, n = mt / (p.tiles_x * p.tiles_y);
-                const int w0 = tx * RW_TW - p.pad, h0 = ty * RW_TH - p.pad;
+            RowsTile<CL> t;
+            for (int k = 0; rows_tile<CL>(p, k, rank, t); ++k) {
+                const int nt = t.nt, n = t.n;
+                const int w0 = t.tx * RW_TW - p.pad, h0 = t.ty * RW_TH - p.pad;
                 for (int cb = 0; cb < p.cblks; ++cb) {
                     for (int s = 0; s < 3; ++s) {
                         const uint32_t st = smem0 + stage * Cfg::STAGE_BYTES, fb = full0 + 8 * stage;
@@ -221,7 +285,15 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         else {
                             mbar_expect_tx(fb, Cfg::STAGE_BYTES);
                             tma_load_4d(st, &map_a, fb, cb * 64, w0 + s, h0, n);
-                            tma_load_4d(st + RW_A_BYTES, &map_b, fb, cb * 64, nt * BN, 0, s);     // (c, n, r = 0..2, s)
+                            if constexpr (CL == 1) {
+                                tma_load_4d(st + RW_A_BYTES, &map_b, fb, cb * 64, nt * BN, 0, s);     // (c, n, r = 0..2, s)
+                            } else {
+                                constexpr int PART = BN / CL;                                         // my rows of every weight slab
+#pragma unroll
+                                for (int r = 0; r < 3; ++r)
+                                    tma_load_4d_mc(st + RW_A_BYTES + r * Cfg::B_BYTES + rank * (PART * 128), &map_b, fb, cb * 64,
+                                                   nt * BN + (int)rank * PART, r, s, MC_MASK);
+                            }
                         }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
@@ -235,7 +307,8 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const uint64_t bdesc0 = smem_desc(smem0 + RW_A_BYTES, 16, 1024, 2);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        RowsTile<CL> t;
+        for (int kk = 0; rows_tile<CL>(p, kk, rank, t); ++kk) {
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
             fence_after();
             const uint32_t tmem_d = tmem_base + acc * BN;
@@ -253,7 +326,8 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         for (int k = 0; k < 4; ++k)
                             umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | r | k) != 0);
                     }
-                    umma_commit(empty0 + 8 * stage);
+                    if constexpr (CL == 1) umma_commit(empty0 + 8 * stage);
+                    else umma_commit_mc(empty0 + 8 * stage, MC_MASK);
                     if (it == stages_per_tile - 1) umma_commit(tfull0 + 8 * acc);
                 }
                 __syncwarp();
@@ -264,14 +338,15 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     } else {
         // ===================================================== epilogue: 8 warps (2..9)
         bool narrow = false;
-        if constexpr (BN <= 64) narrow = p.tiles_co == 1 && !(p.debug & 32);
+        if constexpr (BN <= 64) narrow = p.tiles_co == 1 && p.stats != nullptr && !p.accumulate && !(p.debug & 32);
         if constexpr (BN <= 64) {
-            if (narrow) rows_epilogue<BN, true>(p, warp, lane, tmem_base, tfull0, tempty0, s_stats);
+            if (narrow) rows_epilogue<BN, true, CL>(p, warp, lane, tmem_base, tfull0, tempty0, s_stats, rank);
         }
-        if (!narrow) rows_epilogue<BN, false>(p, warp, lane, tmem_base, tfull0, tempty0, s_stats);
+        if (!narrow) rows_epilogue<BN, false, CL>(p, warp, lane, tmem_base, tfull0, tempty0, s_stats, rank);
     }
     fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();      // no CTA leaves while a peer's commit may still arrive on its barriers
     if (warp == 1) { fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
@@ -279,16 +354,73 @@ bool tc_conv_rows_supported(int Ca, int Nout, int R, int S, int stride, int Ho, 
     return R == 3 && S == 3 && stride == 1 && Ca % 64 == 0 && Nout % 32 == 0 && Ho >= 16 && Wo >= 8;
 }
 
-template <int BN>
-static void launch_rows(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const RowsParams& p) {
+// largest number of CL-CTA clusters of this kernel that can be resident at once (persistent grid = that many clusters)
+template <int BN, int CL>
+static int rows_max_clusters() {
+    static int cached = -1;
+    if (cached < 0) {
+        using Cfg = RowsCfg<BN>;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(num_sms() / CL * CL); cfg.blockDim = dim3(RW_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, conv_tc_rows_kernel<BN, CL>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = 0; }
+        cached = n;
+    }
+    return cached;
+}
+template <int BN, int CL>
+static void launch_rows(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, RowsParams p) {
     using Cfg = RowsCfg<BN>;
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(conv_tc_rows_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaFuncSetAttribute(conv_tc_rows_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         configured = true;
     }
-    const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    conv_tc_rows_kernel<BN><<<grid, RW_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+    if constexpr (CL == 1) {
+        const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+        conv_tc_rows_kernel<BN, 1><<<grid, RW_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+    } else {
+        const int clusters = std::min(rows_max_clusters<BN, CL>(), p.total_groups);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(clusters * CL); cfg.blockDim = dim3(RW_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_rows_kernel<BN, CL>, ma, mb, p);
+        if (e != cudaSuccess) throw std::runtime_error(std::string("conv_tc_rows cluster launch failed: ") + cudaGetErrorString(e));
+    }
+}
+// cluster size for the weight multicast: env SALT_TC_CLUSTER = 1 | 2 | 4 (default 4 when the device can co-schedule it)
+static int rows_cluster_pref() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SALT_TC_CLUSTER"); v = e ? atoi(e) : 4; if (v != 1 && v != 2 && v != 4) v = 1; }
+    return v;
+}
+template <int BN>
+static void launch_rows_any(cudaStream_t st, const CUtensorMap& ma, const void* Wp, int Ca, int Nout, RowsParams p) {
+    int cl = rows_cluster_pref();
+    // a cluster only pays when there are enough pixel tiles to fill it and the machine with whole groups
+    while (cl > 1 && (p.m_tiles < cl * 8 || (cl == 4 ? rows_max_clusters<BN, 4>() : rows_max_clusters<BN, 2>()) * cl < num_sms() * 3 / 4)) cl >>= 1;
+    p.total_groups = cdiv(p.m_tiles, cl) * p.tiles_co;
+    // weights Wp[n][(r*3+s)*Ca + c] viewed as a 4-D tensor (c, n, r, s).  CL == 1: one box = [3 taps r][BN][64 c];
+    // CL > 1: a box is this CTA's BN/CL rows of ONE tap slab, multicast to the whole cluster
+    CUtensorMap mb;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Ca, (cuuint64_t)Nout, 3, 3};
+        cuuint64_t strides[3] = {(cuuint64_t)9 * Ca * 2, (cuuint64_t)3 * Ca * 2, (cuuint64_t)Ca * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)(BN / cl), cl == 1 ? 3u : 1u, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = get_encode()(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(Wp), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(weights 4d) failed with code " + std::to_string((int)r));
+    }
+    if (cl == 4) launch_rows<BN, 4>(st, ma, mb, p);
+    else if (cl == 2) launch_rows<BN, 2>(st, ma, mb, p);
+    else launch_rows<BN, 1>(st, ma, mb, p);
 }
 
 // out[n,y,x,k] (+)= sum_{r,s,c} A[n, y+r-pad, x+s-pad, c] * Wp[k][(r*3+s)*Ca + c]      (3x3, stride 1)
@@ -304,19 +436,8 @@ void k_conv_tc_rows(cudaStream_t st, const void* A, int B, int Ha, int Wa, int C
     p.accumulate = accumulate ? 1 : 0; p.bias = bias; p.stats = stats; p.out = (bf16*)out;
     { const char* e = getenv("SALT_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
     CUtensorMap ma = make_map_nhwc(A, Ca, Wa, Ha, B, 64, RW_TW, RW_TH + 2, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B);
-    // weights Wp[n][(r*3+s)*Ca + c] viewed as a 4-D tensor (c, n, r, s): one box = [3 taps r][BN][64 c]
-    CUtensorMap mb;
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)Ca, (cuuint64_t)Nout, 3, 3};
-        cuuint64_t strides[3] = {(cuuint64_t)9 * Ca * 2, (cuuint64_t)3 * Ca * 2, (cuuint64_t)Ca * 2};
-        cuuint32_t box[4] = {64, (cuuint32_t)BN, 3, 1};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = get_encode()(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(Wp), dims, strides, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(weights 4d) failed with code " + std::to_string((int)r));
-    }
-    if (BN == 128) launch_rows<128>(st, ma, mb, p);
-    else if (BN == 64) launch_rows<64>(st, ma, mb, p);
-    else launch_rows<32>(st, ma, mb, p);
+    p.m_tiles = p.tiles_x * p.tiles_y * B; p.total_groups = 0;
+    if (BN == 128) launch_rows_any<128>(st, ma, Wp, Ca, Nout, p);
+    else if (BN == 64) launch_rows_any<64>(st, ma, Wp, Ca, Nout, p);
+    else launch_rows_any<32>(st, ma, Wp, Ca, Nout, p);
 }

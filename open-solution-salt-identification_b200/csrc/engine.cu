@@ -309,14 +309,15 @@ void Engine::build_pack_table() {
     for (ConvLayer* c : all_convs()) {
         PackDesc d; d.w = params_ + c->o_w; d.wp = c->wp; d.wpd = c->wpd; d.Co = c->Co; d.Ci_real = c->Ci_real; d.Ci = c->Ci; d.RS = c->R * c->S;
         descs.push_back(d);
-        start.push_back(start.back() + cdiv((long long)c->Co * c->R * c->S * c->Ci, 256));
+        start.push_back(start.back() + pack_blocks(c->Co, c->Ci, c->R * c->S));
+        pack_max_rs_ = std::max(pack_max_rs_, c->R * c->S);
     }
     pack_layers_ = (int)descs.size(); pack_blocks_ = start.back();
     cudaMemcpy(d_pack_, descs.data(), sizeof(PackDesc) * descs.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(d_pack_start_, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice);
 }
 void Engine::pack_all(cudaStream_t st) {
-    k_pack_all(st, cfg_.dt, d_pack_, d_pack_start_, pack_layers_, pack_blocks_);
+    k_pack_all(st, cfg_.dt, d_pack_, d_pack_start_, pack_layers_, pack_blocks_, pack_max_rs_);
     packed_dirty_ = false;
 }
 // one launch: transpose every tensor-core wgrad scratch into the reference-layout gradient

@@ -163,6 +163,7 @@ private:
     bool packed_dirty_ = true;
     // batched pack / unpack tables (device copies live in the workspace)
     PackDesc* d_pack_ = nullptr; int* d_pack_start_ = nullptr; int pack_layers_ = 0, pack_blocks_ = 0;
+    int pack_max_rs_ = 1;
     UnpackDesc* d_unpack_ = nullptr; int* d_unpack_start_ = nullptr; int unpack_layers_ = 0, unpack_blocks_ = 0, unpack_max_rs_ = 1;
     bool unpack_table_dirty_ = false;
     bool trained_forward_ = false;

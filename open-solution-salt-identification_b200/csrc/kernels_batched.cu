@@ -13,21 +13,56 @@ __device__ __forceinline__ int find_layer(const int* __restrict__ blk_start, int
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
+// One block = a 32 (k) x CT (c) x RS tile of one layer, staged through shared memory so that the fp32 master weights are read
+// as contiguous runs ([c][t] for one k) and both packed copies are written as contiguous runs (wp: c for one (k,t); wpd: k for
+// one (c,t)).  The first version (one thread per element, strided reads, 2-byte scattered wpd stores) ran at 0.6 TB/s.
 template <typename T>
-__global__ void pack_all_kernel(const PackDesc* __restrict__ descs, const int* __restrict__ blk_start, int nlayers) {
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackDesc* __restrict__ descs, const int* __restrict__ blk_start, int nlayers) {
+    extern __shared__ float tile[];                  // [32 k][CT * RS + 1]
     const int l = find_layer(blk_start, nlayers, blockIdx.x);
     const PackDesc d = descs[l];
-    const int idx = (blockIdx.x - blk_start[l]) * 256 + threadIdx.x;
-    const int total = d.Co * d.RS * d.Ci;
-    if (idx >= total) return;
-    const int c = idx % d.Ci, t = (idx / d.Ci) % d.RS, k = idx / (d.Ci * d.RS);
-    const float v = c < d.Ci_real ? d.w[((size_t)k * d.Ci_real + c) * d.RS + t] : 0.f;
-    st1((T*)d.wp + idx, v);
-    st1((T*)d.wpd + ((size_t)c * d.RS + (d.RS - 1 - t)) * d.Co + k, v);       // flipped taps, see kernels_conv_simt.cu
+    const int b = blockIdx.x - blk_start[l];
+    const int RS = d.RS, CT = pack_ct(RS), pitch = CT * RS + 1;
+    const int ktiles = (d.Co + 31) >> 5;
+    const int k0 = (b % ktiles) * 32, c0 = (b / ktiles) * CT;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int creal = max(0, min(CT, d.Ci_real - c0));         // channels of this tile that exist in the master weights
+    const int cmem = min(CT, d.Ci - c0);                       // channels of this tile that exist in the packed copies (zero pad)
+    const int ncols = creal * RS;
+    for (int k = ty; k < 32; k += 8) {
+        const float* src = d.w + ((size_t)(k0 + k) * d.Ci_real + c0) * RS;
+        for (int j = tx; j < CT * RS; j += 32) tile[k * pitch + j] = (k0 + k < d.Co && j < ncols) ? src[j] : 0.f;
+    }
+    __syncthreads();
+    T* wp = (T*)d.wp;
+    T* wpd = (T*)d.wpd;
+    // wp[k][t][c]
+    for (int kt = ty; kt < 32 * RS; kt += 8) {
+        const int k = kt / RS, t = kt - k * RS;
+        if (k0 + k >= d.Co) continue;
+        for (int c = tx; c < cmem; c += 32) st1(wp + ((size_t)(k0 + k) * RS + t) * d.Ci + c0 + c, tile[k * pitch + c * RS + t]);
+    }
+    // wpd[c][RS-1-t][k]  (flipped taps, see kernels_conv_simt.cu)
+    if (k0 + tx < d.Co) {
+        for (int ct = ty; ct < cmem * RS; ct += 8) {
+            const int c = ct / RS, t = ct - c * RS;
+            st1(wpd + ((size_t)(c0 + c) * RS + (RS - 1 - t)) * d.Co + k0 + tx, tile[tx * pitch + c * RS + t]);
+        }
+    }
 }
-void k_pack_all(cudaStream_t st, DType dt, const PackDesc* descs, const int* blk_start, int nlayers, int total_blocks) {
+void k_pack_all(cudaStream_t st, DType dt, const PackDesc* descs, const int* blk_start, int nlayers, int total_blocks, int max_rs) {
     SALT_COUNT(1);
-    SALT_DISPATCH(dt, T, (pack_all_kernel<T><<<total_blocks, 256, 0, st>>>(descs, blk_start, nlayers)));
+    const size_t smem = sizeof(float) * 32 * (pack_ct(max_rs) * max_rs + 1);
+    const size_t smem9 = sizeof(float) * 32 * (pack_ct(9) * 9 + 1);
+    const size_t need = smem > smem9 ? smem : smem9;
+    SALT_DISPATCH(dt, T, {
+        static size_t configured = 0;
+        if (need > configured) {
+            cudaFuncSetAttribute(pack_all_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+            configured = need;
+        }
+        pack_all_kernel<T><<<total_blocks, 256, need, st>>>(descs, blk_start, nlayers);
+    });
 }
 
 // ------------------------------------------------------------------------------------------------ wgrad unpack

@@ -12,5 +12,8 @@ struct UnpackDesc {          // dw[k][c][t] = dwp[t][c][k]
     float* dw;
     int Co, Ci_real, Ci_pad, RS;
 };
-void k_pack_all(cudaStream_t st, DType dt, const PackDesc* descs, const int* blk_start, int nlayers, int total_blocks);
+// channel-tile width of the pack kernel for a filter with RS taps (shared-memory tile = 32 k x pack_ct(RS) c x RS)
+__host__ __device__ static inline int pack_ct(int RS) { return RS <= 9 ? 32 : 4; }
+static inline int pack_blocks(int Co, int Ci, int RS) { return ((Co + 31) / 32) * ((Ci + pack_ct(RS) - 1) / pack_ct(RS)); }
+void k_pack_all(cudaStream_t st, DType dt, const PackDesc* descs, const int* blk_start, int nlayers, int total_blocks, int max_rs);
 void k_unpack_all(cudaStream_t st, const UnpackDesc* descs, const int* blk_start, int nlayers, int total_blocks, int max_rs);

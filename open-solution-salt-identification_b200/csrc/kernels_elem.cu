@@ -135,7 +135,8 @@ __device__ __forceinline__ void block_reduce_add(const Vf<N>& v, int cg, D* dst,
 static inline int reduce_blocks(long long npix, int cg) {
     int lanes = EW_THREADS / cg;
     long long b = (npix + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
-    if (b > 148 * 2) b = 148 * 2;      // few fat blocks: the final per-channel atomics hit the same 2*C addresses
+    if (b > 148 * 6) b = 148 * 6;      // 1536 threads per SM keep enough 16-byte loads in flight; 2 blocks per SM (the first
+                                       // choice, to limit the per-channel atomics) left these passes latency-bound at ~3 TB/s
     if (b < 1) b = 1;
     return (int)b;
 }
@@ -249,44 +250,67 @@ void k_bn_bwd_finalize(cudaStream_t st, const BNRef& bn, double count) {
 template <typename T>
 __global__ void bn_apply_kernel(const T* __restrict__ raw, const float* __restrict__ scale, const float* __restrict__ shift,
                                 const float* __restrict__ gate, const T* __restrict__ res, const float* __restrict__ rscale,
-                                const float* __restrict__ rshift, int relu, T* __restrict__ out, int H, int W, int C, int pt, int pb,
-                                int pl, int pr) {
-    // one block per image row (and per slab of EW_THREADS channel groups when C is very wide); a thread keeps ONE channel
-    // group (its scale/shift live in registers) and walks along x
+                                const float* __restrict__ rshift, int relu, T* __restrict__ out, int nrows, int rows_per_block, int H,
+                                int W, int C, int pt, int pb, int pl, int pr) {
+    // one block per `rows_per_block` image rows (and per slab of EW_THREADS channel groups when C is very wide); a thread keeps
+    // ONE channel group (its scale/shift live in registers) and walks along x, two pixels per iteration so that two (four with
+    // a residual) independent 16-byte loads are in flight.  Single-row blocks moved only ~8 KB each and were latency-bound.
     constexpr int N = VW<T>::N;
     const int cg = min(C / N, EW_THREADS), lanes = EW_THREADS / cg;
     const int cv = blockIdx.y * cg + threadIdx.x % cg, lane = threadIdx.x / cg, c = cv * N;
-    const int row = blockIdx.x, n = row / H, y = row - n * H;
     Vf<N> sc = ldp<N>(scale + c);
     const Vf<N> sh = ldp<N>(shift + c);
     Vf<N> rsc = vzero<N>(), rsh = vzero<N>();
     if (res && rscale) { rsc = ldp<N>(rscale + c); rsh = ldp<N>(rshift + c); }
-    Vf<N> gt = vzero<N>();
-    if (gate) gt = ldp<N>(gate + (size_t)n * C + c);          // per-(image, channel) SE gate: (raw*scale+shift)*gate
     const int Hp = H + pt + pb, Wp = W + pl + pr;
-    const int y0 = (y == 0) ? 0 : y + pt, y1 = (y == H - 1) ? Hp - 1 : y + pt;
-    for (int x = lane; x < W; x += lanes) {
-        const size_t src = ((size_t)row * W + x) * C + c;
-        Vf<N> v = vfma(ldv(raw + src), sc, sh);
-        if (gate) v = vmul(v, gt);
-        if (res) {
-            Vf<N> r = ldv(res + src);
-            if (rscale) r = vfma(r, rsc, rsh);
-            v = vadd(v, r);
+    const int row_end = min(nrows, (int)(blockIdx.x + 1) * rows_per_block);
+    for (int row = blockIdx.x * rows_per_block; row < row_end; ++row) {
+        const int n = row / H, y = row - n * H;
+        Vf<N> gt = vzero<N>();
+        if (gate) gt = ldp<N>(gate + (size_t)n * C + c);          // per-(image, channel) SE gate: (raw*scale+shift)*gate
+        const int y0 = (y == 0) ? 0 : y + pt, y1 = (y == H - 1) ? Hp - 1 : y + pt;
+        auto finish = [&](int x, Vf<N> v, Vf<N> r) {
+            v = vfma(v, sc, sh);
+            if (gate) v = vmul(v, gt);
+            if (res) {
+                if (rscale) r = vfma(r, rsc, rsh);
+                v = vadd(v, r);
+            }
+            if (relu) v = vrelu(v);
+            const int x0 = (x == 0) ? 0 : x + pl, x1 = (x == W - 1) ? Wp - 1 : x + pl;
+            for (int yy = y0; yy <= y1; ++yy)
+                for (int xx = x0; xx <= x1; ++xx) stv(out + (((size_t)n * Hp + yy) * Wp + xx) * C + c, v);
+        };
+        int x = lane;
+        for (; x + lanes < W; x += 2 * lanes) {
+            const size_t s0 = ((size_t)row * W + x) * C + c, s1 = s0 + (size_t)lanes * C;
+            const Vf<N> a0 = ldv(raw + s0), a1 = ldv(raw + s1);
+            Vf<N> r0 = vzero<N>(), r1 = vzero<N>();
+            if (res) { r0 = ldv(res + s0); r1 = ldv(res + s1); }
+            finish(x, a0, r0);
+            finish(x + lanes, a1, r1);
         }
-        if (relu) v = vrelu(v);
-        const int x0 = (x == 0) ? 0 : x + pl, x1 = (x == W - 1) ? Wp - 1 : x + pl;
-        for (int yy = y0; yy <= y1; ++yy)
-            for (int xx = x0; xx <= x1; ++xx) stv(out + (((size_t)n * Hp + yy) * Wp + xx) * C + c, v);
+        if (x < W) {
+            const size_t s0 = ((size_t)row * W + x) * C + c;
+            const Vf<N> a0 = ldv(raw + s0);
+            Vf<N> r0 = vzero<N>();
+            if (res) r0 = ldv(res + s0);
+            finish(x, a0, r0);
+        }
     }
 }
 void k_bn_apply(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const Tensor* res,
                 const float* rscale, const float* rshift, bool relu, const Tensor& out, const float* gate) {
     SALT_COUNT(1);
     SALT_DISPATCH(raw.dt, T, {
-        dim3 grid(raw.B * raw.H, cdiv(raw.C / VW<T>::N, EW_THREADS));
+        const int nrows = raw.B * raw.H;
+        const long long row_bytes = (long long)raw.W * raw.C * sizeof(T);
+        int rpb = (int)std::max<long long>(1, std::min<long long>(8, 32768 / std::max<long long>(1, row_bytes)));
+        while (rpb > 1 && cdiv(nrows, rpb) < 148 * 4) rpb >>= 1;           // keep every SM busy on small layers
+        dim3 grid(cdiv(nrows, rpb), cdiv(raw.C / VW<T>::N, EW_THREADS));
         bn_apply_kernel<T><<<grid, EW_THREADS, 0, st>>>((const T*)raw.p, scale, shift, gate, res ? (const T*)res->p : nullptr, rscale,
-                                                        rshift, relu ? 1 : 0, (T*)out.p, raw.H, raw.W, raw.C, out.pt, out.pb, out.pl, out.pr);
+                                                        rshift, relu ? 1 : 0, (T*)out.p, nrows, rpb, raw.H, raw.W, raw.C, out.pt, out.pb,
+                                                        out.pl, out.pr);
     });
 }
 
@@ -622,20 +646,24 @@ __global__ void se_fc_wgrad_kernel(SERef se, int B) {
     if (idx < C * Cr) {
         { const int c = idx / Cr, j = idx - c * Cr;        // dw2[c][j] = sum_n dpre2[n][c] * hid[n][j]
           float a = 0.f;
+#pragma unroll 8
           for (int n = 0; n < B; ++n) a = fmaf(se.part[n * pstride + c], se.hid[(size_t)n * Cr + j], a);
           se.dw2[idx] += a; }
         { const int j = idx / C, c = idx - j * C;          // dw1[j][c] = sum_n dhid[n][j] * gap[n][c]
           float a = 0.f;
+#pragma unroll 8
           for (int n = 0; n < B; ++n) a = fmaf(se.dhid[(size_t)n * Cr + j], se.gap[(size_t)n * C + c], a);
           se.dw1[idx] += a; }
     }
     if (idx < C) {
         float a = 0.f;
+#pragma unroll 8
         for (int n = 0; n < B; ++n) a += se.part[n * pstride + idx];
         se.db2[idx] += a;
     }
     if (idx < Cr) {
         float a = 0.f;
+#pragma unroll 8
         for (int n = 0; n < B; ++n) a += se.dhid[(size_t)n * Cr + idx];
         se.db1[idx] += a;
     }
@@ -758,18 +786,36 @@ template <typename T>
 __global__ void final_fwd_kernel(const T* __restrict__ raw, const float* __restrict__ scale, const float* __restrict__ shift,
                                  const float* __restrict__ w, const float* __restrict__ b, int K, float* __restrict__ logits,
                                  unsigned npix, int HW, int C) {
-    constexpr int N = 8;
-    const unsigned cg = C / N;
-    const unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
-    unsigned pix = idx / cg;
-    const int cv = idx - pix * cg, c = cv * N;
-    const bool ok = pix < npix;
-    if (!ok) pix = npix - 1;
-    const Vf<N> z = vrelu(vfma(ldv8(raw + (size_t)pix * C + c), ldp<N>(scale + c), ldp<N>(shift + c)));
-    const int n = pix / HW, p = pix - n * HW;
-    for (int k = 0; k < K; ++k) {
-        const float d = group_sum(vdot(z, ldp<N>(w + k * C + c)), cg);
-        if (ok && cv == 0) logits[((size_t)n * K + k) * HW + p] = d + b[k];
+    // a thread keeps one 8-channel group (BN coefficients and the K weight vectors in registers) and handles FINAL_PPT pixels
+    // whose loads are issued together; the cg lanes of a pixel combine their partial dot products with shuffles
+    constexpr int N = 8, PPT = 4, KMAX = 4;
+    const unsigned cg = C / N, lanes = EW_THREADS / cg;
+    const int cv = threadIdx.x % cg, lane = threadIdx.x / cg, c = cv * N;
+    const Vf<N> sc = ldp<N>(scale + c), sh = ldp<N>(shift + c);
+    Vf<N> wk[KMAX];
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) wk[k] = k < K ? ldp<N>(w + k * C + c) : vzero<N>();
+    const unsigned base = (blockIdx.x * PPT) * lanes + lane;
+    Vf<N> x[PPT];
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const unsigned pix = min(base + i * lanes, npix - 1);
+        x[i] = ldv8(raw + (size_t)pix * C + c);
+    }
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+        const unsigned pix = base + i * lanes;
+        const bool ok = pix < npix;
+        const Vf<N> z = vrelu(vfma(x[i], sc, sh));
+        const unsigned pc = ok ? pix : npix - 1;
+        const int n = pc / HW, p = pc - n * HW;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            if (k < K) {
+                const float d = group_sum(vdot(z, wk[k]), cg);
+                if (ok && cv == 0) logits[((size_t)n * K + k) * HW + p] = d + b[k];
+            }
+        }
     }
 }
 void k_final_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const float* w, const float* b,
@@ -778,9 +824,11 @@ void k_final_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const f
     const unsigned npix = (unsigned)raw.B * raw.H * raw.W;
     const int cg = raw.C / 8;
     if (raw.C % 8 || cg > 32 || (cg & (cg - 1))) throw std::runtime_error("final 1x1 conv: channel count must be 8 * 2^k <= 256");
+    if (K < 1 || K > 4) throw std::runtime_error("final 1x1 conv: 1..4 output classes");
     SALT_DISPATCH(raw.dt, T, {
-        final_fwd_kernel<T><<<cdiv((long long)npix * cg, EW_THREADS), EW_THREADS, 0, st>>>((const T*)raw.p, scale, shift, w, b, K, logits,
-                                                                                       npix, raw.H * raw.W, raw.C);
+        const int lanes = EW_THREADS / cg;
+        final_fwd_kernel<T><<<cdiv(npix, (long long)lanes * 4), EW_THREADS, 0, st>>>((const T*)raw.p, scale, shift, w, b, K, logits,
+                                                                                npix, raw.H * raw.W, raw.C);
     });
 }
 template <typename T, int K>

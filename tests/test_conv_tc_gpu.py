@@ -23,6 +23,12 @@ TC_CASES = [
     (2, 32, 64, 34, 34, 3, 1, 0),        # dec1.conv2-like: Cin = 32
     (2, 320, 64, 18, 18, 3, 1, 0),       # final.0-like: Cin = 320
     (1, 768, 512, 10, 10, 3, 1, 0),      # dec5.conv1-like
+    # enough pixel tiles for the thread-block-cluster (weight multicast) variant of the row-halo kernel
+    (7, 64, 64, 32, 24, 3, 1, 1),        # 42 pixel tiles: the last cluster group is short (dropped dummy tiles), ragged width
+    (6, 128, 128, 32, 32, 3, 1, 1),      # BN = 128, two 64-channel blocks per tap row
+    (5, 128, 256, 32, 32, 3, 1, 1),      # two channel tiles per pixel tile
+    (5, 320, 64, 34, 66, 3, 1, 0),       # final.0-like at cluster size: forward 5 channel blocks, dgrad 5 channel tiles of 64
+    (4, 64, 32, 66, 66, 3, 1, 0),        # N = 32 (8-row multicast parts), bordered input
 ]
 
 

@@ -188,8 +188,29 @@ def test_cuda_graph_replay_matches_eager_steps(monkeypatch, loss):
     (l0, p0, b0, n0, g0), (l1, p1, b1, n1, g1) = runs['0'], runs['1']
     print('eager', l0, 'graph', l1)
     assert g0 == 0 and g1 == 1 and n0 == n1 == 6
-    assert np.allclose(l0, l1, rtol=1e-4, atol=1e-6)
-    # parameters after 6 Adam steps of lr 1e-4 moved by <= 6e-4; graph and eager agree far inside that
-    frac = ((p0 - p1).abs() > 1e-4).float().mean().item()
-    assert frac <= 0.01, frac
-    assert torch.allclose(b0, b1, rtol=1e-3, atol=1e-5)
+    # The first Adam steps move every weight by ~lr*sign(g): the sign of a near-zero gradient depends on the summation order
+    # of the atomics, so two runs (eager or not) drift apart at the 1e-4 level - steps 1-2 are eager in BOTH runs and already do.
+    assert np.allclose(l0, l1, rtol=3e-3, atol=1e-5)
+    frac = ((p0 - p1).abs() > 3e-4).float().mean().item()
+    assert frac <= 0.02, frac
+    assert torch.allclose(b0, b1, rtol=5e-2, atol=5e-3)
+    # decisive check: with identical parameters and inputs a replayed forward graph equals the eager forward (the re-pack of the
+    # weights Adam just changed is part of the graph), and the replayed backward graph fills the same gradients
+    m.engine.adam_step(lr=1e-3)                              # change the parameters AFTER the capture
+    st = m._gs
+    gf, gb, _, _ = st['graphs'][B]
+    st['x'][:B].copy_(xs[0].cuda()); st['t'][:B].copy_(ts[0].cuda())
+    gf.replay()
+    logits_g = st['logits'][:B].clone()
+    logits_e = m.engine.forward(st['x'][:B], train=True)
+    assert float((logits_g - logits_e).abs().max()) <= 1e-5 * max(1.0, float(logits_e.abs().max()))
+    name, fn, w = m.loss_function[0]
+    fn.dlogits = st['dlogits'][:B]
+    fn(logits_e, st['t'][:B])
+    gb.replay()
+    g_graph = m.engine.grads.clone()
+    m.engine.backward(st['dlogits'][:B])
+    g_eager = m.engine.grads
+    rel = float((g_graph - g_eager).norm() / (g_eager.norm() + 1e-20))
+    print('graph vs eager: logits max diff %.2e, gradient rel-L2 %.2e' % (float((logits_g - logits_e).abs().max()), rel))
+    assert rel <= 1e-4

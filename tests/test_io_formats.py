@@ -114,10 +114,15 @@ def test_forward_tiles_equals_forward_of_adapted_input(precision):
         a = eng.forward(torch.from_numpy(x).cuda(), train=False).clone()
         b = eng.forward_tiles(torch.from_numpy(tiles).cuda(), train=False, hflip=flip)
         assert torch.equal(a, b)
-    # train mode goes through the same stem patches: the step after it must agree too
+    # train mode reads the same stem patches; the BatchNorm sums are combined with atomics whose order is not fixed, so two
+    # train-mode passes agree to rounding (fp32) / to a few bf16 ulps amplified by 3-image batch statistics (bf16), not bit for bit
     a = eng.forward(torch.from_numpy(io_oracle.adapt_tiles(tiles, 128)).cuda(), train=True).clone()
     b = eng.forward_tiles(torch.from_numpy(tiles).cuda(), train=True)
-    assert torch.equal(a, b)
+    a2 = eng.forward(torch.from_numpy(io_oracle.adapt_tiles(tiles, 128)).cuda(), train=True)
+    tol = (1e-4 if precision == 'fp32' else 0.03) * float(a.abs().max())
+    print('train-mode tiles vs tensor: %.3e, tensor vs tensor (run-to-run): %.3e, tol %.3e'
+          % (float((a - b).abs().max()), float((a - a2).abs().max()), tol))
+    assert float((a - b).abs().max()) <= tol
 
 
 @gpu
