@@ -4,6 +4,10 @@ mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/pytest_gpu_c.log 2>&1
 echo "pytest(cl4) rc=$?" > gpurun_out/summary_c.txt
 tail -4 gpurun_out/pytest_gpu_c.log
+if ! grep -q "pytest(cl4) rc=0" gpurun_out/summary_c.txt; then
+  SALT_TC_CLUSTER=1 timeout 1200 python -m pytest tests -m gpu -q -p no:cacheprovider > gpurun_out/pytest_gpu_c_cl1.log 2>&1
+  echo "pytest(cl1) rc=$?" >> gpurun_out/summary_c.txt
+fi
 SALT_TC_CLUSTER=2 timeout 600 python -m pytest tests/test_conv_tc_gpu.py -m gpu -q -p no:cacheprovider > gpurun_out/pytest_conv_cl2.log 2>&1
 echo "pytest conv (cl2) rc=$?" >> gpurun_out/summary_c.txt
 for cl in 4 2 1; do
