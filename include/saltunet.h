@@ -125,6 +125,8 @@ int salt_get_activation(salt_engine* h, const char* name, float* out_nchw, int s
 
 /* Number of CUDA kernels this library has launched so far in this process. */
 unsigned long long salt_launch_count(void);
+/* ... of which launched as thread-block clusters (convolutions whose weight stages are TMA-multicast; env SALT_TC_CLUSTER=1 disables). */
+unsigned long long salt_cluster_launch_count(void);
 
 /* Measurement aid (bench.py roofline): bracket every convolution launch with CUDA events on its stream.
  * kernel_class: 0 = conv forward, 1 = conv dgrad, 2 = conv wgrad.  salt_profile_read synchronises and returns the

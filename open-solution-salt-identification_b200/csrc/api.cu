@@ -148,6 +148,7 @@ int salt_get_activation(salt_engine* h, const char* name, float* out, int shape[
     return check_cuda("salt_get_activation");
 }
 unsigned long long salt_launch_count(void) { return g_salt_launches; }
+unsigned long long salt_cluster_launch_count(void) { return g_salt_cluster_launches; }
 int salt_profile_enable(salt_engine* h, int on) { h->e->profile_enable(on != 0); return 0; }
 int salt_profile_read(salt_engine* h, int kernel_class, double* ms, double* flops, long long* launches) {
     if (kernel_class < 0 || kernel_class >= Engine::PROF_NCLASS) return fail("salt_profile_read: unknown kernel class");

@@ -71,5 +71,6 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf
 
 extern unsigned long long g_salt_launches;   // kernels launched by this library (bench.py: gpu_launches)
 #define SALT_COUNT(n) (g_salt_launches += (n))
+extern unsigned long long g_salt_cluster_launches;   // of which: thread-block-cluster launches (TMA-multicast convolutions)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -360,6 +360,8 @@ static int rows_max_clusters() {
     static int cached = -1;
     if (cached < 0) {
         using Cfg = RowsCfg<BN>;
+        // the occupancy query honours the opt-in shared-memory limit only once it has been raised on the function
+        cudaFuncSetAttribute(conv_tc_rows_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(num_sms() / CL * CL); cfg.blockDim = dim3(RW_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
         cudaLaunchAttribute at[1];
@@ -391,6 +393,7 @@ static void launch_rows(cudaStream_t st, const CUtensorMap& ma, const CUtensorMa
         cfg.attrs = at; cfg.numAttrs = 1;
         cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_rows_kernel<BN, CL>, ma, mb, p);
         if (e != cudaSuccess) throw std::runtime_error(std::string("conv_tc_rows cluster launch failed: ") + cudaGetErrorString(e));
+        ++g_salt_cluster_launches;
     }
 }
 // cluster size for the weight multicast: env SALT_TC_CLUSTER = 1 | 2 | 4 (default 4 when the device can co-schedule it)

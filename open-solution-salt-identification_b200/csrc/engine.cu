@@ -4,6 +4,7 @@
 #include <algorithm>
 
 unsigned long long g_salt_launches = 0;
+unsigned long long g_salt_cluster_launches = 0;
 
 static const float BN_EPS = 1e-5f, BN_MOMENTUM = 0.1f;
 static const int MAX_CONVS = 128;       // capacity of the batched pack / unpack descriptor tables

@@ -135,8 +135,8 @@ __device__ __forceinline__ void block_reduce_add(const Vf<N>& v, int cg, D* dst,
 static inline int reduce_blocks(long long npix, int cg) {
     int lanes = EW_THREADS / cg;
     long long b = (npix + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
-    if (b > 148 * 6) b = 148 * 6;      // 1536 threads per SM keep enough 16-byte loads in flight; 2 blocks per SM (the first
-                                       // choice, to limit the per-channel atomics) left these passes latency-bound at ~3 TB/s
+    if (b > 148 * 2) b = 148 * 2;      // few fat blocks: the final per-channel atomics hit the same 2*C addresses (6 blocks per SM
+                                       // measured 30 % SLOWER for bn_bwd_reduce: profiles/r1_notes.md)
     if (b < 1) b = 1;
     return (int)b;
 }
@@ -646,24 +646,20 @@ __global__ void se_fc_wgrad_kernel(SERef se, int B) {
     if (idx < C * Cr) {
         { const int c = idx / Cr, j = idx - c * Cr;        // dw2[c][j] = sum_n dpre2[n][c] * hid[n][j]
           float a = 0.f;
-#pragma unroll 8
           for (int n = 0; n < B; ++n) a = fmaf(se.part[n * pstride + c], se.hid[(size_t)n * Cr + j], a);
           se.dw2[idx] += a; }
         { const int j = idx / C, c = idx - j * C;          // dw1[j][c] = sum_n dhid[n][j] * gap[n][c]
           float a = 0.f;
-#pragma unroll 8
           for (int n = 0; n < B; ++n) a = fmaf(se.dhid[(size_t)n * Cr + j], se.gap[(size_t)n * C + c], a);
           se.dw1[idx] += a; }
     }
     if (idx < C) {
         float a = 0.f;
-#pragma unroll 8
         for (int n = 0; n < B; ++n) a += se.part[n * pstride + idx];
         se.db2[idx] += a;
     }
     if (idx < Cr) {
         float a = 0.f;
-#pragma unroll 8
         for (int n = 0; n < B; ++n) a += se.dhid[(size_t)n * Cr + idx];
         se.db1[idx] += a;
     }
@@ -786,36 +782,18 @@ template <typename T>
 __global__ void final_fwd_kernel(const T* __restrict__ raw, const float* __restrict__ scale, const float* __restrict__ shift,
                                  const float* __restrict__ w, const float* __restrict__ b, int K, float* __restrict__ logits,
                                  unsigned npix, int HW, int C) {
-    // a thread keeps one 8-channel group (BN coefficients and the K weight vectors in registers) and handles FINAL_PPT pixels
-    // whose loads are issued together; the cg lanes of a pixel combine their partial dot products with shuffles
-    constexpr int N = 8, PPT = 4, KMAX = 4;
-    const unsigned cg = C / N, lanes = EW_THREADS / cg;
-    const int cv = threadIdx.x % cg, lane = threadIdx.x / cg, c = cv * N;
-    const Vf<N> sc = ldp<N>(scale + c), sh = ldp<N>(shift + c);
-    Vf<N> wk[KMAX];
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) wk[k] = k < K ? ldp<N>(w + k * C + c) : vzero<N>();
-    const unsigned base = (blockIdx.x * PPT) * lanes + lane;
-    Vf<N> x[PPT];
-#pragma unroll
-    for (int i = 0; i < PPT; ++i) {
-        const unsigned pix = min(base + i * lanes, npix - 1);
-        x[i] = ldv8(raw + (size_t)pix * C + c);
-    }
-#pragma unroll
-    for (int i = 0; i < PPT; ++i) {
-        const unsigned pix = base + i * lanes;
-        const bool ok = pix < npix;
-        const Vf<N> z = vrelu(vfma(x[i], sc, sh));
-        const unsigned pc = ok ? pix : npix - 1;
-        const int n = pc / HW, p = pc - n * HW;
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-            if (k < K) {
-                const float d = group_sum(vdot(z, wk[k]), cg);
-                if (ok && cv == 0) logits[((size_t)n * K + k) * HW + p] = d + b[k];
-            }
-        }
+    constexpr int N = 8;
+    const unsigned cg = C / N;
+    const unsigned idx = blockIdx.x * EW_THREADS + threadIdx.x;
+    unsigned pix = idx / cg;
+    const int cv = idx - pix * cg, c = cv * N;
+    const bool ok = pix < npix;
+    if (!ok) pix = npix - 1;
+    const Vf<N> z = vrelu(vfma(ldv8(raw + (size_t)pix * C + c), ldp<N>(scale + c), ldp<N>(shift + c)));
+    const int n = pix / HW, p = pix - n * HW;
+    for (int k = 0; k < K; ++k) {
+        const float d = group_sum(vdot(z, ldp<N>(w + k * C + c)), cg);
+        if (ok && cv == 0) logits[((size_t)n * K + k) * HW + p] = d + b[k];
     }
 }
 void k_final_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const float* w, const float* b,
@@ -824,11 +802,9 @@ void k_final_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const f
     const unsigned npix = (unsigned)raw.B * raw.H * raw.W;
     const int cg = raw.C / 8;
     if (raw.C % 8 || cg > 32 || (cg & (cg - 1))) throw std::runtime_error("final 1x1 conv: channel count must be 8 * 2^k <= 256");
-    if (K < 1 || K > 4) throw std::runtime_error("final 1x1 conv: 1..4 output classes");
     SALT_DISPATCH(raw.dt, T, {
-        const int lanes = EW_THREADS / cg;
-        final_fwd_kernel<T><<<cdiv(npix, (long long)lanes * 4), EW_THREADS, 0, st>>>((const T*)raw.p, scale, shift, w, b, K, logits,
-                                                                                npix, raw.H * raw.W, raw.C);
+        final_fwd_kernel<T><<<cdiv((long long)npix * cg, EW_THREADS), EW_THREADS, 0, st>>>((const T*)raw.p, scale, shift, w, b, K, logits,
+                                                                                       npix, raw.H * raw.W, raw.C);
     });
 }
 template <typename T, int K>

@@ -59,6 +59,7 @@ PROTOTYPES = {
     'salt_validation_counts': (_i, [_fp, _fp, _i, _i, _i, _i, _vp, C.POINTER(C.c_double), _i, _vp, _vp, _vp, _vp]),
     'salt_get_activation': (_i, [_vp, C.c_char_p, _fp, C.POINTER(_i), _vp]),
     'salt_launch_count': (C.c_ulonglong, []),
+    'salt_cluster_launch_count': (C.c_ulonglong, []),
     'salt_profile_enable': (_i, [_vp, _i]),
     'salt_profile_read': (_i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     'salt_op_conv_forward': (_i, [C.POINTER(SaltConvDesc), _vp, _fp, _fp, _vp, _dp, _vp]),

@@ -47,8 +47,14 @@ def test_conv_tc_forward_and_dgrad(case):
     xd, wd, bd = _to_nhwc(x, 'bf16'), w.cuda().contiguous(), bias.cuda()
     out = torch.full((B, Ho, Wo, Co), float('nan'), dtype=torch.bfloat16, device='cuda')
     stats = torch.zeros(2 * Co, dtype=torch.float64, device='cuda')
+    cl0 = lib.salt_cluster_launch_count()
     _lib.check(lib.salt_op_conv_forward(C.byref(d), xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), out.data_ptr(), stats.data_ptr(), None))
     torch.cuda.synchronize()
+    import os
+    m_tiles = B * ((Ho + 15) // 16) * ((Wo + 7) // 8)
+    if k == 3 and s == 1 and Ci % 64 == 0 and Co % 32 == 0 and Ho >= 16 and m_tiles >= 32 and os.environ.get('SALT_TC_CLUSTER', '4') != '1':
+        # large enough for the thread-block-cluster variant: make sure THAT kernel (TMA-multicast weights) produced `out`
+        assert lib.salt_cluster_launch_count() > cl0, 'cluster variant of the row-halo convolution was not launched'
     oks = [report('tc conv fwd %s' % (case,), _from_nhwc(out), y_ref, atol=2e-2, rtol=1e-2)[0]]
     oks.append(report('tc conv stats sum', stats[:Co].cpu().float(), y_ref.sum((0, 2, 3)), atol=5e-2, rtol=2e-3)[0])
     oks.append(report('tc conv stats sumsq', stats[Co:].cpu().float(), (y_ref ** 2).sum((0, 2, 3)), atol=5e-2, rtol=2e-3)[0])
@@ -71,7 +77,7 @@ def test_conv_tc_forward_and_dgrad(case):
     assert all(oks)
 
 
-WG_CASES = TC_CASES + [
+WG_CASES = [c for c in TC_CASES if c[4] != 24] + [      # the wgrad kernel takes 32-pixel row chunks: widths that are multiples of 8 only via padding
     (2, 64, 32, 34, 34, 3, 1, 0),        # dec1.conv1-like: Cout = 32 (zero-filled channel box)
     (4, 64, 64, 128, 128, 3, 1, 1),      # many pixel chunks per CTA
     (2, 256, 512, 16, 16, 3, 2, 1),      # layer4.0.conv1-like, stride 2
