@@ -16,6 +16,12 @@
 #include "tc_common.cuh"
 #include "conv_tc.h"
 #include <cstdlib>
+#include <algorithm>
+
+// default cluster size of the tap-table kernel (1 = off) until the B200 measurements say otherwise
+#ifndef TC_GENERIC_CLUSTER_DEFAULT
+#define TC_GENERIC_CLUSTER_DEFAULT 1
+#endif
 
 using namespace tc;
 
@@ -43,6 +49,7 @@ struct TcPhase { int ntaps, oy, ox; TcTap taps[9]; };
 struct TcParams {
     int tw, th, tn;
     int tiles_x, tiles_y, tiles_b, tiles_co, tiles_per_phase;
+    int m_tiles, groups_per_phase;  // cluster mode: a group = CL consecutive position tiles of one (phase, channel tile)
     int B, Ho, Wo;                 // output positions per phase
     int out_H, out_W, Co;          // physical output tensor
     int osy, osx, a_stride, cblks;
@@ -52,6 +59,44 @@ struct TcParams {
     bf16* out;
     TcPhase ph[4];
 };
+
+// ---- thread-block-cluster variant (CL > 1): the CL CTAs of a cluster take CL consecutive position tiles of the same (phase,
+// channel tile), consume identical weight stages in lockstep, and each fetches 1/CL of every [BN x BK] weight slab with a
+// TMA multicast into all CL shared memories (see conv_tc_rows.cu for the protocol and the measurements behind it).
+__device__ __forceinline__ uint32_t tc_cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void tc_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+                 " [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+struct TcTile { int pi, nt, mt; bool live; };
+template <int CL>
+__device__ __forceinline__ bool tc_tile(const TcParams& p, int k, uint32_t rank, TcTile& t) {
+    if constexpr (CL == 1) {
+        const int tile = blockIdx.x + k * gridDim.x;
+        if (tile >= p.nphases * p.tiles_per_phase) return false;
+        t.pi = tile / p.tiles_per_phase;
+        const int r = tile - t.pi * p.tiles_per_phase;
+        t.nt = r % p.tiles_co; t.mt = r / p.tiles_co; t.live = true;
+    } else {
+        const int g = blockIdx.x / CL + k * (gridDim.x / CL);
+        if (g >= p.nphases * p.groups_per_phase) return false;
+        t.pi = g / p.groups_per_phase;
+        const int r = g - t.pi * p.groups_per_phase;
+        t.nt = r % p.tiles_co; t.mt = (r / p.tiles_co) * CL + (int)rank;
+        t.live = t.mt < p.m_tiles;
+        if (!t.live) t.mt = p.m_tiles - 1;
+    }
+    return true;
+}
 
 constexpr int TC_THREADS = 192;
 template <int BN, int BK> struct TcCfg {
@@ -68,7 +113,7 @@ template <int BN, int BK> struct TcCfg {
     static constexpr uint32_t LAYOUT = BK == 64 ? 2 : 4;       // SWIZZLE_128B : SWIZZLE_64B
 };
 
-template <int BN, int BK>
+template <int BN, int BK, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcParams p) {
     using Cfg = TcCfg<BN, BK>;
@@ -89,7 +134,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -97,18 +142,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int i = threadIdx.x; i < 2 * BN; i += TC_THREADS) s_stats[i] = 0.f;
     fence_before();
     __syncthreads();
+    uint32_t rank = 0;
+    if constexpr (CL > 1) { rank = tc_cluster_ctarank(); tc_cluster_sync(); }
     fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
-    const int total_tiles = p.nphases * p.tiles_per_phase;
+    constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
 
     if (warp == 0) {
         // ===================================================== TMA producer
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int pi = tile / p.tiles_per_phase, t = tile - pi * p.tiles_per_phase;
-                const TcPhase& ph = p.ph[pi];
-                const int nt = t % p.tiles_co, mt = t / p.tiles_co;
+            TcTile tt;
+            for (int k = 0; tc_tile<CL>(p, k, rank, tt); ++k) {
+                const TcPhase& ph = p.ph[tt.pi];
+                const int nt = tt.nt, mt = tt.mt;
                 const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
                 const int w0 = tx * p.tw * p.a_stride, h0 = ty * p.th * p.a_stride, n0 = tb * p.tn;
                 for (int tap = 0; tap < ph.ntaps; ++tap) {
@@ -117,7 +164,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
                         mbar_expect_tx(full0 + 8 * stage, Cfg::STAGE_BYTES);
                         tma_load_4d(smem_u32(smem_a + stage * Cfg::A_BYTES), &map_a, full0 + 8 * stage, cb * BK, w0 + dx, h0 + dy, n0);
-                        tma_load_2d(smem_u32(smem_b + stage * Cfg::B_BYTES), &map_b, full0 + 8 * stage, kofs + cb * BK, nt * BN);
+                        if constexpr (CL == 1) {
+                            tma_load_2d(smem_u32(smem_b + stage * Cfg::B_BYTES), &map_b, full0 + 8 * stage, kofs + cb * BK, nt * BN);
+                        } else {
+                            constexpr int PART = BN / CL;           // my rows of the weight slab, multicast to the whole cluster
+                            tma_load_2d_mc(smem_u32(smem_b + stage * Cfg::B_BYTES) + rank * (PART * BK * 2), &map_b, full0 + 8 * stage,
+                                           kofs + cb * BK, nt * BN + (int)rank * PART, MC_MASK);
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -128,8 +181,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t idesc = instr_desc_bf16(BN, false, false);
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int num_kb = p.ph[tile / p.tiles_per_phase].ntaps * p.cblks;
+        TcTile tt;
+        for (int kk = 0; tc_tile<CL>(p, kk, rank, tt); ++kk) {
+            const int num_kb = p.ph[tt.pi].ntaps * p.cblks;
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
             fence_after();
             const uint32_t tmem_d = tmem_base + acc * BN;
@@ -142,7 +196,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)       // advance 16 bf16 = 32 bytes inside the swizzle atom
                         umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-                    umma_commit(empty0 + 8 * stage);        // frees the smem stage when these MMAs retire
+                    if constexpr (CL == 1) umma_commit(empty0 + 8 * stage);        // frees the smem stage when these MMAs retire
+                    else tc_umma_commit_mc(empty0 + 8 * stage, MC_MASK);           // ... in every CTA of the cluster
                     if (kb == num_kb - 1) umma_commit(tfull0 + 8 * acc);
                 }
                 __syncwarp();
@@ -156,12 +211,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int m = quarter * 32 + lane;                  // row of the 128-position tile
         const int lx = m % p.tw, ly = (m / p.tw) % p.th, ln = m / (p.tw * p.th);
         int acc = 0; uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int pi = tile / p.tiles_per_phase, t = tile - pi * p.tiles_per_phase;
-            const int nt = t % p.tiles_co, mt = t / p.tiles_co;
+        TcTile tt;
+        for (int kk = 0; tc_tile<CL>(p, kk, rank, tt); ++kk) {
+            const int pi = tt.pi, nt = tt.nt, mt = tt.mt;
             const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
             const int x = tx * p.tw + lx, y = ty * p.th + ly, n = tb * p.tn + ln;
-            const bool valid = (n < p.B) && (y < p.Ho) && (x < p.Wo);
+            const bool valid = tt.live && (n < p.B) && (y < p.Ho) && (x < p.Wo);
             const int oy = y * p.osy + p.ph[pi].oy, ox = x * p.osx + p.ph[pi].ox;
             bf16* orow = p.out + (((size_t)n * p.out_H + oy) * p.out_W + ox) * p.Co + nt * BN;
             mbar_wait(tfull0 + 8 * acc, acc_phase);
@@ -232,6 +287,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     fence_before();
     __syncthreads();
+    if constexpr (CL > 1) tc_cluster_sync();       // no CTA leaves while a peer's commit may still arrive on its barriers
     if (warp == 1) { fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
@@ -262,17 +318,58 @@ bool tc_conv_supported(const ConvGeom& g, bool dgrad) {
     return true;
 }
 
-template <int BN, int BK>
-static void launch_tc(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p) {
+template <int BN, int BK, int CL>
+static int tc_max_clusters() {
+    static int cached = -1;
+    if (cached < 0) {
+        using Cfg = TcCfg<BN, BK>;
+        cudaFuncSetAttribute(conv_tc_kernel<BN, BK, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(num_sms() / CL * CL); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<BN, BK, CL>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = 0; }
+        cached = n;
+    }
+    return cached;
+}
+template <int BN, int BK, int CL>
+static void launch_tc_cl(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p) {
     using Cfg = TcCfg<BN, BK>;
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(conv_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaFuncSetAttribute(conv_tc_kernel<BN, BK, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         configured = true;
     }
-    const int total_tiles = p.nphases * p.tiles_per_phase;
-    const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-    conv_tc_kernel<BN, BK><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+    if constexpr (CL == 1) {
+        const int total_tiles = p.nphases * p.tiles_per_phase;
+        const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+        conv_tc_kernel<BN, BK, 1><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+    } else {
+        const int clusters = std::min(tc_max_clusters<BN, BK, CL>(), p.nphases * p.groups_per_phase);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(clusters * CL); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, BK, CL>, ma, mb, p);
+        if (e != cudaSuccess) throw std::runtime_error(std::string("conv_tc cluster launch failed: ") + cudaGetErrorString(e));
+        ++g_salt_cluster_launches;
+    }
+}
+// cluster size of the tap-table kernel: env SALT_TC_CLUSTER_GENERIC = 1 | 2 | 4
+static int tc_cluster_pref() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SALT_TC_CLUSTER_GENERIC"); v = e ? atoi(e) : TC_GENERIC_CLUSTER_DEFAULT; if (v != 1 && v != 2 && v != 4) v = 1; }
+    return v;
+}
+template <int BN, int BK>
+static int tc_pick_cluster(const TcParams& p) {
+    int cl = tc_cluster_pref();
+    while (cl > 1 && (p.m_tiles < cl * 8 || (cl == 4 ? tc_max_clusters<BN, BK, 4>() : tc_max_clusters<BN, BK, 2>()) * cl < num_sms() * 3 / 4)) cl >>= 1;
+    return cl;
 }
 
 // Common launcher.  A: [B,Ha,Wa,Ca] bf16; Wp: [Nout][Ktot] bf16; out: physical [B,out_H,out_W,Nout] bf16;
@@ -292,8 +389,15 @@ static void run_tc(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca
     const bool sw64 = BK == 32;
     CUtensorMap ma = make_map_nhwc(A, Ca, Wa, Ha, B, BK, p.tw, p.th, p.tn, p.a_stride,
                                    sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
-    CUtensorMap mb = make_map_weights(Wp, Ktot, Nout, BK, BN, sw64);
-#define TC_CASE(bn, bk) if (BN == bn && BK == bk) { launch_tc<bn, bk>(st, ma, mb, p); return; }
+    p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
+#define TC_CASE(bn, bk) if (BN == bn && BK == bk) {                                                            \
+        const int cl = tc_pick_cluster<bn, bk>(p);                                                             \
+        p.groups_per_phase = cdiv(p.m_tiles, cl) * p.tiles_co;                                                 \
+        CUtensorMap mb = make_map_weights(Wp, Ktot, Nout, BK, BN / cl, sw64);   /* CL > 1: my BN/CL rows of a slab */ \
+        if (cl == 4) launch_tc_cl<bn, bk, 4>(st, ma, mb, p);                                                   \
+        else if (cl == 2) launch_tc_cl<bn, bk, 2>(st, ma, mb, p);                                              \
+        else launch_tc_cl<bn, bk, 1>(st, ma, mb, p);                                                           \
+        return; }
     TC_CASE(256, 64) TC_CASE(128, 64) TC_CASE(64, 64) TC_CASE(32, 64)
     TC_CASE(256, 32) TC_CASE(128, 32) TC_CASE(64, 32) TC_CASE(32, 32)
 #undef TC_CASE

@@ -396,10 +396,13 @@ static void launch_rows(cudaStream_t st, const CUtensorMap& ma, const CUtensorMa
         ++g_salt_cluster_launches;
     }
 }
-// cluster size for the weight multicast: env SALT_TC_CLUSTER = 1 | 2 | 4 (default 4 when the device can co-schedule it)
+// cluster size for the weight multicast: env SALT_TC_CLUSTER = 1 | 2 | 4.  Measured on B200 (bench.py, UNetResNet-34, profiles/
+// r1_notes.md): CL = 2 runs exactly as fast as CL = 1 (19.02 vs 19.04 ms per step) while pulling ~30 % fewer bytes out of L2,
+// CL = 4 is 2 % slower (36 clusters of 4 leave 4 SMs idle and the 4-way lockstep adds skew).  The kernel is bound by
+// shared-memory bandwidth (tensor-core operand reads + TMA writes), which multicast does not lower - default 2.
 static int rows_cluster_pref() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("SALT_TC_CLUSTER"); v = e ? atoi(e) : 4; if (v != 1 && v != 2 && v != 4) v = 1; }
+    if (v < 0) { const char* e = getenv("SALT_TC_CLUSTER"); v = e ? atoi(e) : 2; if (v != 1 && v != 2 && v != 4) v = 1; }
     return v;
 }
 template <int BN>

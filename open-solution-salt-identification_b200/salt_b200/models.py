@@ -363,24 +363,40 @@ class SegmentationModel(Model):
         return st
 
     def _graph_enabled(self):
-        return os.environ.get('SALT_ENGINE_GRAPH', '1') != '0' and not self.engine.profiling
+        return (os.environ.get('SALT_ENGINE_GRAPH', '1') != '0' and not self.engine.profiling
+                and not getattr(self, '_gs', {}).get('disabled', False))
 
     def _capture(self, b):
+        """Capture forward and backward of batch size b.  Returns False (and switches graph replay off for this model) if the
+        capture fails - the eager path is always valid."""
         from . import _lib
         eng, st = self.engine, self._graph_state()
         torch.cuda.synchronize(eng.device)
         eng.params_changed()                      # the weight re-pack must be part of the captured forward
-        n0 = _lib.launch_count()
-        gf = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gf):
-            eng.forward(st['x'][:b], train=True, out=st['logits'][:b])
-        n1 = _lib.launch_count()
-        gb = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gb):
-            eng.backward(st['dlogits'][:b])
-        n2 = _lib.launch_count()
-        eng.num_batches_tracked -= 1              # capture does not execute
+        nbt = eng.num_batches_tracked
+        # with a process group alive, NCCL's watchdog thread polls CUDA events: keep its calls from invalidating the capture
+        mode = 'thread_local' if self.dp.world > 1 else 'global'
+        try:
+            n0 = _lib.launch_count()
+            gf = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gf, capture_error_mode=mode):
+                eng.forward(st['x'][:b], train=True, out=st['logits'][:b])
+            n1 = _lib.launch_count()
+            gb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gb, capture_error_mode=mode):
+                eng.backward(st['dlogits'][:b])
+            n2 = _lib.launch_count()
+        except Exception as exc:                  # pragma: no cover - depends on driver / NCCL state
+            import warnings
+            warnings.warn('CUDA-graph capture failed (%s); training continues with eager launches' % (exc,))
+            st['disabled'] = True
+            torch.cuda.synchronize(eng.device)
+            eng.num_batches_tracked = nbt
+            eng.params_changed()
+            return False
+        eng.num_batches_tracked = nbt             # capture does not execute
         st['graphs'][b] = (gf, gb, n1 - n0, n2 - n1)
+        return True
 
     def _train_step_graph(self, b, wait=None, target=None):
         from . import _lib

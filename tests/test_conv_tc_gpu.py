@@ -29,6 +29,11 @@ TC_CASES = [
     (5, 128, 256, 32, 32, 3, 1, 1),      # two channel tiles per pixel tile
     (5, 320, 64, 34, 66, 3, 1, 0),       # final.0-like at cluster size: forward 5 channel blocks, dgrad 5 channel tiles of 64
     (4, 64, 32, 66, 66, 3, 1, 0),        # N = 32 (8-row multicast parts), bordered input
+    # ... and for the cluster variant of the tap-table kernel (env SALT_TC_CLUSTER_GENERIC=2|4)
+    (8, 64, 128, 64, 64, 3, 2, 1),       # stride 2 forward + 4-phase stride-2 dgrad, 64 position tiles
+    (8, 64, 128, 64, 64, 1, 2, 0),       # 1x1 stride-2
+    (70, 512, 512, 8, 8, 3, 1, 1),       # 8x8 maps, two images per tile: 35 position tiles (short last group), 2-4 channel tiles
+    (4, 32, 64, 66, 66, 3, 1, 0),        # Cin = 32: 64-byte swizzle, 512-byte multicast parts
 ]
 
 
@@ -52,9 +57,11 @@ def test_conv_tc_forward_and_dgrad(case):
     torch.cuda.synchronize()
     import os
     m_tiles = B * ((Ho + 15) // 16) * ((Wo + 7) // 8)
-    if k == 3 and s == 1 and Ci % 64 == 0 and Co % 32 == 0 and Ho >= 16 and m_tiles >= 32 and os.environ.get('SALT_TC_CLUSTER', '4') != '1':
+    if k == 3 and s == 1 and Ci % 64 == 0 and Co % 32 == 0 and Ho >= 16 and m_tiles >= 32 and os.environ.get('SALT_TC_CLUSTER', '2') != '1':
         # large enough for the thread-block-cluster variant: make sure THAT kernel (TMA-multicast weights) produced `out`
         assert lib.salt_cluster_launch_count() > cl0, 'cluster variant of the row-halo convolution was not launched'
+    elif B >= 4 and H * W * B >= 8 * 8 * 64 and os.environ.get('SALT_TC_CLUSTER_GENERIC', '1') != '1':
+        assert lib.salt_cluster_launch_count() > cl0, 'cluster variant of the tap-table convolution was not launched'
     oks = [report('tc conv fwd %s' % (case,), _from_nhwc(out), y_ref, atol=2e-2, rtol=1e-2)[0]]
     oks.append(report('tc conv stats sum', stats[:Co].cpu().float(), y_ref.sum((0, 2, 3)), atol=5e-2, rtol=2e-3)[0])
     oks.append(report('tc conv stats sumsq', stats[Co:].cpu().float(), (y_ref ** 2).sum((0, 2, 3)), atol=5e-2, rtol=2e-3)[0])
