@@ -81,6 +81,23 @@ def test_host_threshold_selection_edge_cases():
     assert r['threshold'] == 0.5 and r['iout'] == 1.0 and r['iou'] == 1.0
 
 
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_io_ops_have_no_cpu_fallback():
+    """Without a CUDA device the product entry points raise instead of computing on the host (the oracle is never used)."""
+    import ctypes as C
+    from salt_b200 import _lib, io_ops, validation
+    lib = _lib.load()
+    with pytest.raises(_lib.SaltEngineError):
+        io_ops.adapt_tiles(torch.zeros((1, 101, 101), dtype=torch.uint8))
+    with pytest.raises(_lib.SaltEngineError):
+        io_ops.encode_rle([np.zeros((101, 101), np.uint8)])
+    with pytest.raises(_lib.SaltEngineError):
+        validation.validation_counts(torch.zeros(1, 2, 128, 128), torch.zeros((1, 101, 101), dtype=torch.uint8))
+    buf = (C.c_ubyte * 16)()
+    assert lib.salt_rle_encode(buf, 1, 4, 4, 8, buf, buf, None) != 0 and b'no CUDA device' in lib.salt_last_error()
+    assert lib.salt_adapt_tiles(buf, 1, 4, 4, 8, 0.5, 0.5, 0, buf, None) != 0 and b'no CUDA device' in lib.salt_last_error()
+
+
 # ------------------------------------------------------------------------------------------------- GPU: kernels vs oracle
 @gpu
 def test_adapt_tiles_bit_exact(gold, inp):
