@@ -28,7 +28,7 @@ enum { SALT_ARCH_UNET_RESNET = 0, SALT_ARCH_UNET_SERESNET = 1 };
 typedef struct salt_config {
     int arch;            /* SALT_ARCH_UNET_RESNET   <- models.py:15-18 ARCHITECTURES['UNetResNet']   (unet.py:22-109)
                             SALT_ARCH_UNET_SERESNET <- models.py:19-24 ARCHITECTURES['UNetSeResNet'] (unet.py:112-172)    */
-    int encoder_depth;   /* UNetResNet: 18 or 34 (encoders.py:10-13); UNetSeResNet: 50 (encoders.py:52-53)              */
+    int encoder_depth;   /* UNetResNet: 18 or 34 (encoders.py:10-13); UNetSeResNet: 50, 101 or 152 (encoders.py:52-57) */
     int num_classes;     /* out_channels           <- models.py:182                                             */
     int max_batch;       /* largest batch any call will pass                                                    */
     int height, width;   /* network input size, multiples of 32 (128 for the 101x101 tiles, loaders.py)         */

@@ -7,7 +7,7 @@ unsigned long long g_salt_launches = 0;
 unsigned long long g_salt_cluster_launches = 0;
 
 static const float BN_EPS = 1e-5f, BN_MOMENTUM = 0.1f;
-static const int MAX_CONVS = 128;       // capacity of the batched pack / unpack descriptor tables
+static const int MAX_CONVS = 192;       // capacity of the batched pack / unpack descriptor tables
 
 // ------------------------------------------------------------------------------------------------
 // plan construction
@@ -15,7 +15,8 @@ static const int MAX_CONVS = 128;       // capacity of the batched pack / unpack
 Engine::Engine(const EngineConfig& cfg) : cfg_(cfg) {
     if (cfg.arch == 0 && cfg.depth != 18 && cfg.depth != 34)
         throw std::runtime_error("UNetResNet: only encoder_depth 18 and 34 are implemented in this engine");
-    if (cfg.arch == 1 && cfg.depth != 50) throw std::runtime_error("UNetSeResNet: only encoder_depth 50 is implemented in this engine");
+    if (cfg.arch == 1 && cfg.depth != 50 && cfg.depth != 101 && cfg.depth != 152)
+        throw std::runtime_error("UNetSeResNet: encoder_depth must be 50, 101 or 152 (reference encoders.py:52-59)");
     if (cfg.arch != 0 && cfg.arch != 1) throw std::runtime_error("unknown architecture id");
     if (cfg.H % 32 || cfg.W % 32) throw std::runtime_error("input height/width must be multiples of 32");
     if (cfg.num_classes < 1 || cfg.num_classes > 4) throw std::runtime_error("num_classes must be 1..4");
@@ -128,8 +129,9 @@ void Engine::build() {
     blocks_.clear(); bnecks_.clear(); gradbufs_.clear();
     if (counting_) infos_.clear();
     const int B = cfg_.max_batch, H = cfg_.H, W = cfg_.W;
-    const int nblk18[4] = {2, 2, 2, 2}, nblk34[4] = {3, 4, 6, 3};
-    const int* nblk = cfg_.depth == 18 ? nblk18 : nblk34;      // SE-ResNet-50 shares [3,4,6,3]
+    const int nblk18[4] = {2, 2, 2, 2}, nblk34[4] = {3, 4, 6, 3}, nblk101[4] = {3, 4, 23, 3}, nblk152[4] = {3, 8, 36, 3};
+    // ResNet-34 and SE-ResNet-50 share [3,4,6,3]; se_resnet101 / se_resnet152 differ only in the block counts
+    const int* nblk = cfg_.depth == 18 ? nblk18 : cfg_.depth == 101 ? nblk101 : cfg_.depth == 152 ? nblk152 : nblk34;
     const int chans[4] = {64, 128, 256, 512};
 
     // BN statistic arenas: sized on the counting pass

@@ -20,7 +20,7 @@ def _ptr(t):
 
 class UNetEngine:
     """UNetResNet (reference architectures/unet.py:22-109; encoder_depth 18/34) or UNetSeResNet (unet.py:112-172;
-    encoder_depth 50, architecture='UNetSeResNet') on the CUDA engine.
+    encoder_depth 50/101/152, architecture='UNetSeResNet') on the CUDA engine.
 
     precision: 'fp32' (parity mode: fp32 storage, fp32 FMA) or 'bf16' (bf16 activations / weights copies,
     fp32 accumulation, fp32 master weights and optimiser state).
@@ -35,7 +35,7 @@ class UNetEngine:
         self.encoder_depth, self.num_classes, self.max_batch, self.size = encoder_depth, num_classes, max_batch, size
         self.precision = precision
         if architecture is None:
-            architecture = 'UNetSeResNet' if encoder_depth == 50 else 'UNetResNet'
+            architecture = 'UNetSeResNet' if encoder_depth >= 50 else 'UNetResNet'
         self.architecture = architecture
         arch_id = {'UNetResNet': _lib.ARCH_UNET_RESNET, 'UNetSeResNet': _lib.ARCH_UNET_SERESNET}[architecture]
         cfg = _lib.SaltConfig(arch_id, encoder_depth, num_classes, max_batch, size, size,

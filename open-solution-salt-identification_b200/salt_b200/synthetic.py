@@ -10,13 +10,13 @@ STD = (0.229, 0.224, 0.225)    # reference main.py:56
 
 
 def resnet_block_counts(depth):
-    return {18: (2, 2, 2, 2), 34: (3, 4, 6, 3), 50: (3, 4, 6, 3)}[depth]
+    return {18: (2, 2, 2, 2), 34: (3, 4, 6, 3), 50: (3, 4, 6, 3), 101: (3, 4, 23, 3), 152: (3, 8, 36, 3)}[depth]
 
 
 def param_specs(depth=34, num_classes=2):
     """Canonical (name, shape, kind) list of every tensor the network owns.
 
-    depth 18/34 -> UNetResNet (unet.py:22-109), depth 50 -> UNetSeResNet
+    depth 18/34 -> UNetResNet (unet.py:22-109), depth 50/101/152 -> UNetSeResNet
     (unet.py:112-172, SE-ResNet-50 encoder).  Names are the reference's
     ``state_dict`` keys under ``encoders.encoder.*`` (the aliases
     ``encoders.conv1.*`` / ``encoders.encoderN.*`` share storage, reference
@@ -31,7 +31,7 @@ def param_specs(depth=34, num_classes=2):
         specs.append((prefix + '.running_var', (c,), 'bn_rv'))
 
     e = 'encoders.encoder.'
-    se50 = depth == 50
+    se50 = depth >= 50          # SE-ResNet-50 / 101 / 152 (reference encoders.py:52-57)
     specs.append((e + ('layer0.conv1.weight' if se50 else 'conv1.weight'), (64, 3, 7, 7), 'conv_w'))
     bn(e + ('layer0.bn1' if se50 else 'bn1'), 64)
     cin = 64
@@ -104,7 +104,7 @@ def synth_state_dict(depth=34, num_classes=2, seed=0):
         elif kind == 'bn_w':
             # the last BN of a residual branch gets a small gain so that eval-mode activations (running
             # statistics, no renormalisation) stay O(1) through 16 residual blocks
-            last = 'bn3.weight' if depth == 50 else 'bn2.weight'
+            last = 'bn3.weight' if depth >= 50 else 'bn2.weight'
             a = rng.uniform(0.1, 0.5, shape) if name.endswith(last) else rng.uniform(0.5, 1.5, shape)
         elif kind == 'bn_b':
             a = rng.standard_normal(shape) * 0.1

@@ -29,6 +29,7 @@ CASES = [
     # UNetSeResNet-50 (BASELINE.json configs[3] architecture): the reference's own UNetSeResNet / SeResNetEncoders classes
     # on top of oracle/senet_restated.py (pretrainedmodels is absent - see that file's header)
     ('se50_b2_s64', 50, 2, 64, 2, 777),
+    ('se101_b2_s64', 101, 2, 64, 4, 555),     # depth variant of the same class (encoders.py:54-55: se_resnet101, layers [3,4,23,3])
 ]
 
 GRAD_KEYS = ['encoders.encoder.conv1.weight', 'encoders.encoder.layer1.0.conv1.weight',
@@ -49,11 +50,11 @@ GRAD_KEYS_SE50 = ['encoders.encoder.layer0.conv1.weight', 'encoders.encoder.laye
 
 
 def grad_keys(depth):
-    return GRAD_KEYS_SE50 if depth == 50 else GRAD_KEYS
+    return GRAD_KEYS_SE50 if depth >= 50 else GRAD_KEYS
 
 
 def stem_bn(depth):
-    return 'encoders.encoder.layer0.bn1' if depth == 50 else 'encoders.encoder.bn1'
+    return 'encoders.encoder.layer0.bn1' if depth >= 50 else 'encoders.encoder.bn1'
 
 
 MAX_SAMPLES = 8192

@@ -166,7 +166,8 @@ def install():
     if isinstance(sys.modules['pretrainedmodels'], _StubModule):
         # encoders.py:52-53 looks the constructor up in the package __dict__; the package is absent, use the restatement
         from . import senet_restated
-        sys.modules['pretrainedmodels'].__dict__['se_resnet50'] = senet_restated.se_resnet50
+        for fn in ('se_resnet50', 'se_resnet101', 'se_resnet152'):
+            sys.modules['pretrainedmodels'].__dict__[fn] = getattr(senet_restated, fn)
     _install_cocomask_stub()
     sys.modules['steppy.base'].BaseTransformer = BaseTransformer
     sys.modules['toolkit.pytorch_transformers.models'].Model = Model
@@ -189,8 +190,8 @@ def reference_unet(depth, num_classes=2):
     from common_blocks.architectures import unet
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
-        if depth == 50:
-            return unet.UNetSeResNet(encoder_depth=50, num_classes=num_classes, dropout_2d=0.0, pretrained=None,
+        if depth >= 50:
+            return unet.UNetSeResNet(encoder_depth=depth, num_classes=num_classes, dropout_2d=0.0, pretrained=None,
                                      use_hypercolumn=True, pool0=False)
         return unet.UNetResNet(encoder_depth=depth, num_classes=num_classes, dropout_2d=0.0,
                                pretrained=False, use_hypercolumn=True, pool0=False)

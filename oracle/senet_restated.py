@@ -98,3 +98,13 @@ class SENet(nn.Module):
 def se_resnet50(num_classes=1000, pretrained=None):
     """Same call signature as the pinned package; there is no network here, so pretrained weights are never loaded."""
     return SENet((3, 4, 6, 3), reduction=16, num_classes=num_classes)
+
+
+def se_resnet101(num_classes=1000, pretrained=None):
+    """pretrainedmodels se_resnet101: the same SEResNetBottleneck, layers [3, 4, 23, 3] (reference encoders.py:54-55)."""
+    return SENet((3, 4, 23, 3), reduction=16, num_classes=num_classes)
+
+
+def se_resnet152(num_classes=1000, pretrained=None):
+    """pretrainedmodels se_resnet152: layers [3, 8, 36, 3] (reference encoders.py:56-57)."""
+    return SENet((3, 8, 36, 3), reduction=16, num_classes=num_classes)

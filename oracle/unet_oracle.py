@@ -38,7 +38,7 @@ def alias_keys(depth=34):
     """alias key -> canonical key, for the duplicated registrations the reference
     creates in ResNetEncoders (encoders.py:21-36)."""
     amap = {}
-    stem = 'encoders.encoder.layer0.' if depth == 50 else 'encoders.encoder.'       # encoders.py:59-66 vs :21-28
+    stem = 'encoders.encoder.layer0.' if depth >= 50 else 'encoders.encoder.'       # encoders.py:59-66 vs :21-28
     for s in ('weight',):
         amap['encoders.conv1.0.' + s] = stem + 'conv1.' + s
     for s in ('weight', 'bias', 'running_mean', 'running_var', 'num_batches_tracked'):
@@ -95,8 +95,8 @@ def _se_bottleneck(sd, p, x, stride, train):
 def encoder_forward(sd, x, depth, train):
     # encoders.py:38-45 / :76-83 with pool0=False (no maxpool)
     e = 'encoders.encoder.'
-    stem = e + ('layer0.' if depth == 50 else '')
-    block = _se_bottleneck if depth == 50 else _basic_block
+    stem = e + ('layer0.' if depth >= 50 else '')
+    block = _se_bottleneck if depth >= 50 else _basic_block
     y = F.conv2d(x, sd[stem + 'conv1.weight'], None, stride=2, padding=3)
     y = F.relu(_bn(sd, stem + 'bn1', y, train))
     feats = []

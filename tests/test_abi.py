@@ -50,6 +50,28 @@ def test_plan_table_matches_reference_state_dict(lib):
         lib.salt_destroy(h)
 
 
+def test_plan_table_seresnet_depth_variants(lib):
+    """UNetSeResNet with the three encoder depths the reference class accepts (encoders.py:52-59): state_dict keys and shapes."""
+    from salt_b200 import _lib
+    from oracle import synth
+    for depth in (50, 101, 152):
+        cfg = _lib.SaltConfig(_lib.ARCH_UNET_SERESNET, depth, 2, 2, 64, 64, _lib.PREC_BF16, 1)
+        h = C.c_void_p()
+        _lib.check(lib.salt_create(C.byref(cfg), C.byref(h)))
+        name = C.create_string_buffer(256)
+        shape = (C.c_int * 4)()
+        ndim, isbuf, off, numel = C.c_int(), C.c_int(), C.c_size_t(), C.c_size_t()
+        got = {}
+        for i in range(lib.salt_num_tensors(h)):
+            _lib.check(lib.salt_tensor_info(h, i, name, 256, shape, C.byref(ndim), C.byref(off), C.byref(numel), C.byref(isbuf)))
+            got[name.value.decode()] = tuple(shape[:ndim.value])
+        assert got == {n: s for n, s, _ in synth.param_specs(depth, 2)}
+        lib.salt_destroy(h)
+    cfg = _lib.SaltConfig(_lib.ARCH_UNET_SERESNET, 34, 2, 2, 64, 64, _lib.PREC_BF16, 1)
+    h = C.c_void_p()
+    assert lib.salt_create(C.byref(cfg), C.byref(h)) != 0 and b'50, 101 or 152' in lib.salt_last_error()
+
+
 def test_bad_config_is_rejected(lib):
     from salt_b200 import _lib
     h = C.c_void_p()

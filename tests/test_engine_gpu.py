@@ -214,7 +214,7 @@ def test_train_step_fp32(depth, b, s, loss_name):
     assert worst <= 1e-6
 
 
-@pytest.mark.parametrize('tag', ['r18_b2_s64', 'r34_b2_s64', 'r18_b8_s128', 'se50_b2_s64'])
+@pytest.mark.parametrize('tag', ['r18_b2_s64', 'r34_b2_s64', 'r18_b8_s128', 'se50_b2_s64', 'se101_b2_s64'])
 def test_golden_fixtures_fp32(golden_dir, tag):
     """Engine vs vectors produced by the unmodified reference modules (tests/golden, oracle/make_golden.py)."""
     g = np.load(os.path.join(golden_dir, tag + '.npz'))

@@ -9,7 +9,7 @@ import torch
 from oracle import synth, unet_oracle, losses_oracle
 from oracle.make_golden import sample, grad_keys, stem_bn
 
-CASES = ['r18_b2_s64', 'r34_b2_s64', 'se50_b2_s64']
+CASES = ['r18_b2_s64', 'r34_b2_s64', 'se50_b2_s64', 'se101_b2_s64']
 
 
 def _load(golden_dir, tag):
