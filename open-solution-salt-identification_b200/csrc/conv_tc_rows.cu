@@ -7,9 +7,15 @@
 //     (16 output rows + vertical halo) is loaded.  A pixel row of 8 pixels x 64 channels is exactly one 1024-byte swizzle atom,
 //     so the vertical taps r = 0,1,2 are the SAME buffer read at byte offsets r*1024 - the UMMA descriptor start address stays
 //     1024-byte aligned and the canonical K-major 128B-swizzled layout is untouched (A traffic: 3 x 18 KB instead of 9 x 16 KB);
-//   * the three weight slabs [BN x 64] of taps (0..2, s) arrive with ONE 4-D TMA box (c, n, r, s) in the same stage;
+//   * the three weight slabs [BN x 64] of taps (0..2, s) arrive in the same stage (one 4-D TMA box (c, n, r, s), or CL multicast parts);
 //   * the issuer waits once and issues 12 MMAs (3 taps x 4 K-steps) per stage, then one tcgen05.commit frees the stage.
-// Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue (as conv_tc.cu), two TMEM accumulators, persistent CTAs.
+// Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-9 = epilogue (two per TMEM lane quarter), two TMEM accumulators, persistent CTAs.
+//
+// Three variants share the epilogue (rows_epilogue):
+//   conv_tc_rows_kernel<BN, 1>       one CTA per tile
+//   conv_tc_rows_kernel<BN, 2|4>     thread-block cluster, weight slabs TMA-multicast (default CL = 2; SALT_TC_CLUSTER)
+//   conv_tc_rows_pair_kernel<BN>     CTA pair, cta_group::2 MMAs with M = 256 (experimental, SALT_TC_PAIR=1)
+// With the current kernel the shared-memory port (MMA operand reads + TMA writes), not L2/HBM or the tensor pipe, is the bound.
 #include "tc_common.cuh"
 #include "conv_tc.h"
 #include <cstdlib>
