@@ -89,3 +89,25 @@ def test_single_process_context_is_identity():
     ctx = DataParallelContext(0, 1, 0, None, None)
     g = torch.ones(4)
     assert ctx.allreduce_grads(g) == 1.0 and ctx.shard(128) == (0, 128) and ctx.max_over_ranks(3.5) == 3.5
+
+
+def test_fit_prefetch_order_and_termination():
+    """Host logic of SegmentationModel._prefetch (no CUDA): batch i+1 is staged BEFORE batch i is handed to the training step,
+    every batch is staged exactly once and in order, and the generator ends with the loader."""
+    sys.path.insert(0, os.path.join(ROOT, 'open-solution-salt-identification_b200'))
+    from salt_b200.models import SegmentationModel
+    log = []
+
+    class Fake:
+        def _stage(self, data):
+            if data is not None:
+                log.append(('stage', data))
+            return data
+    fake = Fake()
+    out = []
+    for item in SegmentationModel._prefetch(fake, iter(range(4))):
+        log.append(('step', item))
+        out.append(item)
+    assert out == [0, 1, 2, 3]
+    assert log == [('stage', 0), ('stage', 1), ('step', 0), ('stage', 2), ('step', 1), ('stage', 3), ('step', 2), ('step', 3)]
+    assert list(SegmentationModel._prefetch(fake, iter(()))) == []
