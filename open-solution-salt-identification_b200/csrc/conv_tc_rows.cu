@@ -291,6 +291,159 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
     }
 }
 
+// Sub-tile `sub` of work item k of this CTA in the multi-tile kernel: S consecutive pixel tiles of one channel tile share every
+// weight stage; sub-tiles past the end of the tensor are clamped and dropped (`live` = false).
+template <int S>
+__device__ __forceinline__ bool multi_tile(const RowsParams& p, int k, int sub, RowsTile<1>& t) {
+    const int g = blockIdx.x + k * gridDim.x;
+    if (g >= p.total_groups) return false;
+    t.nt = g % p.tiles_co;
+    int mt = (g / p.tiles_co) * S + sub;
+    t.live = mt < p.m_tiles;
+    if (!t.live) mt = p.m_tiles - 1;
+    t.tx = mt % p.tiles_x; t.ty = (mt / p.tiles_x) % p.tiles_y; t.n = mt / (p.tiles_x * p.tiles_y);
+    return true;
+}
+// Epilogue of the multi-tile kernel: rows_epilogue with S accumulators per finished group (a textual twin of the function above,
+// kept separate until the multi-tile kernel has been measured on the GPU so that the validated path stays byte-identical).
+template <int BN, bool NARROW, int S>
+__device__ __forceinline__ void rows_epilogue_multi(const RowsParams& p, const int warp, const int lane, const uint32_t tmem_base,
+                                            const uint32_t tfull0, const uint32_t tempty0, float* s_stats) {
+    // Epilogue, 8 warps (2..9).  Warp w may touch TMEM lanes 32*(w%4)..+31;
+    // the two warps of a lane quarter split the 32-column chunks between them, so every scheduler has two epilogue warps
+    // to interleave (the shuffle/convert chains of a single warp left the issue slots idle - profiles/r1_notes.md).
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    float* my_stats = s_stats + (warp - 2) * (2 * BN);  // private per-warp accumulators: no shared-memory atomics
+    const int m = quarter * 32 + lane;                  // row of the 128-position tile: 16 rows x 8 columns
+    const int lx = m & (RW_TW - 1), ly = m >> 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    // Narrow layers (BN <= 64, one channel tile): every epilogue warp owns ONE fixed 32-column chunk for the whole kernel, so
+    // its bias lives in registers and the BatchNorm sums are accumulated per THREAD (one pixel row each) across all tiles of
+    // the CTA; the cross-lane butterfly runs once per kernel instead of once per tile.  For K = 576 layers the per-tile
+    // butterflies (62 shuffles per chunk) made the epilogue longer than the MMA phase (profiles/r1_notes.md).
+    const bool own_chunk = half < BN / 32;
+    float rs1[32], rs2[32], rbias[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { rs1[i] = 0.f; rs2[i] = 0.f; rbias[i] = 0.f; }
+    if (NARROW && own_chunk && p.bias) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rbias[i] = __ldg(p.bias + half * 32 + i);
+    }
+    RowsTile<1> t;
+    for (int k = 0;; ++k) {
+      bool more = true;
+#pragma unroll 1
+      for (int sub = 0; sub < S; ++sub) {
+        more = multi_tile<S>(p, k, sub, t);
+        if (!more) break;
+        const int nt = t.nt, n = t.n;
+        const int x = t.tx * RW_TW + lx, y = t.ty * RW_TH + ly;
+        const bool valid = t.live && (y < p.Ho) && (x < p.Wo) && !(p.debug & (4 | 16));
+        bf16* orow = p.out + (((size_t)n * p.Ho + y) * p.Wo + x) * p.Co + nt * BN;
+        // accumulate mode (dgrad into an existing gradient): the old values of the first chunk are fetched BEFORE waiting for the
+        // accumulator, so their DRAM latency hides behind the MMA phase instead of serialising the epilogue
+        uint4 old[4];
+        const bool accum = !NARROW && p.accumulate;
+        if (accum && valid && half < BN / 32) {
+            const uint4* o4 = reinterpret_cast<const uint4*>(orow + half * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) old[q] = o4[q];
+        }
+        if (sub == 0) mbar_wait(tfull0 + 8 * acc, acc_phase);      // all S accumulators of the group complete together
+        fence_after();
+#pragma unroll 1
+        for (int ch = half; ch < BN / 32; ch += 2) {
+            float v[32];
+            if (accum && valid && ch != half) {
+                const uint4* o4 = reinterpret_cast<const uint4*>(orow + ch * 32);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) old[q] = o4[q];
+            }
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (acc * S + sub) * BN + ch * 32, v);
+            if constexpr (NARROW) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += rbias[i];
+            } else if (p.bias) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + nt * BN + ch * 32 + i);
+            }
+            if (valid) {
+                uint4* o4 = reinterpret_cast<uint4*>(orow + ch * 32);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (accum) {
+                        const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old[q]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float2 f = __bfloat1622float2(ob[j]);
+                            v[q * 8 + 2 * j] += f.x; v[q * 8 + 2 * j + 1] += f.y;
+                        }
+                    }
+                    uint4 pk;
+                    __nv_bfloat162 b0 = __floats2bfloat162_rn(v[q * 8 + 0], v[q * 8 + 1]);
+                    __nv_bfloat162 b1 = __floats2bfloat162_rn(v[q * 8 + 2], v[q * 8 + 3]);
+                    __nv_bfloat162 b2 = __floats2bfloat162_rn(v[q * 8 + 4], v[q * 8 + 5]);
+                    __nv_bfloat162 b3 = __floats2bfloat162_rn(v[q * 8 + 6], v[q * 8 + 7]);
+                    pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+                    o4[q] = pk;
+                }
+            }
+            if (p.stats && !(p.debug & (4 | 8))) {
+                if constexpr (NARROW) {
+                    if (valid) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) { rs1[i] += v[i]; rs2[i] = fmaf(v[i], v[i], rs2[i]); }
+                    }
+                } else {
+                    float sq[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { v[i] = valid ? v[i] : 0.f; sq[i] = v[i] * v[i]; }
+                    float s1 = rows_butterfly_reduce32(v, lane);
+                    float s2 = rows_butterfly_reduce32(sq, lane);
+                    my_stats[ch * 32 + lane] += s1;
+                    my_stats[BN + ch * 32 + lane] += s2;
+                }
+            }
+        }
+        if (sub == S - 1) {
+            fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (p.stats && p.tiles_co > 1) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int tt = threadIdx.x - 64;
+            for (int i = tt; i < 2 * BN; i += RW_EPI_THREADS) {
+                float val = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) { val += s_stats[w8 * 2 * BN + i]; s_stats[w8 * 2 * BN + i] = 0.f; }
+                if (val != 0.f) atomicAdd(p.stats + (i < BN ? nt * BN + i : p.Co + nt * BN + (i - BN)), (double)val);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+      }
+      if (!more) break;
+    }
+    if (NARROW && p.stats && own_chunk) {
+        const float s1 = rows_butterfly_reduce32(rs1, lane);
+        const float s2 = rows_butterfly_reduce32(rs2, lane);
+        my_stats[half * 32 + lane] += s1;
+        my_stats[BN + half * 32 + lane] += s2;
+    }
+    if (p.stats && p.tiles_co == 1) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const int tt = threadIdx.x - 64;
+        for (int i = tt; i < 2 * BN; i += RW_EPI_THREADS) {
+            float val = 0.f;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) val += s_stats[w8 * 2 * BN + i];
+            atomicAdd(p.stats + (i < BN ? i : p.Co + (i - BN)), (double)val);
+        }
+    }
+}
+
 // CL = thread-block-cluster size.  CL > 1: the CL CTAs of a cluster work on CL different pixel tiles of the same channel tile and
 // share every weight stage: each CTA fetches 1/CL of the three weight slabs and TMA-multicasts it into the shared memory of all
 // CL CTAs (map_b then has a [64 c][BN/CL n] box).  Weights are 60-75 % of the bytes a stage pulls through L2, and the L2 -> SM
@@ -548,6 +701,146 @@ conv_tc_rows_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     if (warp == 1) { fence_after(); tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); }
 }
 
+
+// ================================================================================================
+// EXPERIMENTAL (env SALT_TC_MULTI=1, off by default; written at the end of round 1, not yet run on a GPU): every weight stage is
+// re-used for S pixel sub-tiles inside ONE CTA.  Round-1 measurements (profiles/r1_notes.md): the bytes that have to enter an SM
+// per MMA bound conv_tc_rows_kernel (~45 B/clk/SM arrive in every shape) and 60-75 % of them are weights.  TMEM holds 512 columns,
+// i.e. 2 x S accumulators of BN columns with S = 4 (BN <= 64) or 2 (BN = 128); per 12 MMAs a CTA then loads 18 + 24/S KB instead of
+// 42 KB (BN = 64) or 18 + 48/S instead of 66 KB (BN = 128).
+// Two shared-memory rings with their own barriers: weights (NB stages of the 3 slabs of a kernel row) and activations (NA boxes).
+//   producer:  per (channel block, s): weight stage, then the S activation boxes of the group's sub-tiles
+//   issuer:    per weight stage: for each sub-tile wait its box, 12 MMAs into accumulator (acc, sub), commit -> box free;
+//              after the S sub-tiles commit -> weight stage free; after the last stage commit -> tfull[acc]
+//   epilogue:  rows_epilogue_multi drains the S accumulators of the finished group, then frees them with one tempty arrival per warp
+template <int BN, int S> struct MultiCfg {
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int W_STAGE = 3 * B_BYTES;                          // three tap slabs of one kernel row
+    static constexpr int NB = 2;
+    static constexpr int NA = BN == 128 ? 5 : 8;
+    static constexpr int TMEM_COLS = 2 * S * BN < 32 ? 32 : 2 * S * BN;
+    static constexpr int A_OFF = NB * W_STAGE;
+    static constexpr int BAR_OFF = A_OFF + NA * RW_A_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 512 + 8 * 2 * BN * 4;
+    static_assert(TMEM_COLS <= 512, "accumulators do not fit TMEM");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+template <int BN, int S>
+__global__ void __launch_bounds__(RW_THREADS, 1)
+conv_tc_rows_multi_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const RowsParams p) {
+    using Cfg = MultiCfg<BN, S>;
+    constexpr int NA = Cfg::NA, NB = Cfg::NB;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+    // bars: bfull[NB], bempty[NB], afull[NA], aempty[NA], tmem_full[2], tmem_empty[2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * NB + 2 * NA + 4);
+    float* s_stats = reinterpret_cast<float*>(smem + Cfg::BAR_OFF + 512);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t bfull0 = smem_u32(bars), bempty0 = bfull0 + 8 * NB, afull0 = bempty0 + 8 * NB, aempty0 = afull0 + 8 * NA,
+                   tfull0 = aempty0 + 8 * NA, tempty0 = tfull0 + 16;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        for (int i = 0; i < NB; ++i) { mbar_init(bfull0 + 8 * i, 1); mbar_init(bempty0 + 8 * i, 1); }
+        for (int i = 0; i < NA; ++i) { mbar_init(afull0 + 8 * i, 1); mbar_init(aempty0 + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), Cfg::TMEM_COLS);
+    for (int i = threadIdx.x; i < 8 * 2 * BN; i += RW_THREADS) s_stats[i] = 0.f;
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const int stages_per_group = p.cblks * 3;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer
+        if (elect_one()) {
+            int bs = 0, as = 0; uint32_t bphase = 0, aphase = 0;
+            RowsTile<1> t[S];
+            for (int k = 0;; ++k) {
+                bool more = true;
+                for (int sub = 0; sub < S; ++sub) more = multi_tile<S>(p, k, sub, t[sub]) && more;
+                if (!more) break;
+                for (int cb = 0; cb < p.cblks; ++cb) {
+                    for (int s = 0; s < 3; ++s) {
+                        mbar_wait(bempty0 + 8 * bs, bphase ^ 1);
+                        mbar_expect_tx(bfull0 + 8 * bs, Cfg::W_STAGE);
+                        tma_load_4d(smem0 + bs * Cfg::W_STAGE, &map_b, bfull0 + 8 * bs, cb * 64, t[0].nt * BN, 0, s);   // (c, n, r = 0..2, s)
+                        if (++bs == NB) { bs = 0; bphase ^= 1; }
+#pragma unroll
+                        for (int sub = 0; sub < S; ++sub) {
+                            mbar_wait(aempty0 + 8 * as, aphase ^ 1);
+                            mbar_expect_tx(afull0 + 8 * as, RW_A_BYTES);
+                            tma_load_4d(smem0 + Cfg::A_OFF + as * RW_A_BYTES, &map_a, afull0 + 8 * as, cb * 64,
+                                        t[sub].tx * RW_TW - p.pad + s, t[sub].ty * RW_TH - p.pad, t[sub].n);
+                            if (++as == NA) { as = 0; aphase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== MMA issuer: S x 12 MMAs per weight stage
+        const uint32_t idesc = instr_desc_bf16(BN, false, false);
+        const uint64_t adesc0 = smem_desc(smem0 + Cfg::A_OFF, 16, 1024, 2);
+        const uint64_t bdesc0 = smem_desc(smem0, 16, 1024, 2);
+        int bs = 0, as = 0; uint32_t bphase = 0, aphase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        RowsTile<1> t0;
+        for (int kk = 0; multi_tile<S>(p, kk, 0, t0); ++kk) {
+            mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+            fence_after();
+            for (int it = 0; it < stages_per_group; ++it) {
+                mbar_wait(bfull0 + 8 * bs, bphase);
+                const uint64_t boff = (uint64_t)((bs * Cfg::W_STAGE) >> 4);
+#pragma unroll 1
+                for (int sub = 0; sub < S; ++sub) {
+                    mbar_wait(afull0 + 8 * as, aphase);
+                    fence_after();
+                    if (elect_one()) {
+                        const uint32_t tmem_d = tmem_base + (acc * S + sub) * BN;
+                        const uint64_t aoff = (uint64_t)((as * RW_A_BYTES) >> 4);
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+                            const uint64_t adesc = adesc0 + aoff + (uint64_t)((r * 1024) >> 4);
+                            const uint64_t bdesc = bdesc0 + boff + (uint64_t)((r * Cfg::B_BYTES) >> 4);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | r | k) != 0);
+                        }
+                        umma_commit(aempty0 + 8 * as);                                   // this activation box is free again
+                        if (sub == S - 1) {
+                            umma_commit(bempty0 + 8 * bs);                               // ... and so is the weight stage
+                            if (it == stages_per_group - 1) umma_commit(tfull0 + 8 * acc);
+                        }
+                    }
+                    __syncwarp();
+                    if (++as == NA) { as = 0; aphase ^= 1; }
+                }
+                if (++bs == NB) { bs = 0; bphase ^= 1; }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ===================================================== epilogue: 8 warps (2..9)
+        bool narrow = false;
+        if constexpr (BN <= 64) narrow = p.tiles_co == 1 && p.stats != nullptr && !p.accumulate && !(p.debug & 32);
+        if constexpr (BN <= 64) {
+            if (narrow) rows_epilogue_multi<BN, true, S>(p, warp, lane, tmem_base, tfull0, tempty0, s_stats);
+        }
+        if (!narrow) rows_epilogue_multi<BN, false, S>(p, warp, lane, tmem_base, tfull0, tempty0, s_stats);
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) { fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+}
+
 bool tc_conv_rows_supported(int Ca, int Nout, int R, int S, int stride, int Ho, int Wo) {
     return R == 3 && S == 3 && stride == 1 && Ca % 64 == 0 && Nout % 32 == 0 && Ho >= 16 && Wo >= 8;
 }
@@ -603,6 +896,47 @@ static int rows_cluster_pref() {
     if (v < 0) { const char* e = getenv("SALT_TC_CLUSTER"); v = e ? atoi(e) : 2; if (v != 1 && v != 2 && v != 4) v = 1; }
     return v;
 }
+static int rows_multi_pref() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SALT_TC_MULTI"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v;
+}
+template <int BN, int S>
+static void launch_rows_multi_s(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, RowsParams p) {
+    using Cfg = MultiCfg<BN, S>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(conv_tc_rows_multi_kernel<BN, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        configured = true;
+    }
+    p.total_groups = cdiv(p.m_tiles, S) * p.tiles_co;
+    const int grid = p.total_groups < num_sms() ? p.total_groups : num_sms();
+    conv_tc_rows_multi_kernel<BN, S><<<grid, RW_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+}
+// S sub-tiles per weight stage: as many as TMEM allows, fewer when the layer has too few pixel tiles to keep every SM busy
+template <int BN>
+static bool launch_rows_multi(cudaStream_t st, const CUtensorMap& ma, const void* Wp, int Ca, int Nout, const RowsParams& p) {
+    int S = BN == 128 ? 2 : 4;
+    while (S > 1 && (long long)cdiv(p.m_tiles, S) * p.tiles_co < 2LL * num_sms()) S >>= 1;
+    if (S == 1) return false;
+    CUtensorMap mb;          // weights (c, n, r, s): one box = [3 taps r][BN][64 c]
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Ca, (cuuint64_t)Nout, 3, 3};
+        cuuint64_t strides[3] = {(cuuint64_t)9 * Ca * 2, (cuuint64_t)3 * Ca * 2, (cuuint64_t)Ca * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)BN, 3, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = get_encode()(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(Wp), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(weights 4d, multi) failed with code " + std::to_string((int)r));
+    }
+    if constexpr (BN == 128) {
+        launch_rows_multi_s<BN, 2>(st, ma, mb, p);
+    } else {
+        if (S == 4) launch_rows_multi_s<BN, 4>(st, ma, mb, p); else launch_rows_multi_s<BN, 2>(st, ma, mb, p);
+    }
+    return true;
+}
 static int rows_pair_pref() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("SALT_TC_PAIR"); v = (e && e[0] == '1') ? 1 : 0; }
@@ -644,6 +978,7 @@ static bool launch_rows_pair(cudaStream_t st, const CUtensorMap& ma, const void*
 }
 template <int BN>
 static void launch_rows_any(cudaStream_t st, const CUtensorMap& ma, const void* Wp, int Ca, int Nout, RowsParams p) {
+    if (rows_multi_pref() && launch_rows_multi<BN>(st, ma, Wp, Ca, Nout, p)) return;
     if (rows_pair_pref() && launch_rows_pair<BN>(st, ma, Wp, Ca, Nout, p)) return;
     int cl = rows_cluster_pref();
     // a cluster only pays when there are enough pixel tiles to fill it and the machine with whole groups
