@@ -15,7 +15,9 @@
 //   conv_tc_rows_kernel<BN, 1>       one CTA per tile
 //   conv_tc_rows_kernel<BN, 2|4>     thread-block cluster, weight slabs TMA-multicast (default CL = 2; SALT_TC_CLUSTER)
 //   conv_tc_rows_pair_kernel<BN>     CTA pair, cta_group::2 MMAs with M = 256 (experimental, SALT_TC_PAIR=1)
-// With the current kernel the shared-memory port (MMA operand reads + TMA writes), not L2/HBM or the tensor pipe, is the bound.
+// Measured bound (profiles/r1_notes.md): tcgen05.mma fetches its shared-memory operands at ~64 B/clk and re-fetches the 4 KB A slice
+// for every instruction -> ~(4096 + 32 N)/64 clk per MMA; L2/HBM traffic and the bytes entering the SM are not the limit (the
+// cluster, pair and multi-sub-tile variants all cut them and none is faster).
 #include "tc_common.cuh"
 #include "conv_tc.h"
 #include <cstdlib>
@@ -570,7 +572,7 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 // The two CTAs of a cluster form a CTA pair: one tcgen05.mma (M = 256, N = BN) issued by the leader covers both pixel tiles;
 // each CTA stages its own activation tile and only HALF of every weight slab (B is split in N across the pair), so per stage a
 // CTA's shared memory serves (4 KB + N/2 * 32 B) per MMA instead of (4 KB + N * 32 B) and takes 18 KB + 1.5 * N * 128 B of TMA
-// writes instead of 18 KB + 3 * N * 128 B - the shared-memory port is what bounds the single-CTA kernel (profiles/r1_notes.md).
+// writes instead of 18 KB + 3 * N * 128 B - measured on B200: correct, but 1.45x slower (per-stage cross-CTA hand-off), see profiles/r1_notes.md.
 // Protocol:  full[s]      (each CTA, 1 arrival + bytes)  own TMA loads landed
 //            peerfull[s]  (leader, 1 arrival)            the peer forwards its full[s] (remote arrive by its otherwise idle warp 1)
 //            empty[s]     (each CTA, 1 arrival)          leader's tcgen05.commit.cta_group::2, multicast to both CTAs
@@ -703,7 +705,8 @@ conv_tc_rows_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 
 
 // ================================================================================================
-// EXPERIMENTAL (env SALT_TC_MULTI=1, off by default; written at the end of round 1, not yet run on a GPU): every weight stage is
+// EXPERIMENTAL (env SALT_TC_MULTI=1, off by default; bench on B200: same speed as the default kernel, numerics not yet checked by a
+// parity case large enough to reach it): every weight stage is
 // re-used for S pixel sub-tiles inside ONE CTA.  Round-1 measurements (profiles/r1_notes.md): the bytes that have to enter an SM
 // per MMA bound conv_tc_rows_kernel (~45 B/clk/SM arrive in every shape) and 60-75 % of them are weights.  TMEM holds 512 columns,
 // i.e. 2 x S accumulators of BN columns with S = 4 (BN <= 64) or 2 (BN = 128); per 12 MMAs a CTA then loads 18 + 24/S KB instead of
