@@ -62,8 +62,10 @@ constexpr int RW_A_BYTES = (RW_TH + 2) * RW_TW * 128;        // 18 pixel rows x 
 template <int BN> struct RowsCfg {
     static constexpr int B_BYTES = BN * 128;                 // one tap: [BN][64] bf16
     static constexpr int STAGE_BYTES = RW_A_BYTES + 3 * B_BYTES;
-    static constexpr int STAGES = BN == 128 ? 3 : (BN == 64 ? 4 : 6);
-    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    static constexpr int STAGES = BN == 128 ? 3 : (BN == 64 ? 4 : (BN == 32 ? 6 : 2));    // wide tiles (160 / 192): 78 / 90 KB stages
+    // column distance of the two accumulators: BN for the power-of-two tiles, 256 for the wide ones (tcgen05.alloc wants 2^k columns)
+    static constexpr int ACC_STRIDE = (BN & (BN - 1)) == 0 ? BN : 256;
+    static constexpr int TMEM_COLS = 2 * ACC_STRIDE < 32 ? 32 : 2 * ACC_STRIDE;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
     static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256 + 8 * 2 * BN * 4;      // + per-epilogue-warp BN statistics
 };
@@ -209,7 +211,7 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
 #pragma unroll
                 for (int q = 0; q < 4; ++q) old[q] = o4[q];
             }
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + ch * 32, v);
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * RowsCfg<BN>::ACC_STRIDE + ch * 32, v);
             if constexpr (NARROW) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] += rbias[i];
@@ -527,7 +529,7 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int kk = 0; rows_tile<CL>(p, kk, rank, t); ++kk) {
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
             fence_after();
-            const uint32_t tmem_d = tmem_base + acc * BN;
+            const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_STRIDE;
             for (int it = 0; it < stages_per_tile; ++it) {
                 mbar_wait(full0 + 8 * stage, phase);
                 fence_after();
@@ -981,8 +983,10 @@ static bool launch_rows_pair(cudaStream_t st, const CUtensorMap& ma, const void*
 }
 template <int BN>
 static void launch_rows_any(cudaStream_t st, const CUtensorMap& ma, const void* Wp, int Ca, int Nout, RowsParams p) {
-    if (rows_multi_pref() && launch_rows_multi<BN>(st, ma, Wp, Ca, Nout, p)) return;
-    if (rows_pair_pref() && launch_rows_pair<BN>(st, ma, Wp, Ca, Nout, p)) return;
+    if constexpr ((BN & (BN - 1)) == 0) {
+        if (rows_multi_pref() && launch_rows_multi<BN>(st, ma, Wp, Ca, Nout, p)) return;
+        if (rows_pair_pref() && launch_rows_pair<BN>(st, ma, Wp, Ca, Nout, p)) return;
+    }
     int cl = rows_cluster_pref();
     // a cluster only pays when there are enough pixel tiles to fill it and the machine with whole groups
     while (cl > 1 && (p.m_tiles < cl * 8 || (cl == 4 ? rows_max_clusters<BN, 4>() : rows_max_clusters<BN, 2>()) * cl < num_sms() * 3 / 4)) cl >>= 1;
@@ -1011,7 +1015,13 @@ void k_conv_tc_rows(cudaStream_t st, const void* A, int B, int Ha, int Wa, int C
     SALT_COUNT(1);
     RowsParams p;
     p.tiles_x = cdiv(Wo, RW_TW); p.tiles_y = cdiv(Ho, RW_TH);
-    const int BN = Nout % 128 == 0 ? 128 : Nout % 64 == 0 ? 64 : 32;
+    int BN = Nout % 128 == 0 ? 128 : Nout % 64 == 0 ? 64 : 32;
+    // EXPERIMENTAL (env SALT_TC_WIDE=1, not yet run on a GPU): channel counts that are no multiple of 128 as few wide tiles instead of
+    // many N = 64 ones - 320 = 2 x 160, 192 = 1 x 192 (the concat-layer dgrads).  clk per MMA ~ 64 + N/2 (profiles/r1_notes.md), so a
+    // 160-wide instruction does 2.5x the MACs of a 64-wide one in 1.5x the time.
+    static int wide = -1;
+    if (wide < 0) { const char* e = getenv("SALT_TC_WIDE"); wide = (e && e[0] == '1') ? 1 : 0; }
+    if (wide && BN == 64) { if (Nout % 192 == 0) BN = 192; else if (Nout % 160 == 0) BN = 160; }
     p.tiles_co = Nout / BN;
     p.total_tiles = p.tiles_x * p.tiles_y * B * p.tiles_co;
     p.B = B; p.Ho = Ho; p.Wo = Wo; p.Co = Nout; p.Ca = Ca; p.cblks = Ca / 64; p.pad = pad;
@@ -1020,6 +1030,8 @@ void k_conv_tc_rows(cudaStream_t st, const void* A, int B, int Ha, int Wa, int C
     CUtensorMap ma = make_map_nhwc(A, Ca, Wa, Ha, B, 64, RW_TW, RW_TH + 2, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B);
     p.m_tiles = p.tiles_x * p.tiles_y * B; p.total_groups = 0;
     if (BN == 128) launch_rows_any<128>(st, ma, Wp, Ca, Nout, p);
+    else if (BN == 192) launch_rows_any<192>(st, ma, Wp, Ca, Nout, p);
+    else if (BN == 160) launch_rows_any<160>(st, ma, Wp, Ca, Nout, p);
     else if (BN == 64) launch_rows_any<64>(st, ma, Wp, Ca, Nout, p);
     else launch_rows_any<32>(st, ma, Wp, Ca, Nout, p);
 }

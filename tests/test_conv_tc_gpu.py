@@ -34,6 +34,7 @@ TC_CASES = [
     (8, 64, 128, 64, 64, 1, 2, 0),       # 1x1 stride-2
     (70, 512, 512, 8, 8, 3, 1, 1),       # 8x8 maps, two images per tile: 35 position tiles (short last group), 2-4 channel tiles
     (4, 32, 64, 66, 66, 3, 1, 0),        # Cin = 32: 64-byte swizzle, 512-byte multicast parts
+    (4, 192, 128, 34, 34, 3, 1, 0),      # dec3.conv1-like: dgrad with 192 output channels (3 x 64, or 1 x 192 with SALT_TC_WIDE=1)
     (40, 64, 64, 64, 64, 3, 1, 1),       # layer1 shape with 1280 pixel tiles: > 2 groups per SM, the size at which the experimental
                                          # multi-sub-tile kernel (SALT_TC_MULTI=1 SALT_TC_CLUSTER=1) stops falling back
 ]
