@@ -15,7 +15,6 @@ Extra engine knobs come from the environment so reference callers need no change
 import os
 from collections import OrderedDict
 
-import numpy as np
 import torch
 
 from . import dist as sdist
