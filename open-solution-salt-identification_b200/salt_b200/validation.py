@@ -68,13 +68,14 @@ class ValidationScorer:
     best-threshold selection: thresholds walk from 0.5 down to 0.3 and stop at the first one that does not improve IoUT
     (callbacks.py:502-512)."""
 
-    def __init__(self, thresholds=SWEEP_THRESHOLDS, dp=None):
+    def __init__(self, thresholds=SWEEP_THRESHOLDS, dp=None, counts_fn=None):
         self.thresholds = np.asarray(thresholds, dtype=np.float64)
         self.dp = dp                 # salt_b200.dist.DataParallelContext: ranks score disjoint shards of the validation set
+        self._counts_fn = counts_fn or validation_counts     # (logits, gt, thresholds, logits_flip) -> inter, pred, gtsum tensors
         self._parts = []
 
     def update(self, logits, gt, logits_flip=None):
-        self._parts.append(validation_counts(logits, gt, self.thresholds, logits_flip))
+        self._parts.append(self._counts_fn(logits, gt, self.thresholds, logits_flip))
 
     def counts(self):
         inter = torch.cat([p[0] for p in self._parts]).cpu().numpy()
@@ -102,3 +103,114 @@ def select_threshold(inter, pred, gtsum, thresholds=SWEEP_THRESHOLDS):
         k_best = int(np.argmin(np.abs(np.asarray(thresholds) - 0.5)))
     return {'threshold': float(thresholds[k_best]), 'iout': float(iout[k_best]), 'iou': float(iou[:, k_best].mean()),
             'iout_per_threshold': iout}
+
+
+Y_COLUMN = 'file_path_mask'          # callbacks.py:25
+ORIGINAL_SIZE = (101, 101)           # callbacks.py:26
+
+
+def read_masks(masks_filepaths):
+    """utils.py:82-88: mask PNG -> uint8 {0,1} array."""
+    from PIL import Image
+    masks = []
+    for path in masks_filepaths:
+        mask = Image.open(path)
+        masks.append(np.asarray(mask.convert('L').point(lambda x: 0 if x < 128 else 1)).astype(np.uint8))
+    return masks
+
+
+class ValidationMonitor:
+    """Drop-in for the reference's ``callbacks.ValidationMonitor`` (callbacks.py:455-527), same constructor arguments and callback
+    surface (``set_params / on_train_begin / on_epoch_begin / on_epoch_end / on_batch_begin / on_batch_end / on_train_end /
+    training_break / get_validation_loss``), writing the same ``transformer.validation_loss[epoch] = {'sum', 'iou', 'iout'}``.
+
+    What changes underneath: ``_transform`` keeps the logits on the GPU, and the 21-threshold sweep (crop -> binarize ->
+    IoUT, callbacks.py:499-520) is ONE counts kernel per validation batch (``salt_validation_counts``) plus O(images x thresholds)
+    host arithmetic, instead of a device-to-host copy, a numpy sigmoid and up to 21 steppy post-processing pipelines with
+    pycocotools calls per image.  ``y_true`` may be passed directly (list / array of uint8 [101,101] masks) instead of being read from
+    ``meta_valid['file_path_mask']``."""
+
+    def __init__(self, data_dir=None, loader_mode='resize_and_pad', epoch_every=None, batch_every=None, use_depth=False, y_true=None,
+                 scorer_factory=None):
+        self.epoch_every = False if epoch_every == 0 else epoch_every
+        self.batch_every = False if batch_every == 0 else batch_every
+        if loader_mode != 'resize_and_pad':
+            raise NotImplementedError('only the crop post-processing of loader_mode resize_and_pad is implemented (callbacks.py:833-834)')
+        if use_depth:
+            raise NotImplementedError('use_depth models are outside the engine (callbacks.py:568-588)')
+        self.data_dir, self.loader_mode, self.use_depth = data_dir, loader_mode, use_depth
+        self.meta_valid, self.y_true = None, y_true
+        self.epoch_id = self.batch_id = None
+        self._scorer_factory = scorer_factory or (lambda dp: ValidationScorer(dp=dp))
+        self.last_result = None
+
+    # ---- callbacks.Callback surface (callbacks.py:29-75)
+    def set_params(self, transformer, validation_datagen, meta_valid=None, *args, **kwargs):
+        self.transformer = transformer
+        self.model, self.optimizer = transformer.model, transformer.optimizer
+        self.loss_function, self.output_names = transformer.loss_function, transformer.output_names
+        self.activation_func = transformer.activation_func
+        self.validation_datagen, self.meta_valid = validation_datagen, meta_valid
+        if self.y_true is None and meta_valid is not None:
+            self.y_true = read_masks(meta_valid[Y_COLUMN].values)
+
+    def on_train_begin(self, *args, **kwargs):
+        self.epoch_id, self.batch_id = 0, 0
+
+    def on_train_end(self, *args, **kwargs):
+        pass
+
+    def on_epoch_begin(self, *args, **kwargs):
+        pass
+
+    def on_batch_begin(self, *args, **kwargs):
+        pass
+
+    def on_batch_end(self, *args, **kwargs):
+        self.batch_id += 1
+
+    def training_break(self, *args, **kwargs):
+        return False
+
+    def on_epoch_end(self, *args, **kwargs):
+        if self.epoch_every and ((self.epoch_id % self.epoch_every) == 0):
+            self.model.eval()
+            self.get_validation_loss()
+            self.model.train()
+        self.epoch_id += 1
+
+    def get_validation_loss(self):
+        return self._get_validation_loss()
+
+    # ---- callbacks.py:499-566
+    def _get_validation_loss(self):
+        if self.activation_func != 'sigmoid':
+            raise Exception('Only softmax and sigmoid activations are allowed')        # callbacks.py:563 (softmax: no engine path)
+        scorer = self._scorer_factory(getattr(self.transformer, 'dp', None))
+        self.model.eval()
+        batch_gen, steps = self.validation_datagen
+        (name, loss_function_one, weight) = self.loss_function[0]
+        partial_batch_losses, seen = [], 0
+        for batch_id, data in enumerate(batch_gen):
+            X, target = data[0], data[1]
+            outputs_batch = self.model(X)
+            partial_batch_losses.append(loss_function_one(outputs_batch, target).clone() * weight)
+            b = int(outputs_batch.shape[0])
+            gt = np.stack([np.asarray(m) for m in self.y_true[seen:seen + b]]).astype(np.uint8)
+            if len(gt) != b:
+                raise ValueError('validation masks (%d) do not cover the validation loader (batch %d at image %d)'
+                                 % (len(self.y_true), b, seen))
+            scorer.update(outputs_batch, torch.from_numpy(gt).to(outputs_batch.device))
+            seen += b
+            if batch_id == steps:
+                break
+        self.model.train()
+        epoch_loss = sum(partial_batch_losses) / steps                                  # callbacks.py:552
+        r = scorer.result()
+        self.last_result = r
+        if not self.transformer.validation_loss:
+            self.transformer.validation_loss = {}
+        self.transformer.validation_loss.setdefault(self.epoch_id, {'sum': epoch_loss,
+                                                                    'iou': torch.Tensor([r['iou']]),
+                                                                    'iout': torch.Tensor([r['iout']])})
+        return self.transformer.validation_loss[self.epoch_id]

@@ -202,3 +202,73 @@ def test_validation_counts_and_sweep(gold, inp):
     i2, p2, _ = validation.validation_counts(lg, gt, logits_flip=lf)
     oi2, op2, _ = io_oracle.validation_counts(inp['logits'], inp['y_true'], logits_flip=lf.cpu().numpy())
     assert np.abs(p2.cpu().numpy() - op2).max() <= 2 and np.abs(i2.cpu().numpy() - oi2).max() <= 2
+
+
+def test_validation_monitor_dropin_logic(gold, inp):
+    """salt_b200.validation.ValidationMonitor (drop-in for callbacks.py:455-527) on a fake transformer: the callback surface, the
+    epoch_every gate, the averaged validation loss and the reference's threshold / IoU / IoUT (counts supplied by the oracle, so this
+    runs without a GPU; the GPU test below runs the real kernel through the same class)."""
+    from salt_b200 import validation
+
+    def oracle_counts(logits, gt, thresholds, logits_flip):
+        return tuple(torch.from_numpy(np.ascontiguousarray(a)) for a in
+                     io_oracle.validation_counts(logits.numpy(), gt.numpy(), thresholds=thresholds))
+
+    class FakeModel:
+        training = True
+        def eval(self): self.training = False; return self
+        def train(self): self.training = True; return self
+        def __call__(self, X): assert not self.training; return X        # the "network" returns its input as logits
+
+    class FakeTransformer:
+        model, optimizer, output_names, activation_func, validation_loss, dp = FakeModel(), None, ['mask'], 'sigmoid', {}, None
+        loss_function = [('mask', lambda out, tgt: torch.tensor([float(out.shape[0])]), 0.5)]
+
+    lg = torch.from_numpy(inp['logits'])
+    batches = [[lg[:4], None], [lg[4:], None]]
+    mon = validation.ValidationMonitor(epoch_every=2, y_true=list(inp['y_true']),
+                                       scorer_factory=lambda dp: validation.ValidationScorer(dp=dp, counts_fn=oracle_counts))
+    tr = FakeTransformer()
+    mon.set_params(tr, validation_datagen=(batches, 2), meta_valid=None)
+    mon.on_train_begin()
+    mon.on_epoch_end()                       # epoch 0: 0 % 2 == 0 -> validates
+    assert set(tr.validation_loss) == {0} and tr.model.training
+    v = tr.validation_loss[0]
+    assert abs(float(v['sum'][0]) - (4 + 2) * 0.5 / 2) < 1e-6            # sum of weighted batch losses / steps (callbacks.py:552)
+    assert abs(float(v['iou'][0]) - float(gold['val_iou'])) < 1e-6 and abs(float(v['iout'][0]) - float(gold['val_iout'])) < 1e-6
+    assert mon.last_result['threshold'] == float(gold['val_threshold'])
+    mon.on_epoch_end()                       # epoch 1: skipped
+    assert set(tr.validation_loss) == {0} and mon.epoch_id == 2
+    with pytest.raises(NotImplementedError):
+        validation.ValidationMonitor(loader_mode='resize')
+
+
+@gpu
+def test_validation_monitor_on_engine(monkeypatch):
+    """The same class on the real engine: eval forward on the GPU, counts kernel, reference selection logic; compared with the
+    oracle sweep over the engine's own logits."""
+    from oracle import synth
+    from salt_b200 import validation
+    from salt_b200.models import SegmentationModel
+    for k, v in dict(SALT_ENGINE_PRECISION='fp32', SALT_ENGINE_MAX_BATCH='4', SALT_ENGINE_SIZE='128', SALT_ENGINE_LOSS='lovasz').items():
+        monkeypatch.setenv(k, v)
+    arch = {'model_params': {'architecture': 'UNetResNet', 'encoder_depth': 18, 'in_channels': 3, 'out_channels': 2, 'activation': 'sigmoid'},
+            'optimizer_params': {'lr': 1e-4}, 'regularizer_params': {'regularize': True, 'weight_decay_conv2d': 1e-4},
+            'weights_init': {'function': 'he', 'pretrained': False}}
+    m = SegmentationModel(arch, {'epochs': 1}, {})
+    m.engine.load_state(synth.synth_state_dict(18, 2, 0))
+    xs = [torch.from_numpy(synth.synth_inputs(4, 128, 50 + i)) for i in range(2)]
+    ts = [torch.from_numpy(synth.synth_targets(4, 128, 50 + i)) for i in range(2)]
+    y_true = [t[i, 1, 13:114, 14:115].numpy().astype(np.uint8) for t in ts for i in range(4)]
+    mon = validation.ValidationMonitor(epoch_every=1, y_true=y_true)
+    mon.set_params(m, validation_datagen=(list(zip(xs, ts)), 2))
+    mon.on_train_begin()
+    mon.on_epoch_end()
+    v = m.validation_loss[0]
+    logits = np.concatenate([m.engine.forward(x.cuda(), train=False).cpu().numpy() for x in xs])
+    ref = io_oracle.validation_sweep(logits, y_true)
+    print('validation monitor:', mon.last_result['threshold'], float(v['iou'][0]), float(v['iout'][0]), 'oracle', ref)
+    assert mon.last_result['threshold'] == ref['threshold']
+    # (a pixel whose probability is within 1 ulp of the threshold may flip: one pixel moves an image's IoU by ~1e-4)
+    assert abs(float(v['iou'][0]) - ref['iou']) < 2e-4 and abs(float(v['iout'][0]) - ref['iout']) < 1e-6
+    assert np.isfinite(float(v['sum'][0]))
