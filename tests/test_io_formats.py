@@ -163,8 +163,10 @@ def test_rle_encode_bit_exact(gold, inp):
     assert int(nruns[0]) == 5101 and runs.shape == (1, 16, 2)
     assert runs[0].cpu().numpy().reshape(-1).tolist() == io_oracle.run_length_encoding(m[0])[:32]
     assert io_ops.encode_rle(torch.zeros((0, 101, 101), dtype=torch.uint8)) == []
-    rows = io_ops.create_submission(['a', 'b'], [inp['masks'][1], inp['masks'][0]])
-    assert rows == [['a', '1 10201'], ['b', '']]
+    import pandas as pd
+    sub = io_ops.create_submission(pd.DataFrame({'id': ['a', 'b']}), [inp['masks'][1], inp['masks'][0]])
+    assert list(sub.columns) == ['id', 'rle_mask'] and sub.values.tolist() == [['a', '1 10201'], ['b', '']]
+    assert io_ops.create_submission(['a'], [inp['masks'][4]]).values.tolist() == [['a', '1 1 10201 1']]
 
 
 @gpu
