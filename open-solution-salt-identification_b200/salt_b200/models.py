@@ -120,23 +120,27 @@ class EngineModule:
         return self
 
 
-class EngineAdam:
-    """``self.optimizer`` facade: torch.optim.Adam(weight_regularization(...), lr) of models.py:74-75.  The
-    learning-rate schedulers of the reference mutate ``param_groups[0]['lr']`` (callbacks.py:219-241)."""
+class EngineAdam(torch.optim.Optimizer):
+    """``self.optimizer``: torch.optim.Adam(weight_regularization(...), lr) of models.py:74-75, as a real
+    ``torch.optim.Optimizer`` so the reference's schedulers accept it: ``ReduceLROnPlateauScheduler`` / ``ExponentialLRScheduler``
+    build ``torch.optim.lr_scheduler.*(optimizer=self.optimizer)`` and mutate ``param_groups[0]['lr']`` (callbacks.py:181,
+    219-241), loggers read ``state_dict()['param_groups'][0]['lr']``.  One parameter group over the engine's flat fp32
+    parameter buffer; ``step()`` is ONE fused kernel (``salt_adam_step``: L2 term, moments, bias correction, update).  The
+    moments live in engine-owned flat buffers, so ``self.state`` stays empty (the reference never saves optimiser state)."""
 
     def __init__(self, engine, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8):
         self.engine = engine
-        self.param_groups = [{'params': [engine.params], 'lr': lr, 'weight_decay': weight_decay, 'betas': betas, 'eps': eps}]
+        super().__init__([engine.params], dict(lr=lr, weight_decay=weight_decay, betas=betas, eps=eps))
 
-    def zero_grad(self):
+    def zero_grad(self, set_to_none=True):
         pass      # salt_backward() zeroes the flat gradient buffer itself
 
-    def step(self, grad_scale=1.0):
+    def step(self, closure=None, grad_scale=1.0):
+        loss = closure() if closure is not None else None
         g = self.param_groups[0]
-        self.engine.adam_step(lr=g['lr'], weight_decay=g['weight_decay'], betas=g['betas'], eps=g['eps'], grad_scale=grad_scale)
-
-    def state_dict(self):
-        return {'state': {}, 'param_groups': [{k: v for k, v in g.items() if k != 'params'} for g in self.param_groups]}
+        self.engine.adam_step(lr=float(g['lr']), weight_decay=float(g['weight_decay']), betas=tuple(g['betas']), eps=float(g['eps']),
+                              grad_scale=grad_scale)
+        return loss
 
 
 class _NullCallbacks:
@@ -152,13 +156,29 @@ class _NullCallbacks:
     def training_break(self, *a, **k): return False
 
 
-def callbacks_network(callbacks_config):
-    """models.py:300-312 when the reference package is importable, otherwise no callbacks."""
+# callbacks that write files or talk to an experiment tracker: under torchrun only rank 0 keeps them
+_RANK0_ONLY_CALLBACKS = ('ModelCheckpoint', 'NeptuneMonitor', 'ExperimentTiming', 'TrainingMonitor')
+
+
+def callbacks_network(callbacks_config, dp=None):
+    """models.py:300-312 when the reference package is importable, otherwise no callbacks (with a warning).  Only a missing
+    reference package takes the fallback: configuration errors (a mistyped callbacks_config key, ...) propagate, so a model can
+    never train silently without its checkpoint / early-stopping callbacks.  With more than one rank, the callbacks that write
+    to disk or log (``_RANK0_ONLY_CALLBACKS``) are kept on rank 0 only; the ones that steer training (validation, LR scheduler,
+    early stopping) run on every rank on identical parameters and therefore take identical decisions."""
+    if not callbacks_config:                  # None / {}: no callbacks requested (extension; the reference always passes its 7 sections)
+        return _NullCallbacks()
     try:
         from common_blocks.models import callbacks_network as ref_callbacks_network
-        return ref_callbacks_network(callbacks_config)
-    except Exception:
+    except ImportError as exc:
+        import warnings
+        warnings.warn('reference package common_blocks is not importable (%s): SegmentationModel runs WITHOUT callbacks '
+                      '(no checkpoints, no early stopping, no LR schedule)' % (exc,))
         return _NullCallbacks()
+    cbs = ref_callbacks_network(callbacks_config)
+    if dp is not None and dp.world > 1 and dp.rank != 0 and hasattr(cbs, 'callbacks'):
+        cbs.callbacks = [c for c in cbs.callbacks if type(c).__name__ not in _RANK0_ONLY_CALLBACKS]
+    return cbs
 
 
 class Model:
@@ -183,10 +203,14 @@ class Model:
         return self.transform(*args, **kwargs)
 
     def persist(self, filepath):
-        d = os.path.dirname(filepath)
-        if d:
-            os.makedirs(d, exist_ok=True)
-        torch.save(self.model.state_dict(), filepath)
+        dp = getattr(self, 'dp', None)
+        if dp is None or dp.rank == 0:           # every rank holds the same parameters: one writer
+            d = os.path.dirname(filepath)
+            if d:
+                os.makedirs(d, exist_ok=True)
+            torch.save(self.model.state_dict(), filepath)
+        if dp is not None:
+            dp.barrier()
 
 
 class _EngineLoss:
@@ -200,11 +224,54 @@ class _EngineLoss:
 
     def __call__(self, output, target):
         target = torch.as_tensor(target).to(self.engine.device, torch.float32).contiguous()
+        if tuple(target.shape) != tuple(output.shape):
+            raise ValueError('loss: target shape %s != output shape %s' % (tuple(target.shape), tuple(output.shape)))
+        if output.shape[0] > self.engine.max_batch:
+            raise ValueError('loss: batch %d exceeds the engine max_batch %d' % (output.shape[0], self.engine.max_batch))
+        # the kernels write logits.shape[0] images of gradient: never hand them a buffer of another batch size
+        if self.dlogits is None or tuple(self.dlogits.shape) != tuple(output.shape) or self.dlogits.device != output.device:
+            self.dlogits = torch.empty_like(output)
         if self.kind == 'lovasz':
             loss, self.dlogits = self.engine.loss_lovasz(output, target, self.dlogits)
         else:
             loss, self.dlogits = self.engine.loss_bce_dice(output, target, self.dlogits, group=self.group)
-        return loss
+        return loss.clone()          # a fresh 1-element tensor per call, as the reference returns (callbacks may keep it)
+
+
+class _PinnedSink:
+    """Device -> host path of ``transform``: the copy of batch i runs on a side stream into one of two pinned buffers while
+    batch i+1 is computed (models.py:167 does a synchronous ``.data.cpu().numpy()`` per batch); ``finish()`` returns the
+    per-image list of utils.py:316-320 ``get_list_of_image_predictions``."""
+
+    def __init__(self, device, max_batch):
+        self.device, self.max_batch = device, max_batch
+        self.stream = torch.cuda.Stream(device)
+        self.slots, self.n, self.pending, self.out = [None, None], 0, None, []
+
+    def _drain(self):
+        if self.pending is not None:
+            ev, host, b = self.pending
+            ev.synchronize()
+            self.out.extend(list(host[:b].numpy().copy()))
+            self.pending = None
+
+    def push(self, probs):
+        b, slot = int(probs.shape[0]), self.n & 1
+        self.n += 1
+        if self.slots[slot] is None or self.slots[slot].shape[0] < b:
+            self.slots[slot] = torch.empty((max(b, self.max_batch),) + tuple(probs.shape[1:]), dtype=torch.float32, pin_memory=True)
+        done = torch.cuda.Event()
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.stream):
+            self.slots[slot][:b].copy_(probs, non_blocking=True)
+            probs.record_stream(self.stream)
+            done.record(self.stream)
+        self._drain()                   # batch i-1: its copy overlapped this batch's forward pass
+        self.pending = (done, self.slots[slot], b)
+
+    def finish(self):
+        self._drain()
+        return self.out
 
 
 class SegmentationModel(Model):
@@ -218,7 +285,7 @@ class SegmentationModel(Model):
         reg = architecture_config.get('regularizer_params', {'regularize': True, 'weight_decay_conv2d': 1e-4})
         wd = reg.get('weight_decay_conv2d', 0.0) if reg.get('regularize', False) else 0.0
         self.optimizer = EngineAdam(self.engine, lr=opt.get('lr', 1e-4), weight_decay=wd)
-        self.callbacks = callbacks_network(self.callbacks_config)
+        self.callbacks = callbacks_network(self.callbacks_config, self.dp)
 
     # models.py:179-184
     def set_model(self):
@@ -453,19 +520,21 @@ class SegmentationModel(Model):
             raise Exception('Only softmax and sigmoid activations are allowed')
         return outputs
 
-    # models.py:149-177 with the numpy sigmoid of utils.py:173 fused on the GPU
+    # models.py:149-177 with the numpy sigmoid of utils.py:173 fused on the GPU; device->host through _PinnedSink
     def _transform(self, datagen, validation_datagen=None, **kwargs):
         self.model.eval()
         batch_gen, steps = datagen
         name = self.output_names[0]
-        preds = []
+        eng = self.engine
+        sink = _PinnedSink(eng.device, eng.max_batch)
         for batch_id, data in enumerate(batch_gen):
             X = data[0] if isinstance(data, (list, tuple)) else data
             logits = self.model(X)
-            probs, _ = self.engine.predict(logits, None, crop=min(101, self.engine.size), want_mask=False)
-            preds.extend(list(probs.cpu().numpy()))
+            probs, _ = eng.predict(logits, None, crop=min(101, eng.size), want_mask=False)
+            sink.push(probs)
             if batch_id == steps:
                 break
+        preds = sink.finish()
         self.model.train()
         return {'{}_prediction'.format(name): preds}
 

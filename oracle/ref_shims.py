@@ -171,6 +171,7 @@ def install():
     _install_cocomask_stub()
     sys.modules['steppy.base'].BaseTransformer = BaseTransformer
     sys.modules['toolkit.pytorch_transformers.models'].Model = Model
+    _install_callers()
     import joblib
     import sklearn
     ext = _stub('sklearn.externals')
@@ -205,3 +206,150 @@ def load_numpy_state(module, sd_np, depth):
         for k, v in sd_np.items():
             own[k].copy_(torch.from_numpy(v))
     return module
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# steppy==0.1.6 / steppy-toolkit==0.1.5 pieces that the reference's CALLERS of the hot path need (both packages are absent from
+# the image and from /root/reference).  Restated from their call sites, only as far as those call sites go:
+#   utils.py:415-486 FineTuneStep(Step)            -> Step: constructor arguments, exp_dir_* paths, transformer_is_cached
+#   callbacks.py:832-866 postprocessing_pipeline   -> Step.transform(data) recursion over input_steps, Adapter / E, IdentityOperation
+#   callbacks.py:16-17,72-76,150-161,776-794       -> Averager, persist_torch_model, score_model
+# They let tests/test_boundary_reference_cpu.py drive the UNMODIFIED callbacks_network / FineTuneStep against the drop-in.
+# ---------------------------------------------------------------------------------------------------------------------
+class E:
+    """steppy.adapter.E(input_name, key): 'take `key` from the output dict of step / data entry `input_name`'."""
+
+    def __init__(self, input_name, key):
+        self.input_name, self.key = input_name, key
+
+
+class Adapter:
+    """steppy.adapter.Adapter({kwarg: E(...)}) - maps upstream outputs to the transformer's keyword arguments."""
+
+    def __init__(self, adapting_recipes):
+        self.adapting_recipes = adapting_recipes
+
+    def adapt(self, all_ouputs):
+        out = {}
+        for name, recipe in self.adapting_recipes.items():
+            if isinstance(recipe, E):
+                out[name] = all_ouputs[recipe.input_name][recipe.key]
+            elif isinstance(recipe, (list, tuple)):
+                out[name] = type(recipe)(all_ouputs[r.input_name][r.key] if isinstance(r, E) else r for r in recipe)
+            else:
+                out[name] = recipe
+        return out
+
+
+class IdentityOperation(BaseTransformer):
+    def transform(self, **kwargs):
+        return kwargs
+
+
+class Step:
+    """steppy.base.Step as used by utils.py:415-486 and callbacks.py:832-866 (no output caching, no structure persistence)."""
+
+    def __init__(self, name, transformer, experiment_directory, input_data=None, input_steps=None, adapter=None,
+                 is_trainable=False, cache_output=False, persist_output=False, load_persisted_output=False, force_fitting=False,
+                 persist_upstream_pipeline_structure=False):
+        self.name, self.transformer = name, transformer
+        self.input_steps, self.input_data, self.adapter = input_steps or [], input_data or [], adapter
+        self.is_trainable, self.force_fitting = is_trainable, force_fitting
+        self.cache_output, self.persist_output, self.load_persisted_output = cache_output, persist_output, load_persisted_output
+        self.exp_dir = os.path.join(experiment_directory)
+        self.exp_dir_transformers = os.path.join(self.exp_dir, 'transformers')
+        self.exp_dir_outputs = os.path.join(self.exp_dir, 'outputs')
+        self.exp_dir_cache = os.path.join(self.exp_dir, 'cache')
+        for d in (self.exp_dir_transformers, self.exp_dir_outputs, self.exp_dir_cache):
+            os.makedirs(d, exist_ok=True)
+        self.exp_dir_transformers_step = os.path.join(self.exp_dir_transformers, name)
+        self.exp_dir_outputs_step = os.path.join(self.exp_dir_outputs, '{}'.format(name))
+        self.exp_dir_cache_step = os.path.join(self.exp_dir_cache, '{}'.format(name))
+
+    @property
+    def transformer_is_cached(self):
+        return os.path.exists(self.exp_dir_transformers_step)
+
+    def _step_inputs(self, data, how):
+        outputs = {s.name: getattr(s, how)(data) for s in self.input_steps}
+        for name in self.input_data:
+            outputs[name] = data[name]
+        if self.adapter is not None:
+            return self.adapter.adapt(outputs)
+        merged = {}
+        for o in outputs.values():
+            merged.update(o)
+        return merged
+
+    def fit_transform(self, data):
+        return self._cached_fit_transform(self._step_inputs(data, 'fit_transform'))
+
+    def transform(self, data):
+        return self._cached_transform(self._step_inputs(data, 'transform'))
+
+    def _cached_fit_transform(self, step_inputs):
+        if self.is_trainable:
+            out = self.transformer.fit_transform(**step_inputs)
+            self.transformer.persist(self.exp_dir_transformers_step)
+            return out
+        return self.transformer.transform(**step_inputs)
+
+    def _cached_transform(self, step_inputs):
+        if self.is_trainable:
+            self.transformer.load(self.exp_dir_transformers_step)
+        return self.transformer.transform(**step_inputs)
+
+    def _persist_output(self, output_data, filepath):
+        import joblib
+        joblib.dump(output_data, filepath)
+
+
+class Averager:
+    """toolkit.pytorch_transformers.utils.Averager: running mean fed by send() (callbacks.py:150-161,342-354)."""
+
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.currently_sum, self.count = 0.0, 0
+
+    def send(self, value):
+        self.currently_sum += value
+        self.count += 1
+
+    @property
+    def value(self):
+        return self.currently_sum / self.count if self.count else 0.0
+
+
+def persist_torch_model(model, path):
+    """toolkit.pytorch_transformers.utils.persist_torch_model as called at callbacks.py:791."""
+    import torch
+    model.eval()
+    torch.save(model.state_dict(), path)
+    model.train()
+
+
+def score_model(model, loss_function, datagen):
+    """toolkit.pytorch_transformers.validation.score_model as called at callbacks.py:72-76: mean of the weighted loss over
+    the validation batches -> {'sum': 1-element tensor}."""
+    batch_gen, steps = datagen
+    losses = []
+    for batch_id, data in enumerate(batch_gen):
+        X, targets = data[0], data[1:]
+        outputs = model(X)
+        (name, fn, weight), target = loss_function[0], targets[0]
+        losses.append(fn(outputs, target) * weight)
+        if batch_id == steps:
+            break
+    return {'sum': sum(losses) / steps}
+
+
+def _install_callers():
+    """the restated steppy / toolkit classes, so that common_blocks.callbacks / common_blocks.utils.FineTuneStep run (part of install())."""
+    sb, sa = sys.modules['steppy.base'], sys.modules['steppy.adapter']
+    sb.Step, sb.IdentityOperation, sb.BaseTransformer = Step, IdentityOperation, BaseTransformer
+    sa.Adapter, sa.E = Adapter, E
+    tu, tv = sys.modules['toolkit.pytorch_transformers.utils'], sys.modules['toolkit.pytorch_transformers.validation']
+    tu.Averager, tu.persist_torch_model = Averager, persist_torch_model
+    tv.score_model = score_model
