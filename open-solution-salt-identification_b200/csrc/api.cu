@@ -181,15 +181,23 @@ int salt_op_conv_forward(const salt_conv_desc* d, const void* in, const float* w
     DType dt = d->precision == SALT_PREC_FP32 ? DT_F32 : DT_BF16;
     PackedTmp pk(d, w, st);
     ConvGeom g = to_geom(d, d->in_c);
+    float* part = nullptr;                  // per-CTA partial slots of the BatchNorm sums (kernels.h), reduced in slot order below
+    if (stats) {
+        const size_t pb = sizeof(float) * SALT_STAT_SLOTS * 2 * g.Co;
+        if (cudaMalloc(&part, pb) != cudaSuccess) return fail("salt_op_conv_forward: out of device memory");
+        cudaMemsetAsync(part, 0, pb, st);
+    }
     try {
         if (d->use_tensor_cores) {
-            if (dt != DT_BF16 || !tc_conv_supported(g, false)) return fail("salt_op_conv_forward: geometry not supported by the tensor-core kernel");
-            k_conv_tc(st, in, g.B, g.Hi, g.Wi, g.Ci, pk.wp, g.Co, g.R, g.S, g.stride, g.pad, out, g.Ho, g.Wo, bias, stats, false);
+            if (dt != DT_BF16 || !tc_conv_supported(g, false)) { cudaFree(part); return fail("salt_op_conv_forward: geometry not supported by the tensor-core kernel"); }
+            k_conv_tc(st, in, g.B, g.Hi, g.Wi, g.Ci, pk.wp, g.Co, g.R, g.S, g.stride, g.pad, out, g.Ho, g.Wo, bias, part, false);
         } else {
-            k_conv_fwd_simt(st, dt, in, pk.wp, bias, out, stats, g);
+            k_conv_fwd_simt(st, dt, in, pk.wp, bias, out, part, g);
         }
-    } catch (const std::exception& ex) { return fail(std::string("salt_op_conv_forward: ") + ex.what()); }
+        if (stats) k_stats_reduce(st, part, SALT_STAT_SLOTS, g.Co, stats);
+    } catch (const std::exception& ex) { cudaFree(part); return fail(std::string("salt_op_conv_forward: ") + ex.what()); }
     cudaStreamSynchronize(st);
+    cudaFree(part);
     return check_cuda("salt_op_conv_forward");
 }
 int salt_op_conv_dgrad(const salt_conv_desc* d, const void* gout, const float* w, void* gin, int accumulate, void* stream) {

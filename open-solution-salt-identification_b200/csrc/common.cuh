@@ -73,4 +73,7 @@ extern unsigned long long g_salt_launches;   // kernels launched by this library
 #define SALT_COUNT(n) (g_salt_launches += (n))
 extern unsigned long long g_salt_cluster_launches;   // of which: thread-block-cluster launches (TMA-multicast convolutions)
 
+constexpr int SALT_STAT_SLOTS = 296;       // BatchNorm partial-sum slots per layer (kernels.h): >= the grid of every producing kernel
+constexpr int SALT_STAT_SLOTS_CONV = 148;  // slots a persistent tensor-core convolution can touch (its grid is capped at this)
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -55,7 +55,7 @@ struct TcParams {
     int osy, osx, a_stride, cblks;
     int accumulate, nphases;
     const float* bias;
-    double* stats;
+    float* stats;              // [SALT_STAT_SLOTS_CONV][2*Co] partial slots, slot = blockIdx.x
     bf16* out;
     TcPhase ph[4];
 };
@@ -107,7 +107,7 @@ template <int BN, int BK> struct TcCfg {
     static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * BN * 4 /*stats*/;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * 2 * BN * 4 /*per-epilogue-warp stats*/;
     // canonical K-major swizzled layout: rows of BK*2 bytes, 8-row groups SBO apart
     static constexpr uint32_t SBO = 8 * BK * 2;
     static constexpr uint32_t LAYOUT = BK == 64 ? 2 : 4;       // SWIZZLE_128B : SWIZZLE_64B
@@ -139,7 +139,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), Cfg::TMEM_COLS);
-    for (int i = threadIdx.x; i < 2 * BN; i += TC_THREADS) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < 4 * 2 * BN; i += TC_THREADS) s_stats[i] = 0.f;
     fence_before();
     __syncthreads();
     uint32_t rank = 0;
@@ -208,6 +208,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else {
         // ===================================================== epilogue (warps 2..5 <-> TMEM lane quarters 2,3,0,1)
         const int quarter = warp & 3;
+        float* my_stats = s_stats + (warp - 2) * (2 * BN);  // private per-warp accumulators, merged in warp order: no atomics, bit-reproducible
+        float* slot = p.stats ? p.stats + (size_t)blockIdx.x * 2 * p.Co : nullptr;
         const int m = quarter * 32 + lane;                  // row of the 128-position tile
         const int lx = m % p.tw, ly = (m / p.tw) % p.th, ln = m / (p.tw * p.th);
         int acc = 0; uint32_t acc_phase = 0;
@@ -258,8 +260,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     for (int i = 0; i < 32; ++i) { v[i] = valid ? v[i] : 0.f; sq[i] = v[i] * v[i]; }
                     float s1 = butterfly_reduce32(v, lane);
                     float s2 = butterfly_reduce32(sq, lane);
-                    atomicAdd(s_stats + ch * 32 + lane, s1);
-                    atomicAdd(s_stats + BN + ch * 32 + lane, s2);
+                    my_stats[ch * 32 + lane] += s1;
+                    my_stats[BN + ch * 32 + lane] += s2;
                 }
             }
             fence_before();
@@ -271,9 +273,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 const int tt = threadIdx.x - 64;
                 for (int i = tt; i < 2 * BN; i += 128) {
-                    float val = s_stats[i];
-                    if (val != 0.f) atomicAdd(p.stats + (i < BN ? nt * BN + i : p.Co + nt * BN + (i - BN)), (double)val);
-                    s_stats[i] = 0.f;
+                    float val = 0.f;
+#pragma unroll
+                    for (int w4 = 0; w4 < 4; ++w4) { val += s_stats[w4 * 2 * BN + i]; s_stats[w4 * 2 * BN + i] = 0.f; }
+                    slot[i < BN ? nt * BN + i : p.Co + nt * BN + (i - BN)] += val;      // this CTA's own slot: plain read-modify-write
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
             }
@@ -281,8 +284,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (p.stats && p.tiles_co == 1) {
             asm volatile("bar.sync 1, 128;" ::: "memory");
             const int tt = threadIdx.x - 64;
-            for (int i = tt; i < 2 * BN; i += 128)
-                atomicAdd(p.stats + (i < BN ? i : p.Co + (i - BN)), (double)s_stats[i]);
+            for (int i = tt; i < 2 * BN; i += 128) {
+                float val = 0.f;
+#pragma unroll
+                for (int w4 = 0; w4 < 4; ++w4) val += s_stats[w4 * 2 * BN + i];
+                slot[i < BN ? i : p.Co + (i - BN)] = val;
+            }
         }
     }
     fence_before();
@@ -411,7 +418,7 @@ static bool rows_enabled() {
 }
 // out[n,y,x,k] (+)= sum_{r,s,c} A[n, y*stride+r-pad, x*stride+s-pad, c] * Wp[k][(r*S+s)*Ca + c]
 void k_conv_tc(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca, const void* Wp, int Nout, int R, int S, int stride,
-               int pad, void* out, int Ho, int Wo, const float* bias, double* stats, bool accumulate) {
+               int pad, void* out, int Ho, int Wo, const float* bias, float* stats, bool accumulate) {
     if (rows_enabled() && tc_conv_rows_supported(Ca, Nout, R, S, stride, Ho, Wo)) {
         k_conv_tc_rows(st, A, B, Ha, Wa, Ca, Wp, Nout, pad, out, Ho, Wo, bias, stats, accumulate);
         return;

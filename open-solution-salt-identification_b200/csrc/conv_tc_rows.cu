@@ -51,7 +51,7 @@ struct RowsParams {
     int debug;                 // timing experiments only (env SALT_TC_DEBUG): 1 = skip loads, 4 = skip stores+stats, 8 = skip stats, 16 = skip stores,
                                // 32 = per-tile butterflies for the BatchNorm sums also on narrow layers (the pre-round-1b epilogue)
     const float* bias;
-    double* stats;
+    float* stats;              // [SALT_STAT_SLOTS_CONV][2*Co] partial slots, slot = blockIdx.x
     bf16* out;
 };
 
@@ -272,7 +272,7 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
                 float val = 0.f;
 #pragma unroll
                 for (int w8 = 0; w8 < 8; ++w8) { val += s_stats[w8 * 2 * BN + i]; s_stats[w8 * 2 * BN + i] = 0.f; }
-                if (val != 0.f) atomicAdd(p.stats + (i < BN ? nt * BN + i : p.Co + nt * BN + (i - BN)), (double)val);
+                p.stats[(size_t)blockIdx.x * 2 * p.Co + (i < BN ? nt * BN + i : p.Co + nt * BN + (i - BN))] += val;   // own slot
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
@@ -290,7 +290,7 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
             float val = 0.f;
 #pragma unroll
             for (int w8 = 0; w8 < 8; ++w8) val += s_stats[w8 * 2 * BN + i];
-            atomicAdd(p.stats + (i < BN ? i : p.Co + (i - BN)), (double)val);
+            p.stats[(size_t)blockIdx.x * 2 * p.Co + (i < BN ? i : p.Co + (i - BN))] = val;                                      // own slot
         }
     }
 }
@@ -423,7 +423,7 @@ __device__ __forceinline__ void rows_epilogue_multi(const RowsParams& p, const i
                 float val = 0.f;
 #pragma unroll
                 for (int w8 = 0; w8 < 8; ++w8) { val += s_stats[w8 * 2 * BN + i]; s_stats[w8 * 2 * BN + i] = 0.f; }
-                if (val != 0.f) atomicAdd(p.stats + (i < BN ? nt * BN + i : p.Co + nt * BN + (i - BN)), (double)val);
+                p.stats[(size_t)blockIdx.x * 2 * p.Co + (i < BN ? nt * BN + i : p.Co + nt * BN + (i - BN))] += val;   // own slot
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
         }
@@ -443,7 +443,7 @@ __device__ __forceinline__ void rows_epilogue_multi(const RowsParams& p, const i
             float val = 0.f;
 #pragma unroll
             for (int w8 = 0; w8 < 8; ++w8) val += s_stats[w8 * 2 * BN + i];
-            atomicAdd(p.stats + (i < BN ? i : p.Co + (i - BN)), (double)val);
+            p.stats[(size_t)blockIdx.x * 2 * p.Co + (i < BN ? i : p.Co + (i - BN))] = val;                                      // own slot
         }
     }
 }
@@ -1011,7 +1011,7 @@ static void launch_rows_any(cudaStream_t st, const CUtensorMap& ma, const void* 
 
 // out[n,y,x,k] (+)= sum_{r,s,c} A[n, y+r-pad, x+s-pad, c] * Wp[k][(r*3+s)*Ca + c]      (3x3, stride 1)
 void k_conv_tc_rows(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca, const void* Wp, int Nout, int pad, void* out,
-                    int Ho, int Wo, const float* bias, double* stats, bool accumulate) {
+                    int Ho, int Wo, const float* bias, float* stats, bool accumulate) {
     SALT_COUNT(1);
     RowsParams p;
     p.tiles_x = cdiv(Wo, RW_TW); p.tiles_y = cdiv(Ho, RW_TH);

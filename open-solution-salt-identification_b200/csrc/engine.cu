@@ -78,8 +78,8 @@ BNLayer Engine::make_bn(const std::string& prefix, int c) {
     b.o_beta = add_param(prefix + ".bias", {c});
     b.o_rm = add_buffer(prefix + ".running_mean", {c});
     b.o_rv = add_buffer(prefix + ".running_var", {c});
-    b.sums = stats_arena_ + stats_cursor_; stats_cursor_ += 2 * c;
-    b.bsums = bstats_arena_ + bstats_cursor_; bstats_cursor_ += 2 * c;
+    b.sums = stats_arena_ + stats_cursor_; stats_cursor_ += (size_t)SALT_STAT_SLOTS * 2 * c;
+    b.bsums = bstats_arena_ + bstats_cursor_; bstats_cursor_ += (size_t)SALT_STAT_SLOTS * 2 * c;
     float* f = (float*)ws_alloc(sizeof(float) * 6 * c);
     b.scale = f; b.shift = f + c; b.mean = f + 2 * c; b.invstd = f + 3 * c; b.cb = f + 4 * c; b.cc = f + 5 * c;
     return b;
@@ -135,8 +135,8 @@ void Engine::build() {
     const int chans[4] = {64, 128, 256, 512};
 
     // BN statistic arenas: sized on the counting pass
-    stats_arena_ = (double*)ws_alloc(sizeof(double) * std::max<size_t>(stats_doubles_, 1));
-    bstats_arena_ = (double*)ws_alloc(sizeof(double) * std::max<size_t>(bstats_doubles_, 1));
+    stats_arena_ = (float*)ws_alloc(sizeof(float) * std::max<size_t>(stats_floats_, 1));
+    bstats_arena_ = (float*)ws_alloc(sizeof(float) * std::max<size_t>(bstats_floats_, 1));
     dwp_arena_ = (float*)ws_alloc(sizeof(float) * std::max<size_t>(cfg_.dt == DT_BF16 ? dwp_floats_ : 0, 4));
 
     // ---- encoder, parameter order = state_dict order
@@ -247,7 +247,7 @@ void Engine::build() {
     }
     loss_sums_ = (double*)ws_alloc(sizeof(double) * 16);
     for (int i = 0; i < 4; ++i) scratch_[i] = ws_alloc(std::max<size_t>(scratch_bytes_[i], 256));
-    if (counting_) { stats_doubles_ = stats_cursor_; bstats_doubles_ = bstats_cursor_; dwp_floats_ = dwp_cursor_; }
+    if (counting_) { stats_floats_ = stats_cursor_; bstats_floats_ = bstats_cursor_; dwp_floats_ = dwp_cursor_; }
 }
 
 void Engine::bind(float* params, float* grads, float* m, float* v, float* buffers, void* ws, size_t ws_bytes) {
@@ -376,14 +376,15 @@ void Engine::conv_fwd(const ConvLayer& c, const Tensor& in, const Tensor& out, B
     ConvGeom g = geom(c, in, out);
     const float* bias = c.o_b >= 0 ? params_ + c.o_b : nullptr;
     prof_begin(PROF_CONV_FWD, conv_flops(g, c.Ci_real), st);
-    double* stats = (bn && train) ? bn->sums : nullptr;
-    if (cfg_.dt == DT_BF16 && cfg_.use_tc && tc_conv_supported(g, false))
+    float* stats = (bn && train) ? bn->sums : nullptr;
+    const bool tc = cfg_.dt == DT_BF16 && cfg_.use_tc && tc_conv_supported(g, false);
+    if (tc)
         k_conv_tc(st, in.p, g.B, g.Hi, g.Wi, g.Ci, c.wp, g.Co, g.R, g.S, g.stride, g.pad, out.p, g.Ho, g.Wo, bias, stats, false);
     else
         k_conv_fwd_simt(st, cfg_.dt, in.p, c.wp, bias, out.p, stats, g);
     prof_end(st);
     if (bn) {
-        if (train) k_bn_finalize_train(st, bn_ref(*bn), (double)B_ * out.H * out.W, BN_MOMENTUM, BN_EPS);
+        if (train) k_bn_finalize_train(st, bn_ref(*bn), tc ? SALT_STAT_SLOTS_CONV : SALT_STAT_SLOTS, (double)B_ * out.H * out.W, BN_MOMENTUM, BN_EPS);
         else k_bn_finalize_eval(st, bn_ref(*bn), BN_EPS);
     }
 }
@@ -491,7 +492,7 @@ void Engine::forward_tiles(const uint8_t* tiles, int B, const TileGeom& g, float
 }
 void Engine::forward_body(int B, float* logits_nchw, bool train, cudaStream_t st) {
     if (packed_dirty_) pack_all(st);
-    if (train) k_zero(st, stats_arena_, sizeof(double) * stats_doubles_);
+    if (train) k_zero(st, stats_arena_, sizeof(float) * stats_floats_);
     Tensor x4 = view(x4_), sraw = view(stem_raw_);
     conv_fwd(stem_, x4, sraw, &stem_bn_, train, st);
     k_bn_apply(st, sraw, stem_bn_.scale, stem_bn_.shift, nullptr, nullptr, nullptr, true, view(stem_out_.t));
@@ -621,7 +622,7 @@ void Engine::backward(const float* dlogits, cudaStream_t st) {
     if (!grads_) throw std::runtime_error("engine bound without gradient buffers");
     if (!trained_forward_) throw std::runtime_error("backward() requires a preceding forward(train=1)");
     k_zero(st, grads_, sizeof(float) * n_params_);
-    k_zero(st, bstats_arena_, sizeof(double) * bstats_doubles_);
+    k_zero(st, bstats_arena_, sizeof(float) * bstats_floats_);
     if (cfg_.dt == DT_BF16 && cfg_.use_tc) k_zero(st, dwp_arena_, sizeof(float) * dwp_floats_);
     for (auto& g : gradbufs_) g->fresh = true;
     // ---- final

@@ -30,7 +30,7 @@ struct ConvLayer {
 struct BNLayer {
     int C = 0;
     size_t o_gamma = 0, o_beta = 0, o_rm = 0, o_rv = 0;
-    double *sums = nullptr, *bsums = nullptr;
+    float *sums = nullptr, *bsums = nullptr;      // [SALT_STAT_SLOTS][2C] partial slots
     float *scale = nullptr, *shift = nullptr, *mean = nullptr, *invstd = nullptr, *cb = nullptr, *cc = nullptr;
 };
 struct SELayer {
@@ -189,8 +189,8 @@ private:
     std::vector<std::unique_ptr<GradBuf>> gradbufs_;
 
     // stats arenas (zeroed per pass)
-    double* stats_arena_ = nullptr; size_t stats_doubles_ = 0;
-    double* bstats_arena_ = nullptr; size_t bstats_doubles_ = 0;
+    float* stats_arena_ = nullptr; size_t stats_floats_ = 0;
+    float* bstats_arena_ = nullptr; size_t bstats_floats_ = 0;
     size_t stats_cursor_ = 0, bstats_cursor_ = 0;
     float* dwp_arena_ = nullptr; size_t dwp_floats_ = 0, dwp_cursor_ = 0;
     // scratch pool

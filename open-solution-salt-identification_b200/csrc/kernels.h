@@ -15,8 +15,14 @@ struct ConvGeom {
 void k_pack_weights(cudaStream_t st, DType dt, const float* w_master /*[Co][Ci_real][R][S]*/, void* wp, void* wpd,
                     int Co, int Ci_real, int Ci, int R, int S);
 
+// BatchNorm statistics are reduced in two fixed-order stages so that a forward / backward pass is bit-reproducible run to run:
+// every producing CTA owns one SLOT of per-channel partial sums, stats[slot][2*C] floats (slot = blockIdx.x; the arena is zeroed once
+// per pass), and the finalize kernels add the slots in slot order in fp64.  No floating-point atomics on this path.
+// (SALT_STAT_SLOTS, SALT_STAT_SLOTS_CONV: common.cuh)
 void k_conv_fwd_simt(cudaStream_t st, DType dt, const void* in, const void* wp, const float* bias, void* out,
-                     double* stats, const ConvGeom& g);
+                     float* stats, const ConvGeom& g);
+// out[2C] (fp64) = sum over slots, in slot order (C-ABI single-operator entry points; the engine uses the finalize kernels)
+void k_stats_reduce(cudaStream_t st, const float* stats, int nslots, int C, double* out);
 void k_conv_dgrad_simt(cudaStream_t st, DType dt, const void* gout, const void* wpd, void* gin, bool accumulate,
                        const ConvGeom& g);
 void k_conv_wgrad_simt(cudaStream_t st, DType dt, const void* in, const void* gout, float* dw, int Ci_real,
@@ -58,14 +64,14 @@ struct BNRef {                 // device pointers describing one BatchNorm layer
     const float *gamma, *beta;
     float *rmean, *rvar;
     float *dgamma, *dbeta;
-    double* sums;              // [2C] forward  sum(x), sum(x^2)
-    double* bsums;             // [2C] backward sum(g), sum(g*xhat)
+    float* sums;               // [SALT_STAT_SLOTS][2C] forward  per-CTA partials of sum(x), sum(x^2)
+    float* bsums;              // [SALT_STAT_SLOTS][2C] backward per-CTA partials of sum(g), sum(g*xhat)
     float *scale, *shift;      // y = x*scale + shift
     float *mean, *invstd;      // batch statistics of the last training forward
     float *cb, *cc;            // backward coefficients: g_raw = scale*(g - cb - cc*(x-mean))
 };
 
-void k_bn_finalize_train(cudaStream_t st, const BNRef& bn, double count, float momentum, float eps);
+void k_bn_finalize_train(cudaStream_t st, const BNRef& bn, int nslots, double count, float momentum, float eps);
 void k_bn_finalize_eval(cudaStream_t st, const BNRef& bn, float eps);
 void k_bn_bwd_finalize(cudaStream_t st, const BNRef& bn, double count);
 

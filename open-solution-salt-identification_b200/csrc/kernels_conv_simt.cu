@@ -54,7 +54,7 @@ struct IGemmArgs {
 template <typename T, bool DGRAD>
 __global__ void __launch_bounds__(256) conv_igemm_simt_kernel(const T* __restrict__ src, const T* __restrict__ w,
                                                               const float* __restrict__ bias, T* __restrict__ dst,
-                                                              double* __restrict__ stats, IGemmArgs a) {
+                                                              float* __restrict__ stats, IGemmArgs a) {
     __shared__ __align__(16) float As[2][TK][TM + SPAD];
     __shared__ __align__(16) float Bs[2][TK][TN + SPAD];
     __shared__ float red[16][TN];
@@ -156,14 +156,16 @@ __global__ void __launch_bounds__(256) conv_igemm_simt_kernel(const T* __restric
                 float t = 0.f;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) t += red[i][tid];
-                atomicAdd(stats + pass * a.N + n0 + tid, (double)t);
+                // many M-tiles share a slot: the fp32 parity mode keeps float atomics here (its activations are fp32, so a last-bit
+                // difference in a sum is not amplified the way bf16 storage amplifies it)
+                atomicAdd(stats + (size_t)(blockIdx.x % SALT_STAT_SLOTS) * 2 * a.N + pass * a.N + n0 + tid, t);
             }
             __syncthreads();
         }
     }
 }
 
-void k_conv_fwd_simt(cudaStream_t st, DType dt, const void* in, const void* wp, const float* bias, void* out, double* stats,
+void k_conv_fwd_simt(cudaStream_t st, DType dt, const void* in, const void* wp, const float* bias, void* out, float* stats,
                      const ConvGeom& g) {
     SALT_COUNT(1);
     IGemmArgs a;

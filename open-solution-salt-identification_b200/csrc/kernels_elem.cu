@@ -132,11 +132,28 @@ __device__ __forceinline__ void block_reduce_add(const Vf<N>& v, int cg, D* dst,
     }
     __syncthreads();
 }
+// Same reduction, but the block's sum is STORED into the block's own partial slot (dst already points at the slot): the
+// finalize kernel adds the slots in a fixed order, so the result does not depend on block scheduling.
+template <int N>
+__device__ __forceinline__ void block_reduce_slot(const Vf<N>& v, int cg, float* dst, float* red) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < N; ++i) red[i * EW_THREADS + tid] = v.v[i];
+    __syncthreads();
+    if (tid < cg) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            float s = 0.f;
+            for (int t = tid; t < EW_THREADS; t += cg) s += red[i * EW_THREADS + t];
+            dst[tid * N + i] = s;
+        }
+    }
+    __syncthreads();
+}
 static inline int reduce_blocks(long long npix, int cg) {
     int lanes = EW_THREADS / cg;
     long long b = (npix + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
-    if (b > 148 * 2) b = 148 * 2;      // few fat blocks: the final per-channel atomics hit the same 2*C addresses (6 blocks per SM
-                                       // measured 30 % SLOWER for bn_bwd_reduce: profiles/r1_notes.md)
+    if (b > SALT_STAT_SLOTS) b = SALT_STAT_SLOTS;      // one partial slot per block (kernels.h); 2 blocks per SM
     if (b < 1) b = 1;
     return (int)b;
 }
@@ -198,11 +215,43 @@ void k_stem_im2col(cudaStream_t st, DType dt, const float* x, void* patches, int
 // ------------------------------------------------------------------------------------------------
 // BatchNorm finalisation (nn.BatchNorm2d: eps 1e-5, momentum 0.1, biased var to normalise, unbiased to track)
 // ------------------------------------------------------------------------------------------------
-__global__ void bn_finalize_train_kernel(BNRef bn, double count, float momentum, float eps) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= bn.C) return;
-    double mean = bn.sums[c] / count;
-    double var = bn.sums[bn.C + c] / count - mean * mean;
+// Fixed-order sum of the partial slots of channel c = blockIdx.x*32 + threadIdx.x: thread row y adds slots y, y+8, ... in fp64,
+// then row 0 adds the 8 row sums in order.  Block = (32, 8).  Returns the two sums in row 0 (other rows return garbage).
+__device__ __forceinline__ void slot_sums(const float* __restrict__ part, int nslots, int C, int c, double& s0, double& s1) {
+    __shared__ double sm[8][2][32];
+    double a = 0.0, b = 0.0;
+    if (c < C) {
+#pragma unroll 4
+        for (int slot = threadIdx.y; slot < nslots; slot += 8) {
+            a += (double)__ldcg(part + (size_t)slot * 2 * C + c);
+            b += (double)__ldcg(part + (size_t)slot * 2 * C + C + c);
+        }
+    }
+    sm[threadIdx.y][0][threadIdx.x] = a; sm[threadIdx.y][1][threadIdx.x] = b;
+    __syncthreads();
+    s0 = 0.0; s1 = 0.0;
+    if (threadIdx.y == 0) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) { s0 += sm[g][0][threadIdx.x]; s1 += sm[g][1][threadIdx.x]; }
+    }
+}
+__global__ void stats_reduce_kernel(const float* __restrict__ part, int nslots, int C, double* __restrict__ out) {
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double s0, s1;
+    slot_sums(part, nslots, C, c, s0, s1);
+    if (threadIdx.y == 0 && c < C) { out[c] = s0; out[C + c] = s1; }
+}
+void k_stats_reduce(cudaStream_t st, const float* stats, int nslots, int C, double* out) {
+    SALT_COUNT(1);
+    stats_reduce_kernel<<<cdiv(C, 32), dim3(32, 8), 0, st>>>(stats, nslots, C, out);
+}
+__global__ void bn_finalize_train_kernel(BNRef bn, int nslots, double count, float momentum, float eps) {
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double s0, s1;
+    slot_sums(bn.sums, nslots, bn.C, c, s0, s1);
+    if (threadIdx.y != 0 || c >= bn.C) return;
+    double mean = s0 / count;
+    double var = s1 / count - mean * mean;
     if (var < 0) var = 0;
     double invstd = 1.0 / sqrt(var + (double)eps);
     float sc = (float)(bn.gamma[c] * invstd);
@@ -214,9 +263,9 @@ __global__ void bn_finalize_train_kernel(BNRef bn, double count, float momentum,
     bn.rmean[c] = (float)((1.0 - momentum) * bn.rmean[c] + momentum * mean);
     bn.rvar[c] = (float)((1.0 - momentum) * bn.rvar[c] + momentum * unbiased);
 }
-void k_bn_finalize_train(cudaStream_t st, const BNRef& bn, double count, float momentum, float eps) {
+void k_bn_finalize_train(cudaStream_t st, const BNRef& bn, int nslots, double count, float momentum, float eps) {
     SALT_COUNT(1);
-    bn_finalize_train_kernel<<<cdiv(bn.C, 128), 128, 0, st>>>(bn, count, momentum, eps);
+    bn_finalize_train_kernel<<<cdiv(bn.C, 32), dim3(32, 8), 0, st>>>(bn, nslots, count, momentum, eps);
 }
 __global__ void bn_finalize_eval_kernel(BNRef bn, float eps) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -231,9 +280,10 @@ void k_bn_finalize_eval(cudaStream_t st, const BNRef& bn, float eps) {
     bn_finalize_eval_kernel<<<cdiv(bn.C, 128), 128, 0, st>>>(bn, eps);
 }
 __global__ void bn_bwd_finalize_kernel(BNRef bn, double count) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= bn.C) return;
-    double sg = bn.bsums[c], sgx = bn.bsums[bn.C + c];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double sg, sgx;
+    slot_sums(bn.bsums, SALT_STAT_SLOTS, bn.C, c, sg, sgx);
+    if (threadIdx.y != 0 || c >= bn.C) return;
     bn.dbeta[c] += (float)sg;
     bn.dgamma[c] += (float)sgx;
     bn.cb[c] = (float)(sg / count);
@@ -241,7 +291,7 @@ __global__ void bn_bwd_finalize_kernel(BNRef bn, double count) {
 }
 void k_bn_bwd_finalize(cudaStream_t st, const BNRef& bn, double count) {
     SALT_COUNT(1);
-    bn_bwd_finalize_kernel<<<cdiv(bn.C, 128), 128, 0, st>>>(bn, count);
+    bn_bwd_finalize_kernel<<<cdiv(bn.C, 32), dim3(32, 8), 0, st>>>(bn, count);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -753,8 +803,8 @@ __global__ void scse_bwd_apply_kernel(const T* __restrict__ gout, const T* __res
             if (cv == 0) sbs += dsp;
         }
     }
-    block_reduce_add<N, double>(sg, cg, bn.bsums, red);
-    block_reduce_add<N, double>(sgx, cg, bn.bsums + C, red);
+    block_reduce_slot<N>(sg, cg, bn.bsums + (size_t)blockIdx.x * 2 * C, red);
+    block_reduce_slot<N>(sgx, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + C, red);
     block_reduce_add<N, float>(sws, cg, se.dws, red);
     red[threadIdx.x] = sbs;
     __syncthreads();
@@ -837,8 +887,8 @@ __global__ void final_bwd_kernel(const float* __restrict__ dlogits, const T* __r
         sg = vadd(sg, gz);
         sgx = vfma(gz, vxhat(x, mu, is), sgx);
     }
-    block_reduce_add<N, double>(sg, cg, bn.bsums, red);
-    block_reduce_add<N, double>(sgx, cg, bn.bsums + C, red);
+    block_reduce_slot<N>(sg, cg, bn.bsums + (size_t)blockIdx.x * 2 * C, red);
+    block_reduce_slot<N>(sgx, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + C, red);
     for (int k = 0; k < K; ++k) block_reduce_add<N, float>(sdw[k], cg, dw + k * C, red);
     for (int k = 0; k < K; ++k) {
         red[threadIdx.x] = sdb[k];
@@ -904,8 +954,8 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restric
         sgx = vfma(gv, vxhat(x, mu, is), sgx);
     }
     const int coff = blockIdx.y * cg * N;
-    block_reduce_add<N, double>(sg, cg, bn.bsums + coff, red);
-    block_reduce_add<N, double>(sgx, cg, bn.bsums + C + coff, red);
+    block_reduce_slot<N>(sg, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + coff, red);
+    block_reduce_slot<N>(sgx, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + C + coff, red);
 }
 void k_bn_bwd_reduce(cudaStream_t st, const Tensor& g, const Tensor& raw, const BNRef& bn, bool self_mask, const float* gate,
                      const float* addc) {

@@ -147,7 +147,10 @@ inline CUtensorMap make_map_nhwc(const void* base, int C, int W, int H, int B, i
 }
 inline int num_sms() {
     static int n = 0;
-    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
+    if (!n) {
+        int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n > SALT_STAT_SLOTS_CONV) n = SALT_STAT_SLOTS_CONV;      // persistent grids index BatchNorm partial slots by blockIdx.x
+    }
     return n;
 }
 
