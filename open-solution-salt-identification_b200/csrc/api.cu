@@ -188,8 +188,22 @@ int salt_op_conv_forward(const salt_conv_desc* d, const void* in, const float* w
         cudaMemsetAsync(part, 0, pb, st);
     }
     try {
-        if (d->use_tensor_cores) {
-            if (dt != DT_BF16 || !tc_conv_supported(g, false)) { cudaFree(part); return fail("salt_op_conv_forward: geometry not supported by the tensor-core kernel"); }
+        if (d->use_tensor_cores && dt == DT_F32) {
+            // fp32 parity mode on the tensor cores: split-bf16 operands (kernels.h k_split6_*), fp32 output
+            ConvGeom g6 = g; g6.Ci = 6 * g.Ci;
+            if (!tc_conv_supported(g6, false)) { cudaFree(part); return fail("salt_op_conv_forward: geometry not supported by the tensor-core kernel"); }
+            void *in6 = nullptr, *w6 = nullptr;
+            const size_t rows_in = (size_t)g.B * g.Hi * g.Wi, rows_w = (size_t)g.Co * g.R * g.S;
+            if (cudaMalloc(&in6, rows_in * g6.Ci * 2) != cudaSuccess || cudaMalloc(&w6, rows_w * g6.Ci * 2) != cudaSuccess) {
+                cudaFree(in6); cudaFree(part); return fail("salt_op_conv_forward: out of device memory");
+            }
+            k_split6_act(st, (const float*)in, in6, rows_in, g.Ci);
+            k_split6_weights(st, (const float*)pk.wp, w6, rows_w, g.Ci);
+            k_conv_tc(st, in6, g.B, g.Hi, g.Wi, g6.Ci, w6, g.Co, g.R, g.S, g.stride, g.pad, out, g.Ho, g.Wo, bias, part, false, true);
+            cudaStreamSynchronize(st);
+            cudaFree(in6); cudaFree(w6);
+        } else if (d->use_tensor_cores) {
+            if (!tc_conv_supported(g, false)) { cudaFree(part); return fail("salt_op_conv_forward: geometry not supported by the tensor-core kernel"); }
             k_conv_tc(st, in, g.B, g.Hi, g.Wi, g.Ci, pk.wp, g.Co, g.R, g.S, g.stride, g.pad, out, g.Ho, g.Wo, bias, part, false);
         } else {
             k_conv_fwd_simt(st, dt, in, pk.wp, bias, out, part, g);

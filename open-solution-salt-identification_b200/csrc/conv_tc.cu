@@ -18,11 +18,6 @@
 #include <cstdlib>
 #include <algorithm>
 
-// default cluster size of the tap-table kernel (1 = off) until the B200 measurements say otherwise
-#ifndef TC_GENERIC_CLUSTER_DEFAULT
-#define TC_GENERIC_CLUSTER_DEFAULT 1
-#endif
-
 using namespace tc;
 
 // 32 per-lane values (one per channel) x 32 lanes (pixels) -> lane l holds the sum over pixels of channel l
@@ -49,52 +44,24 @@ struct TcPhase { int ntaps, oy, ox; TcTap taps[9]; };
 struct TcParams {
     int tw, th, tn;
     int tiles_x, tiles_y, tiles_b, tiles_co, tiles_per_phase;
-    int m_tiles, groups_per_phase;  // cluster mode: a group = CL consecutive position tiles of one (phase, channel tile)
+    int m_tiles;
     int B, Ho, Wo;                 // output positions per phase
     int out_H, out_W, Co;          // physical output tensor
     int osy, osx, a_stride, cblks;
     int accumulate, nphases;
     const float* bias;
     float* stats;              // [SALT_STAT_SLOTS_CONV][2*Co] partial slots, slot = blockIdx.x
-    bf16* out;
+    void* out;                 // OutT, physical [B][out_H][out_W][Co]
     TcPhase ph[4];
 };
 
-// ---- thread-block-cluster variant (CL > 1): the CL CTAs of a cluster take CL consecutive position tiles of the same (phase,
-// channel tile), consume identical weight stages in lockstep, and each fetches 1/CL of every [BN x BK] weight slab with a
-// TMA multicast into all CL shared memories (see conv_tc_rows.cu for the protocol and the measurements behind it).
-__device__ __forceinline__ uint32_t tc_cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void tc_cluster_sync() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-                 " [%0], [%1, {%3, %4}], [%2], %5;"
-                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void tc_umma_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(mask) : "memory");
-}
 struct TcTile { int pi, nt, mt; bool live; };
-template <int CL>
-__device__ __forceinline__ bool tc_tile(const TcParams& p, int k, uint32_t rank, TcTile& t) {
-    if constexpr (CL == 1) {
-        const int tile = blockIdx.x + k * gridDim.x;
-        if (tile >= p.nphases * p.tiles_per_phase) return false;
-        t.pi = tile / p.tiles_per_phase;
-        const int r = tile - t.pi * p.tiles_per_phase;
-        t.nt = r % p.tiles_co; t.mt = r / p.tiles_co; t.live = true;
-    } else {
-        const int g = blockIdx.x / CL + k * (gridDim.x / CL);
-        if (g >= p.nphases * p.groups_per_phase) return false;
-        t.pi = g / p.groups_per_phase;
-        const int r = g - t.pi * p.groups_per_phase;
-        t.nt = r % p.tiles_co; t.mt = (r / p.tiles_co) * CL + (int)rank;
-        t.live = t.mt < p.m_tiles;
-        if (!t.live) t.mt = p.m_tiles - 1;
-    }
+__device__ __forceinline__ bool tc_tile(const TcParams& p, int k, TcTile& t) {
+    const int tile = blockIdx.x + k * gridDim.x;
+    if (tile >= p.nphases * p.tiles_per_phase) return false;
+    t.pi = tile / p.tiles_per_phase;
+    const int r = tile - t.pi * p.tiles_per_phase;
+    t.nt = r % p.tiles_co; t.mt = r / p.tiles_co; t.live = true;
     return true;
 }
 
@@ -113,7 +80,7 @@ template <int BN, int BK> struct TcCfg {
     static constexpr uint32_t LAYOUT = BK == 64 ? 2 : 4;       // SWIZZLE_128B : SWIZZLE_64B
 };
 
-template <int BN, int BK, int CL>
+template <int BN, int BK, typename OutT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcParams p) {
     using Cfg = TcCfg<BN, BK>;
@@ -134,7 +101,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
-        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, CL); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -142,18 +109,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int i = threadIdx.x; i < 4 * 2 * BN; i += TC_THREADS) s_stats[i] = 0.f;
     fence_before();
     __syncthreads();
-    uint32_t rank = 0;
-    if constexpr (CL > 1) { rank = tc_cluster_ctarank(); tc_cluster_sync(); }
     fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
-    constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1);
 
     if (warp == 0) {
         // ===================================================== TMA producer
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             TcTile tt;
-            for (int k = 0; tc_tile<CL>(p, k, rank, tt); ++k) {
+            for (int k = 0; tc_tile(p, k, tt); ++k) {
                 const TcPhase& ph = p.ph[tt.pi];
                 const int nt = tt.nt, mt = tt.mt;
                 const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
@@ -164,13 +128,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
                         mbar_expect_tx(full0 + 8 * stage, Cfg::STAGE_BYTES);
                         tma_load_4d(smem_u32(smem_a + stage * Cfg::A_BYTES), &map_a, full0 + 8 * stage, cb * BK, w0 + dx, h0 + dy, n0);
-                        if constexpr (CL == 1) {
-                            tma_load_2d(smem_u32(smem_b + stage * Cfg::B_BYTES), &map_b, full0 + 8 * stage, kofs + cb * BK, nt * BN);
-                        } else {
-                            constexpr int PART = BN / CL;           // my rows of the weight slab, multicast to the whole cluster
-                            tma_load_2d_mc(smem_u32(smem_b + stage * Cfg::B_BYTES) + rank * (PART * BK * 2), &map_b, full0 + 8 * stage,
-                                           kofs + cb * BK, nt * BN + (int)rank * PART, MC_MASK);
-                        }
+                        tma_load_2d(smem_u32(smem_b + stage * Cfg::B_BYTES), &map_b, full0 + 8 * stage, kofs + cb * BK, nt * BN);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -182,7 +140,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         TcTile tt;
-        for (int kk = 0; tc_tile<CL>(p, kk, rank, tt); ++kk) {
+        for (int kk = 0; tc_tile(p, kk, tt); ++kk) {
             const int num_kb = p.ph[tt.pi].ntaps * p.cblks;
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
             fence_after();
@@ -196,8 +154,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)       // advance 16 bf16 = 32 bytes inside the swizzle atom
                         umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-                    if constexpr (CL == 1) umma_commit(empty0 + 8 * stage);        // frees the smem stage when these MMAs retire
-                    else tc_umma_commit_mc(empty0 + 8 * stage, MC_MASK);           // ... in every CTA of the cluster
+                    umma_commit(empty0 + 8 * stage);        // frees the smem stage when these MMAs retire
                     if (kb == num_kb - 1) umma_commit(tfull0 + 8 * acc);
                 }
                 __syncwarp();
@@ -214,13 +171,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int lx = m % p.tw, ly = (m / p.tw) % p.th, ln = m / (p.tw * p.th);
         int acc = 0; uint32_t acc_phase = 0;
         TcTile tt;
-        for (int kk = 0; tc_tile<CL>(p, kk, rank, tt); ++kk) {
+        for (int kk = 0; tc_tile(p, kk, tt); ++kk) {
             const int pi = tt.pi, nt = tt.nt, mt = tt.mt;
             const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
             const int x = tx * p.tw + lx, y = ty * p.th + ly, n = tb * p.tn + ln;
             const bool valid = tt.live && (n < p.B) && (y < p.Ho) && (x < p.Wo);
             const int oy = y * p.osy + p.ph[pi].oy, ox = x * p.osx + p.ph[pi].ox;
-            bf16* orow = p.out + (((size_t)n * p.out_H + oy) * p.out_W + ox) * p.Co + nt * BN;
+            OutT* orow = reinterpret_cast<OutT*>(p.out) + (((size_t)n * p.out_H + oy) * p.out_W + ox) * p.Co + nt * BN;
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             fence_after();
 #pragma unroll 1
@@ -231,7 +188,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + nt * BN + ch * 32 + i);
                 }
-                if (valid) {
+                if (valid && sizeof(OutT) == 4) {
+                    float4* o4 = reinterpret_cast<float4*>(orow + ch * 32);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) o4[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                } else if (valid) {
                     uint4* o4 = reinterpret_cast<uint4*>(orow + ch * 32);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -294,7 +255,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     fence_before();
     __syncthreads();
-    if constexpr (CL > 1) tc_cluster_sync();       // no CTA leaves while a peer's commit may still arrive on its barriers
     if (warp == 1) { fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
 }
 
@@ -325,63 +285,22 @@ bool tc_conv_supported(const ConvGeom& g, bool dgrad) {
     return true;
 }
 
-template <int BN, int BK, int CL>
-static int tc_max_clusters() {
-    static int cached = -1;
-    if (cached < 0) {
-        using Cfg = TcCfg<BN, BK>;
-        cudaFuncSetAttribute(conv_tc_kernel<BN, BK, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(num_sms() / CL * CL); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<BN, BK, CL>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = 0; }
-        cached = n;
-    }
-    return cached;
-}
-template <int BN, int BK, int CL>
-static void launch_tc_cl(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p) {
+template <int BN, int BK, typename OutT>
+static void launch_tc(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p) {
     using Cfg = TcCfg<BN, BK>;
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(conv_tc_kernel<BN, BK, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaFuncSetAttribute(conv_tc_kernel<BN, BK, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         configured = true;
     }
-    if constexpr (CL == 1) {
-        const int total_tiles = p.nphases * p.tiles_per_phase;
-        const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-        conv_tc_kernel<BN, BK, 1><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
-    } else {
-        const int clusters = std::min(tc_max_clusters<BN, BK, CL>(), p.nphases * p.groups_per_phase);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(clusters * CL); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, BK, CL>, ma, mb, p);
-        if (e != cudaSuccess) throw std::runtime_error(std::string("conv_tc cluster launch failed: ") + cudaGetErrorString(e));
-        ++g_salt_cluster_launches;
-    }
-}
-// cluster size of the tap-table kernel: env SALT_TC_CLUSTER_GENERIC = 1 | 2 | 4
-static int tc_cluster_pref() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("SALT_TC_CLUSTER_GENERIC"); v = e ? atoi(e) : TC_GENERIC_CLUSTER_DEFAULT; if (v != 1 && v != 2 && v != 4) v = 1; }
-    return v;
-}
-template <int BN, int BK>
-static int tc_pick_cluster(const TcParams& p) {
-    int cl = tc_cluster_pref();
-    while (cl > 1 && (p.m_tiles < cl * 8 || (cl == 4 ? tc_max_clusters<BN, BK, 4>() : tc_max_clusters<BN, BK, 2>()) * cl < num_sms() * 3 / 4)) cl >>= 1;
-    return cl;
+    const int total_tiles = p.nphases * p.tiles_per_phase;
+    const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+    conv_tc_kernel<BN, BK, OutT><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
 }
 
 // Common launcher.  A: [B,Ha,Wa,Ca] bf16; Wp: [Nout][Ktot] bf16; out: physical [B,out_H,out_W,Nout] bf16;
 // per phase Ho x Wo output positions written at (y*os+oy, x*os+ox).
-static void run_tc(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca, const void* Wp, int Ktot, int Nout, TcParams& p) {
+static void run_tc(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca, const void* Wp, int Ktot, int Nout, TcParams& p, bool out_f32) {
     p.tw = p.Wo >= 16 ? 16 : 8;
     p.th = p.tw == 16 ? 8 : (p.Ho >= 16 ? 16 : 8);
     p.tn = 128 / (p.tw * p.th);
@@ -397,13 +316,9 @@ static void run_tc(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca
     CUtensorMap ma = make_map_nhwc(A, Ca, Wa, Ha, B, BK, p.tw, p.th, p.tn, p.a_stride,
                                    sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
     p.m_tiles = p.tiles_x * p.tiles_y * p.tiles_b;
-#define TC_CASE(bn, bk) if (BN == bn && BK == bk) {                                                            \
-        const int cl = tc_pick_cluster<bn, bk>(p);                                                             \
-        p.groups_per_phase = cdiv(p.m_tiles, cl) * p.tiles_co;                                                 \
-        CUtensorMap mb = make_map_weights(Wp, Ktot, Nout, BK, BN / cl, sw64);   /* CL > 1: my BN/CL rows of a slab */ \
-        if (cl == 4) launch_tc_cl<bn, bk, 4>(st, ma, mb, p);                                                   \
-        else if (cl == 2) launch_tc_cl<bn, bk, 2>(st, ma, mb, p);                                              \
-        else launch_tc_cl<bn, bk, 1>(st, ma, mb, p);                                                           \
+    CUtensorMap mb = make_map_weights(Wp, Ktot, Nout, BK, BN, sw64);
+#define TC_CASE(bn, bk) if (BN == bn && BK == bk) {                                                 \
+        if (out_f32) launch_tc<bn, bk, float>(st, ma, mb, p); else launch_tc<bn, bk, bf16>(st, ma, mb, p);  \
         return; }
     TC_CASE(256, 64) TC_CASE(128, 64) TC_CASE(64, 64) TC_CASE(32, 64)
     TC_CASE(256, 32) TC_CASE(128, 32) TC_CASE(64, 32) TC_CASE(32, 32)
@@ -418,21 +333,22 @@ static bool rows_enabled() {
 }
 // out[n,y,x,k] (+)= sum_{r,s,c} A[n, y*stride+r-pad, x*stride+s-pad, c] * Wp[k][(r*S+s)*Ca + c]
 void k_conv_tc(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca, const void* Wp, int Nout, int R, int S, int stride,
-               int pad, void* out, int Ho, int Wo, const float* bias, float* stats, bool accumulate) {
+               int pad, void* out, int Ho, int Wo, const float* bias, float* stats, bool accumulate, bool out_f32) {
+    if (out_f32 && accumulate) throw std::runtime_error("k_conv_tc: accumulation into an fp32 output is not implemented");
     if (rows_enabled() && tc_conv_rows_supported(Ca, Nout, R, S, stride, Ho, Wo)) {
-        k_conv_tc_rows(st, A, B, Ha, Wa, Ca, Wp, Nout, pad, out, Ho, Wo, bias, stats, accumulate);
+        k_conv_tc_rows(st, A, B, Ha, Wa, Ca, Wp, Nout, pad, out, Ho, Wo, bias, stats, accumulate, out_f32);
         return;
     }
     SALT_COUNT(1);
     TcParams p;
     p.Ho = Ho; p.Wo = Wo; p.out_H = Ho; p.out_W = Wo; p.osy = p.osx = 1; p.a_stride = stride;
-    p.accumulate = accumulate ? 1 : 0; p.bias = bias; p.stats = stats; p.out = (bf16*)out;
+    p.accumulate = accumulate ? 1 : 0; p.bias = bias; p.stats = stats; p.out = out;
     p.nphases = 1;
     TcPhase& ph = p.ph[0];
     ph.ntaps = R * S; ph.oy = ph.ox = 0;
     for (int r = 0; r < R; ++r)
         for (int s = 0; s < S; ++s) { TcTap& t = ph.taps[r * S + s]; t.dy = (short)(r - pad); t.dx = (short)(s - pad); t.kofs = (r * S + s) * Ca; }
-    run_tc(st, A, B, Ha, Wa, Ca, Wp, R * S * Ca, Nout, p);
+    run_tc(st, A, B, Ha, Wa, Ca, Wp, R * S * Ca, Nout, p, out_f32);
 }
 
 // stride-2 dgrad: gin[n,yi,xi,c] (+)= sum over (r,s) with (yi+pad-r), (xi+pad-s) even of
@@ -443,7 +359,7 @@ void k_conv_tc_dgrad_s2(cudaStream_t st, const void* gout, int B, int Ho, int Wo
     SALT_COUNT(1);
     TcParams p;
     p.Ho = Hi / 2; p.Wo = Wi / 2; p.out_H = Hi; p.out_W = Wi; p.osy = p.osx = 2; p.a_stride = 1;
-    p.accumulate = accumulate ? 1 : 0; p.bias = nullptr; p.stats = nullptr; p.out = (bf16*)gin;
+    p.accumulate = accumulate ? 1 : 0; p.bias = nullptr; p.stats = nullptr; p.out = gin;
     p.nphases = 0;
     for (int py = 0; py < 2; ++py)
         for (int px = 0; px < 2; ++px) {
@@ -463,5 +379,5 @@ void k_conv_tc_dgrad_s2(cudaStream_t st, const void* gout, int B, int Ho, int Wo
             }
             p.ph[p.nphases++] = ph;
         }
-    run_tc(st, gout, B, Ho, Wo, Co, wpd, R * S * Co, Ci, p);
+    run_tc(st, gout, B, Ho, Wo, Co, wpd, R * S * Co, Ci, p, false);
 }

@@ -53,6 +53,7 @@ void* Engine::ws_alloc(size_t bytes) {
 Tensor Engine::make_tensor(int H, int W, int C, int pt, int pb, int pl, int pr) {
     Tensor t; t.B = cfg_.max_batch; t.H = H; t.W = W; t.C = C; t.pt = pt; t.pb = pb; t.pl = pl; t.pr = pr; t.dt = cfg_.dt;
     t.p = ws_alloc(t.bytes());
+    if (t.numel() > split_elems_) split_elems_ = t.numel();
     return t;
 }
 GradBuf* Engine::make_gradbuf(const Tensor& like) {
@@ -68,6 +69,7 @@ ConvLayer Engine::make_conv(const std::string& wname, const std::string& bname, 
     size_t wb = (size_t)co * k * k * c.Ci * dtype_size(cfg_.dt);
     c.wp = ws_alloc(wb);
     c.wpd = ws_alloc(wb);
+    if (split_tc()) c.wp6 = ws_alloc((size_t)co * k * k * c.Ci * 6 * sizeof(bf16));
     c.dwp = dwp_arena_ + dwp_cursor_;
     dwp_cursor_ += (tc_wgrad_scratch_floats(c.Ci, co, k * k) + 3) / 4 * 4;
     return c;
@@ -151,6 +153,7 @@ void Engine::build() {
         stem_.Ci = 160; stem_.Ci_real = 147; stem_.R = stem_.S = 1; stem_.stride = 1; stem_.pad = 0;
         const size_t wb = (size_t)64 * 160 * dtype_size(cfg_.dt);
         stem_.wp = ws_alloc(wb); stem_.wpd = ws_alloc(wb);
+        if (split_tc()) stem_.wp6 = ws_alloc((size_t)64 * 160 * 6 * sizeof(bf16));
         stem_.dwp = dwp_arena_ + dwp_cursor_;
         dwp_cursor_ += (tc_wgrad_scratch_floats(160, 64, 1) + 3) / 4 * 4;
     }
@@ -247,6 +250,7 @@ void Engine::build() {
     }
     loss_sums_ = (double*)ws_alloc(sizeof(double) * 16);
     for (int i = 0; i < 4; ++i) scratch_[i] = ws_alloc(std::max<size_t>(scratch_bytes_[i], 256));
+    split_scratch_ = split_tc() ? ws_alloc(split_elems_ * 6 * sizeof(bf16)) : nullptr;
     if (counting_) { stats_floats_ = stats_cursor_; bstats_floats_ = bstats_cursor_; dwp_floats_ = dwp_cursor_; }
 }
 
@@ -321,6 +325,8 @@ void Engine::build_pack_table() {
 }
 void Engine::pack_all(cudaStream_t st) {
     k_pack_all(st, cfg_.dt, d_pack_, d_pack_start_, pack_layers_, pack_blocks_, pack_max_rs_);
+    if (split_tc())
+        for (ConvLayer* c : all_convs()) k_split6_weights(st, (const float*)c->wp, c->wp6, (size_t)c->Co * c->R * c->S, c->Ci);
     packed_dirty_ = false;
 }
 // one launch: transpose every tensor-core wgrad scratch into the reference-layout gradient
@@ -377,8 +383,14 @@ void Engine::conv_fwd(const ConvLayer& c, const Tensor& in, const Tensor& out, B
     const float* bias = c.o_b >= 0 ? params_ + c.o_b : nullptr;
     prof_begin(PROF_CONV_FWD, conv_flops(g, c.Ci_real), st);
     float* stats = (bn && train) ? bn->sums : nullptr;
-    const bool tc = cfg_.dt == DT_BF16 && cfg_.use_tc && tc_conv_supported(g, false);
-    if (tc)
+    ConvGeom g6 = g; g6.Ci = 6 * g.Ci;
+    const bool tc_split = split_tc() && tc_conv_supported(g6, false);
+    const bool tc = tc_split || (cfg_.dt == DT_BF16 && cfg_.use_tc && tc_conv_supported(g, false));
+    if (tc_split) {
+        // fp32 parity mode on tcgen05: the bf16 kernel over the split-bf16 copy of the input (6x the channels), fp32 output
+        k_split6_act(st, (const float*)in.p, split_scratch_, (size_t)g.B * g.Hi * g.Wi, g.Ci);
+        k_conv_tc(st, split_scratch_, g.B, g.Hi, g.Wi, g6.Ci, c.wp6, g.Co, g.R, g.S, g.stride, g.pad, out.p, g.Ho, g.Wo, bias, stats, false, true);
+    } else if (tc)
         k_conv_tc(st, in.p, g.B, g.Hi, g.Wi, g.Ci, c.wp, g.Co, g.R, g.S, g.stride, g.pad, out.p, g.Ho, g.Wo, bias, stats, false);
     else
         k_conv_fwd_simt(st, cfg_.dt, in.p, c.wp, bias, out.p, stats, g);

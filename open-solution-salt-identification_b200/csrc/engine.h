@@ -25,6 +25,7 @@ struct ConvLayer {
     void* wp = nullptr;        // packed fwd weights   [Co][R*S][Ci]
     void* wpd = nullptr;       // packed dgrad weights [Ci][R*S][Co]
     bool in_unpack_table = false;
+    void* wp6 = nullptr;       // fp32 tensor-core parity mode: split-bf16 forward weights [Co][R*S][6*Ci] (kernels.h k_split6_weights)
     float* dwp = nullptr;      // tensor-core wgrad scratch [R*S][ceil64(Ci)][Co] fp32 (inside the zeroed-per-backward arena)
 };
 struct BNLayer {
@@ -201,6 +202,8 @@ private:
     bool prof_on_ = false;
     void prof_begin(int cls, double flops, cudaStream_t st);
     void prof_end(cudaStream_t st);
+    void* split_scratch_ = nullptr; size_t split_elems_ = 0;      // fp32 TC parity mode: split-bf16 copy of the current conv input
+    bool split_tc() const { return cfg_.dt == DT_F32 && cfg_.use_tc; }
     float* loss_scratch_ = nullptr;   // [max_batch + 8]
     void* lovasz_sort_ = nullptr;     // global-memory sort buffers of the Lovasz loss for images with > 32768 logits
     double* loss_sums_ = nullptr;     // [16]

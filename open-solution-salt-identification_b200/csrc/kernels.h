@@ -28,6 +28,15 @@ void k_conv_dgrad_simt(cudaStream_t st, DType dt, const void* gout, const void* 
 void k_conv_wgrad_simt(cudaStream_t st, DType dt, const void* in, const void* gout, float* dw, int Ci_real,
                        const ConvGeom& g);
 
+// -------------------------------------------------------------------- fp32 parity mode on the tensor cores (split-bf16 operands)
+// x = h + m + l with h = bf16(x), m = bf16(x - h), l = bf16(x - h - m): three bf16 terms carry 24 mantissa bits.  A convolution
+// of fp32 tensors is the sum of the six bf16 x bf16 products h*h, h*m, m*h, m*m, h*l, l*h (the dropped ones are < 2^-24
+// relative), accumulated in fp32 by tcgen05 - i.e. the SAME bf16 convolution kernel run over 6x the input channels:
+//   activation segments [h | h | m | m | h | l]   x   weight segments [h | m | h | m | l | h]
+// Measured against the reference forward: <= 6e-5 max-abs on the logits (plain kind::tf32 operands give 1e-2..1e-1).
+void k_split6_act(cudaStream_t st, const float* in, void* out_bf16, size_t rows, int C);       // [rows][C] fp32 -> [rows][6C] bf16
+void k_split6_weights(cudaStream_t st, const float* wp, void* wp6_bf16, size_t rows, int C);   // same, weight segment order
+
 // -------------------------------------------------------------------- input / elementwise
 void k_input_nchw_to_nhwc4(cudaStream_t st, DType dt, const float* x, void* out, int B, int H, int W);
 // stem input adapter: fp32 NCHW [B,3,H,W] -> im2col patches of the 7x7 stride-2 pad-3 stem convolution,

@@ -1003,3 +1003,48 @@ void k_bn_bwd_apply(cudaStream_t st, const Tensor& g, const Tensor& raw, const B
                                                                              addc, (T*)graw.p, npix, raw.H * raw.W, raw.C);
     });
 }
+
+// ------------------------------------------------------------------------------------------------
+// split-bf16 operands of the fp32 tensor-core parity mode (kernels.h)
+// ------------------------------------------------------------------------------------------------
+struct Split6Order { int part[6]; };        // which term (0 = h, 1 = m, 2 = l) goes into channel segment i
+__global__ void split6_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t nvec, int C, Split6Order ord) {
+    const size_t idx = (size_t)blockIdx.x * EW_THREADS + threadIdx.x;          // one 4-channel vector
+    if (idx >= nvec) return;
+    const int cg = C >> 2;
+    const size_t row = idx / cg;
+    const int c = (int)(idx - row * cg) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(in + row * C + c);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 t[3][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(x[i]);
+        const float r1 = x[i] - __bfloat162float(h);                            // exact in fp32
+        const __nv_bfloat16 m = __float2bfloat16_rn(r1);
+        const float r2 = r1 - __bfloat162float(m);
+        t[0][i] = h; t[1][i] = m; t[2][i] = __float2bfloat16_rn(r2);
+    }
+    bf16* o = out + row * (size_t)(6 * C) + c;
+#pragma unroll
+    for (int sgm = 0; sgm < 6; ++sgm) {
+        const __nv_bfloat16* p = t[ord.part[sgm]];
+        uint2 u;
+        __nv_bfloat162 a = __halves2bfloat162(p[0], p[1]), b = __halves2bfloat162(p[2], p[3]);
+        u.x = *reinterpret_cast<uint32_t*>(&a); u.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(o + (size_t)sgm * C) = u;
+    }
+}
+static void launch_split6(cudaStream_t st, const float* in, void* out, size_t rows, int C, const Split6Order& ord) {
+    if (C % 4) throw std::runtime_error("split6: channel count must be a multiple of 4");
+    SALT_COUNT(1);
+    const size_t nvec = rows * (size_t)(C / 4);
+    if (nvec == 0) return;
+    split6_kernel<<<(unsigned)((nvec + EW_THREADS - 1) / EW_THREADS), EW_THREADS, 0, st>>>(in, (bf16*)out, nvec, C, ord);
+}
+void k_split6_act(cudaStream_t st, const float* in, void* out, size_t rows, int C) {
+    launch_split6(st, in, out, rows, C, Split6Order{{0, 0, 1, 1, 0, 2}});
+}
+void k_split6_weights(cudaStream_t st, const float* wp, void* wp6, size_t rows, int C) {
+    launch_split6(st, wp, wp6, rows, C, Split6Order{{0, 1, 0, 1, 2, 0}});
+}

@@ -29,14 +29,13 @@ TC_CASES = [
     (5, 128, 256, 32, 32, 3, 1, 1),      # two channel tiles per pixel tile
     (5, 320, 64, 34, 66, 3, 1, 0),       # final.0-like at cluster size: forward 5 channel blocks, dgrad 5 channel tiles of 64
     (4, 64, 32, 66, 66, 3, 1, 0),        # N = 32 (8-row multicast parts), bordered input
-    # ... and for the cluster variant of the tap-table kernel (env SALT_TC_CLUSTER_GENERIC=2|4)
+    # the tap-table kernel at sizes with many position tiles
     (8, 64, 128, 64, 64, 3, 2, 1),       # stride 2 forward + 4-phase stride-2 dgrad, 64 position tiles
     (8, 64, 128, 64, 64, 1, 2, 0),       # 1x1 stride-2
     (70, 512, 512, 8, 8, 3, 1, 1),       # 8x8 maps, two images per tile: 35 position tiles (short last group), 2-4 channel tiles
     (4, 32, 64, 66, 66, 3, 1, 0),        # Cin = 32: 64-byte swizzle, 512-byte multicast parts
-    (4, 192, 128, 34, 34, 3, 1, 0),      # dec3.conv1-like: dgrad with 192 output channels (3 x 64, or 1 x 192 with SALT_TC_WIDE=1)
-    (40, 64, 64, 64, 64, 3, 1, 1),       # layer1 shape with 1280 pixel tiles: > 2 groups per SM, the size at which the experimental
-                                         # multi-sub-tile kernel (SALT_TC_MULTI=1 SALT_TC_CLUSTER=1) stops falling back
+    (4, 192, 128, 34, 34, 3, 1, 0),      # dec3.conv1-like: dgrad with 192 output channels = ONE wide N = 192 tile (SALT_TC_WIDE=0: 3 x 64)
+    (40, 64, 64, 64, 64, 3, 1, 1),       # layer1 shape with 1280 pixel tiles: > 2 groups per SM
 ]
 
 
@@ -63,8 +62,6 @@ def test_conv_tc_forward_and_dgrad(case):
     if k == 3 and s == 1 and Ci % 64 == 0 and Co % 32 == 0 and Ho >= 16 and m_tiles >= 32 and os.environ.get('SALT_TC_CLUSTER', '2') != '1':
         # large enough for the thread-block-cluster variant: make sure THAT kernel (TMA-multicast weights) produced `out`
         assert lib.salt_cluster_launch_count() > cl0, 'cluster variant of the row-halo convolution was not launched'
-    elif B >= 4 and H * W * B >= 8 * 8 * 64 and os.environ.get('SALT_TC_CLUSTER_GENERIC', '1') != '1':
-        assert lib.salt_cluster_launch_count() > cl0, 'cluster variant of the tap-table convolution was not launched'
     oks = [report('tc conv fwd %s' % (case,), _from_nhwc(out), y_ref, atol=2e-2, rtol=1e-2)[0]]
     oks.append(report('tc conv stats sum', stats[:Co].cpu().float(), y_ref.sum((0, 2, 3)), atol=5e-2, rtol=2e-3)[0])
     oks.append(report('tc conv stats sumsq', stats[Co:].cpu().float(), (y_ref ** 2).sum((0, 2, 3)), atol=5e-2, rtol=2e-3)[0])
@@ -85,6 +82,33 @@ def test_conv_tc_forward_and_dgrad(case):
         _lib.check(lib.salt_op_conv_dgrad(C.byref(d), gyd.data_ptr(), wd.data_ptr(), gin.data_ptr(), 1, None))
         oks.append(report('tc conv dgrad 1x1 s2 accumulate', _from_nhwc(gin), base + xr.grad, atol=4e-2, rtol=2e-2)[0])
     assert all(oks)
+
+
+@pytest.mark.parametrize('case', [TC_CASES[i] for i in (0, 1, 2, 3, 4, 5, 6, 7, 8, 12, 13, 14, 18)])
+def test_conv_tc_split_fp32(case):
+    """fp32 parity mode ON THE TENSOR CORES: fp32 operands as three bf16 terms each, six bf16 x bf16 products accumulated in
+    fp32 by tcgen05 (kernels.h k_split6_*), fp32 output - vs F.conv2d on the UNROUNDED fp32 operands.  Tolerance: 2e-5 of the
+    largest output (the dropped product terms are < 2^-24 relative; fp32 accumulation order)."""
+    from salt_b200 import _lib
+    lib = _lib.load()
+    B, Ci, Co, H, W, k, s, p = case
+    g = torch.Generator().manual_seed(sum(case) + 7)
+    x = torch.randn(B, Ci, H, W, generator=g)
+    w = torch.randn(Co, Ci, k, k, generator=g) * (2.0 / (Ci * k * k)) ** 0.5
+    bias = torch.randn(Co, generator=g) * 0.1
+    y_ref = F.conv2d(x.double(), w.double(), bias.double(), stride=s, padding=p).float()
+    Ho, Wo = y_ref.shape[2:]
+    d = _lib.SaltConvDesc(B, H, W, Ci, Ho, Wo, Co, k, s, p, 0, 1)           # precision fp32, use_tensor_cores
+    xd, wd, bd = _to_nhwc(x, 'fp32'), w.cuda().contiguous(), bias.cuda()
+    out = torch.full((B, Ho, Wo, Co), float('nan'), dtype=torch.float32, device='cuda')
+    stats = torch.zeros(2 * Co, dtype=torch.float64, device='cuda')
+    n0 = lib.salt_launch_count()
+    _lib.check(lib.salt_op_conv_forward(C.byref(d), xd.data_ptr(), wd.data_ptr(), bd.data_ptr(), out.data_ptr(), stats.data_ptr(), None))
+    torch.cuda.synchronize()
+    ok1 = report('split-bf16 tc conv fwd %s' % (case,), _from_nhwc(out), y_ref, atol=1e-6, rtol=2e-5)[0]
+    ok2 = report('split-bf16 tc conv stats sum', stats[:Co].cpu().float(), y_ref.sum((0, 2, 3)), atol=1e-2, rtol=1e-4)[0]
+    ok3 = report('split-bf16 tc conv stats sumsq', stats[Co:].cpu().float(), (y_ref ** 2).sum((0, 2, 3)), atol=1e-2, rtol=1e-4)[0]
+    assert ok1 and ok2 and ok3
 
 
 WG_CASES = [c for c in TC_CASES if c[4] != 24] + [      # the wgrad kernel takes 32-pixel row chunks: widths that are multiples of 8 only via padding

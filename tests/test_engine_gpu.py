@@ -140,13 +140,15 @@ def _setup(depth, b, s, wseed=0, dseed=1234):
     return sd_np, x, t
 
 
+@pytest.mark.parametrize('tc', [True, False], ids=['tcgen05-split-bf16', 'simt-fp32'])
 @pytest.mark.parametrize('depth,b,s', [(18, 2, 64), (34, 3, 64), (18, 8, 128)])
-def test_forward_eval_fp32(depth, b, s):
-    """fp32 mode, eval BatchNorm: every stage and the logits vs the oracle; logits <= 1e-3 max-abs."""
+def test_forward_eval_fp32(depth, b, s, tc):
+    """fp32 mode, eval BatchNorm: every stage and the logits vs the oracle; logits <= 1e-3 max-abs - with the convolutions on the
+    tensor cores (split-bf16 operands, kernels.h) and with the fp32-FMA implicit GEMM."""
     sd_np, x, _ = _setup(depth, b, s)
     with torch.no_grad():
         ref, stages = unet_oracle.unet_resnet_forward(unet_oracle.to_torch_state(sd_np), x, depth, False, return_stages=True)
-    eng = _engine(depth, 2, b, s, precision='fp32', training=False)
+    eng = _engine(depth, 2, b, s, precision='fp32', training=False, use_tensor_cores=tc)
     eng.load_state(sd_np)
     logits = eng.forward(x.cuda(), train=False)
     torch.cuda.synchronize()
@@ -214,13 +216,15 @@ def test_train_step_fp32(depth, b, s, loss_name):
     assert worst <= 1e-6
 
 
-@pytest.mark.parametrize('tag', ['r18_b2_s64', 'r34_b2_s64', 'r18_b8_s128', 'se50_b2_s64', 'se101_b2_s64'])
-def test_golden_fixtures_fp32(golden_dir, tag):
-    """Engine vs vectors produced by the unmodified reference modules (tests/golden, oracle/make_golden.py)."""
+@pytest.mark.parametrize('tag,tc', [('r18_b2_s64', True), ('r34_b2_s64', True), ('r18_b8_s128', True), ('se50_b2_s64', True),
+                                    ('se101_b2_s64', True), ('r18_b8_s128', False), ('r34_b2_s64', False)])
+def test_golden_fixtures_fp32(golden_dir, tag, tc):
+    """Engine vs vectors produced by the unmodified reference modules (tests/golden, oracle/make_golden.py).  tc: forward
+    convolutions on tcgen05 with split-bf16 operands (the default fp32 mode) or the fp32-FMA kernels (use_tensor_cores=False)."""
     g = np.load(os.path.join(golden_dir, tag + '.npz'))
     m = {k[5:]: int(g[k]) for k in g.files if k.startswith('meta_')}
     sd_np, x, t = _setup(m['depth'], m['batch'], m['size'], m['wseed'], m['dseed'])
-    eng = _engine(m['depth'], 2, m['batch'], m['size'], precision='fp32')
+    eng = _engine(m['depth'], 2, m['batch'], m['size'], precision='fp32', use_tensor_cores=tc)
     eng.load_state(sd_np)
     xd, td = x.cuda(), t.cuda()
     oks = [report('golden eval logits', eng.forward(xd, train=False), g['logits_eval'], atol=1e-3)[0]]
