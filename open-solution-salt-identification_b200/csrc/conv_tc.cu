@@ -46,12 +46,13 @@ struct TcParams {
     int tiles_x, tiles_y, tiles_b, tiles_co, tiles_per_phase;
     int m_tiles;
     int B, Ho, Wo;                 // output positions per phase
-    int out_H, out_W, Co;          // physical output tensor
+    int Co;                        // output channels; physical output tensor: ep.Hp x ep.Wp
     int osy, osx, a_stride, cblks;
     int accumulate, nphases;
     const float* bias;
     float* stats;              // [SALT_STAT_SLOTS_CONV][2*Co] partial slots, slot = blockIdx.x
-    void* out;                 // OutT, physical [B][out_H][out_W][Co]
+    void* out;                 // OutT, physical [B][ep.Hp][ep.Wp][Co]
+    EpiParams ep;
     TcPhase ph[4];
 };
 
@@ -177,44 +178,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int x = tx * p.tw + lx, y = ty * p.th + ly, n = tb * p.tn + ln;
             const bool valid = tt.live && (n < p.B) && (y < p.Ho) && (x < p.Wo);
             const int oy = y * p.osy + p.ph[pi].oy, ox = x * p.osx + p.ph[pi].ox;
-            OutT* orow = reinterpret_cast<OutT*>(p.out) + (((size_t)n * p.out_H + oy) * p.out_W + ox) * p.Co + nt * BN;
+            // physical output positions of this pixel: one, unless it sits on an edge of a replicate-bordered tensor (stride-1 only)
+            const EpiParams& ep = p.ep;
+            const bool bordered = p.osy == 1;
+            const int py0 = (bordered && y == 0) ? 0 : oy + ep.pt, py1 = (bordered && y == p.Ho - 1) ? ep.Hp - 1 : oy + ep.pt;
+            const int px0 = (bordered && x == 0) ? 0 : ox + ep.pl, px1 = (bordered && x == p.Wo - 1) ? ep.Wp - 1 : ox + ep.pl;
+            OutT* obase = reinterpret_cast<OutT*>(p.out) + (size_t)n * ep.Hp * ep.Wp * p.Co + nt * BN;
+            // accumulate mode (dgrad into an existing gradient) or the residual branch of an eval-mode fused block
+            const OutT* rrow = nullptr;
+            if (p.accumulate) rrow = obase + ((size_t)(oy + ep.pt) * ep.Wp + ox + ep.pl) * p.Co;
+            else if (ep.res) rrow = reinterpret_cast<const OutT*>(ep.res) + (((size_t)n * p.Ho + y) * p.Wo + x) * p.Co + nt * BN;
+            const bool has_r = rrow != nullptr && valid;
             mbar_wait(tfull0 + 8 * acc, acc_phase);
             fence_after();
 #pragma unroll 1
             for (int ch = 0; ch < BN / 32; ++ch) {
                 float v[32];
+                uint4 old[4];
+                if (sizeof(OutT) == 2 && has_r) {
+                    const uint4* o4 = reinterpret_cast<const uint4*>(rrow + ch * 32);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) old[q] = o4[q];
+                }
                 tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + ch * 32, v);
                 if (p.bias) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + nt * BN + ch * 32 + i);
                 }
-                if (valid && sizeof(OutT) == 4) {
-                    float4* o4 = reinterpret_cast<float4*>(orow + ch * 32);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) o4[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                } else if (valid) {
-                    uint4* o4 = reinterpret_cast<uint4*>(orow + ch * 32);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (p.accumulate) {
-                            uint4 old = o4[q];
-                            const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float2 f = __bfloat1622float2(ob[j]);
-                                v[q * 8 + 2 * j] += f.x; v[q * 8 + 2 * j + 1] += f.y;
-                            }
-                        }
-                        uint4 pk;
-                        __nv_bfloat162 b0 = __floats2bfloat162_rn(v[q * 8 + 0], v[q * 8 + 1]);
-                        __nv_bfloat162 b1 = __floats2bfloat162_rn(v[q * 8 + 2], v[q * 8 + 3]);
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(v[q * 8 + 4], v[q * 8 + 5]);
-                        __nv_bfloat162 b3 = __floats2bfloat162_rn(v[q * 8 + 6], v[q * 8 + 7]);
-                        pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
-                        pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
-                        o4[q] = pk;
-                    }
+                if (ep.scale) epi_affine32(v, ep.scale + nt * BN + ch * 32, ep.shift + nt * BN + ch * 32);
+                if (has_r) {
+                    if constexpr (sizeof(OutT) == 2) epi_add32(v, old);
+                    else epi_add32(v, reinterpret_cast<const float*>(rrow) + ch * 32);
                 }
+                if (ep.relu) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+                if (valid) epi_store32(v, obase + ch * 32, py0, py1, px0, px1, ep.Wp, p.Co);
                 if (p.stats) {
                     float sq[32];
 #pragma unroll
@@ -333,15 +333,18 @@ static bool rows_enabled() {
 }
 // out[n,y,x,k] (+)= sum_{r,s,c} A[n, y*stride+r-pad, x*stride+s-pad, c] * Wp[k][(r*S+s)*Ca + c]
 void k_conv_tc(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca, const void* Wp, int Nout, int R, int S, int stride,
-               int pad, void* out, int Ho, int Wo, const float* bias, float* stats, bool accumulate, bool out_f32) {
+               int pad, void* out, int Ho, int Wo, const float* bias, float* stats, bool accumulate, bool out_f32, const EpiParams* ep) {
     if (out_f32 && accumulate) throw std::runtime_error("k_conv_tc: accumulation into an fp32 output is not implemented");
+    if (ep && accumulate) throw std::runtime_error("k_conv_tc: a fused epilogue cannot be combined with accumulation");
     if (rows_enabled() && tc_conv_rows_supported(Ca, Nout, R, S, stride, Ho, Wo)) {
-        k_conv_tc_rows(st, A, B, Ha, Wa, Ca, Wp, Nout, pad, out, Ho, Wo, bias, stats, accumulate, out_f32);
+        k_conv_tc_rows(st, A, B, Ha, Wa, Ca, Wp, Nout, pad, out, Ho, Wo, bias, stats, accumulate, out_f32, ep);
         return;
     }
     SALT_COUNT(1);
     TcParams p;
-    p.Ho = Ho; p.Wo = Wo; p.out_H = Ho; p.out_W = Wo; p.osy = p.osx = 1; p.a_stride = stride;
+    if (ep) p.ep = *ep;
+    if (p.ep.Hp == 0) { p.ep.Hp = Ho; p.ep.Wp = Wo; p.ep.pt = p.ep.pl = 0; }
+    p.Ho = Ho; p.Wo = Wo; p.osy = p.osx = 1; p.a_stride = stride;
     p.accumulate = accumulate ? 1 : 0; p.bias = bias; p.stats = stats; p.out = out;
     p.nphases = 1;
     TcPhase& ph = p.ph[0];
@@ -358,7 +361,7 @@ void k_conv_tc_dgrad_s2(cudaStream_t st, const void* gout, int B, int Ho, int Wo
                         int pad, void* gin, int Hi, int Wi, bool accumulate) {
     SALT_COUNT(1);
     TcParams p;
-    p.Ho = Hi / 2; p.Wo = Wi / 2; p.out_H = Hi; p.out_W = Wi; p.osy = p.osx = 2; p.a_stride = 1;
+    p.Ho = Hi / 2; p.Wo = Wi / 2; p.ep.Hp = Hi; p.ep.Wp = Wi; p.osy = p.osx = 2; p.a_stride = 1;
     p.accumulate = accumulate ? 1 : 0; p.bias = nullptr; p.stats = nullptr; p.out = gin;
     p.nphases = 0;
     for (int py = 0; py < 2; ++py)

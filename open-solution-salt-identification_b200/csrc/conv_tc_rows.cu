@@ -50,7 +50,8 @@ struct RowsParams {
     int accumulate;
     const float* bias;
     float* stats;              // [SALT_STAT_SLOTS_CONV][2*Co] partial slots, slot = blockIdx.x
-    void* out;                 // OutT [B][Ho][Wo][Co]
+    void* out;                 // OutT, physical [B][ep.Hp][ep.Wp][Co]
+    EpiParams ep;
 };
 
 constexpr int RW_THREADS = 320;                              // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
@@ -137,13 +138,23 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
         const int nt = t.nt, n = t.n;
         const int x = t.tx * RW_TW + lx, y = t.ty * RW_TH + ly;
         const bool valid = t.live && (y < p.Ho) && (x < p.Wo);
-        OutT* orow = reinterpret_cast<OutT*>(p.out) + (((size_t)n * p.Ho + y) * p.Wo + x) * p.Co + nt * BN;
-        // accumulate mode (dgrad into an existing gradient): the old values of the first chunk are fetched BEFORE waiting for the
-        // accumulator, so their DRAM latency hides behind the MMA phase instead of serialising the epilogue
+        // physical output positions of this pixel (one, unless it sits on an edge of a replicate-bordered tensor)
+        const EpiParams& ep = p.ep;
+        const int py0 = (y == 0) ? 0 : y + ep.pt, py1 = (y == p.Ho - 1) ? ep.Hp - 1 : y + ep.pt;
+        const int px0 = (x == 0) ? 0 : x + ep.pl, px1 = (x == p.Wo - 1) ? ep.Wp - 1 : x + ep.pl;
+        OutT* obase = reinterpret_cast<OutT*>(p.out) + (size_t)n * ep.Hp * ep.Wp * p.Co + nt * BN;
+        // values added to the tile before it is stored: the old gradient (accumulate mode: dgrad into an existing gradient, an
+        // unbordered tensor) or the residual branch (eval-mode fused BasicBlock).  For bf16 the first chunk is fetched BEFORE
+        // waiting for the accumulator, so its DRAM latency hides behind the MMA phase instead of serialising the epilogue.
+        const OutT* rrow = nullptr;
+        if constexpr (!NARROW) {
+            if (p.accumulate) rrow = obase + ((size_t)(y + ep.pt) * ep.Wp + x + ep.pl) * p.Co;
+            else if (ep.res) rrow = reinterpret_cast<const OutT*>(ep.res) + (((size_t)n * p.Ho + y) * p.Wo + x) * p.Co + nt * BN;
+        }
+        const bool has_r = rrow != nullptr && valid;
         uint4 old[4];
-        const bool accum = !NARROW && p.accumulate && sizeof(OutT) == 2;       // accumulation is a bf16 dgrad feature
-        if (accum && valid && half < BN / 32) {
-            const uint4* o4 = reinterpret_cast<const uint4*>(orow + half * 32);
+        if (sizeof(OutT) == 2 && has_r && half < BN / 32) {
+            const uint4* o4 = reinterpret_cast<const uint4*>(rrow + half * 32);
 #pragma unroll
             for (int q = 0; q < 4; ++q) old[q] = o4[q];
         }
@@ -152,8 +163,8 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
 #pragma unroll 1
         for (int ch = half; ch < BN / 32; ch += 2) {
             float v[32];
-            if (accum && valid && ch != half) {
-                const uint4* o4 = reinterpret_cast<const uint4*>(orow + ch * 32);
+            if (sizeof(OutT) == 2 && has_r && ch != half) {
+                const uint4* o4 = reinterpret_cast<const uint4*>(rrow + ch * 32);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) old[q] = o4[q];
             }
@@ -161,36 +172,22 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
             if constexpr (NARROW) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] += rbias[i];
-            } else if (p.bias) {
+            } else {
+                if (p.bias) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + nt * BN + ch * 32 + i);
-            }
-            if (valid && sizeof(OutT) == 4) {
-                float4* o4 = reinterpret_cast<float4*>(orow + ch * 32);
+                    for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + nt * BN + ch * 32 + i);
+                }
+                if (ep.scale) epi_affine32(v, ep.scale + nt * BN + ch * 32, ep.shift + nt * BN + ch * 32);
+                if (has_r) {
+                    if constexpr (sizeof(OutT) == 2) epi_add32(v, old);
+                    else epi_add32(v, reinterpret_cast<const float*>(rrow) + ch * 32);
+                }
+                if (ep.relu) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) o4[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-            } else if (valid) {
-                uint4* o4 = reinterpret_cast<uint4*>(orow + ch * 32);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (accum) {
-                        const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old[q]);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float2 f = __bfloat1622float2(ob[j]);
-                            v[q * 8 + 2 * j] += f.x; v[q * 8 + 2 * j + 1] += f.y;
-                        }
-                    }
-                    uint4 pk;
-                    __nv_bfloat162 b0 = __floats2bfloat162_rn(v[q * 8 + 0], v[q * 8 + 1]);
-                    __nv_bfloat162 b1 = __floats2bfloat162_rn(v[q * 8 + 2], v[q * 8 + 3]);
-                    __nv_bfloat162 b2 = __floats2bfloat162_rn(v[q * 8 + 4], v[q * 8 + 5]);
-                    __nv_bfloat162 b3 = __floats2bfloat162_rn(v[q * 8 + 6], v[q * 8 + 7]);
-                    pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
-                    pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
-                    o4[q] = pk;
+                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
                 }
             }
+            if (valid) epi_store32(v, obase + ch * 32, py0, py1, px0, px1, ep.Wp, p.Co);
             if (p.stats) {
                 if constexpr (NARROW) {
                     if (valid) {
@@ -446,10 +443,12 @@ static void launch_rows_any(cudaStream_t st, const CUtensorMap& ma, const void* 
 
 // out[n,y,x,k] (+)= sum_{r,s,c} A[n, y+r-pad, x+s-pad, c] * Wp[k][(r*3+s)*Ca + c]      (3x3, stride 1); out_f32: fp32 output tensor
 void k_conv_tc_rows(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca, const void* Wp, int Nout, int pad, void* out,
-                    int Ho, int Wo, const float* bias, float* stats, bool accumulate, bool out_f32) {
+                    int Ho, int Wo, const float* bias, float* stats, bool accumulate, bool out_f32, const EpiParams* ep) {
     SALT_COUNT(1);
     if (out_f32 && accumulate) throw std::runtime_error("k_conv_tc_rows: accumulation into an fp32 output is not implemented");
     RowsParams p;
+    if (ep) p.ep = *ep;
+    if (p.ep.Hp == 0) { p.ep.Hp = Ho; p.ep.Wp = Wo; p.ep.pt = p.ep.pl = 0; }
     p.tiles_x = cdiv(Wo, RW_TW); p.tiles_y = cdiv(Ho, RW_TH);
     int BN = Nout % 128 == 0 ? 128 : Nout % 64 == 0 ? 64 : 32;
     // channel counts that are no multiple of 128 as few WIDE tiles instead of many N = 64 ones: 320 = 2 x 160, 192 = 1 x 192 (the

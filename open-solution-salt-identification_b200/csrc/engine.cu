@@ -2,6 +2,7 @@
 #include <stdexcept>
 #include <cstring>
 #include <algorithm>
+#include <cstdlib>
 
 unsigned long long g_salt_launches = 0;
 unsigned long long g_salt_cluster_launches = 0;
@@ -251,6 +252,7 @@ void Engine::build() {
     loss_sums_ = (double*)ws_alloc(sizeof(double) * 16);
     for (int i = 0; i < 4; ++i) scratch_[i] = ws_alloc(std::max<size_t>(scratch_bytes_[i], 256));
     split_scratch_ = split_tc() ? ws_alloc(split_elems_ * 6 * sizeof(bf16)) : nullptr;
+    ones_ = (float*)ws_alloc(sizeof(float) * 2 * 4096); zeros_ = ones_ + 4096;
     if (counting_) { stats_floats_ = stats_cursor_; bstats_floats_ = bstats_cursor_; dwp_floats_ = dwp_cursor_; }
 }
 
@@ -264,6 +266,14 @@ void Engine::bind(float* params, float* grads, float* m, float* v, float* buffer
     build_pack_table();
     unpack_table_dirty_ = true;
     packed_dirty_ = true;
+    eval_coef_dirty_ = true;
+    {
+        std::vector<float> id(2 * 4096, 0.f);
+        std::fill(id.begin(), id.begin() + 4096, 1.f);
+        cudaMemcpy(ones_, id.data(), sizeof(float) * id.size(), cudaMemcpyHostToDevice);
+        const char* e = getenv("SALT_ENGINE_FUSE_EVAL");
+        fuse_eval_ = !(e && e[0] == '0');
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -400,6 +410,44 @@ void Engine::conv_fwd(const ConvLayer& c, const Tensor& in, const Tensor& out, B
         else k_bn_finalize_eval(st, bn_ref(*bn), BN_EPS);
     }
 }
+std::vector<BNLayer*> Engine::all_bns() {
+    std::vector<BNLayer*> v;
+    v.push_back(&stem_bn_);
+    for (auto& b : blocks_) { v.push_back(&b->b1); v.push_back(&b->b2); if (b->down) v.push_back(&b->bd); }
+    for (auto& b : bnecks_) { v.push_back(&b->b1); v.push_back(&b->b2); v.push_back(&b->b3); if (b->down) v.push_back(&b->bd); }
+    v.push_back(&center0_.bn); v.push_back(&center1_.bn);
+    for (auto& d : dec_) { v.push_back(&d.u1.bn); v.push_back(&d.u2.bn); }
+    v.push_back(&final0_.bn);
+    return v;
+}
+// eval-mode coefficients of every BatchNorm layer; they only change with the parameters / running statistics
+void Engine::finalize_eval_all(cudaStream_t st) {
+    for (BNLayer* b : all_bns()) k_bn_finalize_eval(st, bn_ref(*b), BN_EPS);
+    eval_coef_dirty_ = false;
+}
+bool Engine::fusable(const ConvLayer& c, const Tensor& in, const Tensor& out) const {
+    if (!fuse_eval_ || !cfg_.use_tc) return false;
+    ConvGeom g = geom(c, in, out);
+    if (cfg_.dt == DT_F32) g.Ci *= 6;
+    return tc_conv_supported(g, false);
+}
+void Engine::conv_bn_fused(const ConvLayer& c, const Tensor& in, const Tensor& dst, const BNLayer& bn, const Tensor* res, bool relu,
+                           cudaStream_t st) {
+    ConvGeom g = geom(c, in, dst);
+    const float* bias = c.o_b >= 0 ? params_ + c.o_b : nullptr;
+    EpiParams ep;
+    ep.scale = bn.scale; ep.shift = bn.shift; ep.res = res ? res->p : nullptr; ep.relu = relu ? 1 : 0;
+    ep.Hp = dst.Hp(); ep.Wp = dst.Wp(); ep.pt = dst.pt; ep.pl = dst.pl;
+    prof_begin(PROF_CONV_FWD, conv_flops(g, c.Ci_real), st);
+    if (cfg_.dt == DT_F32) {
+        k_split6_act(st, (const float*)in.p, split_scratch_, (size_t)g.B * g.Hi * g.Wi, g.Ci);
+        k_conv_tc(st, split_scratch_, g.B, g.Hi, g.Wi, 6 * g.Ci, c.wp6, g.Co, g.R, g.S, g.stride, g.pad, dst.p, g.Ho, g.Wo, bias, nullptr,
+                  false, true, &ep);
+    } else {
+        k_conv_tc(st, in.p, g.B, g.Hi, g.Wi, g.Ci, c.wp, g.Co, g.R, g.S, g.stride, g.pad, dst.p, g.Ho, g.Wo, bias, nullptr, false, false, &ep);
+    }
+    prof_end(st);
+}
 void Engine::conv_dgrad(const ConvLayer& c, const Tensor& gout, const Tensor& gin, bool accumulate, cudaStream_t st) {
     ConvGeom g = geom(c, gin, gout);
     prof_begin(PROF_CONV_DGRAD, conv_flops(g, c.Ci_real), st);
@@ -448,6 +496,18 @@ void Engine::gather_bwd(const std::vector<Source>& srcs, const Tensor& gP, cudaS
 // ------------------------------------------------------------------------------------------------
 void Engine::block_fwd(BasicBlock& b, bool train, cudaStream_t st) {
     Tensor x = view(b.x->t), raw1 = view(b.raw1), a1 = view(b.a1), raw2 = view(b.raw2), out = view(b.out.t);
+    if (!train && fusable(b.c1, x, a1) && fusable(b.c2, a1, out) && (!b.down || fusable(b.cd, x, out))) {
+        // inference: 2 (3 with a projection shortcut) kernels per block, no BatchNorm / ReLU / residual passes
+        conv_bn_fused(b.c1, x, a1, b.b1, nullptr, true, st);
+        if (b.down) {
+            Tensor rawd = view(b.rawd);
+            conv_bn_fused(b.cd, x, rawd, b.bd, nullptr, false, st);
+            conv_bn_fused(b.c2, a1, out, b.b2, &rawd, true, st);
+        } else {
+            conv_bn_fused(b.c2, a1, out, b.b2, &x, true, st);
+        }
+        return;
+    }
     conv_fwd(b.c1, x, raw1, &b.b1, train, st);
     k_bn_apply(st, raw1, b.b1.scale, b.b1.shift, nullptr, nullptr, nullptr, true, a1);
     conv_fwd(b.c2, a1, raw2, &b.b2, train, st);
@@ -462,6 +522,22 @@ void Engine::block_fwd(BasicBlock& b, bool train, cudaStream_t st) {
 void Engine::bneck_fwd(Bottleneck& b, bool train, cudaStream_t st) {
     Tensor x = view(b.x->t), raw1 = view(b.raw1), a1 = view(b.a1), raw2 = view(b.raw2), a2 = view(b.a2), raw3 = view(b.raw3),
            out = view(b.out.t);
+    if (!train && fusable(b.c1, x, a1) && fusable(b.c2, a1, a2) && fusable(b.c3, a2, raw3) && (!b.down || fusable(b.cd, x, raw3))) {
+        // inference: BatchNorm (+ ReLU) folded into the convolutions; the SE gate needs the pooled bn3 output, so the gated
+        // residual sum stays one separate pass over already-normalised tensors (identity coefficients)
+        conv_bn_fused(b.c1, x, a1, b.b1, nullptr, true, st);
+        conv_bn_fused(b.c2, a1, a2, b.b2, nullptr, true, st);
+        conv_bn_fused(b.c3, a2, raw3, b.b3, nullptr, false, st);
+        k_se_gate_fwd(st, raw3, ones_, zeros_, se_ref(b.se));
+        if (b.down) {
+            Tensor rawd = view(b.rawd);
+            conv_bn_fused(b.cd, x, rawd, b.bd, nullptr, false, st);
+            k_bn_apply(st, raw3, ones_, zeros_, &rawd, nullptr, nullptr, true, out, b.se.cse);
+        } else {
+            k_bn_apply(st, raw3, ones_, zeros_, &x, nullptr, nullptr, true, out, b.se.cse);
+        }
+        return;
+    }
     conv_fwd(b.c1, x, raw1, &b.b1, train, st);
     k_bn_apply(st, raw1, b.b1.scale, b.b1.shift, nullptr, nullptr, nullptr, true, a1);
     conv_fwd(b.c2, a1, raw2, &b.b2, train, st);
@@ -481,6 +557,13 @@ void Engine::cbr_fwd(ConvBnRelu& u, bool train, cudaStream_t st) {
 }
 void Engine::decoder_fwd(DecoderBlock& d, bool train, cudaStream_t st) {
     gather_fwd(d.srcs, view(d.u1.P), st);
+    if (!train && fusable(d.u1.c, view(d.u1.P), view(d.u1.raw)) && fusable(d.u2.c, view(d.u2.P), view(d.u2.raw))) {
+        // inference: conv1 writes relu(bn(.)) straight into conv2's replicate-bordered input, conv2 leaves z = relu(bn(.)) for scSE
+        conv_bn_fused(d.u1.c, view(d.u1.P), view(d.u2.P), d.u1.bn, nullptr, true, st);
+        conv_bn_fused(d.u2.c, view(d.u2.P), view(d.u2.raw), d.u2.bn, nullptr, true, st);
+        k_scse_fwd(st, view(d.u2.raw), ones_, zeros_, se_ref(d.se), view(d.out.t));
+        return;
+    }
     cbr_fwd(d.u1, train, st);
     k_bn_apply(st, view(d.u1.raw), d.u1.bn.scale, d.u1.bn.shift, nullptr, nullptr, nullptr, true, view(d.u2.P));
     cbr_fwd(d.u2, train, st);
@@ -504,23 +587,39 @@ void Engine::forward_tiles(const uint8_t* tiles, int B, const TileGeom& g, float
 }
 void Engine::forward_body(int B, float* logits_nchw, bool train, cudaStream_t st) {
     if (packed_dirty_) pack_all(st);
-    if (train) k_zero(st, stats_arena_, sizeof(float) * stats_floats_);
+    if (train) { k_zero(st, stats_arena_, sizeof(float) * stats_floats_); eval_coef_dirty_ = true; }
+    else if (eval_coef_dirty_ && fuse_eval_) finalize_eval_all(st);
     Tensor x4 = view(x4_), sraw = view(stem_raw_);
-    conv_fwd(stem_, x4, sraw, &stem_bn_, train, st);
-    k_bn_apply(st, sraw, stem_bn_.scale, stem_bn_.shift, nullptr, nullptr, nullptr, true, view(stem_out_.t));
+    if (!train && fusable(stem_, x4, sraw)) {
+        conv_bn_fused(stem_, x4, view(stem_out_.t), stem_bn_, nullptr, true, st);
+    } else {
+        conv_fwd(stem_, x4, sraw, &stem_bn_, train, st);
+        k_bn_apply(st, sraw, stem_bn_.scale, stem_bn_.shift, nullptr, nullptr, nullptr, true, view(stem_out_.t));
+    }
     for (auto& b : blocks_) block_fwd(*b, train, st);
     for (auto& b : bnecks_) bneck_fwd(*b, train, st);
     // center
     gather_fwd(center_src_, view(center0_.P), st);
-    cbr_fwd(center0_, train, st);
-    k_bn_apply(st, view(center0_.raw), center0_.bn.scale, center0_.bn.shift, nullptr, nullptr, nullptr, true, view(center1_.P));
-    cbr_fwd(center1_, train, st);
-    k_bn_relu_avgpool(st, view(center1_.raw), center1_.bn.scale, center1_.bn.shift, view(center_out_.t));
+    if (!train && fusable(center0_.c, view(center0_.P), view(center0_.raw)) && fusable(center1_.c, view(center1_.P), view(center1_.raw))) {
+        conv_bn_fused(center0_.c, view(center0_.P), view(center1_.P), center0_.bn, nullptr, true, st);
+        conv_bn_fused(center1_.c, view(center1_.P), view(center1_.raw), center1_.bn, nullptr, true, st);
+        k_bn_relu_avgpool(st, view(center1_.raw), ones_, zeros_, view(center_out_.t));
+    } else {
+        cbr_fwd(center0_, train, st);
+        k_bn_apply(st, view(center0_.raw), center0_.bn.scale, center0_.bn.shift, nullptr, nullptr, nullptr, true, view(center1_.P));
+        cbr_fwd(center1_, train, st);
+        k_bn_relu_avgpool(st, view(center1_.raw), center1_.bn.scale, center1_.bn.shift, view(center_out_.t));
+    }
     for (auto& d : dec_) decoder_fwd(d, train, st);
     gather_fwd(final_src_, view(final0_.P), st);
-    cbr_fwd(final0_, train, st);
-    k_final_fwd(st, view(final0_.raw), final0_.bn.scale, final0_.bn.shift, params_ + o_final_w_, params_ + o_final_b_,
-                cfg_.num_classes, logits_nchw);
+    if (!train && fusable(final0_.c, view(final0_.P), view(final0_.raw))) {
+        conv_bn_fused(final0_.c, view(final0_.P), view(final0_.raw), final0_.bn, nullptr, true, st);
+        k_final_fwd(st, view(final0_.raw), ones_, zeros_, params_ + o_final_w_, params_ + o_final_b_, cfg_.num_classes, logits_nchw);
+    } else {
+        cbr_fwd(final0_, train, st);
+        k_final_fwd(st, view(final0_.raw), final0_.bn.scale, final0_.bn.shift, params_ + o_final_w_, params_ + o_final_b_,
+                    cfg_.num_classes, logits_nchw);
+    }
     trained_forward_ = train;
 }
 
@@ -692,6 +791,7 @@ void Engine::adam(float lr, float wd, float b1, float b2, float eps, int step, f
     if (!adam_m_ || !adam_v_ || !grads_) throw std::runtime_error("engine bound without optimiser state");
     k_adam(st, params_, grads_, adam_m_, adam_v_, n_params_, lr, wd, b1, b2, eps, step, grad_scale);
     packed_dirty_ = true;
+    eval_coef_dirty_ = true;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -100,7 +100,7 @@ public:
     void forward_tiles(const uint8_t* tiles, int B, const TileGeom& g, float* logits_nchw, bool train, cudaStream_t st);
     void backward(const float* dlogits_nchw, cudaStream_t st);
     void adam(float lr, float wd, float b1, float b2, float eps, int step, float grad_scale, cudaStream_t st);
-    void mark_params_dirty() { packed_dirty_ = true; }
+    void mark_params_dirty() { packed_dirty_ = true; eval_coef_dirty_ = true; }
     // copy a named internal activation (NHWC T, border dropped) into fp32 NCHW; returns false if unknown
     bool get_activation(const std::string& name, float* out_nchw, int* shape4, cudaStream_t st);
 
@@ -138,6 +138,12 @@ private:
     ConvGeom geom(const ConvLayer& c, const Tensor& in, const Tensor& out) const;
     void pack_all(cudaStream_t st);
     void conv_fwd(const ConvLayer& c, const Tensor& in, const Tensor& out, BNLayer* bn, bool train, cudaStream_t st);
+    // eval mode: convolution + folded BatchNorm (+ residual) (+ ReLU) in ONE kernel, stored straight into `dst` (which may carry a
+    // replicate border).  fusable(): the tensor-core kernels can run this layer (otherwise the caller takes the unfused path)
+    bool fusable(const ConvLayer& c, const Tensor& in, const Tensor& out) const;
+    void conv_bn_fused(const ConvLayer& c, const Tensor& in, const Tensor& dst, const BNLayer& bn, const Tensor* res, bool relu, cudaStream_t st);
+    std::vector<BNLayer*> all_bns();
+    void finalize_eval_all(cudaStream_t st);
     void conv_dgrad(const ConvLayer& c, const Tensor& gout, const Tensor& gin, bool accumulate, cudaStream_t st);
     void conv_wgrad(ConvLayer& c, const Tensor& in, const Tensor& gout, cudaStream_t st);
     std::vector<ConvLayer*> all_convs();
@@ -168,6 +174,9 @@ private:
     UnpackDesc* d_unpack_ = nullptr; int* d_unpack_start_ = nullptr; int unpack_layers_ = 0, unpack_blocks_ = 0, unpack_max_rs_ = 1;
     bool unpack_table_dirty_ = false;
     bool trained_forward_ = false;
+    bool eval_coef_dirty_ = true;      // eval-mode BatchNorm (scale, shift) must be recomputed from the running statistics
+    bool fuse_eval_ = true;            // env SALT_ENGINE_FUSE_EVAL=0: eval forward through the separate BatchNorm passes (A/B testing)
+    float *ones_ = nullptr, *zeros_ = nullptr;   // identity BatchNorm coefficients for consumers of already-normalised tensors
     void forward_body(int B, float* logits_nchw, bool train, cudaStream_t st);
     int B_ = 0;
 

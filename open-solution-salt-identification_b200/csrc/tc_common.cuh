@@ -2,6 +2,7 @@
 // encoders and the host-side tensor-map helper.
 #pragma once
 #include "common.cuh"
+#include "tc_epilogue.h"
 #include <cuda.h>
 #include <stdexcept>
 #include <string>
@@ -115,6 +116,67 @@ __device__ __forceinline__ uint32_t instr_desc_bf16(int n, bool a_mn, bool b_mn)
     d |= (uint32_t)(n >> 3) << 17;
     d |= (uint32_t)(128 >> 4) << 24;
     return d;
+}
+
+// ------------------------------------------------------------------------------------------------ fused epilogue tail
+// What the convolution epilogues can do with a finished fp32 tile besides the bias: eval-mode BatchNorm folded to one per-channel
+// affine (scale, shift), a residual add, ReLU, and a store into a tensor with a physical replicate border (the decoder's
+// ReplicationPad2d((0,2,2,0)) inputs) - so that an inference forward needs no separate BatchNorm / ReLU / border pass.
+__device__ __forceinline__ void epi_affine32(float* v, const float* __restrict__ sc, const float* __restrict__ sh) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(sc) + q), b = __ldg(reinterpret_cast<const float4*>(sh) + q);
+        v[4 * q + 0] = fmaf(v[4 * q + 0], a.x, b.x); v[4 * q + 1] = fmaf(v[4 * q + 1], a.y, b.y);
+        v[4 * q + 2] = fmaf(v[4 * q + 2], a.z, b.z); v[4 * q + 3] = fmaf(v[4 * q + 3], a.w, b.w);
+    }
+}
+__device__ __forceinline__ void epi_add32(float* v, const uint4* old) {        // + 32 bf16 values held in 4 registers quads
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const __nv_bfloat162* ob = reinterpret_cast<const __nv_bfloat162*>(&old[q]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(ob[j]);
+            v[q * 8 + 2 * j] += f.x; v[q * 8 + 2 * j + 1] += f.y;
+        }
+    }
+}
+__device__ __forceinline__ void epi_add32(float* v, const float* __restrict__ r) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float4 a = *(reinterpret_cast<const float4*>(r) + q);
+        v[4 * q + 0] += a.x; v[4 * q + 1] += a.y; v[4 * q + 2] += a.z; v[4 * q + 3] += a.w;
+    }
+}
+__device__ __forceinline__ void epi_pack32(const float* v, uint4* pk) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        __nv_bfloat162 b0 = __floats2bfloat162_rn(v[q * 8 + 0], v[q * 8 + 1]);
+        __nv_bfloat162 b1 = __floats2bfloat162_rn(v[q * 8 + 2], v[q * 8 + 3]);
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(v[q * 8 + 4], v[q * 8 + 5]);
+        __nv_bfloat162 b3 = __floats2bfloat162_rn(v[q * 8 + 6], v[q * 8 + 7]);
+        pk[q].x = *reinterpret_cast<uint32_t*>(&b0); pk[q].y = *reinterpret_cast<uint32_t*>(&b1);
+        pk[q].z = *reinterpret_cast<uint32_t*>(&b2); pk[q].w = *reinterpret_cast<uint32_t*>(&b3);
+    }
+}
+// store 32 channels of one pixel to every physical position it owns: rows py0..py1, columns px0..px1 (one position unless on a border)
+__device__ __forceinline__ void epi_store32(const float* v, bf16* obase, int py0, int py1, int px0, int px1, int Wp, int Co) {
+    uint4 pk[4];
+    epi_pack32(v, pk);
+    for (int yy = py0; yy <= py1; ++yy)
+        for (int xx = px0; xx <= px1; ++xx) {
+            uint4* o4 = reinterpret_cast<uint4*>(obase + ((size_t)yy * Wp + xx) * Co);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o4[q] = pk[q];
+        }
+}
+__device__ __forceinline__ void epi_store32(const float* v, float* obase, int py0, int py1, int px0, int px1, int Wp, int Co) {
+    for (int yy = py0; yy <= py1; ++yy)
+        for (int xx = px0; xx <= px1; ++xx) {
+            float4* o4 = reinterpret_cast<float4*>(obase + ((size_t)yy * Wp + xx) * Co);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o4[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        }
 }
 
 // ------------------------------------------------------------------------------------------------ host side

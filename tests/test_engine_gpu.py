@@ -311,6 +311,34 @@ def test_bf16_mode(depth, b, s):
         assert cos >= 0.90, k
 
 
+@pytest.mark.parametrize('depth,prec', [(34, 'bf16'), (34, 'fp32'), (50, 'bf16')])
+def test_eval_forward_fused_epilogue(depth, prec, monkeypatch):
+    """Inference folds BatchNorm (+ residual, + ReLU, + the replicate border of the decoder inputs) into the convolution
+    epilogues.  Same logits as the pass-per-operation path (SALT_ENGINE_FUSE_EVAL=0) up to the rounding the fusion removes
+    (the unfused bf16 path rounds the raw convolution output to bf16 before BatchNorm), far fewer launches."""
+    from salt_b200 import _lib
+    b, s = 4, 128
+    sd_np, x, _ = _setup(depth, b, s)
+    with torch.no_grad():
+        ref = unet_oracle.unet_resnet_forward(unet_oracle.to_torch_state(sd_np), x, depth, False)
+    outs, launches = {}, {}
+    for fuse in ('1', '0'):
+        monkeypatch.setenv('SALT_ENGINE_FUSE_EVAL', fuse)
+        eng = _engine(depth, 2, b, s, precision=prec, training=False)
+        eng.load_state(sd_np)
+        eng.forward(x.cuda(), train=False)                      # packs the weights, computes the eval coefficients
+        n0 = _lib.launch_count()
+        outs[fuse] = eng.forward(x.cuda(), train=False).clone()
+        torch.cuda.synchronize()
+        launches[fuse] = _lib.launch_count() - n0
+    bound = 1e-3 if prec == 'fp32' else 0.05 + 0.03 * ref.abs().max().item()
+    e1, e0 = (outs['1'].cpu() - ref).abs().max().item(), (outs['0'].cpu() - ref).abs().max().item()
+    print('eval forward %s depth %d: fused err %.3e (%d launches), unfused err %.3e (%d launches)' % (prec, depth, e1, launches['1'], e0, launches['0']))
+    assert e1 <= bound and e0 <= bound
+    assert (outs['1'] - outs['0']).abs().max().item() <= (1e-4 if prec == 'fp32' else bound)
+    assert launches['1'] < 0.75 * launches['0']
+
+
 def test_loss_kernels_edge_cases():
     """Lovasz / BCE-Dice kernels alone: empty masks, full masks, single pixels, ties."""
     b, s = 6, 64
