@@ -164,3 +164,22 @@ def synth_targets(batch, size=128, seed=1234):
             hh, ww = rng.integers(4, size // 2 + 4, 2)
             m[i, y0:min(size, y0 + hh), x0:min(size, x0 + ww)] = 1.0
     return np.stack([1.0 - m, m], axis=1).astype(np.float32)
+
+
+def synth_salt_scenes(batch, size=128, seed=1234):
+    """(x fp32 [B,3,S,S], target fp32 [B,2,S,S]) where the salt mask can be LEARNED from the image: inside the salt rectangles of
+    ``synth_targets`` the grey tile is brighter and smoother than outside.  Used to train a network for a few dozen steps so that the
+    inference parity checks (BASELINE config 5: masks / IoU vs the reference path) run on confident, non-trivial masks instead of
+    the all-background output of a random initialisation."""
+    tile = size - 27 if size >= 64 else size
+    t = synth_targets(batch, size, seed)
+    rng = np.random.default_rng(seed + 2)
+    dv = size - tile
+    top, left = dv // 2, dv - dv // 2
+    salt = t[:, 1, top:top + tile, left:left + tile]
+    noise = rng.integers(0, 256, (batch, tile, tile)).astype(np.float32)
+    p = np.pad(noise, ((0, 0), (1, 1), (1, 1)), mode='edge')
+    smooth = sum(p[:, dy:dy + tile, dx:dx + tile] for dy in range(3) for dx in range(3)) / 9.0
+    img = np.where(salt > 0, 150.0 + 0.35 * (smooth - 128.0), 70.0 + 0.8 * (noise - 128.0) * 0.5)
+    tiles = np.clip(img, 0, 255).astype(np.uint8)
+    return adapt_tiles(tiles, size), t

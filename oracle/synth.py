@@ -11,4 +11,4 @@ if _PKG not in sys.path:
     sys.path.insert(0, _PKG)
 
 from salt_b200.synthetic import (MEAN, STD, adapt_tiles, param_specs, resnet_block_counts, synth_inputs,  # noqa: E402,F401
-                                 synth_state_dict, synth_targets, synth_tiles_u8)
+                                 synth_salt_scenes, synth_state_dict, synth_targets, synth_tiles_u8)

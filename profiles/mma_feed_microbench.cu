@@ -48,6 +48,11 @@ __device__ __forceinline__ uint32_t idesc(int m, int n, int fmt) {
     d |= (uint32_t)(m >> 4) << 24;
     return d;
 }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n.reg .b32 %%rx;\n.reg .pred %%px;\nelect.sync %%rx|%%px, %1;\n@%%px mov.s32 %0, 1;\n}\n" : "+r"(pred) : "r"(0xffffffffu));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -56,12 +61,13 @@ __device__ __forceinline__ void cluster_sync_all() {
 
 enum { MODE_SS = 0, MODE_TS = 1, MODE_SS2 = 2, MODE_TF32 = 3 };
 
-struct Args { int mode, n, iters, na, tma; const uint8_t* gsrc; unsigned long long* cycles; };
+struct Args { int n, iters, na, tma; const uint8_t* gsrc; unsigned long long* cycles; };
 
 constexpr int A_SLAB = 128 * 128;     // 128 rows x 128 bytes
 constexpr int B_SLAB = 256 * 128;
 constexpr int TMA_RING = 4, TMA_CHUNK = 16384;
 
+template <int MODE>
 __global__ void __launch_bounds__(96, 1) feed_kernel(Args a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -71,7 +77,7 @@ __global__ void __launch_bounds__(96, 1) feed_kernel(Args a) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(sT + TMA_RING * TMA_CHUNK);
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool pair = a.mode == MODE_SS2;
+    constexpr bool pair = MODE == MODE_SS2;
     const uint32_t rank = pair ? cluster_ctarank() : 0;
     for (int i = threadIdx.x * 16; i < a.na * A_SLAB + B_SLAB; i += 96 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
     const uint32_t done = smem_u32(bars), tbar0 = smem_u32(bars + 1);
@@ -98,8 +104,10 @@ __global__ void __launch_bounds__(96, 1) feed_kernel(Args a) {
     fence_after();
     const uint32_t tmem = *tmem_ptr;
 
-    if (warp == 0 && lane == 0 && rank == 0) {
-        const int fmt = a.mode == MODE_TF32 ? 2 : 1;
+    if (warp == 0 && rank == 0) {
+      // warp-uniform branch + elect.sync: the tcgen05 instructions live on the uniform datapath
+      if (elect_one()) {
+        constexpr int fmt = MODE == MODE_TF32 ? 2 : 1;
         const uint32_t id = idesc(pair ? 256 : 128, a.n, fmt);
         const uint64_t ad0 = smem_desc(smem_u32(sA), 16, 1024, 2), bd0 = smem_desc(smem_u32(sB), 16, 1024, 2);
         const uint32_t tmem_a = tmem + 256;               // TS mode: A operand columns (content irrelevant)
@@ -107,13 +115,13 @@ __global__ void __launch_bounds__(96, 1) feed_kernel(Args a) {
         for (int i = 0; i < a.iters; ++i) {
             const uint64_t koff = (uint64_t)((i & 3) * 2);
             const uint64_t ad = ad0 + (uint64_t)(((i % a.na) * A_SLAB) >> 4) + koff, bd = bd0 + koff;
-            if (a.mode == MODE_SS)
+            if constexpr (MODE == MODE_SS)
                 asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
                              ::"r"(tmem), "l"(ad), "l"(bd), "r"(id), "r"(1) : "memory");
-            else if (a.mode == MODE_TF32)
+            else if constexpr (MODE == MODE_TF32)
                 asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
                              ::"r"(tmem), "l"(ad), "l"(bd), "r"(id), "r"(1) : "memory");
-            else if (a.mode == MODE_TS)
+            else if constexpr (MODE == MODE_TS)
                 asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
                              ::"r"(tmem), "r"(tmem_a + (uint32_t)((i & 3) * 8)), "l"(bd), "r"(id), "r"(1) : "memory");
             else
@@ -128,7 +136,9 @@ __global__ void __launch_bounds__(96, 1) feed_kernel(Args a) {
         long long t1 = clock64();
         a.cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
         stop_flag = 1;
-    } else if (warp == 1 && lane == 0 && a.tma) {
+      }
+      __syncwarp();
+    } else if (warp == 1 && lane == 0 && a.tma && rank == 0) {
         // stream bulk copies into the scratch ring until the MMA thread is done
         int slot = 0; uint32_t phase = 0; long long n = 0;
         while (!stop_flag) {
@@ -157,9 +167,10 @@ __global__ void __launch_bounds__(96, 1) feed_kernel(Args a) {
 }
 
 static void run(const char* name, int mode, int n, int grid, int na, int tma, const uint8_t* gsrc, unsigned long long* dcyc) {
-    Args a; a.mode = mode; a.n = n; a.iters = 4096; a.na = na; a.tma = tma; a.gsrc = gsrc; a.cycles = dcyc;
+    Args a; a.n = n; a.iters = 4096; a.na = na; a.tma = tma; a.gsrc = gsrc; a.cycles = dcyc;
     const int smem = 1024 + na * A_SLAB + B_SLAB + TMA_RING * TMA_CHUNK + 256;
-    cudaFuncSetAttribute(feed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    void (*kern)(Args) = mode == MODE_SS ? feed_kernel<MODE_SS> : mode == MODE_TS ? feed_kernel<MODE_TS> : mode == MODE_SS2 ? feed_kernel<MODE_SS2> : feed_kernel<MODE_TF32>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaMemset(dcyc, 0, sizeof(unsigned long long) * 2 * 148);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(96); cfg.dynamicSmemBytes = smem;
@@ -167,7 +178,9 @@ static void run(const char* name, int mode, int n, int grid, int na, int tma, co
     at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = mode == MODE_SS2 ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     for (int rep = 0; rep < 2; ++rep) {                   // first launch warms up
-        cudaError_t e = cudaLaunchKernelEx(&cfg, feed_kernel, a);
+        cudaError_t e = cudaSuccess;
+        if (mode == MODE_SS2) e = cudaLaunchKernelEx(&cfg, kern, a);
+        else { kern<<<grid, 96, smem>>>(a); e = cudaGetLastError(); }
         if (e != cudaSuccess) { printf("%s N=%d launch failed: %s\n", name, n, cudaGetErrorString(e)); return; }
         e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("%s N=%d failed: %s\n", name, n, cudaGetErrorString(e)); exit(1); }
