@@ -32,7 +32,18 @@ DEPTH, SIZE, BATCH_PER_GPU, CLASSES = 34, 128, 128, 2
 WORKLOAD = 'UNetResNet-34 train step (fwd + BCE+Dice + bwd + Adam-L2), 3x128x128 inputs (padded 101x101 tiles), bf16, batch 128 per GPU'
 # algorithmic conv FLOPs of one training step per image: fwd + dgrad + wgrad
 TRAIN_GFLOP_PER_IMAGE = 58.42
-CPU_SAMPLE_BATCH = 8
+CPU_REFERENCE_BATCH = 128      # --impl reference: the SAME 128-image batch as the GPU arm (one CPU step is ~5 s on 16 cores)
+CPU_SAMPLE_BATCH = 32          # cpu_baseline inside the GPU arm's line: a bounded sample (3 steps, ~10 s)
+
+
+def conv_source_sha():
+    """sha1 over the tensor-core convolution sources: profiles/roofline_traffic.json is only valid for the kernels it was captured on."""
+    import hashlib
+    h = hashlib.sha1()
+    for f in ('conv_tc.cu', 'conv_tc_rows.cu', 'conv_wgrad_tc.cu', 'tc_common.cuh'):
+        with open(os.path.join(PKG, 'csrc', f), 'rb') as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 def _peaks():
@@ -90,7 +101,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------- CPU arm
-def cpu_train_steps(steps, warmup, batch=CPU_SAMPLE_BATCH, threads=None):
+def cpu_train_steps(steps, warmup, batch, threads=None):
     """The reference algorithm's CPU path (oracle port, plain PyTorch fp32 on the host cores): `steps` timed training
     steps on a bounded sample of `batch` images of the workload.  Returns (images_per_s, seconds_per_step, threads)."""
     from oracle import synth, unet_oracle, losses_oracle
@@ -122,11 +133,12 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    ips, sec_step, threads = cpu_train_steps(args.steps, args.warmup)
-    sample = '%d-image sample of the 128-image batch per step, oracle port (PyTorch fp32 CPU), %d threads' % (CPU_SAMPLE_BATCH, threads)
+    ips, sec_step, threads = cpu_train_steps(args.steps, args.warmup, CPU_REFERENCE_BATCH)
+    sample = ('the full %d-image batch per step; PORT of the reference algorithm (oracle/, plain PyTorch fp32 on the host cores, pinned to '
+              'the unmodified reference modules by oracle/make_golden.py), %d threads' % (CPU_REFERENCE_BATCH, threads))
     line = {'impl': 'reference', 'metric': 'images/sec', 'value': ips, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': sec_step * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'sample': sample},
+            'dtype': 'f32', 'data': 'synthetic', 'config': {'workload': WORKLOAD, 'global_batch': CPU_REFERENCE_BATCH, 'loss': 'bce_dice', 'sample': sample},
             'cpu_baseline': {'value': ips, 'unit': 'images/s', 'cores': threads, 'kind': 'port', 'sample': sample},
             'e2e': {'value': ips, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(line))
@@ -177,6 +189,32 @@ def se50_train_step(ctx, timed, batch=64, size=256):
     del eng, x, t
     torch.cuda.empty_cache()
     return out
+
+
+def tta_parity(eng, synth, dev, tiles=32, train_steps=40):
+    """Accuracy side of BASELINE configs[4] ("throughput + IoU vs ref"): train the engine briefly on learnable synthetic scenes
+    so that the masks are non-trivial, then compare TTA masks / logits of `tiles` tiles with the oracle (CPU, fp32)."""
+    from oracle import unet_oracle, losses_oracle
+    for it in range(train_steps):
+        x, t = synth.synth_salt_scenes(64, SIZE, 1000 + it)
+        logits = eng.forward(torch.from_numpy(x).to(dev), train=True)
+        _, dl = eng.loss_bce_dice(logits, torch.from_numpy(t).to(dev))
+        eng.backward(dl)
+        eng.adam_step(lr=3e-4)
+    sd_np = {k: eng.view(k).cpu().numpy().copy() for k in eng.table}
+    x = torch.from_numpy(synth.synth_salt_scenes(tiles, SIZE, 77)[0])
+    sd = unet_oracle.to_torch_state(sd_np)
+    with torch.no_grad():
+        ro = unet_oracle.unet_resnet_forward(sd, x, DEPTH, train=False)
+        rf = unet_oracle.unet_resnet_forward(sd, torch.flip(x, dims=[3]), DEPTH, train=False)
+    _, mask_ref = losses_oracle.predict_masks(ro.numpy(), rf.numpy(), 101, 0.5)
+    xd = x.to(dev)
+    lo = eng.forward(xd, train=False).clone()
+    lf = eng.forward(torch.flip(xd, dims=[3]).contiguous(), train=False)
+    _, mask = eng.predict(lo, lf, crop=101, threshold=0.5, want_probs=False)
+    return {'iou_vs_oracle': losses_oracle.iou_masks(mask.cpu().numpy(), mask_ref), 'logits_max_abs': float((lo.cpu() - ro).abs().max()),
+            'oracle_logit_range': float(ro.abs().max()), 'salt_fraction': float(mask_ref.mean()),
+            'parity_sample': '%d tiles (x2 flips) after %d training steps on synthetic scenes, bf16 engine vs fp32 CPU oracle' % (tiles, train_steps)}
 
 
 def run_ours(args):
@@ -239,6 +277,7 @@ def run_ours(args):
     for _ in range(2):
         step_device()
     prof = eng.profile_read()
+    prof_groups = eng.profile_read_groups()
     eng.profile(False)
 
     # ---- secondary measurements (not the headline): Lovasz-hinge training step (BASELINE configs[2] loss) and fused
@@ -252,10 +291,17 @@ def run_ours(args):
             eng.adam_step(grad_scale=ctx.allreduce_grads(eng.grads))
         x_flip = torch.flip(x_d, dims=[3]).contiguous()
 
+        # BASELINE configs[4]: 512 network inputs = 256 tiles x {orig, h-flip}; the engine takes them as 2 x (128 + 128)
+        x2_d = torch.from_numpy(synth.synth_inputs(B, SIZE, 777 + ctx.rank)).to(dev)
+        x2_flip = torch.flip(x2_d, dims=[3]).contiguous()
+
         def infer_tta():
-            lo = eng.forward(x_d, train=False)
-            lf = eng.forward(x_flip, train=False)
-            return eng.predict(lo, lf, crop=101, threshold=0.5, want_probs=False)
+            out = []
+            for a, b in ((x_d, x_flip), (x2_d, x2_flip)):
+                lo = eng.forward(a, train=False).clone()
+                lf = eng.forward(b, train=False)
+                out.append(eng.predict(lo, lf, crop=101, threshold=0.5, want_probs=False)[1])
+            return out
         # SURVEY.md 8(f) N2 + N3 end to end: raw u8 101x101 tiles in pinned host memory -> H2D (1.3 MB instead of 25 MB) ->
         # adapter fused into the stem (orig + h-flipped tile) -> fused sigmoid/un-flip/mean/crop/threshold -> column-major RLE
         # on the device -> D2H of the run table; and N1: the 21-threshold validation sweep counts for the same batch
@@ -288,8 +334,9 @@ def run_ours(args):
         if not args.no_se50:
             se50 = se50_train_step(ctx, timed)
         extra = {'lovasz_train_step': {'value': B * ctx.world * 5 / (ms_lv / 1e3), 'unit': 'images/s', 'ms_per_step': ms_lv / 5},
-                 'inference_tta_hflip': {'value': B * ctx.world * 5 / (ms_inf / 1e3), 'unit': 'tiles/s', 'ms_per_batch': ms_inf / 5,
-                                         'what': '%d tiles per GPU per pass = %d network inputs (orig + h-flip), fused sigmoid/un-flip/mean/crop/threshold -> u8 masks' % (B, 2 * B)}}
+                 'inference_tta_hflip': {'value': 2 * B * ctx.world * 5 / (ms_inf / 1e3), 'unit': 'tiles/s', 'ms_per_batch': ms_inf / 5,
+                                         'network_inputs_per_batch': 4 * B,
+                                         'what': '%d tiles per GPU per pass = %d network inputs (orig + h-flip), eval forward with BatchNorm/ReLU/residual folded into the convolution epilogues, fused sigmoid/un-flip/mean/crop/threshold -> u8 masks' % (2 * B, 4 * B)}}
 
         extra['inference_u8_tiles_to_rle_e2e'] = {
             'value': B * ctx.world * 5 / (ms_rle / 1e3), 'unit': 'tiles/s', 'ms_per_batch': ms_rle / 5,
@@ -300,6 +347,8 @@ def run_ours(args):
             'what': 'eval forward + 21-threshold intersection/prediction counts in one kernel + host IoU/IoUT selection (callbacks.py:499-527)'}
         if se50:
             extra['seresnet50_256_train_step'] = se50
+        if ctx.rank == 0 and ctx.world == 1 and not args.no_cpu_baseline:
+            extra['inference_tta_hflip'].update(tta_parity(eng, synth, dev))
 
     if ctx.rank != 0:
         return
@@ -312,10 +361,20 @@ def run_ours(args):
     tot_ms = sum(v[0] for v in prof.values())
     tot_fl = sum(v[1] for v in prof.values())
     achieved = tot_fl / (tot_ms * 1e-3) / 1e12 if tot_ms > 0 else 0.0
-    traffic = None
+    traffic, traffic_note = None, 'no ncu capture committed'
     tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get('traffic')
+        tj = json.load(open(tp))
+        if tj.get('conv_source_sha') == conv_source_sha():
+            traffic, traffic_note = tj.get('traffic'), tj.get('source')
+        else:
+            traffic_note = 'stale: profiles/roofline_traffic.json was captured on other kernel sources (%s != %s)' % (tj.get('conv_source_sha'), conv_source_sha())
+    per_group = {}
+    for gname, d in prof_groups.items():
+        g_ms = sum(v[0] for v in d.values()); g_fl = sum(v[1] for v in d.values())
+        if g_ms > 0:
+            per_group[gname] = {'ms_per_step': g_ms / 2, 'tflops': g_fl / (g_ms * 1e-3) / 1e12, 'frac': g_fl / (g_ms * 1e-3) / 1e12 / peaks['tflops'],
+                                'fwd_tflops': d['conv_fwd'][1] / (d['conv_fwd'][0] * 1e-3) / 1e12 if d['conv_fwd'][0] > 0 else None}
     line = {
         'metric': 'images/sec', 'value': value, 'unit': 'images/s', 'n_gpus': n, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -329,7 +388,8 @@ def run_ours(args):
                 'api': 'salt_b200.models.SegmentationModel.fit(datagen=(batches, steps)) - pinned host tensors in, H2D of every step inside the timed region, loss read back every step'},
         'gpu_launches': int(launches),
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
-                     'frac': achieved / peaks['tflops'], 'traffic': traffic, 'peak_source': peaks['source'],
+                     'frac': achieved / peaks['tflops'], 'traffic': traffic, 'traffic_source': traffic_note, 'peak_source': peaks['source'],
+                     'per_group': per_group,
                      'kernel': 'implicit-GEMM convolution (forward + dgrad + wgrad launches of one step, algorithmic FLOPs / CUDA-event time)',
                      'conv_share_of_step': (tot_ms / 2) / (ms / args.steps), 'per_class': kern,
                      'step_tflops': value / n * TRAIN_GFLOP_PER_IMAGE / 1e3,
@@ -338,9 +398,10 @@ def run_ours(args):
     if extra:
         line['extra'] = extra
     if n == 1 and not args.no_cpu_baseline:
-        ips, sec_step, threads = cpu_train_steps(2, 1)
+        ips, sec_step, threads = cpu_train_steps(2, 1, CPU_SAMPLE_BATCH)
         line['cpu_baseline'] = {'value': ips, 'unit': 'images/s', 'cores': threads, 'kind': 'port',
-                                'sample': '%d-image sample of the batch, 2 timed training steps of the oracle port (PyTorch fp32 CPU)' % CPU_SAMPLE_BATCH}
+                                'sample': '%d-image sample of the batch, 2 timed training steps of the oracle PORT (PyTorch fp32 CPU); '
+                                          '--impl reference times the full 128-image batch' % CPU_SAMPLE_BATCH}
     print(json.dumps(line))
 
 

@@ -133,6 +133,9 @@ unsigned long long salt_cluster_launch_count(void);
  * accumulated device milliseconds, algorithmic FLOPs (2*B*Ho*Wo*Cout*Cin*R*S per launch) and launch count. */
 int salt_profile_enable(salt_engine* h, int on);
 int salt_profile_read(salt_engine* h, int kernel_class, double* ms, double* flops, long long* launches);
+/* the same restricted to one layer group: 0 stem, 1-4 encoder layer1..layer4, 5 center, 6-10 dec5..dec1, 11 hypercolumn + final;
+ * -1 = all groups (bench.py: roofline.per_group) */
+int salt_profile_read_group(salt_engine* h, int kernel_class, int layer_group, double* ms, double* flops, long long* launches);
 
 /* ---- single-operator entry points (unit tests; tensors NHWC in the given precision) ------------------ */
 typedef struct salt_conv_desc {

@@ -25,7 +25,13 @@ def _newest_dep():
     return t
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, timing=False):
+    """timing=True: a second library, libsaltunet_timing.so, compiled with -DSALT_TC_TIMING (pipeline-stall counters in the row-halo
+    convolution, profiles/rows_timing.py); the shipped libsaltunet.so never carries them."""
+    global OBJ, LIB, FLAGS
+    if timing:
+        OBJ, LIB = os.path.join(HERE, 'build_timing'), os.path.join(HERE, 'libsaltunet_timing.so')
+        FLAGS = FLAGS + ['-DSALT_TC_TIMING']
     os.makedirs(OBJ, exist_ok=True)
     dep_t = _newest_dep()
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= dep_t:
@@ -56,4 +62,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv, timing='--timing' in sys.argv))

@@ -151,8 +151,12 @@ unsigned long long salt_launch_count(void) { return g_salt_launches; }
 unsigned long long salt_cluster_launch_count(void) { return g_salt_cluster_launches; }
 int salt_profile_enable(salt_engine* h, int on) { h->e->profile_enable(on != 0); return 0; }
 int salt_profile_read(salt_engine* h, int kernel_class, double* ms, double* flops, long long* launches) {
+    return salt_profile_read_group(h, kernel_class, -1, ms, flops, launches);
+}
+int salt_profile_read_group(salt_engine* h, int kernel_class, int layer_group, double* ms, double* flops, long long* launches) {
     if (kernel_class < 0 || kernel_class >= Engine::PROF_NCLASS) return fail("salt_profile_read: unknown kernel class");
-    h->e->profile_read(kernel_class, ms, flops, launches);
+    if (layer_group < -1 || layer_group >= Engine::PROF_NGROUPS) return fail("salt_profile_read: unknown layer group");
+    h->e->profile_read(kernel_class, ms, flops, launches, layer_group);
     return check_cuda("salt_profile_read");
 }
 
@@ -199,7 +203,7 @@ int salt_op_conv_forward(const salt_conv_desc* d, const void* in, const float* w
             }
             k_split6_act(st, (const float*)in, in6, rows_in, g.Ci);
             k_split6_weights(st, (const float*)pk.wp, w6, rows_w, g.Ci);
-            k_conv_tc(st, in6, g.B, g.Hi, g.Wi, g6.Ci, w6, g.Co, g.R, g.S, g.stride, g.pad, out, g.Ho, g.Wo, bias, part, false, true);
+            k_conv_tc(st, in6, g.B, g.Hi, g.Wi, g6.Ci, w6, g.Co, g.R, g.S, g.stride, g.pad, out, g.Ho, g.Wo, bias, part, false, true, nullptr, g.Ci);
             cudaStreamSynchronize(st);
             cudaFree(in6); cudaFree(w6);
         } else if (d->use_tensor_cores) {

@@ -49,6 +49,7 @@ struct TcParams {
     int Co;                        // output channels; physical output tensor: ep.Hp x ep.Wp
     int osy, osx, a_stride, cblks;
     int accumulate, nphases;
+    int split_c;                   // fp32-output instantiations: channels of one operand term (K-blocks below it hold the h*h products)
     const float* bias;
     float* stats;              // [SALT_STAT_SLOTS_CONV][2*Co] partial slots, slot = blockIdx.x
     void* out;                 // OutT, physical [B][ep.Hp][ep.Wp][Co]
@@ -75,6 +76,7 @@ template <int BN, int BK> struct TcCfg {
     static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    static constexpr int TMEM_COLS_SPLIT = 4 * BN < 32 ? 32 : 4 * BN;      // fp32 output: main + correction accumulator per tile (conv_tc_rows.cu)
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * 2 * BN * 4 /*per-epilogue-warp stats*/;
     // canonical K-major swizzled layout: rows of BK*2 bytes, 8-row groups SBO apart
     static constexpr uint32_t SBO = 8 * BK * 2;
@@ -106,7 +108,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), Cfg::TMEM_COLS);
+    constexpr bool SPLIT = sizeof(OutT) == 4;
+    constexpr int TMEM_COLS = SPLIT ? Cfg::TMEM_COLS_SPLIT : Cfg::TMEM_COLS, ACC_STRIDE = SPLIT ? 2 * BN : BN;
+    if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
     for (int i = threadIdx.x; i < 4 * 2 * BN; i += TC_THREADS) s_stats[i] = 0.f;
     fence_before();
     __syncthreads();
@@ -145,8 +149,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int num_kb = p.ph[tt.pi].ntaps * p.cblks;
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
             fence_after();
-            const uint32_t tmem_d = tmem_base + acc * BN;
+            const uint32_t tmem_d0 = tmem_base + acc * ACC_STRIDE;
+            uint32_t used = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
+                const uint32_t sub = (SPLIT && (kb % p.cblks) * BK >= p.split_c) ? 1u : 0u;
+                const uint32_t tmem_d = tmem_d0 + sub * BN;
+                const uint32_t fresh = ((used >> sub) & 1u) ^ 1u;
+                used |= 1u << sub;
                 mbar_wait(full0 + 8 * stage, phase);
                 fence_after();
                 if (elect_one()) {
@@ -154,7 +163,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                     const uint64_t bdesc = smem_desc(smem_u32(smem_b + stage * Cfg::B_BYTES), 16, Cfg::SBO, Cfg::LAYOUT);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)       // advance 16 bf16 = 32 bytes inside the swizzle atom
-                        umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+                        umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, fresh ? (uint32_t)k : 1u);
                     umma_commit(empty0 + 8 * stage);        // frees the smem stage when these MMAs retire
                     if (kb == num_kb - 1) umma_commit(tfull0 + 8 * acc);
                 }
@@ -200,7 +209,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
                     for (int q = 0; q < 4; ++q) old[q] = o4[q];
                 }
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + ch * 32, v);
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * ACC_STRIDE + ch * 32, v);
+                if constexpr (SPLIT) {
+                    float v2[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * ACC_STRIDE + BN + ch * 32, v2);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += v2[i];
+                }
                 if (p.bias) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) v[i] += __ldg(p.bias + nt * BN + ch * 32 + i);
@@ -255,7 +270,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     fence_before();
     __syncthreads();
-    if (warp == 1) { fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+    if (warp == 1) { fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -307,6 +322,7 @@ static void run_tc(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca
     p.tiles_x = cdiv(p.Wo, p.tw); p.tiles_y = cdiv(p.Ho, p.th); p.tiles_b = cdiv(B, p.tn);
     const int BK = (Ca % 64 == 0) ? 64 : 32;
     int BN = Nout % 256 == 0 ? 256 : Nout % 128 == 0 ? 128 : Nout % 64 == 0 ? 64 : 32;
+    if (out_f32 && BN == 256) BN = 128;          // two accumulators per tile in the fp32-output mode: 4 x BN TMEM columns
     // prefer more, smaller channel tiles when the tile count would leave SMs idle
     while (BN > 64 && (long long)p.nphases * p.tiles_x * p.tiles_y * p.tiles_b * (Nout / BN) < num_sms()) BN >>= 1;
     p.tiles_co = Nout / BN;
@@ -320,8 +336,10 @@ static void run_tc(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca
 #define TC_CASE(bn, bk) if (BN == bn && BK == bk) {                                                 \
         if (out_f32) launch_tc<bn, bk, float>(st, ma, mb, p); else launch_tc<bn, bk, bf16>(st, ma, mb, p);  \
         return; }
-    TC_CASE(256, 64) TC_CASE(128, 64) TC_CASE(64, 64) TC_CASE(32, 64)
-    TC_CASE(256, 32) TC_CASE(128, 32) TC_CASE(64, 32) TC_CASE(32, 32)
+    if (BN == 256 && BK == 64) { launch_tc<256, 64, bf16>(st, ma, mb, p); return; }
+    if (BN == 256 && BK == 32) { launch_tc<256, 32, bf16>(st, ma, mb, p); return; }
+    TC_CASE(128, 64) TC_CASE(64, 64) TC_CASE(32, 64)
+    TC_CASE(128, 32) TC_CASE(64, 32) TC_CASE(32, 32)
 #undef TC_CASE
     throw std::runtime_error("k_conv_tc: unsupported tile configuration");
 }
@@ -333,15 +351,18 @@ static bool rows_enabled() {
 }
 // out[n,y,x,k] (+)= sum_{r,s,c} A[n, y*stride+r-pad, x*stride+s-pad, c] * Wp[k][(r*S+s)*Ca + c]
 void k_conv_tc(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca, const void* Wp, int Nout, int R, int S, int stride,
-               int pad, void* out, int Ho, int Wo, const float* bias, float* stats, bool accumulate, bool out_f32, const EpiParams* ep) {
+               int pad, void* out, int Ho, int Wo, const float* bias, float* stats, bool accumulate, bool out_f32, const EpiParams* ep,
+               int split_c) {
     if (out_f32 && accumulate) throw std::runtime_error("k_conv_tc: accumulation into an fp32 output is not implemented");
     if (ep && accumulate) throw std::runtime_error("k_conv_tc: a fused epilogue cannot be combined with accumulation");
     if (rows_enabled() && tc_conv_rows_supported(Ca, Nout, R, S, stride, Ho, Wo)) {
-        k_conv_tc_rows(st, A, B, Ha, Wa, Ca, Wp, Nout, pad, out, Ho, Wo, bias, stats, accumulate, out_f32, ep);
+        k_conv_tc_rows(st, A, B, Ha, Wa, Ca, Wp, Nout, pad, out, Ho, Wo, bias, stats, accumulate, out_f32, ep, split_c);
         return;
     }
     SALT_COUNT(1);
+    if (out_f32 && (split_c <= 0 || split_c > Ca)) throw std::runtime_error("k_conv_tc: fp32 output needs the split-operand channel count");
     TcParams p;
+    p.split_c = split_c;
     if (ep) p.ep = *ep;
     if (p.ep.Hp == 0) { p.ep.Hp = Ho; p.ep.Wp = Wo; p.ep.pt = p.ep.pl = 0; }
     p.Ho = Ho; p.Wo = Wo; p.osy = p.osx = 1; p.a_stride = stride;
@@ -361,7 +382,7 @@ void k_conv_tc_dgrad_s2(cudaStream_t st, const void* gout, int B, int Ho, int Wo
                         int pad, void* gin, int Hi, int Wi, bool accumulate) {
     SALT_COUNT(1);
     TcParams p;
-    p.Ho = Hi / 2; p.Wo = Wi / 2; p.ep.Hp = Hi; p.ep.Wp = Wi; p.osy = p.osx = 2; p.a_stride = 1;
+    p.Ho = Hi / 2; p.Wo = Wi / 2; p.ep.Hp = Hi; p.ep.Wp = Wi; p.osy = p.osx = 2; p.a_stride = 1; p.split_c = 0;
     p.accumulate = accumulate ? 1 : 0; p.bias = nullptr; p.stats = nullptr; p.out = gin;
     p.nphases = 0;
     for (int py = 0; py < 2; ++py)

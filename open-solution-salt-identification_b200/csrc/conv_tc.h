@@ -10,12 +10,13 @@ bool tc_conv_supported(const ConvGeom& g, bool dgrad);
 // A: [B,Ha,Wa,Ca] bf16;  Wp: [Nout][R*S*Ca] bf16;  out: [B,Ho,Wo,Nout] bf16 (fp32 when out_f32: the split-bf16 parity mode);  stats: zeroed [SALT_STAT_SLOTS_CONV][2*Nout] float partial slots or NULL
 void k_conv_tc(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca, const void* Wp, int Nout, int R, int S, int stride,
                int pad, void* out, int Ho, int Wo, const float* bias, float* stats, bool accumulate, bool out_f32 = false,
-               const EpiParams* ep = nullptr);
+               const EpiParams* ep = nullptr, int split_c = 0);
 
 // 3x3 stride-1 variant with shared-memory row-halo reuse of the activation tile (conv_tc_rows.cu); env SALT_TC_ROWS=0 disables it
 bool tc_conv_rows_supported(int Ca, int Nout, int R, int S, int stride, int Ho, int Wo);
 void k_conv_tc_rows(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca, const void* Wp, int Nout, int pad, void* out,
-                    int Ho, int Wo, const float* bias, float* stats, bool accumulate, bool out_f32 = false, const EpiParams* ep = nullptr);
+                    int Ho, int Wo, const float* bias, float* stats, bool accumulate, bool out_f32 = false, const EpiParams* ep = nullptr,
+                    int split_c = 0);
 
 // stride-2 dgrad as four parity phases of the same kernel; wpd = flipped-tap packing [Ci][R*S*Co]
 void k_conv_tc_dgrad_s2(cudaStream_t st, const void* gout, int B, int Ho, int Wo, int Co, const void* wpd, int Ci, int R, int S,

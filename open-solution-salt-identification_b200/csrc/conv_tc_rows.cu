@@ -43,11 +43,27 @@ __device__ __forceinline__ float rows_butterfly_reduce32(float* v, int lane) {
     return v[0];
 }
 
+// ---- optional pipeline-stall accounting (build.py --timing, -DSALT_TC_TIMING; never in the shipped library): per CTA, the cycles
+// the three roles of conv_tc_rows_kernel spend waiting on each other.  Read back with salt_debug_rows_timing() (profiles/rows_timing.py).
+#ifdef SALT_TC_TIMING
+__device__ unsigned long long g_rows_timing[SALT_STAT_SLOTS_CONV][8];
+#define TCT(...) __VA_ARGS__
+extern "C" int salt_debug_rows_timing(unsigned long long* out, int reset) {
+    cudaDeviceSynchronize();
+    if (out) cudaMemcpyFromSymbol(out, g_rows_timing, sizeof(g_rows_timing));
+    if (reset) { static unsigned long long z[SALT_STAT_SLOTS_CONV][8]; cudaMemcpyToSymbol(g_rows_timing, z, sizeof(z)); }
+    return 0;
+}
+#else
+#define TCT(...)
+#endif
+
 struct RowsParams {
     int tiles_x, tiles_y, tiles_co, total_tiles;
     int m_tiles, total_groups;  // cluster mode: a group = CL consecutive pixel tiles of one channel tile (one per CTA of the cluster)
     int B, Ho, Wo, Co, Ca, cblks, pad;
     int accumulate;
+    int split_c;               // fp32-output instantiations: channels of ONE operand term (stages with cb*64 < split_c hold the h*h products)
     const float* bias;
     float* stats;              // [SALT_STAT_SLOTS_CONV][2*Co] partial slots, slot = blockIdx.x
     void* out;                 // OutT, physical [B][ep.Hp][ep.Wp][Co]
@@ -65,6 +81,11 @@ template <int BN> struct RowsCfg {
     // column distance of the two accumulators: BN for the power-of-two tiles, 256 for the wide ones (tcgen05.alloc wants 2^k columns)
     static constexpr int ACC_STRIDE = (BN & (BN - 1)) == 0 ? BN : 256;
     static constexpr int TMEM_COLS = 2 * ACC_STRIDE < 32 ? 32 : 2 * ACC_STRIDE;
+    // fp32-output (split-bf16) instantiations keep TWO accumulators per tile: the h*h products and the ~2^-8 smaller correction
+    // products.  tcgen05 adds into an fp32 accumulator with truncation at the accumulator's magnitude; keeping the small terms apart
+    // makes their share of that error negligible (measured: 3e-5 -> relative error per convolution, see profiles/r2_notes.md)
+    static constexpr int ACC_STRIDE_SPLIT = 2 * BN;
+    static constexpr int TMEM_COLS_SPLIT = 2 * ACC_STRIDE_SPLIT < 32 ? 32 : 2 * ACC_STRIDE_SPLIT;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
     static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256 + 8 * 2 * BN * 4;      // + per-epilogue-warp BN statistics
 };
@@ -158,7 +179,9 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
 #pragma unroll
             for (int q = 0; q < 4; ++q) old[q] = o4[q];
         }
+        TCT(long long te0 = clock64();)
         mbar_wait(tfull0 + 8 * acc, acc_phase);
+        TCT(if (warp == 2 && lane == 0) g_rows_timing[blockIdx.x][6] += (unsigned long long)(clock64() - te0);)
         fence_after();
 #pragma unroll 1
         for (int ch = half; ch < BN / 32; ch += 2) {
@@ -168,7 +191,15 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
 #pragma unroll
                 for (int q = 0; q < 4; ++q) old[q] = o4[q];
             }
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * RowsCfg<BN>::ACC_STRIDE + ch * 32, v);
+            constexpr bool SPLIT = sizeof(OutT) == 4;
+            constexpr int ACC_STRIDE = SPLIT ? RowsCfg<BN>::ACC_STRIDE_SPLIT : RowsCfg<BN>::ACC_STRIDE;
+            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * ACC_STRIDE + ch * 32, v);
+            if constexpr (SPLIT) {          // + the accumulator of the correction products
+                float v2[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * ACC_STRIDE + BN + ch * 32, v2);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] += v2[i];
+            }
             if constexpr (NARROW) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] += rbias[i];
@@ -267,7 +298,10 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), Cfg::TMEM_COLS);
+    constexpr bool SPLIT = sizeof(OutT) == 4;
+    constexpr int TMEM_COLS = SPLIT ? Cfg::TMEM_COLS_SPLIT : Cfg::TMEM_COLS, ACC_STRIDE = SPLIT ? Cfg::ACC_STRIDE_SPLIT : Cfg::ACC_STRIDE;
+    static_assert(TMEM_COLS <= 512, "accumulators do not fit TMEM");
+    if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
     for (int i = threadIdx.x; i < 8 * 2 * BN; i += RW_THREADS) s_stats[i] = 0.f;
     fence_before();
     __syncthreads();
@@ -283,13 +317,16 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (elect_one()) {
             int stage = 0; uint32_t phase = 0;
             RowsTile<CL> t;
+            TCT(long long tp0 = clock64(); long long tp_wait = 0;)
             for (int k = 0; rows_tile<CL>(p, k, rank, t); ++k) {
                 const int nt = t.nt, n = t.n;
                 const int w0 = t.tx * RW_TW - p.pad, h0 = t.ty * RW_TH - p.pad;
                 for (int cb = 0; cb < p.cblks; ++cb) {
                     for (int s = 0; s < 3; ++s) {
                         const uint32_t st = smem0 + stage * Cfg::STAGE_BYTES, fb = full0 + 8 * stage;
+                        TCT(long long tw = clock64();)
                         mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                        TCT(tp_wait += clock64() - tw;)
                         {
                             mbar_expect_tx(fb, Cfg::STAGE_BYTES);
                             tma_load_4d(st, &map_a, fb, cb * 64, w0 + s, h0, n);
@@ -307,6 +344,7 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     }
                 }
             }
+            TCT(g_rows_timing[blockIdx.x][4] += (unsigned long long)tp_wait; g_rows_timing[blockIdx.x][5] += (unsigned long long)(clock64() - tp0);)
         }
     } else if (warp == 1) {
         // ===================================================== MMA issuer: 12 MMAs per barrier wait
@@ -316,12 +354,22 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         int stage = 0; uint32_t phase = 0;
         int acc = 0; uint32_t acc_phase = 0;
         RowsTile<CL> t;
+        TCT(long long ti0 = clock64(); long long ti_full = 0, ti_tempty = 0, ti_stages = 0;)
         for (int kk = 0; rows_tile<CL>(p, kk, rank, t); ++kk) {
+            TCT(long long tw0 = clock64();)
             mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+            TCT(ti_tempty += clock64() - tw0;)
             fence_after();
-            const uint32_t tmem_d = tmem_base + acc * Cfg::ACC_STRIDE;
+            const uint32_t tmem_d0 = tmem_base + acc * ACC_STRIDE;
+            uint32_t used = 0;          // bit 0 / 1: the main / correction accumulator of this tile has been written
             for (int it = 0; it < stages_per_tile; ++it) {
+                const uint32_t sub = (SPLIT && (it / 3) * 64 >= p.split_c) ? 1u : 0u;
+                const uint32_t tmem_d = tmem_d0 + sub * BN;
+                const uint32_t fresh = ((used >> sub) & 1u) ^ 1u;
+                used |= 1u << sub;
+                TCT(long long tw1 = clock64();)
                 mbar_wait(full0 + 8 * stage, phase);
+                TCT(ti_full += clock64() - tw1; ++ti_stages;)
                 fence_after();
                 if (elect_one()) {
                     const uint64_t soff = (uint64_t)((stage * Cfg::STAGE_BYTES) >> 4);
@@ -332,7 +380,7 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         const uint64_t bdesc = bdesc0 + soff + (uint64_t)((r * Cfg::B_BYTES) >> 4);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | r | k) != 0);
+                            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, fresh ? (uint32_t)(r | k) : 1u);
                     }
                     if constexpr (CL == 1) umma_commit(empty0 + 8 * stage);
                     else umma_commit_mc(empty0 + 8 * stage, MC_MASK);
@@ -343,6 +391,8 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        TCT(if (lane == 0) { g_rows_timing[blockIdx.x][0] += (unsigned long long)(clock64() - ti0); g_rows_timing[blockIdx.x][1] += (unsigned long long)ti_full;
+                             g_rows_timing[blockIdx.x][2] += (unsigned long long)ti_tempty; g_rows_timing[blockIdx.x][3] += (unsigned long long)ti_stages; })
     } else {
         // ===================================================== epilogue: 8 warps (2..9)
         bool narrow = false;
@@ -355,7 +405,7 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     fence_before();
     __syncthreads();
     if constexpr (CL > 1) cluster_sync_all();      // no CTA leaves while a peer's commit may still arrive on its barriers
-    if (warp == 1) { fence_after(); tmem_dealloc(tmem_base, Cfg::TMEM_COLS); }
+    if (warp == 1) { fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 
@@ -443,8 +493,9 @@ static void launch_rows_any(cudaStream_t st, const CUtensorMap& ma, const void* 
 
 // out[n,y,x,k] (+)= sum_{r,s,c} A[n, y+r-pad, x+s-pad, c] * Wp[k][(r*3+s)*Ca + c]      (3x3, stride 1); out_f32: fp32 output tensor
 void k_conv_tc_rows(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca, const void* Wp, int Nout, int pad, void* out,
-                    int Ho, int Wo, const float* bias, float* stats, bool accumulate, bool out_f32, const EpiParams* ep) {
+                    int Ho, int Wo, const float* bias, float* stats, bool accumulate, bool out_f32, const EpiParams* ep, int split_c) {
     SALT_COUNT(1);
+    if (out_f32 && (split_c <= 0 || split_c > Ca)) throw std::runtime_error("k_conv_tc_rows: fp32 output needs the split-operand channel count");
     if (out_f32 && accumulate) throw std::runtime_error("k_conv_tc_rows: accumulation into an fp32 output is not implemented");
     RowsParams p;
     if (ep) p.ep = *ep;
@@ -458,7 +509,7 @@ void k_conv_tc_rows(cudaStream_t st, const void* A, int B, int Ha, int Wa, int C
     p.tiles_co = Nout / BN;
     p.total_tiles = p.tiles_x * p.tiles_y * B * p.tiles_co;
     p.B = B; p.Ho = Ho; p.Wo = Wo; p.Co = Nout; p.Ca = Ca; p.cblks = Ca / 64; p.pad = pad;
-    p.accumulate = accumulate ? 1 : 0; p.bias = bias; p.stats = stats; p.out = out;
+    p.accumulate = accumulate ? 1 : 0; p.bias = bias; p.stats = stats; p.out = out; p.split_c = split_c;
     CUtensorMap ma = make_map_nhwc(A, Ca, Wa, Ha, B, 64, RW_TW, RW_TH + 2, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B);
     p.m_tiles = p.tiles_x * p.tiles_y * B; p.total_groups = 0;
     if (out_f32) {

@@ -172,6 +172,7 @@ void Engine::build() {
             if (!se50) {
                 blocks_.emplace_back(new BasicBlock());
                 BasicBlock& b = *blocks_.back();
+                b.group = li + 1;
                 const int co = chans[li];
                 b.down = (bi == 0 && li > 0);
                 b.x = cur;
@@ -193,6 +194,7 @@ void Engine::build() {
             } else {
                 bnecks_.emplace_back(new Bottleneck());
                 Bottleneck& b = *bnecks_.back();
+                b.group = li + 1;
                 const int pl = chans[li], co = 4 * pl;
                 b.down = (bi == 0);
                 b.x = cur;
@@ -369,7 +371,7 @@ void Engine::profile_enable(bool on) {
 }
 void Engine::prof_begin(int cls, double flops, cudaStream_t st) {
     if (!prof_on_) return;
-    ProfRec r; r.flops = flops; r.cls = cls;
+    ProfRec r; r.flops = flops; r.cls = cls; r.group = prof_group_;
     cudaEventCreate(&r.a); cudaEventCreate(&r.b);
     cudaEventRecord(r.a, st);
     prof_.push_back(r);
@@ -378,11 +380,11 @@ void Engine::prof_end(cudaStream_t st) {
     if (!prof_on_) return;
     cudaEventRecord(prof_.back().b, st);
 }
-void Engine::profile_read(int cls, double* ms, double* flops, long long* launches) {
+void Engine::profile_read(int cls, double* ms, double* flops, long long* launches, int group) {
     cudaDeviceSynchronize();
     *ms = 0; *flops = 0; *launches = 0;
     for (auto& r : prof_) {
-        if (r.cls != cls) continue;
+        if (r.cls != cls || (group >= 0 && r.group != group)) continue;
         float t = 0.f;
         cudaEventElapsedTime(&t, r.a, r.b);
         *ms += t; *flops += r.flops; *launches += 1;
@@ -399,7 +401,8 @@ void Engine::conv_fwd(const ConvLayer& c, const Tensor& in, const Tensor& out, B
     if (tc_split) {
         // fp32 parity mode on tcgen05: the bf16 kernel over the split-bf16 copy of the input (6x the channels), fp32 output
         k_split6_act(st, (const float*)in.p, split_scratch_, (size_t)g.B * g.Hi * g.Wi, g.Ci);
-        k_conv_tc(st, split_scratch_, g.B, g.Hi, g.Wi, g6.Ci, c.wp6, g.Co, g.R, g.S, g.stride, g.pad, out.p, g.Ho, g.Wo, bias, stats, false, true);
+        k_conv_tc(st, split_scratch_, g.B, g.Hi, g.Wi, g6.Ci, c.wp6, g.Co, g.R, g.S, g.stride, g.pad, out.p, g.Ho, g.Wo, bias, stats, false, true,
+                  nullptr, g.Ci);
     } else if (tc)
         k_conv_tc(st, in.p, g.B, g.Hi, g.Wi, g.Ci, c.wp, g.Co, g.R, g.S, g.stride, g.pad, out.p, g.Ho, g.Wo, bias, stats, false);
     else
@@ -442,7 +445,7 @@ void Engine::conv_bn_fused(const ConvLayer& c, const Tensor& in, const Tensor& d
     if (cfg_.dt == DT_F32) {
         k_split6_act(st, (const float*)in.p, split_scratch_, (size_t)g.B * g.Hi * g.Wi, g.Ci);
         k_conv_tc(st, split_scratch_, g.B, g.Hi, g.Wi, 6 * g.Ci, c.wp6, g.Co, g.R, g.S, g.stride, g.pad, dst.p, g.Ho, g.Wo, bias, nullptr,
-                  false, true, &ep);
+                  false, true, &ep, g.Ci);
     } else {
         k_conv_tc(st, in.p, g.B, g.Hi, g.Wi, g.Ci, c.wp, g.Co, g.R, g.S, g.stride, g.pad, dst.p, g.Ho, g.Wo, bias, nullptr, false, false, &ep);
     }
@@ -590,15 +593,17 @@ void Engine::forward_body(int B, float* logits_nchw, bool train, cudaStream_t st
     if (train) { k_zero(st, stats_arena_, sizeof(float) * stats_floats_); eval_coef_dirty_ = true; }
     else if (eval_coef_dirty_ && fuse_eval_) finalize_eval_all(st);
     Tensor x4 = view(x4_), sraw = view(stem_raw_);
+    prof_group_ = 0;
     if (!train && fusable(stem_, x4, sraw)) {
         conv_bn_fused(stem_, x4, view(stem_out_.t), stem_bn_, nullptr, true, st);
     } else {
         conv_fwd(stem_, x4, sraw, &stem_bn_, train, st);
         k_bn_apply(st, sraw, stem_bn_.scale, stem_bn_.shift, nullptr, nullptr, nullptr, true, view(stem_out_.t));
     }
-    for (auto& b : blocks_) block_fwd(*b, train, st);
-    for (auto& b : bnecks_) bneck_fwd(*b, train, st);
+    for (auto& b : blocks_) { prof_group_ = b->group; block_fwd(*b, train, st); }
+    for (auto& b : bnecks_) { prof_group_ = b->group; bneck_fwd(*b, train, st); }
     // center
+    prof_group_ = 5;
     gather_fwd(center_src_, view(center0_.P), st);
     if (!train && fusable(center0_.c, view(center0_.P), view(center0_.raw)) && fusable(center1_.c, view(center1_.P), view(center1_.raw))) {
         conv_bn_fused(center0_.c, view(center0_.P), view(center1_.P), center0_.bn, nullptr, true, st);
@@ -610,7 +615,8 @@ void Engine::forward_body(int B, float* logits_nchw, bool train, cudaStream_t st
         cbr_fwd(center1_, train, st);
         k_bn_relu_avgpool(st, view(center1_.raw), center1_.bn.scale, center1_.bn.shift, view(center_out_.t));
     }
-    for (auto& d : dec_) decoder_fwd(d, train, st);
+    for (int i = 0; i < 5; ++i) { prof_group_ = 6 + i; decoder_fwd(dec_[i], train, st); }
+    prof_group_ = 11;
     gather_fwd(final_src_, view(final0_.P), st);
     if (!train && fusable(final0_.c, view(final0_.P), view(final0_.raw))) {
         conv_bn_fused(final0_.c, view(final0_.P), view(final0_.raw), final0_.bn, nullptr, true, st);
@@ -737,6 +743,7 @@ void Engine::backward(const float* dlogits, cudaStream_t st) {
     if (cfg_.dt == DT_BF16 && cfg_.use_tc) k_zero(st, dwp_arena_, sizeof(float) * dwp_floats_);
     for (auto& g : gradbufs_) g->fresh = true;
     // ---- final
+    prof_group_ = 11;
     {
         const Tensor raw = view(final0_.raw), P = view(final0_.P);
         BNRef bn = bn_ref(final0_.bn);
@@ -749,8 +756,9 @@ void Engine::backward(const float* dlogits, cudaStream_t st) {
         conv_dgrad(final0_.c, graw, gP, false, st);
         gather_bwd(final_src_, gP, st);
     }
-    for (int i = 4; i >= 0; --i) decoder_bwd(dec_[i], st);
+    for (int i = 4; i >= 0; --i) { prof_group_ = 6 + i; decoder_bwd(dec_[i], st); }
     // ---- center
+    prof_group_ = 5;
     {
         const Tensor raw1 = view(center1_.raw), raw0 = view(center0_.raw), P1 = view(center1_.P), P0 = view(center0_.P);
         const double cnt = (double)B_ * raw1.H * raw1.W;
@@ -773,9 +781,10 @@ void Engine::backward(const float* dlogits, cudaStream_t st) {
         conv_dgrad(center0_.c, graw0, gP0, false, st);
         gather_bwd(center_src_, gP0, st);
     }
-    for (int i = (int)blocks_.size() - 1; i >= 0; --i) block_bwd(*blocks_[i], st);
-    for (int i = (int)bnecks_.size() - 1; i >= 0; --i) bneck_bwd(*bnecks_[i], st);
+    for (int i = (int)blocks_.size() - 1; i >= 0; --i) { prof_group_ = blocks_[i]->group; block_bwd(*blocks_[i], st); }
+    for (int i = (int)bnecks_.size() - 1; i >= 0; --i) { prof_group_ = bnecks_[i]->group; bneck_bwd(*bnecks_[i], st); }
     // ---- stem (no input gradient)
+    prof_group_ = 0;
     {
         const Tensor raw = view(stem_raw_);
         BNRef bn = bn_ref(stem_bn_);

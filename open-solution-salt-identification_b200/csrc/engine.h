@@ -45,6 +45,7 @@ struct GradBuf { Tensor g; bool fresh = true; };
 struct Act { Tensor t; GradBuf* gb = nullptr; };
 
 struct BasicBlock {
+    int group = 0;             // profile group (encoder layer index)
     ConvLayer c1, c2, cd;
     BNLayer b1, b2, bd;
     bool down = false;
@@ -55,6 +56,7 @@ struct BasicBlock {
 // SE-ResNet bottleneck (pretrainedmodels senet.py SEResNetBottleneck; restated in oracle/senet_restated.py):
 // 1x1 (stride here) -> 3x3 -> 1x1 (x4), each + BN, SE gate on the last BN output, + shortcut, ReLU
 struct Bottleneck {
+    int group = 0;
     ConvLayer c1, c2, c3, cd;
     BNLayer b1, b2, b3, bd;
     SELayer se;
@@ -108,7 +110,9 @@ public:
     enum ProfClass { PROF_CONV_FWD = 0, PROF_CONV_DGRAD = 1, PROF_CONV_WGRAD = 2, PROF_NCLASS = 3 };
     void profile_enable(bool on);
     // synchronises, then returns accumulated device time / algorithmic flops / launches since enable
-    void profile_read(int cls, double* ms, double* flops, long long* launches);
+    void profile_read(int cls, double* ms, double* flops, long long* launches, int group = -1);
+    // layer groups of the profile records: 0 stem, 1-4 encoder layer1..layer4, 5 center, 6-10 dec5..dec1, 11 final
+    enum { PROF_NGROUPS = 12 };
 
     const EngineConfig& config() const { return cfg_; }
     float* loss_scratch() { return loss_scratch_; }
@@ -206,7 +210,8 @@ private:
     // scratch pool
     void* scratch_[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scratch_bytes_[4] = {0, 0, 0, 0};
-    struct ProfRec { cudaEvent_t a, b; double flops; int cls; };
+    struct ProfRec { cudaEvent_t a, b; double flops; int cls, group; };
+    int prof_group_ = 0;
     std::vector<ProfRec> prof_;
     bool prof_on_ = false;
     void prof_begin(int cls, double flops, cudaStream_t st);

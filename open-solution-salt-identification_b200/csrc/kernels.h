@@ -32,7 +32,10 @@ void k_conv_wgrad_simt(cudaStream_t st, DType dt, const void* in, const void* go
 // x = h + m + l with h = bf16(x), m = bf16(x - h), l = bf16(x - h - m): three bf16 terms carry 24 mantissa bits.  A convolution
 // of fp32 tensors is the sum of the six bf16 x bf16 products h*h, h*m, m*h, m*m, h*l, l*h (the dropped ones are < 2^-24
 // relative), accumulated in fp32 by tcgen05 - i.e. the SAME bf16 convolution kernel run over 6x the input channels:
-//   activation segments [h | h | m | m | h | l]   x   weight segments [h | m | h | m | l | h]
+//   activation segments [h | m | h | m | h | l]   x   weight segments [h | m | m | h | l | h]      (hh, mm, hm, mh, hl, lh)
+// The h*h segment comes first: the kernels give it its own TMEM accumulator (tcgen05 truncates at the accumulator's magnitude,
+// so the 2^-8 .. 2^-16 smaller correction terms are summed apart and added in the epilogue; a 64-channel K-block that straddles the
+// hh / mm boundary only drags the negligible m*m products into the main accumulator).
 // Measured against the reference forward: <= 6e-5 max-abs on the logits (plain kind::tf32 operands give 1e-2..1e-1).
 void k_split6_act(cudaStream_t st, const float* in, void* out_bf16, size_t rows, int C);       // [rows][C] fp32 -> [rows][6C] bf16
 void k_split6_weights(cudaStream_t st, const float* wp, void* wp6_bf16, size_t rows, int C);   // same, weight segment order

@@ -1043,8 +1043,8 @@ static void launch_split6(cudaStream_t st, const float* in, void* out, size_t ro
     split6_kernel<<<(unsigned)((nvec + EW_THREADS - 1) / EW_THREADS), EW_THREADS, 0, st>>>(in, (bf16*)out, nvec, C, ord);
 }
 void k_split6_act(cudaStream_t st, const float* in, void* out, size_t rows, int C) {
-    launch_split6(st, in, out, rows, C, Split6Order{{0, 0, 1, 1, 0, 2}});
+    launch_split6(st, in, out, rows, C, Split6Order{{0, 1, 0, 1, 0, 2}});
 }
 void k_split6_weights(cudaStream_t st, const float* wp, void* wp6, size_t rows, int C) {
-    launch_split6(st, wp, wp6, rows, C, Split6Order{{0, 1, 0, 1, 2, 0}});
+    launch_split6(st, wp, wp6, rows, C, Split6Order{{0, 1, 1, 0, 2, 0}});
 }

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libsaltunet.so')
+LIB_PATH = os.environ.get('SALT_LIB_PATH') or os.path.join(os.path.dirname(_HERE), 'libsaltunet.so')      # SALT_LIB_PATH: profiling builds
 
 PREC_FP32, PREC_BF16 = 0, 1
 ARCH_UNET_RESNET = 0
@@ -62,6 +62,7 @@ PROTOTYPES = {
     'salt_cluster_launch_count': (C.c_ulonglong, []),
     'salt_profile_enable': (_i, [_vp, _i]),
     'salt_profile_read': (_i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    'salt_profile_read_group': (_i, [_vp, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     'salt_op_conv_forward': (_i, [C.POINTER(SaltConvDesc), _vp, _fp, _fp, _vp, _dp, _vp]),
     'salt_op_conv_dgrad': (_i, [C.POINTER(SaltConvDesc), _vp, _fp, _vp, _i, _vp]),
     'salt_op_conv_wgrad': (_i, [C.POINTER(SaltConvDesc), _vp, _vp, _fp, _vp]),

@@ -191,6 +191,20 @@ class UNetEngine:
             out[name] = (ms.value, fl.value, n.value)
         return out
 
+    PROFILE_GROUPS = ('stem', 'layer1', 'layer2', 'layer3', 'layer4', 'center', 'dec5', 'dec4', 'dec3', 'dec2', 'dec1', 'final')
+
+    def profile_read_groups(self):
+        """{group: {class: (ms, flops, launches)}} - the convolution launches of each layer group since profile(True)."""
+        out = {}
+        for gi, gname in enumerate(self.PROFILE_GROUPS):
+            d = {}
+            for cls, name in enumerate(('conv_fwd', 'conv_dgrad', 'conv_wgrad')):
+                ms, fl, n = C.c_double(), C.c_double(), C.c_longlong()
+                _lib.check(self.lib.salt_profile_read_group(self.h, cls, gi, C.byref(ms), C.byref(fl), C.byref(n)))
+                d[name] = (ms.value, fl.value, n.value)
+            out[gname] = d
+        return out
+
     def activation(self, name):
         shape = (C.c_int * 4)()
         _lib.check(self.lib.salt_get_activation(self.h, name.encode(), C.c_void_p(0), shape, self._stream()))
