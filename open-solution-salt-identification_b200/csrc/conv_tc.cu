@@ -142,36 +142,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     } else if (warp == 1) {
         // ===================================================== MMA issuer
         const uint32_t idesc = instr_desc_bf16(BN, false, false);
-        int stage = 0; uint32_t phase = 0;
-        int acc = 0; uint32_t acc_phase = 0;
-        TcTile tt;
-        for (int kk = 0; tc_tile(p, kk, tt); ++kk) {
-            const int num_kb = p.ph[tt.pi].ntaps * p.cblks;
-            mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
-            fence_after();
-            const uint32_t tmem_d0 = tmem_base + acc * ACC_STRIDE;
-            uint32_t used = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const uint32_t sub = (SPLIT && (kb % p.cblks) * BK >= p.split_c) ? 1u : 0u;
-                const uint32_t tmem_d = tmem_d0 + sub * BN;
-                const uint32_t fresh = ((used >> sub) & 1u) ^ 1u;
-                used |= 1u << sub;
-                mbar_wait(full0 + 8 * stage, phase);
-                fence_after();
-                if (elect_one()) {
+        // one elected thread runs the whole loop and probes the next stage's barrier before the last MMA of the current stage
+        // (tcgen05.mma issue is throttled to the execution rate; a barrier probe costs ~90 cycles: see conv_tc_rows.cu)
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            bool stage_ready = false, acc_ready = false;
+            TcTile tt, tn;
+            bool more = tc_tile(p, 0, tt);
+            for (int kk = 0; more; ++kk) {
+                more = tc_tile(p, kk + 1, tn);
+                const int num_kb = p.ph[tt.pi].ntaps * p.cblks;
+                if (!acc_ready) mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+                const uint32_t tmem_d0 = tmem_base + acc * ACC_STRIDE;
+                const int nacc = acc ^ 1;
+                const uint32_t nacc_phase = acc_phase ^ (uint32_t)acc;
+                uint32_t used = 0;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    const uint32_t sub = (SPLIT && (kb % p.cblks) * BK >= p.split_c) ? 1u : 0u;
+                    const uint32_t tmem_d = tmem_d0 + sub * BN;
+                    const uint32_t fresh = ((used >> sub) & 1u) ^ 1u;
+                    used |= 1u << sub;
+                    if (!stage_ready) mbar_wait(full0 + 8 * stage, phase);
+                    fence_after();
+                    const bool last = kb == num_kb - 1;
+                    const int nstage = stage + 1 == STAGES ? 0 : stage + 1;
+                    const uint32_t nphase = stage + 1 == STAGES ? phase ^ 1 : phase;
                     const uint64_t adesc = smem_desc(smem_u32(smem_a + stage * Cfg::A_BYTES), 16, Cfg::SBO, Cfg::LAYOUT);
                     const uint64_t bdesc = smem_desc(smem_u32(smem_b + stage * Cfg::B_BYTES), 16, Cfg::SBO, Cfg::LAYOUT);
+                    uint32_t probe_stage = 0, probe_acc = 0;
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)       // advance 16 bf16 = 32 bytes inside the swizzle atom
+                    for (int k = 0; k < BK / 16; ++k) {     // advance 16 bf16 = 32 bytes inside the swizzle atom
+                        if (k == 1) {
+                            if (!last || more) probe_stage = mbar_try_wait(full0 + 8 * nstage, nphase) ? 1u : 0u;
+                            if (last && more) probe_acc = mbar_try_wait(tempty0 + 8 * nacc, nacc_phase ^ 1) ? 1u : 0u;
+                        }
                         umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, fresh ? (uint32_t)k : 1u);
+                    }
                     umma_commit(empty0 + 8 * stage);        // frees the smem stage when these MMAs retire
-                    if (kb == num_kb - 1) umma_commit(tfull0 + 8 * acc);
+                    if (last) umma_commit(tfull0 + 8 * acc);
+                    stage_ready = probe_stage != 0;
+                    if (last) acc_ready = probe_acc != 0;
+                    stage = nstage; phase = nphase;
                 }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                acc = nacc; acc_phase = nacc_phase;
+                tt = tn;
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        __syncwarp();
     } else {
         // ===================================================== epilogue (warps 2..5 <-> TMEM lane quarters 2,3,0,1)
         const int quarter = warp & 3;

@@ -351,48 +351,69 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const uint32_t idesc = instr_desc_bf16(BN, false, false);
         const uint64_t adesc0 = smem_desc(smem0, 16, 1024, 2);
         const uint64_t bdesc0 = smem_desc(smem0 + RW_A_BYTES, 16, 1024, 2);
-        int stage = 0; uint32_t phase = 0;
-        int acc = 0; uint32_t acc_phase = 0;
-        RowsTile<CL> t;
-        TCT(long long ti0 = clock64(); long long ti_full = 0, ti_tempty = 0, ti_stages = 0;)
-        for (int kk = 0; rows_tile<CL>(p, kk, rank, t); ++kk) {
-            TCT(long long tw0 = clock64();)
-            mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
-            TCT(ti_tempty += clock64() - tw0;)
-            fence_after();
-            const uint32_t tmem_d0 = tmem_base + acc * ACC_STRIDE;
-            uint32_t used = 0;          // bit 0 / 1: the main / correction accumulator of this tile has been written
-            for (int it = 0; it < stages_per_tile; ++it) {
-                const uint32_t sub = (SPLIT && (it / 3) * 64 >= p.split_c) ? 1u : 0u;
-                const uint32_t tmem_d = tmem_d0 + sub * BN;
-                const uint32_t fresh = ((used >> sub) & 1u) ^ 1u;
-                used |= 1u << sub;
-                TCT(long long tw1 = clock64();)
-                mbar_wait(full0 + 8 * stage, phase);
-                TCT(ti_full += clock64() - tw1; ++ti_stages;)
-                fence_after();
-                if (elect_one()) {
+        // ONE elected thread runs the whole issue loop.  tcgen05.mma issue is throttled to the execution rate (the hardware
+        // queue is shallow: profiles/r2_notes.md, rows_timing), so every cycle this thread spends between two MMAs idles the tensor
+        // pipe - and a barrier probe has ~90 cycles of latency even when the barrier completed long ago.  The probe of the NEXT
+        // stage's `full` barrier (and, on a tile's last stage, of the next accumulator's `tmem_empty` barrier) is therefore issued
+        // BEFORE the last two MMAs of the current stage and consumed after them: its latency hides behind their execution.
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            bool stage_ready = false, acc_ready = false;
+            RowsTile<CL> t, tn;
+            TCT(long long ti0 = clock64(); long long ti_full = 0, ti_tempty = 0, ti_stages = 0;)
+            bool more = rows_tile<CL>(p, 0, rank, t);
+            for (int kk = 0; more; ++kk) {
+                more = rows_tile<CL>(p, kk + 1, rank, tn);
+                TCT(long long tw0 = clock64();)
+                if (!acc_ready) mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+                TCT(ti_tempty += clock64() - tw0;)
+                const uint32_t tmem_d0 = tmem_base + acc * ACC_STRIDE;
+                const int nacc = acc ^ 1;
+                const uint32_t nacc_phase = acc_phase ^ (uint32_t)acc;      // the phase flips when acc wraps from 1 to 0
+                uint32_t used = 0;          // bit 0 / 1: the main / correction accumulator of this tile has been written
+                for (int it = 0; it < stages_per_tile; ++it) {
+                    const uint32_t sub = (SPLIT && (it / 3) * 64 >= p.split_c) ? 1u : 0u;
+                    const uint32_t tmem_d = tmem_d0 + sub * BN;
+                    const uint32_t fresh = ((used >> sub) & 1u) ^ 1u;
+                    used |= 1u << sub;
+                    TCT(long long tw1 = clock64();)
+                    if (!stage_ready) mbar_wait(full0 + 8 * stage, phase);
+                    TCT(ti_full += clock64() - tw1; ++ti_stages;)
+                    fence_after();
+                    const bool last = it == stages_per_tile - 1;
+                    const int nstage = stage + 1 == STAGES ? 0 : stage + 1;
+                    const uint32_t nphase = stage + 1 == STAGES ? phase ^ 1 : phase;
                     const uint64_t soff = (uint64_t)((stage * Cfg::STAGE_BYTES) >> 4);
+                    uint32_t probe_stage = 0, probe_acc = 0;
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
                         // vertical tap r = the same A buffer, r pixel-rows (r * 1024 bytes) further down
                         const uint64_t adesc = adesc0 + soff + (uint64_t)((r * 1024) >> 4);
                         const uint64_t bdesc = bdesc0 + soff + (uint64_t)((r * Cfg::B_BYTES) >> 4);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
+                        for (int k = 0; k < 4; ++k) {
+                            if (r == 2 && k == 2) {      // 10 of 12 issued: probe what the next iteration will need
+                                if (!last || more) probe_stage = mbar_try_wait(full0 + 8 * nstage, nphase) ? 1u : 0u;
+                                if (last && more) probe_acc = mbar_try_wait(tempty0 + 8 * nacc, nacc_phase ^ 1) ? 1u : 0u;
+                            }
                             umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, fresh ? (uint32_t)(r | k) : 1u);
+                        }
                     }
                     if constexpr (CL == 1) umma_commit(empty0 + 8 * stage);
                     else umma_commit_mc(empty0 + 8 * stage, MC_MASK);
-                    if (it == stages_per_tile - 1) umma_commit(tfull0 + 8 * acc);
+                    if (last) umma_commit(tfull0 + 8 * acc);
+                    stage_ready = probe_stage != 0;
+                    if (last) acc_ready = probe_acc != 0;
+                    stage = nstage; phase = nphase;
                 }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                acc = nacc; acc_phase = nacc_phase;
+                t = tn;
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            TCT(g_rows_timing[blockIdx.x][0] += (unsigned long long)(clock64() - ti0); g_rows_timing[blockIdx.x][1] += (unsigned long long)ti_full;
+                g_rows_timing[blockIdx.x][2] += (unsigned long long)ti_tempty; g_rows_timing[blockIdx.x][3] += (unsigned long long)ti_stages;)
         }
-        TCT(if (lane == 0) { g_rows_timing[blockIdx.x][0] += (unsigned long long)(clock64() - ti0); g_rows_timing[blockIdx.x][1] += (unsigned long long)ti_full;
-                             g_rows_timing[blockIdx.x][2] += (unsigned long long)ti_tempty; g_rows_timing[blockIdx.x][3] += (unsigned long long)ti_stages; })
+        __syncwarp();
     } else {
         // ===================================================== epilogue: 8 warps (2..9)
         bool narrow = false;

@@ -113,15 +113,22 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
             for (int g = 0; g < Cfg::MAX_GROUPS; ++g)      // odd tail: both halves read the same tile (LBO = 0)
                 adesc0[g] = smem_desc(smem0 + 2 * g * WG_TILE, (2 * g + 1 < nslots) ? WG_TILE : 0, 1024, 2);
             const uint64_t bdesc0 = smem_desc(smem0 + Cfg::MAX_SLOTS * WG_TILE, WG_TILE, 1024, 2);
-            int stage = 0; uint32_t phase = 0;
-            for (int it = 0; it < nchunks; ++it) {
-                mbar_wait(full0 + 8 * stage, phase);
-                fence_after();
-                if (elect_one()) {
+            // one elected thread runs the whole loop; the next stage's barrier is probed before the last slot pair's MMAs so that the
+            // ~90-cycle probe latency hides behind their execution (conv_tc_rows.cu explains the measurement behind this)
+            if (elect_one()) {
+                int stage = 0; uint32_t phase = 0;
+                bool stage_ready = false;
+                for (int it = 0; it < nchunks; ++it) {
+                    if (!stage_ready) mbar_wait(full0 + 8 * stage, phase);
+                    fence_after();
+                    const int nstage = stage + 1 == STAGES ? 0 : stage + 1;
+                    const uint32_t nphase = stage + 1 == STAGES ? phase ^ 1 : phase;
                     const uint64_t soff = (uint64_t)((stage * Cfg::STAGE_BYTES) >> 4);
+                    uint32_t probe = 0;
 #pragma unroll
                     for (int g = 0; g < Cfg::MAX_GROUPS; ++g) {
                         if (g < ngroups) {
+                            if (g == ngroups - 1 && it + 1 < nchunks) probe = mbar_try_wait(full0 + 8 * nstage, nphase) ? 1u : 0u;
 #pragma unroll
                             for (int kk = 0; kk < 2; ++kk)
                                 umma_bf16(tmem_base + g * NK, adesc0[g] + soff + (uint64_t)(kk * 128), bdesc0 + soff + (uint64_t)(kk * 128),
@@ -130,10 +137,11 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
                     }
                     umma_commit(empty0 + 8 * stage);
                     if (it == nchunks - 1) umma_commit(tfull);
+                    stage_ready = probe != 0;
+                    stage = nstage; phase = nphase;
                 }
-                __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
+            __syncwarp();
         } else {
             // ===================================================== epilogue: TMEM -> red.global.add.v4.f32
             const int quarter = warp & 3;
