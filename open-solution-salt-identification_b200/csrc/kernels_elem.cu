@@ -303,8 +303,9 @@ __global__ void bn_apply_kernel(const T* __restrict__ raw, const float* __restri
                                 const float* __restrict__ rshift, int relu, T* __restrict__ out, int nrows, int rows_per_block, int H,
                                 int W, int C, int pt, int pb, int pl, int pr) {
     // one block per `rows_per_block` image rows (and per slab of EW_THREADS channel groups when C is very wide); a thread keeps
-    // ONE channel group (its scale/shift live in registers) and walks along x, two pixels per iteration so that two (four with
-    // a residual) independent 16-byte loads are in flight.  Single-row blocks moved only ~8 KB each and were latency-bound.
+    // ONE channel group (its scale/shift live in registers) and walks over the block's pixels in flat order, FOUR pixels per
+    // iteration so that 4 (8 with a residual) independent 16-byte loads are in flight per thread - the one-row / two-pixel version
+    // ran at 1.9 TB/s, latency-bound (profiles/r1_launches_f_final.md).
     constexpr int N = VW<T>::N;
     const int cg = min(C / N, EW_THREADS), lanes = EW_THREADS / cg;
     const int cv = blockIdx.y * cg + threadIdx.x % cg, lane = threadIdx.x / cg, c = cv * N;
@@ -313,40 +314,36 @@ __global__ void bn_apply_kernel(const T* __restrict__ raw, const float* __restri
     Vf<N> rsc = vzero<N>(), rsh = vzero<N>();
     if (res && rscale) { rsc = ldp<N>(rscale + c); rsh = ldp<N>(rshift + c); }
     const int Hp = H + pt + pb, Wp = W + pl + pr;
-    const int row_end = min(nrows, (int)(blockIdx.x + 1) * rows_per_block);
-    for (int row = blockIdx.x * rows_per_block; row < row_end; ++row) {
-        const int n = row / H, y = row - n * H;
-        Vf<N> gt = vzero<N>();
-        if (gate) gt = ldp<N>(gate + (size_t)n * C + c);          // per-(image, channel) SE gate: (raw*scale+shift)*gate
+    const int q_end = min(nrows, (int)(blockIdx.x + 1) * rows_per_block) * W;     // flat pixel range of this block
+    auto finish = [&](int q, Vf<N> v, Vf<N> r) {
+        const int row = q / W, x = q - row * W, n = row / H, y = row - n * H;
+        v = vfma(v, sc, sh);
+        if (gate) v = vmul(v, ldp<N>(gate + (size_t)n * C + c));          // per-(image, channel) SE gate: (raw*scale+shift)*gate
+        if (res) {
+            if (rscale) r = vfma(r, rsc, rsh);
+            v = vadd(v, r);
+        }
+        if (relu) v = vrelu(v);
         const int y0 = (y == 0) ? 0 : y + pt, y1 = (y == H - 1) ? Hp - 1 : y + pt;
-        auto finish = [&](int x, Vf<N> v, Vf<N> r) {
-            v = vfma(v, sc, sh);
-            if (gate) v = vmul(v, gt);
-            if (res) {
-                if (rscale) r = vfma(r, rsc, rsh);
-                v = vadd(v, r);
-            }
-            if (relu) v = vrelu(v);
-            const int x0 = (x == 0) ? 0 : x + pl, x1 = (x == W - 1) ? Wp - 1 : x + pl;
-            for (int yy = y0; yy <= y1; ++yy)
-                for (int xx = x0; xx <= x1; ++xx) stv(out + (((size_t)n * Hp + yy) * Wp + xx) * C + c, v);
-        };
-        int x = lane;
-        for (; x + lanes < W; x += 2 * lanes) {
-            const size_t s0 = ((size_t)row * W + x) * C + c, s1 = s0 + (size_t)lanes * C;
-            const Vf<N> a0 = ldv(raw + s0), a1 = ldv(raw + s1);
-            Vf<N> r0 = vzero<N>(), r1 = vzero<N>();
-            if (res) { r0 = ldv(res + s0); r1 = ldv(res + s1); }
-            finish(x, a0, r0);
-            finish(x + lanes, a1, r1);
+        const int x0 = (x == 0) ? 0 : x + pl, x1 = (x == W - 1) ? Wp - 1 : x + pl;
+        for (int yy = y0; yy <= y1; ++yy)
+            for (int xx = x0; xx <= x1; ++xx) stv(out + (((size_t)n * Hp + yy) * Wp + xx) * C + c, v);
+    };
+    int q = blockIdx.x * rows_per_block * W + lane;
+    for (; q + 3 * lanes < q_end; q += 4 * lanes) {
+        Vf<N> a[4], r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const size_t o = (size_t)(q + u * lanes) * C + c;
+            a[u] = ldv(raw + o);
+            r[u] = res ? ldv(res + o) : vzero<N>();
         }
-        if (x < W) {
-            const size_t s0 = ((size_t)row * W + x) * C + c;
-            const Vf<N> a0 = ldv(raw + s0);
-            Vf<N> r0 = vzero<N>();
-            if (res) r0 = ldv(res + s0);
-            finish(x, a0, r0);
-        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) finish(q + u * lanes, a[u], r[u]);
+    }
+    for (; q < q_end; q += lanes) {
+        const size_t o = (size_t)q * C + c;
+        finish(q, ldv(raw + o), res ? ldv(res + o) : vzero<N>());
     }
 }
 void k_bn_apply(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const Tensor* res,
@@ -779,14 +776,29 @@ __global__ void scse_bwd_apply_kernel(const T* __restrict__ gout, const T* __res
     Vf<N> sg = vzero<N>(), sgx = vzero<N>(), sws = vzero<N>();
     float sbs = 0.f;
     // all lanes of a pixel group must iterate together (shuffles) -> loop bound on the block's first pixel
-    for (unsigned base = blockIdx.x * lanes; base < npix; base += gridDim.x * lanes) {
-        unsigned pix = base + lane;
-        const bool ok = pix < npix;
-        if (!ok) pix = npix - 1;
+    const unsigned bstep = gridDim.x * lanes;
+    for (unsigned base0 = blockIdx.x * lanes; base0 < npix; base0 += 2 * bstep) {
+      // two pixel groups per iteration: their 4 loads are issued back to back (<= 2 blocks per SM: one partial-sum slot per block)
+      Vf<N> xs[2], gs[2];
+      unsigned pixs[2]; bool oks[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        unsigned pix = base0 + u * bstep + lane;
+        oks[u] = pix < npix;
+        if (!oks[u]) pix = npix - 1;
+        pixs[u] = pix;
+        xs[u] = ldv8(raw + (size_t)pix * C + c);
+        gs[u] = ldv8(gout + (size_t)pix * C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (base0 + u * bstep >= npix) break;               // uniform over the block
+        const unsigned pix = pixs[u];
+        const bool ok = oks[u];
         const int n = pix / HW;
-        const Vf<N> x = ldv8(raw + (size_t)pix * C + c);
+        const Vf<N> x = xs[u];
         const Vf<N> z = vrelu(vfma(x, sc, sh));
-        const Vf<N> g = ldv8(gout + (size_t)pix * C + c);
+        const Vf<N> g = gs[u];
         const float dot = group_sum(vdot(z, w), cg);
         const float s = 1.f / (1.f + expf(-(dot + bs)));
         const float D = group_sum(vdot(g, z), cg);
@@ -802,6 +814,7 @@ __global__ void scse_bwd_apply_kernel(const T* __restrict__ gout, const T* __res
             sws = vaxpy(z, dsp, sws);
             if (cv == 0) sbs += dsp;
         }
+      }
     }
     block_reduce_slot<N>(sg, cg, bn.bsums + (size_t)blockIdx.x * 2 * C, red);
     block_reduce_slot<N>(sgx, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + C, red);
@@ -870,9 +883,17 @@ __global__ void final_bwd_kernel(const float* __restrict__ dlogits, const T* __r
     float sdb[K];
     for (int k = 0; k < K; ++k) { wk[k] = ldp<N>(w + k * C + c); sdw[k] = vzero<N>(); sdb[k] = 0.f; }
     Vf<N> sg = vzero<N>(), sgx = vzero<N>();
-    for (unsigned pix = blockIdx.x * lanes + lane; pix < npix; pix += gridDim.x * lanes) {
+    const unsigned pstep = gridDim.x * lanes;
+    for (unsigned pix0 = blockIdx.x * lanes + lane; pix0 < npix; pix0 += 2 * pstep) {
+      Vf<N> xs[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) xs[u] = ldv8(raw + (size_t)min(pix0 + u * pstep, npix - 1) * C + c);      // both loads in flight
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const unsigned pix = pix0 + u * pstep;
+        if (pix >= npix) break;
         const int n = pix / HW, p = pix - n * HW;
-        const Vf<N> x = ldv8(raw + (size_t)pix * C + c);
+        const Vf<N> x = xs[u];
         const Vf<N> z = vrelu(vfma(x, sc, sh));
         Vf<N> gz = vzero<N>();
 #pragma unroll
@@ -886,6 +907,7 @@ __global__ void final_bwd_kernel(const float* __restrict__ dlogits, const T* __r
         stv8(gbn + (size_t)pix * C + c, gz);
         sg = vadd(sg, gz);
         sgx = vfma(gz, vxhat(x, mu, is), sgx);
+      }
     }
     block_reduce_slot<N>(sg, cg, bn.bsums + (size_t)blockIdx.x * 2 * C, red);
     block_reduce_slot<N>(sgx, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + C, red);
@@ -942,9 +964,7 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restric
     const int cv = blockIdx.y * cg + threadIdx.x % cg, lane = threadIdx.x / cg, c = cv * N;
     const Vf<N> sc = ldp<N>(bn.scale + c), sh = ldp<N>(bn.shift + c), mu = ldp<N>(bn.mean + c), is = ldp<N>(bn.invstd + c);
     Vf<N> sg = vzero<N>(), sgx = vzero<N>();
-    for (unsigned pix = blockIdx.x * lanes + lane; pix < npix; pix += gridDim.x * lanes) {
-        const Vf<N> x = ldv(raw + (size_t)pix * C + c);
-        Vf<N> gv = ldv(g + (size_t)pix * C + c);
+    auto accumulate = [&](unsigned pix, const Vf<N>& x, Vf<N> gv) {
         if (gate) {
             const size_t o = (size_t)(pix / HW) * C + c;
             gv = vfma(gv, ldp<N>(gate + o), ldp<N>(addc + o));
@@ -952,7 +972,19 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restric
         if (self_mask) gv = vmaskpos(gv, vfma(x, sc, sh));
         sg = vadd(sg, gv);
         sgx = vfma(gv, vxhat(x, mu, is), sgx);
+    };
+    // 4 pixels = 8 independent 16-byte loads in flight per thread: with <= 2 blocks per SM (one partial-sum slot per block) a
+    // one-pixel loop left the kernel latency-bound at 1.9 TB/s (profiles/r1_launches_f_final.md)
+    const unsigned step = gridDim.x * lanes;
+    unsigned pix = blockIdx.x * lanes + lane;
+    for (; pix + 3 * step < npix; pix += 4 * step) {
+        Vf<N> xs[4], gs[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { xs[u] = ldv(raw + (size_t)(pix + u * step) * C + c); gs[u] = ldv(g + (size_t)(pix + u * step) * C + c); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) accumulate(pix + u * step, xs[u], gs[u]);
     }
+    for (; pix < npix; pix += step) accumulate(pix, ldv(raw + (size_t)pix * C + c), ldv(g + (size_t)pix * C + c));
     const int coff = blockIdx.y * cg * N;
     block_reduce_slot<N>(sg, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + coff, red);
     block_reduce_slot<N>(sgx, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + C + coff, red);
@@ -978,9 +1010,7 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict
     const int cv = blockIdx.y * cg + threadIdx.x % cg, lane = threadIdx.x / cg, c = cv * N;
     const Vf<N> sc = ldp<N>(bn.scale + c), sh = ldp<N>(bn.shift + c), mu = ldp<N>(bn.mean + c), cb = ldp<N>(bn.cb + c),
                 cc = ldp<N>(bn.cc + c);
-    for (unsigned pix = blockIdx.x * lanes + lane; pix < npix; pix += gridDim.x * lanes) {
-        const Vf<N> x = ldv(raw + (size_t)pix * C + c);
-        Vf<N> gv = ldv(g + (size_t)pix * C + c);
+    auto finish = [&](unsigned pix, const Vf<N>& x, Vf<N> gv) {
         if (gate) {
             const size_t o = (size_t)(pix / HW) * C + c;
             gv = vfma(gv, ldp<N>(gate + o), ldp<N>(addc + o));
@@ -990,7 +1020,17 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict
 #pragma unroll
         for (int i = 0; i < N; ++i) r.v[i] = sc.v[i] * (gv.v[i] - cb.v[i] - cc.v[i] * (x.v[i] - mu.v[i]));
         stv(graw + (size_t)pix * C + c, r);
+    };
+    const unsigned step = gridDim.x * lanes;
+    unsigned pix = blockIdx.x * lanes + lane;
+    for (; pix + 3 * step < npix; pix += 4 * step) {           // 8 independent 16-byte loads in flight per thread
+        Vf<N> xs[4], gs[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { xs[u] = ldv(raw + (size_t)(pix + u * step) * C + c); gs[u] = ldv(g + (size_t)(pix + u * step) * C + c); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) finish(pix + u * step, xs[u], gs[u]);
     }
+    for (; pix < npix; pix += step) finish(pix, ldv(raw + (size_t)pix * C + c), ldv(g + (size_t)pix * C + c));
 }
 void k_bn_bwd_apply(cudaStream_t st, const Tensor& g, const Tensor& raw, const BNRef& bn, bool self_mask, const Tensor& graw,
                     const float* gate, const float* addc) {
