@@ -108,6 +108,66 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(bar), "h"(mask) : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers: one tcgen05.mma spans the tensor cores of both SMs of the pair (M = 256)
+// arrive on the mbarrier at the same shared-memory offset in CTA `cta` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(bar), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// wait on a local mbarrier whose arrivals come from other CTAs of the cluster (acquire at cluster scope); bounded like mbar_wait
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (++spins > (1u << 24)) {
+            printf("tc: cluster mbarrier wait timed out (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+// TMA box load issued by either CTA of a pair into ITS OWN shared memory, completing bytes on the LEADER's mbarrier (the barrier
+// address with the CTA-rank bit of the shared::cluster window cleared - the cta_group::2 form allows the barrier to live in the peer)
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ uint32_t instr_desc_bf16_m256(int n) {
+    uint32_t d = 0;
+    d |= 1u << 4; d |= 1u << 7; d |= 1u << 10;
+    d |= (uint32_t)(n >> 3) << 17;
+    d |= (uint32_t)(256 >> 4) << 24;
+    return d;
+}
+
 // Work item k of this CTA.  CL == 1: tile = blockIdx.x + k*gridDim.x, channel tile fastest.  CL > 1: the CL CTAs of a cluster take
 // CL consecutive pixel tiles of ONE channel tile, so they consume identical weight stages in lockstep; a cluster whose last group
 // is short gives the surplus CTAs a clamped tile whose results are dropped (`live` = false).
@@ -131,7 +191,7 @@ __device__ __forceinline__ bool rows_tile(const RowsParams& p, int k, uint32_t r
     return true;
 }
 
-template <int BN, typename OutT, bool NARROW, int CL>
+template <int BN, typename OutT, bool NARROW, int CL, bool PAIR = false>
 __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int warp, const int lane, const uint32_t tmem_base,
                                       const uint32_t tfull0, const uint32_t tempty0, float* s_stats, const uint32_t rank) {
     // Epilogue, 8 warps (2..9).  Warp w may touch TMEM lanes 32*(w%4)..+31;
@@ -192,7 +252,7 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
                 for (int q = 0; q < 4; ++q) old[q] = o4[q];
             }
             constexpr bool SPLIT = sizeof(OutT) == 4;
-            constexpr int ACC_STRIDE = SPLIT ? RowsCfg<BN>::ACC_STRIDE_SPLIT : RowsCfg<BN>::ACC_STRIDE;
+            constexpr int ACC_STRIDE = SPLIT ? RowsCfg<BN>::ACC_STRIDE_SPLIT : (PAIR ? BN : RowsCfg<BN>::ACC_STRIDE);
             tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * ACC_STRIDE + ch * 32, v);
             if constexpr (SPLIT) {          // + the accumulator of the correction products
                 float v2[32];
@@ -238,7 +298,10 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
         }
         fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+        if (lane == 0) {
+            if (PAIR && rank != 0) mbar_arrive_remote(tempty0 + 8 * acc, 0);       // the accumulator barrier lives in the leader CTA
+            else mbar_arrive(tempty0 + 8 * acc);
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         if (p.stats && p.tiles_co > 1) {
             asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -430,6 +493,145 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 }
 
 
+// ================================================================================================
+// CTA-pair variant (cta_group::2): the two CTAs of a cluster work on two pixel tiles of the same channel tile; ONE tcgen05.mma
+// (M = 256, N = BN) issued by the leader covers both.  Each CTA stages its own activation box and only HALF of every weight slab
+// (B is split in N across the pair), so the bytes a stage pulls into an SM drop from 18 KB + 3*BN*128 to 18 KB + 1.5*BN*128 -
+// that ingest (~47 B/clk/SM measured, profiles/r2_notes.md) is what bounds the single-CTA kernel for BN >= 128 - and BN = 256
+// becomes possible (3 stages of 66 KB).  Measured operand-feed bound of the pair MMA: max(58, BN/2) clk (mma_feed micro-benchmark).
+// Protocol (round 1's pair kernel forwarded every stage through a second barrier and was 1.45x slower; here the hardware does it):
+//   full[s]    leader only, 1 arrival (the leader's producer, expect_tx = the bytes of BOTH CTAs); both producers' TMA loads
+//              complete on it directly (cp.async.bulk.tensor ... .cta_group::2 with the leader's barrier address)
+//   empty[s]   each CTA, 1 arrival: the leader's tcgen05.commit.cta_group::2, multicast to both CTAs
+//   tfull[a]   each CTA, 1 arrival: the same multicast commit after a tile's last MMA; each CTA drains its own 128 TMEM lanes
+//   tempty[a]  leader only, 16 arrivals: the 8 epilogue warps of each CTA (remote arrive from the peer)
+template <int BN> struct PairCfg {
+    static constexpr int B_HALF = (BN / 2) * 128;                        // one tap, my half of the channels: [BN/2][64] bf16
+    static constexpr int STAGE_BYTES = RW_A_BYTES + 3 * B_HALF;
+    static constexpr int STAGES = BN == 256 ? 3 : (BN == 128 ? 4 : 6);
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256 + 8 * 2 * BN * 4;
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+    static_assert(TMEM_COLS <= 512, "accumulators do not fit TMEM");
+};
+template <int BN>
+__global__ void __launch_bounds__(RW_THREADS, 1)
+conv_tc_rows_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const RowsParams p) {
+    using Cfg = PairCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
+    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    float* s_stats = reinterpret_cast<float*>(smem + Cfg::BAR_OFF + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES, tfull0 = empty0 + 8 * STAGES, tempty0 = tfull0 + 16;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 16); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc_pair(smem_u32(tmem_ptr_smem), Cfg::TMEM_COLS);
+    for (int i = threadIdx.x; i < 8 * 2 * BN; i += RW_THREADS) s_stats[i] = 0.f;
+    fence_before();
+    __syncthreads();
+    cluster_sync_all();                 // both CTAs' barriers and TMEM exist before any cross-CTA traffic
+    fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const int stages_per_tile = p.cblks * 3;
+
+    if (warp == 0) {
+        // ===================================================== TMA producer (both CTAs): own activation box + my half of the weights
+        if (elect_one()) {
+            int stage = 0; uint32_t phase = 0;
+            RowsTile<2> t;
+            for (int k = 0; rows_tile<2>(p, k, rank, t); ++k) {
+                const int w0 = t.tx * RW_TW - p.pad, h0 = t.ty * RW_TH - p.pad;
+                for (int cb = 0; cb < p.cblks; ++cb) {
+                    for (int s = 0; s < 3; ++s) {
+                        const uint32_t st = smem0 + stage * Cfg::STAGE_BYTES, fb = full0 + 8 * stage;
+                        mbar_wait_cluster(empty0 + 8 * stage, phase ^ 1);         // released by the leader's multicast commit
+                        if (leader) mbar_expect_tx(fb, 2 * Cfg::STAGE_BYTES);
+                        tma_load_4d_pair(st, &map_a, fb, cb * 64, w0 + s, h0, t.n);
+                        tma_load_4d_pair(st + RW_A_BYTES, &map_b, fb, cb * 64, t.nt * BN + (int)rank * (BN / 2), 0, s);   // (c, n half, r = 0..2, s)
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================================================== leader: MMA issuer for the pair (one elected thread, early barrier probes)
+        if (leader && elect_one()) {
+            const uint32_t idesc = instr_desc_bf16_m256(BN);
+            const uint64_t adesc0 = smem_desc(smem0, 16, 1024, 2);
+            const uint64_t bdesc0 = smem_desc(smem0 + RW_A_BYTES, 16, 1024, 2);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            bool stage_ready = false, acc_ready = false;
+            RowsTile<2> t, tn;
+            bool more = rows_tile<2>(p, 0, rank, t);
+            for (int kk = 0; more; ++kk) {
+                more = rows_tile<2>(p, kk + 1, rank, tn);
+                if (!acc_ready) mbar_wait_cluster(tempty0 + 8 * acc, acc_phase ^ 1);
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                const int nacc = acc ^ 1;
+                const uint32_t nacc_phase = acc_phase ^ (uint32_t)acc;
+                for (int it = 0; it < stages_per_tile; ++it) {
+                    if (!stage_ready) mbar_wait_cluster(full0 + 8 * stage, phase);
+                    fence_after();
+                    const bool last = it == stages_per_tile - 1;
+                    const int nstage = stage + 1 == STAGES ? 0 : stage + 1;
+                    const uint32_t nphase = stage + 1 == STAGES ? phase ^ 1 : phase;
+                    const uint64_t soff = (uint64_t)((stage * Cfg::STAGE_BYTES) >> 4);
+                    uint32_t probe_stage = 0, probe_acc = 0;
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const uint64_t adesc = adesc0 + soff + (uint64_t)((r * 1024) >> 4);
+                        const uint64_t bdesc = bdesc0 + soff + (uint64_t)((r * Cfg::B_HALF) >> 4);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (r == 2 && k == 2) {
+                                if (!last || more) probe_stage = mbar_try_wait_cluster(full0 + 8 * nstage, nphase) ? 1u : 0u;
+                                if (last && more) probe_acc = mbar_try_wait_cluster(tempty0 + 8 * nacc, nacc_phase ^ 1) ? 1u : 0u;
+                            }
+                            umma_bf16_pair(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (uint32_t)(it | r | k));
+                        }
+                    }
+                    umma_commit_pair(empty0 + 8 * stage, 3);
+                    if (last) umma_commit_pair(tfull0 + 8 * acc, 3);
+                    stage_ready = probe_stage != 0;
+                    if (last) acc_ready = probe_acc != 0;
+                    stage = nstage; phase = nphase;
+                }
+                acc = nacc; acc_phase = nacc_phase;
+                t = tn;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================================================== epilogue: each CTA drains its own half (128 rows) of the accumulator
+        bool narrow = false;
+        if constexpr (BN <= 64) narrow = p.tiles_co == 1 && p.stats != nullptr && !p.accumulate;
+        if constexpr (BN <= 64) {
+            if (narrow) rows_epilogue<BN, bf16, true, 2, true>(p, warp, lane, tmem_base, tfull0, tempty0, s_stats, rank);
+        }
+        if (!narrow) rows_epilogue<BN, bf16, false, 2, true>(p, warp, lane, tmem_base, tfull0, tempty0, s_stats, rank);
+    }
+    fence_before();
+    __syncthreads();
+    cluster_sync_all();                 // the peer's shared memory / TMEM stay alive until the leader's last MMA has retired
+    if (warp == 1) { fence_after(); tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS); }
+}
+
 bool tc_conv_rows_supported(int Ca, int Nout, int R, int S, int stride, int Ho, int Wo) {
     return R == 3 && S == 3 && stride == 1 && Ca % 64 == 0 && Nout % 32 == 0 && Ho >= 16 && Wo >= 8;
 }
@@ -489,6 +691,46 @@ static int rows_wide_pref() {
     if (v < 0) { const char* e = getenv("SALT_TC_WIDE"); v = (e && e[0] == '0') ? 0 : 1; }
     return v;
 }
+// CTA-pair kernel: env SALT_TC_PAIR = 0 turns it off (read once)
+static int rows_pair_pref() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SALT_TC_PAIR"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+template <int BN>
+static bool launch_rows_pair(cudaStream_t st, const CUtensorMap& ma, const void* Wp, int Ca, int Nout, RowsParams p) {
+    using Cfg = PairCfg<BN>;
+    static int max_clusters = -1;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(RW_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.attrs = at; cfg.numAttrs = 1;
+    if (max_clusters < 0) {
+        cudaFuncSetAttribute(conv_tc_rows_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cfg.gridDim = dim3(num_sms() / 2 * 2);
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, conv_tc_rows_pair_kernel<BN>, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = 0; }
+        max_clusters = n;
+    }
+    if (p.m_tiles < 16 || max_clusters * 2 < num_sms() * 3 / 4) return false;
+    p.total_groups = cdiv(p.m_tiles, 2) * p.tiles_co;
+    CUtensorMap mb;          // weights (c, n, r, s): one box = [3 taps r][BN/2][64 c] = this CTA's half of a kernel row's slabs
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Ca, (cuuint64_t)Nout, 3, 3};
+        cuuint64_t strides[3] = {(cuuint64_t)9 * Ca * 2, (cuuint64_t)3 * Ca * 2, (cuuint64_t)Ca * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)(BN / 2), 3, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = get_encode()(&mb, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(Wp), dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(weights 4d, pair) failed with code " + std::to_string((int)r));
+    }
+    cfg.gridDim = dim3(std::min(max_clusters, p.total_groups) * 2); cfg.stream = st;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_rows_pair_kernel<BN>, ma, mb, p);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("conv_tc_rows pair launch failed: ") + cudaGetErrorString(e));
+    ++g_salt_cluster_launches;
+    return true;
+}
 template <int BN, typename OutT>
 static void launch_rows_any(cudaStream_t st, const CUtensorMap& ma, const void* Wp, int Ca, int Nout, RowsParams p) {
     int cl = rows_cluster_pref();
@@ -538,6 +780,14 @@ void k_conv_tc_rows(cudaStream_t st, const void* A, int B, int Ha, int Wa, int C
         else if (BN == 64) launch_rows_any<64, float>(st, ma, Wp, Ca, Nout, p);
         else launch_rows_any<32, float>(st, ma, Wp, Ca, Nout, p);
         return;
+    }
+    if (BN == 128 && rows_pair_pref()) {
+        // >= 128 output channels: the CTA-pair kernel (half the weight bytes per SM; N = 256 tiles when the layer has them)
+        if (Nout % 256 == 0) {
+            RowsParams q = p; q.tiles_co = Nout / 256; q.total_tiles = q.tiles_x * q.tiles_y * B * q.tiles_co;
+            if (launch_rows_pair<256>(st, ma, Wp, Ca, Nout, q)) return;
+        }
+        if (launch_rows_pair<128>(st, ma, Wp, Ca, Nout, p)) return;
     }
     if (BN == 128) launch_rows_any<128, bf16>(st, ma, Wp, Ca, Nout, p);
     else if (BN == 192) launch_rows_any<192, bf16>(st, ma, Wp, Ca, Nout, p);
