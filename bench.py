@@ -278,6 +278,7 @@ def run_ours(args):
         step_device()
     prof = eng.profile_read()
     prof_groups = eng.profile_read_groups()
+    prof_passes = eng.profile_read_passes()
     eng.profile(False)
 
     # ---- secondary measurements (not the headline): Lovasz-hinge training step (BASELINE configs[2] loss) and fused
@@ -390,6 +391,8 @@ def run_ours(args):
         'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peaks['tflops'], 'unit': 'TFLOP/s',
                      'frac': achieved / peaks['tflops'], 'traffic': traffic, 'traffic_source': traffic_note, 'peak_source': peaks['source'],
                      'per_group': per_group,
+                     'memory_bound_passes': {k: {'ms_per_step': v[0] / 2, 'algorithmic_GBps': (v[1] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else 0.0),
+                                                 'launches_per_step': v[2] // 2} for k, v in prof_passes.items()},
                      'kernel': 'implicit-GEMM convolution (forward + dgrad + wgrad launches of one step, algorithmic FLOPs / CUDA-event time)',
                      'conv_share_of_step': (tot_ms / 2) / (ms / args.steps), 'per_class': kern,
                      'step_tflops': value / n * TRAIN_GFLOP_PER_IMAGE / 1e3,

@@ -80,6 +80,13 @@ int salt_loss_bce_dice_finish(salt_engine* h, const float* logits, const float* 
 
 /* models.py:133 batch_loss.backward(): fills the flat gradient array (zeroed first). */
 int salt_backward(salt_engine* h, const float* dlogits_nchw, void* stream);
+/* The same pass in three consecutive segments (0: final + decoder + center, 1: encoder layer4 + layer3, 2: layer2 + layer1 + stem),
+ * to be called in that order.  When segment k returns, the gradients of its parameters - the contiguous range
+ * salt_grad_segment(k) of the flat gradient buffer, in floats - are final: a data-parallel caller starts their NCCL all-reduce
+ * while the next segment computes.  Replaces the single gradient reduction nn.DataParallel performs after backward
+ * (common_blocks/models.py:81-82, 133). */
+int salt_backward_segment(salt_engine* h, const float* dlogits_nchw, int segment, void* stream);
+int salt_grad_segment(const salt_engine* h, int segment, size_t* offset, size_t* numel);
 
 /* models.py:74-75,134,289-297: torch.optim.Adam step with L2 `grad += wd*p` on every parameter.
  * grad_scale multiplies the stored gradients first (1/world after a SUM all-reduce). step counts from 1. */

@@ -95,6 +95,13 @@ int salt_loss_bce_dice_finish(salt_engine* h, const float* logits, const float* 
 int salt_backward(salt_engine* h, const float* dlogits, void* stream) {
     SALT_TRY("salt_backward", h->e->backward(dlogits, (cudaStream_t)stream));
 }
+int salt_backward_segment(salt_engine* h, const float* dlogits, int segment, void* stream) {
+    if (segment < 0 || segment > 2) return fail("salt_backward_segment: segment must be 0, 1 or 2");
+    SALT_TRY("salt_backward_segment", h->e->backward(dlogits, (cudaStream_t)stream, segment));
+}
+int salt_grad_segment(const salt_engine* h, int segment, size_t* offset, size_t* numel) {
+    SALT_TRY("salt_grad_segment", h->e->grad_segment(segment, offset, numel));
+}
 int salt_adam_step(salt_engine* h, float lr, float wd, float b1, float b2, float eps, int step, float grad_scale, void* stream) {
     SALT_TRY("salt_adam_step", h->e->adam(lr, wd, b1, b2, eps, step, grad_scale, (cudaStream_t)stream));
 }

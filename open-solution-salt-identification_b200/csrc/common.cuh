@@ -73,7 +73,21 @@ extern unsigned long long g_salt_launches;   // kernels launched by this library
 #define SALT_COUNT(n) (g_salt_launches += (n))
 extern unsigned long long g_salt_cluster_launches;   // of which: thread-block-cluster launches (TMA-multicast convolutions)
 
-constexpr int SALT_STAT_SLOTS = 296;       // BatchNorm partial-sum slots per layer (kernels.h): >= the grid of every producing kernel
+constexpr int SALT_STAT_SLOTS = 296;       // forward BatchNorm partial-sum slots per layer (kernels.h): >= the grid of every producer
 constexpr int SALT_STAT_SLOTS_CONV = 148;  // slots a persistent tensor-core convolution can touch (its grid is capped at this)
+constexpr int SALT_STAT_SLOTS_BWD = 1184;  // backward: up to 8 blocks per SM in the reduction passes, one slot per block
+
+// ---- optional per-kernel-class device timing (Engine::profile_enable; CUDA events on the launch stream).  Classes 0-2 are the
+// convolutions (engine.cu), the rest the memory-bound passes; `work` = algorithmic FLOPs (convolutions) or bytes (passes).
+enum SaltProfClass { SALT_PROF_CONV_FWD = 0, SALT_PROF_CONV_DGRAD = 1, SALT_PROF_CONV_WGRAD = 2, SALT_PROF_BN_APPLY = 3,
+                     SALT_PROF_BN_BWD_REDUCE = 4, SALT_PROF_BN_BWD_APPLY = 5, SALT_PROF_BN_FINALIZE = 6, SALT_PROF_GATHER = 7,
+                     SALT_PROF_GATHER_BWD = 8, SALT_PROF_SCSE = 9, SALT_PROF_OTHER = 10, SALT_PROF_NCLASS = 11 };
+extern void (*g_salt_prof_begin)(int cls, double work, cudaStream_t st);
+extern void (*g_salt_prof_end)(cudaStream_t st);
+struct SaltProfScope {
+    cudaStream_t st; bool on;
+    SaltProfScope(int cls, double work, cudaStream_t s) : st(s), on(g_salt_prof_begin != nullptr) { if (on) g_salt_prof_begin(cls, work, s); }
+    ~SaltProfScope() { if (on && g_salt_prof_end) g_salt_prof_end(st); }
+};
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

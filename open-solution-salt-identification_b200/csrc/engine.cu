@@ -5,6 +5,9 @@
 #include <cstdlib>
 
 unsigned long long g_salt_launches = 0;
+void (*g_salt_prof_begin)(int, double, cudaStream_t) = nullptr;
+void (*g_salt_prof_end)(cudaStream_t) = nullptr;
+static Engine* g_prof_engine = nullptr;
 unsigned long long g_salt_cluster_launches = 0;
 
 static const float BN_EPS = 1e-5f, BN_MOMENTUM = 0.1f;
@@ -82,8 +85,9 @@ BNLayer Engine::make_bn(const std::string& prefix, int c) {
     b.o_rm = add_buffer(prefix + ".running_mean", {c});
     b.o_rv = add_buffer(prefix + ".running_var", {c});
     b.sums = stats_arena_ + stats_cursor_; stats_cursor_ += (size_t)SALT_STAT_SLOTS * 2 * c;
-    b.bsums = bstats_arena_ + bstats_cursor_; bstats_cursor_ += (size_t)SALT_STAT_SLOTS * 2 * c;
-    float* f = (float*)ws_alloc(sizeof(float) * 6 * c);
+    b.bsums = bstats_arena_ + bstats_cursor_; bstats_cursor_ += (size_t)SALT_STAT_SLOTS_BWD * 2 * c;
+    float* f = (float*)ws_alloc(sizeof(float) * 6 * c + 16);
+    b.bslots = (int*)(f + 6 * c);
     b.scale = f; b.shift = f + c; b.mean = f + 2 * c; b.invstd = f + 3 * c; b.cb = f + 4 * c; b.cc = f + 5 * c;
     return b;
 }
@@ -222,6 +226,8 @@ void Engine::build() {
             }
         }
         enc_out_[li] = cur;
+        if (li == 1) seg_bound_[1] = n_params_;      // end of stem + layer1 + layer2
+        if (li == 3) seg_bound_[2] = n_params_;      // end of the encoder
     }
     // ---- center (unet.py:60-63 / :123-126); bc = bottom_channel_nr
     const int bc = se50 ? 2048 : 512, dc = bc / 8;
@@ -245,7 +251,9 @@ void Engine::build() {
     o_final_b_ = add_param("final.1.bias", {cfg_.num_classes});
 
     d_pack_ = (PackDesc*)ws_alloc(sizeof(PackDesc) * MAX_CONVS); d_pack_start_ = (int*)ws_alloc(sizeof(int) * (MAX_CONVS + 1));
-    d_unpack_ = (UnpackDesc*)ws_alloc(sizeof(UnpackDesc) * MAX_CONVS); d_unpack_start_ = (int*)ws_alloc(sizeof(int) * (MAX_CONVS + 1));
+    for (int i = 0; i < 4; ++i) {
+        d_unpack_[i] = (UnpackDesc*)ws_alloc(sizeof(UnpackDesc) * MAX_CONVS); d_unpack_start_[i] = (int*)ws_alloc(sizeof(int) * (MAX_CONVS + 1));
+    }
     loss_scratch_ = (float*)ws_alloc(sizeof(float) * (B + 8));
     {
         const size_t sb = lovasz_sort_scratch_bytes(B, cfg_.num_classes * H * W);
@@ -287,7 +295,7 @@ BNRef Engine::bn_ref(const BNLayer& b) const {
     r.rmean = buffers_ + b.o_rm; r.rvar = buffers_ + b.o_rv;
     r.dgamma = grads_ ? grads_ + b.o_gamma : nullptr; r.dbeta = grads_ ? grads_ + b.o_beta : nullptr;
     r.sums = b.sums; r.bsums = b.bsums; r.scale = b.scale; r.shift = b.shift; r.mean = b.mean; r.invstd = b.invstd;
-    r.cb = b.cb; r.cc = b.cc;
+    r.cb = b.cb; r.cc = b.cc; r.bslots = b.bslots;
     return r;
 }
 SERef Engine::se_ref(const SELayer& s) const {
@@ -342,24 +350,37 @@ void Engine::pack_all(cudaStream_t st) {
     packed_dirty_ = false;
 }
 // one launch: transpose every tensor-core wgrad scratch into the reference-layout gradient
-void Engine::unpack_all(cudaStream_t st) {
+void Engine::unpack_all(cudaStream_t st, int table) {
     if (unpack_table_dirty_) {
-        std::vector<UnpackDesc> descs; std::vector<int> start(1, 0);
-        unpack_max_rs_ = 1;
-        for (ConvLayer* c : all_convs()) {
-            if (!c->in_unpack_table) continue;
-            UnpackDesc d; d.dwp = c->dwp; d.dw = grads_ + c->o_w; d.Co = c->Co; d.Ci_real = c->Ci_real; d.Ci_pad = cdiv(c->Ci, 64) * 64; d.RS = c->R * c->S;
-            descs.push_back(d);
-            start.push_back(start.back() + cdiv(c->Co, 32) * cdiv(c->Ci_real, 32));
-            unpack_max_rs_ = std::max(unpack_max_rs_, d.RS);
-        }
-        unpack_layers_ = (int)descs.size(); unpack_blocks_ = start.back();
+        // all four tables (one per backward segment + the whole network) are rebuilt together, on the eager steps that precede
+        // any CUDA-graph capture (the rebuild synchronises)
         cudaStreamSynchronize(st);
-        cudaMemcpy(d_unpack_, descs.data(), sizeof(UnpackDesc) * descs.size(), cudaMemcpyHostToDevice);
-        cudaMemcpy(d_unpack_start_, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice);
+        for (int tb = 0; tb < 4; ++tb) {
+            std::vector<UnpackDesc> descs; std::vector<int> start(1, 0);
+            unpack_max_rs_[tb] = 1;
+            for (ConvLayer* c : all_convs()) {
+                if (!c->in_unpack_table) continue;
+                const int seg = c->o_w >= seg_bound_[2] ? 0 : (c->o_w >= seg_bound_[1] ? 1 : 2);
+                if (tb < 3 && seg != tb) continue;
+                UnpackDesc d; d.dwp = c->dwp; d.dw = grads_ + c->o_w; d.Co = c->Co; d.Ci_real = c->Ci_real; d.Ci_pad = cdiv(c->Ci, 64) * 64; d.RS = c->R * c->S;
+                descs.push_back(d);
+                start.push_back(start.back() + cdiv(c->Co, 32) * cdiv(c->Ci_real, 32));
+                unpack_max_rs_[tb] = std::max(unpack_max_rs_[tb], d.RS);
+            }
+            unpack_layers_[tb] = (int)descs.size(); unpack_blocks_[tb] = start.back();
+            if (!descs.empty()) cudaMemcpy(d_unpack_[tb], descs.data(), sizeof(UnpackDesc) * descs.size(), cudaMemcpyHostToDevice);
+            cudaMemcpy(d_unpack_start_[tb], start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice);
+        }
         unpack_table_dirty_ = false;
     }
-    if (unpack_layers_ > 0) k_unpack_all(st, d_unpack_, d_unpack_start_, unpack_layers_, unpack_blocks_, unpack_max_rs_);
+    if (unpack_layers_[table] > 0)
+        k_unpack_all(st, d_unpack_[table], d_unpack_start_[table], unpack_layers_[table], unpack_blocks_[table], unpack_max_rs_[table]);
+}
+void Engine::grad_segment(int seg, size_t* offset, size_t* numel) const {
+    if (seg < 0 || seg > 2) throw std::runtime_error("grad_segment: segment must be 0, 1 or 2");
+    const size_t lo = seg == 0 ? seg_bound_[2] : (seg == 1 ? seg_bound_[1] : 0);
+    const size_t hi = seg == 0 ? n_params_ : (seg == 1 ? seg_bound_[2] : seg_bound_[1]);
+    *offset = lo; *numel = hi - lo;
 }
 static double conv_flops(const ConvGeom& g, int ci_real) {
     return 2.0 * g.B * g.Ho * g.Wo * (double)g.Co * ci_real * g.R * g.S;
@@ -368,9 +389,15 @@ void Engine::profile_enable(bool on) {
     for (auto& r : prof_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     prof_.clear();
     prof_on_ = on;
+    prof_depth_ = 0;
+    // the elementwise launchers (kernels_*.cu) report through these hooks
+    g_prof_engine = on ? this : nullptr;
+    g_salt_prof_begin = on ? +[](int cls, double work, cudaStream_t st) { if (g_prof_engine) g_prof_engine->prof_begin(cls, work, st); } : nullptr;
+    g_salt_prof_end = on ? +[](cudaStream_t st) { if (g_prof_engine) g_prof_engine->prof_end(st); } : nullptr;
 }
 void Engine::prof_begin(int cls, double flops, cudaStream_t st) {
     if (!prof_on_) return;
+    if (prof_depth_++ > 0) return;
     ProfRec r; r.flops = flops; r.cls = cls; r.group = prof_group_;
     cudaEventCreate(&r.a); cudaEventCreate(&r.b);
     cudaEventRecord(r.a, st);
@@ -378,6 +405,7 @@ void Engine::prof_begin(int cls, double flops, cudaStream_t st) {
 }
 void Engine::prof_end(cudaStream_t st) {
     if (!prof_on_) return;
+    if (--prof_depth_ > 0) return;
     cudaEventRecord(prof_.back().b, st);
 }
 void Engine::profile_read(int cls, double* ms, double* flops, long long* launches, int group) {
@@ -735,11 +763,14 @@ void Engine::bneck_bwd(Bottleneck& b, cudaStream_t st) {
     gxb->fresh = false;
     if (b.down) conv_dgrad(b.cd, grawd, Gx, true, st);
 }
-void Engine::backward(const float* dlogits, cudaStream_t st) {
+void Engine::backward(const float* dlogits, cudaStream_t st, int seg) {
     if (!grads_) throw std::runtime_error("engine bound without gradient buffers");
     if (!trained_forward_) throw std::runtime_error("backward() requires a preceding forward(train=1)");
+    if (seg < -1 || seg > 2) throw std::runtime_error("backward: segment must be -1 (all), 0, 1 or 2");
+    const bool all = seg < 0;
+    if (all || seg == 0) {
     k_zero(st, grads_, sizeof(float) * n_params_);
-    k_zero(st, bstats_arena_, sizeof(float) * bstats_floats_);
+    // (the backward BatchNorm partial-sum slots need no clearing: every producing block stores its slot and records the slot count)
     if (cfg_.dt == DT_BF16 && cfg_.use_tc) k_zero(st, dwp_arena_, sizeof(float) * dwp_floats_);
     for (auto& g : gradbufs_) g->fresh = true;
     // ---- final
@@ -781,8 +812,19 @@ void Engine::backward(const float* dlogits, cudaStream_t st) {
         conv_dgrad(center0_.c, graw0, gP0, false, st);
         gather_bwd(center_src_, gP0, st);
     }
-    for (int i = (int)blocks_.size() - 1; i >= 0; --i) { prof_group_ = blocks_[i]->group; block_bwd(*blocks_[i], st); }
-    for (int i = (int)bnecks_.size() - 1; i >= 0; --i) { prof_group_ = bnecks_[i]->group; bneck_bwd(*bnecks_[i], st); }
+    if (!all) unpack_all(st, 0);
+    }
+    // encoder blocks in reverse order; segment 1 = layer4 + layer3 (groups 4, 3), segment 2 = layer2 + layer1 (+ stem)
+    for (int i = (int)blocks_.size() - 1; i >= 0; --i) {
+        const int g = blocks_[i]->group;
+        if (all || (seg == 1 && g >= 3) || (seg == 2 && g <= 2)) { prof_group_ = g; block_bwd(*blocks_[i], st); }
+    }
+    for (int i = (int)bnecks_.size() - 1; i >= 0; --i) {
+        const int g = bnecks_[i]->group;
+        if (all || (seg == 1 && g >= 3) || (seg == 2 && g <= 2)) { prof_group_ = g; bneck_bwd(*bnecks_[i], st); }
+    }
+    if (seg == 1) unpack_all(st, 1);
+    if (all || seg == 2) {
     // ---- stem (no input gradient)
     prof_group_ = 0;
     {
@@ -794,7 +836,8 @@ void Engine::backward(const float* dlogits, cudaStream_t st) {
         k_bn_bwd_apply(st, G, raw, bn, true, graw);
         conv_wgrad(stem_, view(x4_), graw, st);
     }
-    unpack_all(st);
+    unpack_all(st, all ? 3 : 2);
+    }
 }
 void Engine::adam(float lr, float wd, float b1, float b2, float eps, int step, float grad_scale, cudaStream_t st) {
     if (!adam_m_ || !adam_v_ || !grads_) throw std::runtime_error("engine bound without optimiser state");

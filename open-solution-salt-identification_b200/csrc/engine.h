@@ -33,6 +33,7 @@ struct BNLayer {
     size_t o_gamma = 0, o_beta = 0, o_rm = 0, o_rv = 0;
     float *sums = nullptr, *bsums = nullptr;      // [SALT_STAT_SLOTS][2C] partial slots
     float *scale = nullptr, *shift = nullptr, *mean = nullptr, *invstd = nullptr, *cb = nullptr, *cc = nullptr;
+    int* bslots = nullptr;
 };
 struct SELayer {
     int C = 0, Cr = 0;
@@ -100,15 +101,23 @@ public:
     // same network, input given as raw u8 tiles [B][th][tw]: the loader's pad / normalise / depth-channel adapter is fused
     // into the stem's im2col
     void forward_tiles(const uint8_t* tiles, int B, const TileGeom& g, float* logits_nchw, bool train, cudaStream_t st);
-    void backward(const float* dlogits_nchw, cudaStream_t st);
+    // seg = -1: the whole backward pass.  seg = 0, 1, 2: one of three consecutive SEGMENTS (0: final + decoder + center, 1: encoder
+    // layer4 + layer3, 2: layer2 + layer1 + stem), called in that order; when segment k returns, the gradients of its parameters -
+    // the contiguous range grad_segment(k) of the flat buffer - are final, so a data-parallel caller can start their all-reduce
+    // while the next segment computes (reference models.py:81-82 reduces all gradients after backward)
+    void backward(const float* dlogits_nchw, cudaStream_t st, int seg = -1);
+    void grad_segment(int seg, size_t* offset, size_t* numel) const;
     void adam(float lr, float wd, float b1, float b2, float eps, int step, float grad_scale, cudaStream_t st);
     void mark_params_dirty() { packed_dirty_ = true; eval_coef_dirty_ = true; }
     // copy a named internal activation (NHWC T, border dropped) into fp32 NCHW; returns false if unknown
     bool get_activation(const std::string& name, float* out_nchw, int* shape4, cudaStream_t st);
 
     // ---- optional per-kernel-class timing with CUDA events on the launch stream (bench.py roofline)
-    enum ProfClass { PROF_CONV_FWD = 0, PROF_CONV_DGRAD = 1, PROF_CONV_WGRAD = 2, PROF_NCLASS = 3 };
+    enum ProfClass { PROF_CONV_FWD = SALT_PROF_CONV_FWD, PROF_CONV_DGRAD = SALT_PROF_CONV_DGRAD, PROF_CONV_WGRAD = SALT_PROF_CONV_WGRAD,
+                     PROF_NCLASS = SALT_PROF_NCLASS };
     void profile_enable(bool on);
+    void prof_begin(int cls, double work, cudaStream_t st);       // (public: called through the g_salt_prof_* hooks)
+    void prof_end(cudaStream_t st);
     // synchronises, then returns accumulated device time / algorithmic flops / launches since enable
     void profile_read(int cls, double* ms, double* flops, long long* launches, int group = -1);
     // layer groups of the profile records: 0 stem, 1-4 encoder layer1..layer4, 5 center, 6-10 dec5..dec1, 11 final
@@ -152,7 +161,7 @@ private:
     void conv_wgrad(ConvLayer& c, const Tensor& in, const Tensor& gout, cudaStream_t st);
     std::vector<ConvLayer*> all_convs();
     void build_pack_table();
-    void unpack_all(cudaStream_t st);
+    void unpack_all(cudaStream_t st, int table = 3);      // table 0-2: the convolutions of one backward segment, 3: all
     void gather_fwd(const std::vector<Source>& srcs, const Tensor& P, cudaStream_t st);
     void gather_bwd(const std::vector<Source>& srcs, const Tensor& gP, cudaStream_t st);
     void block_fwd(BasicBlock& b, bool train, cudaStream_t st);
@@ -175,7 +184,9 @@ private:
     // batched pack / unpack tables (device copies live in the workspace)
     PackDesc* d_pack_ = nullptr; int* d_pack_start_ = nullptr; int pack_layers_ = 0, pack_blocks_ = 0;
     int pack_max_rs_ = 1;
-    UnpackDesc* d_unpack_ = nullptr; int* d_unpack_start_ = nullptr; int unpack_layers_ = 0, unpack_blocks_ = 0, unpack_max_rs_ = 1;
+    UnpackDesc* d_unpack_[4] = {nullptr, nullptr, nullptr, nullptr}; int* d_unpack_start_[4] = {nullptr, nullptr, nullptr, nullptr};
+    int unpack_layers_[4] = {0, 0, 0, 0}, unpack_blocks_[4] = {0, 0, 0, 0}, unpack_max_rs_[4] = {1, 1, 1, 1};
+    size_t seg_bound_[4] = {0, 0, 0, 0};      // parameter offsets: segment 2 = [0, b1), segment 1 = [b1, b2), segment 0 = [b2, n_params)
     bool unpack_table_dirty_ = false;
     bool trained_forward_ = false;
     bool eval_coef_dirty_ = true;      // eval-mode BatchNorm (scale, shift) must be recomputed from the running statistics
@@ -214,8 +225,7 @@ private:
     int prof_group_ = 0;
     std::vector<ProfRec> prof_;
     bool prof_on_ = false;
-    void prof_begin(int cls, double flops, cudaStream_t st);
-    void prof_end(cudaStream_t st);
+    int prof_depth_ = 0;       // only the outermost scope of nested launchers is recorded
     void* split_scratch_ = nullptr; size_t split_elems_ = 0;      // fp32 TC parity mode: split-bf16 copy of the current conv input
     bool split_tc() const { return cfg_.dt == DT_F32 && cfg_.use_tc; }
     float* loss_scratch_ = nullptr;   // [max_batch + 8]

@@ -77,7 +77,8 @@ struct BNRef {                 // device pointers describing one BatchNorm layer
     float *rmean, *rvar;
     float *dgamma, *dbeta;
     float* sums;               // [SALT_STAT_SLOTS][2C] forward  per-CTA partials of sum(x), sum(x^2)
-    float* bsums;              // [SALT_STAT_SLOTS][2C] backward per-CTA partials of sum(g), sum(g*xhat)
+    float* bsums;              // [SALT_STAT_SLOTS_BWD][2C] backward per-block partials of sum(g), sum(g*xhat)
+    int* bslots;               // [1] number of slots the producing kernel of this backward pass wrote (= its grid)
     float *scale, *shift;      // y = x*scale + shift
     float *mean, *invstd;      // batch statistics of the last training forward
     float *cb, *cc;            // backward coefficients: g_raw = scale*(g - cb - cc*(x-mean))

@@ -153,7 +153,7 @@ __device__ __forceinline__ void block_reduce_slot(const Vf<N>& v, int cg, float*
 static inline int reduce_blocks(long long npix, int cg) {
     int lanes = EW_THREADS / cg;
     long long b = (npix + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
-    if (b > SALT_STAT_SLOTS) b = SALT_STAT_SLOTS;      // one partial slot per block (kernels.h); 2 blocks per SM
+    if (b > SALT_STAT_SLOTS_BWD) b = SALT_STAT_SLOTS_BWD;      // one partial slot per block (kernels.h); up to 8 blocks per SM
     if (b < 1) b = 1;
     return (int)b;
 }
@@ -205,6 +205,7 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, T* __restrict__ 
     stv(out + ((size_t)row * Wo + xo) * STEM_PATCH_C + cv * N, v);
 }
 void k_stem_im2col(cudaStream_t st, DType dt, const float* x, void* patches, int B, int H, int W) {
+    SaltProfScope prof_scope(SALT_PROF_OTHER, 0.0, st);
     SALT_COUNT(1);
     SALT_DISPATCH(dt, T, {
         dim3 grid(B * (H / 2), cdiv((W / 2) * (STEM_PATCH_C / VW<T>::N), EW_THREADS));
@@ -215,14 +216,26 @@ void k_stem_im2col(cudaStream_t st, DType dt, const float* x, void* patches, int
 // ------------------------------------------------------------------------------------------------
 // BatchNorm finalisation (nn.BatchNorm2d: eps 1e-5, momentum 0.1, biased var to normalise, unbiased to track)
 // ------------------------------------------------------------------------------------------------
-// Fixed-order sum of the partial slots of channel c = blockIdx.x*32 + threadIdx.x: thread row y adds slots y, y+8, ... in fp64,
-// then row 0 adds the 8 row sums in order.  Block = (32, 8).  Returns the two sums in row 0 (other rows return garbage).
+// Fixed-order sum of the partial slots of channel c = blockIdx.x*32 + threadIdx.x: thread row y adds slots y, y+32, ... in fp64
+// (all its loads are independent and issued together: the kernel costs about one memory round trip), then row 0 adds the 32 row
+// sums in order.  Block = (32, 32).  Returns the two sums in row 0 (other rows return garbage).
+#define SLOT_ROWS 32
 __device__ __forceinline__ void slot_sums(const float* __restrict__ part, int nslots, int C, int c, double& s0, double& s1) {
-    __shared__ double sm[8][2][32];
+    __shared__ double sm[SLOT_ROWS][2][32];
     double a = 0.0, b = 0.0;
     if (c < C) {
-#pragma unroll 4
-        for (int slot = threadIdx.y; slot < nslots; slot += 8) {
+        int slot = threadIdx.y;
+        for (; slot + 3 * SLOT_ROWS < nslots; slot += 4 * SLOT_ROWS) {
+            float va[4], vb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                va[u] = __ldcg(part + (size_t)(slot + u * SLOT_ROWS) * 2 * C + c);
+                vb[u] = __ldcg(part + (size_t)(slot + u * SLOT_ROWS) * 2 * C + C + c);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { a += (double)va[u]; b += (double)vb[u]; }
+        }
+        for (; slot < nslots; slot += SLOT_ROWS) {
             a += (double)__ldcg(part + (size_t)slot * 2 * C + c);
             b += (double)__ldcg(part + (size_t)slot * 2 * C + C + c);
         }
@@ -231,8 +244,8 @@ __device__ __forceinline__ void slot_sums(const float* __restrict__ part, int ns
     __syncthreads();
     s0 = 0.0; s1 = 0.0;
     if (threadIdx.y == 0) {
-#pragma unroll
-        for (int g = 0; g < 8; ++g) { s0 += sm[g][0][threadIdx.x]; s1 += sm[g][1][threadIdx.x]; }
+#pragma unroll 8
+        for (int g = 0; g < SLOT_ROWS; ++g) { s0 += sm[g][0][threadIdx.x]; s1 += sm[g][1][threadIdx.x]; }
     }
 }
 __global__ void stats_reduce_kernel(const float* __restrict__ part, int nslots, int C, double* __restrict__ out) {
@@ -243,7 +256,7 @@ __global__ void stats_reduce_kernel(const float* __restrict__ part, int nslots, 
 }
 void k_stats_reduce(cudaStream_t st, const float* stats, int nslots, int C, double* out) {
     SALT_COUNT(1);
-    stats_reduce_kernel<<<cdiv(C, 32), dim3(32, 8), 0, st>>>(stats, nslots, C, out);
+    stats_reduce_kernel<<<cdiv(C, 32), dim3(32, SLOT_ROWS), 0, st>>>(stats, nslots, C, out);
 }
 __global__ void bn_finalize_train_kernel(BNRef bn, int nslots, double count, float momentum, float eps) {
     const int c = blockIdx.x * 32 + threadIdx.x;
@@ -264,8 +277,9 @@ __global__ void bn_finalize_train_kernel(BNRef bn, int nslots, double count, flo
     bn.rvar[c] = (float)((1.0 - momentum) * bn.rvar[c] + momentum * unbiased);
 }
 void k_bn_finalize_train(cudaStream_t st, const BNRef& bn, int nslots, double count, float momentum, float eps) {
+    SaltProfScope prof_scope(SALT_PROF_BN_FINALIZE, 0.0, st);
     SALT_COUNT(1);
-    bn_finalize_train_kernel<<<cdiv(bn.C, 32), dim3(32, 8), 0, st>>>(bn, nslots, count, momentum, eps);
+    bn_finalize_train_kernel<<<cdiv(bn.C, 32), dim3(32, SLOT_ROWS), 0, st>>>(bn, nslots, count, momentum, eps);
 }
 __global__ void bn_finalize_eval_kernel(BNRef bn, float eps) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -276,13 +290,14 @@ __global__ void bn_finalize_eval_kernel(BNRef bn, float eps) {
     bn.shift[c] = bn.beta[c] - bn.rmean[c] * sc;
 }
 void k_bn_finalize_eval(cudaStream_t st, const BNRef& bn, float eps) {
+    SaltProfScope prof_scope(SALT_PROF_BN_FINALIZE, 0.0, st);
     SALT_COUNT(1);
     bn_finalize_eval_kernel<<<cdiv(bn.C, 128), 128, 0, st>>>(bn, eps);
 }
 __global__ void bn_bwd_finalize_kernel(BNRef bn, double count) {
     const int c = blockIdx.x * 32 + threadIdx.x;
     double sg, sgx;
-    slot_sums(bn.bsums, SALT_STAT_SLOTS, bn.C, c, sg, sgx);
+    slot_sums(bn.bsums, min(*bn.bslots, SALT_STAT_SLOTS_BWD), bn.C, c, sg, sgx);
     if (threadIdx.y != 0 || c >= bn.C) return;
     bn.dbeta[c] += (float)sg;
     bn.dgamma[c] += (float)sgx;
@@ -290,21 +305,22 @@ __global__ void bn_bwd_finalize_kernel(BNRef bn, double count) {
     bn.cc[c] = (float)(sgx / count * (double)bn.invstd[c]);
 }
 void k_bn_bwd_finalize(cudaStream_t st, const BNRef& bn, double count) {
+    SaltProfScope prof_scope(SALT_PROF_BN_FINALIZE, 0.0, st);
     SALT_COUNT(1);
-    bn_bwd_finalize_kernel<<<cdiv(bn.C, 32), dim3(32, 8), 0, st>>>(bn, count);
+    bn_bwd_finalize_kernel<<<cdiv(bn.C, 32), dim3(32, SLOT_ROWS), 0, st>>>(bn, count);
 }
 
 // ------------------------------------------------------------------------------------------------
 // BN apply (+ residual) (+ ReLU), optional replicate border on the output.  grid = (B*H rows, row blocks)
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void bn_apply_kernel(const T* __restrict__ raw, const float* __restrict__ scale, const float* __restrict__ shift,
+__global__ void __launch_bounds__(EW_THREADS, 2) bn_apply_kernel(const T* __restrict__ raw, const float* __restrict__ scale, const float* __restrict__ shift,
                                 const float* __restrict__ gate, const T* __restrict__ res, const float* __restrict__ rscale,
                                 const float* __restrict__ rshift, int relu, T* __restrict__ out, int nrows, int rows_per_block, int H,
                                 int W, int C, int pt, int pb, int pl, int pr) {
     // one block per `rows_per_block` image rows (and per slab of EW_THREADS channel groups when C is very wide); a thread keeps
     // ONE channel group (its scale/shift live in registers) and walks over the block's pixels in flat order, FOUR pixels per
-    // iteration so that 4 (8 with a residual) independent 16-byte loads are in flight per thread - the one-row / two-pixel version
+    // iteration so that 4 independent 16-byte loads are in flight per thread at 3 blocks per SM - the one-row / two-pixel version
     // ran at 1.9 TB/s, latency-bound (profiles/r1_launches_f_final.md).
     constexpr int N = VW<T>::N;
     const int cg = min(C / N, EW_THREADS), lanes = EW_THREADS / cg;
@@ -331,15 +347,25 @@ __global__ void bn_apply_kernel(const T* __restrict__ raw, const float* __restri
     };
     int q = blockIdx.x * rows_per_block * W + lane;
     for (; q + 3 * lanes < q_end; q += 4 * lanes) {
-        Vf<N> a[4], r[4];
+        if (res) {                                   // residual: 2 + 2 pixels (the same 4 loads in flight per half)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const size_t o = (size_t)(q + u * lanes) * C + c;
-            a[u] = ldv(raw + o);
-            r[u] = res ? ldv(res + o) : vzero<N>();
+            for (int h = 0; h < 2; ++h) {
+                Vf<N> a[2], r[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const size_t o = (size_t)(q + (2 * h + u) * lanes) * C + c;
+                    a[u] = ldv(raw + o); r[u] = ldv(res + o);
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) finish(q + (2 * h + u) * lanes, a[u], r[u]);
+            }
+        } else {
+            Vf<N> a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] = ldv(raw + (size_t)(q + u * lanes) * C + c);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) finish(q + u * lanes, a[u], vzero<N>());
         }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) finish(q + u * lanes, a[u], r[u]);
     }
     for (; q < q_end; q += lanes) {
         const size_t o = (size_t)q * C + c;
@@ -348,6 +374,7 @@ __global__ void bn_apply_kernel(const T* __restrict__ raw, const float* __restri
 }
 void k_bn_apply(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const Tensor* res,
                 const float* rscale, const float* rshift, bool relu, const Tensor& out, const float* gate) {
+    SaltProfScope prof_scope(SALT_PROF_BN_APPLY, (double)raw.bytes() * (res ? 2 : 1) + (double)out.bytes(), st);
     SALT_COUNT(1);
     SALT_DISPATCH(raw.dt, T, {
         const int nrows = raw.B * raw.H;
@@ -378,6 +405,7 @@ __global__ void bn_relu_avgpool_kernel(const T* __restrict__ raw, const float* _
     stv(out + ((size_t)row * Wo + x) * C + c, vscale(acc, 0.25f));
 }
 void k_bn_relu_avgpool(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const Tensor& out) {
+    SaltProfScope prof_scope(SALT_PROF_OTHER, (double)raw.bytes() + (double)out.bytes(), st);
     SALT_COUNT(1);
     SALT_DISPATCH(raw.dt, T, {
         dim3 grid(out.B * out.H, cdiv(out.W * (out.C / VW<T>::N), EW_THREADS));
@@ -396,6 +424,7 @@ __global__ void avgpool_bwd_kernel(const T* __restrict__ gout, T* __restrict__ g
     stv(gin + ((size_t)row * Wi + x) * C + c, vscale(ldv(gout + o), 0.25f));
 }
 void k_avgpool_bwd(cudaStream_t st, const Tensor& gout, const Tensor& gin) {
+    SaltProfScope prof_scope(SALT_PROF_OTHER, (double)gin.bytes() + (double)gout.bytes(), st);
     SALT_COUNT(1);
     SALT_DISPATCH(gin.dt, T, {
         dim3 grid(gin.B * gin.H, cdiv(gin.W * (gin.C / VW<T>::N), EW_THREADS));
@@ -469,6 +498,7 @@ __global__ void gather_fwd_kernel(T* __restrict__ out, GatherPlan a, int H, int 
     }
 }
 void k_gather_fwd(cudaStream_t st, const Tensor& out, const GatherSrc* srcs, int nsrc) {
+    SaltProfScope prof_scope(SALT_PROF_GATHER, 2.0 * (double)out.bytes(), st);
     SALT_COUNT(1);
     SALT_DISPATCH(out.dt, T, {
         GatherPlan a; a.n = nsrc; a.item0[0] = 0;
@@ -502,6 +532,7 @@ __global__ void fold_bwd_kernel(const T* __restrict__ gP, int c0, T* __restrict_
     stv(o, acc);
 }
 void k_fold_bwd(cudaStream_t st, const Tensor& gP, int c0, const Tensor& gsrc, bool accumulate) {
+    SaltProfScope prof_scope(SALT_PROF_GATHER_BWD, 2.0 * (double)gsrc.bytes(), st);
     SALT_COUNT(1);
     SALT_DISPATCH(gP.dt, T, {
         dim3 grid(gsrc.B * gsrc.H, cdiv(gsrc.W * (gsrc.C / VW<T>::N), EW_THREADS));
@@ -565,6 +596,7 @@ size_t upsample_bwd_tmp_floats(const Tensor& gP, int f, int Csrc) {
     return (size_t)gP.B * gP.Hp() * (gP.W / f) * Csrc;
 }
 void k_upsample_bwd(cudaStream_t st, const Tensor& gP, int c0, int f, const Tensor& gsrc, float* tmp, bool accumulate) {
+    SaltProfScope prof_scope(SALT_PROF_GATHER_BWD, (double)gP.bytes() * gsrc.C / gP.C + (double)gsrc.bytes(), st);
     SALT_COUNT(2);
     SALT_DISPATCH(gP.dt, T, {
         const int rowlen = (gP.W / f) * (gsrc.C / VW<T>::N);
@@ -720,6 +752,7 @@ static void launch_se_fc_bwd(cudaStream_t st, const SERef& se, int B, int HW) {
 }
 // encoder SE: squeeze bn(raw) (no ReLU) and compute the channel gates se.cse[n][c]
 void k_se_gate_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const SERef& se) {
+    SaltProfScope prof_scope(SALT_PROF_SCSE, (double)raw.bytes(), st);
     SALT_COUNT(2);
     SALT_DISPATCH(raw.dt, T, (launch_se_pool<T, false, false>(st, raw, nullptr, scale, shift, se)));
     launch_se_fc(st, se, raw.B, raw.H * raw.W);
@@ -727,6 +760,7 @@ void k_se_gate_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const
 // encoder SE backward: g = gradient w.r.t. u*cse (already ReLU-masked); accumulates the FC gradients and leaves
 // se.G[n][c] = the per-(image, channel) term that the gap path adds to d loss / d u
 void k_se_gate_bwd(cudaStream_t st, const Tensor& g, const Tensor& raw, const float* scale, const float* shift, const SERef& se) {
+    SaltProfScope prof_scope(SALT_PROF_SCSE, 2.0 * (double)raw.bytes(), st);
     SALT_COUNT(3);
     SALT_DISPATCH(raw.dt, T, (launch_se_pool<T, true, false>(st, raw, g.p, scale, shift, se)));
     launch_se_fc_bwd(st, se, raw.B, raw.H * raw.W);
@@ -752,6 +786,7 @@ __global__ void scse_apply_kernel(const T* __restrict__ raw, const float* __rest
     if (ok) stv8(out + (size_t)pix * C + c, vrelu(vmul(z, gate)));
 }
 void k_scse_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const SERef& se, const Tensor& out) {
+    SaltProfScope prof_scope(SALT_PROF_SCSE, 3.0 * (double)raw.bytes(), st);
     SALT_COUNT(3);
     const int HW = raw.H * raw.W, C = raw.C;
     const unsigned npix = (unsigned)raw.B * HW;
@@ -764,7 +799,7 @@ void k_scse_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const fl
 }
 
 template <typename T>
-__global__ void scse_bwd_apply_kernel(const T* __restrict__ gout, const T* __restrict__ raw, BNRef bn, SERef se,
+__global__ void __launch_bounds__(EW_THREADS, 2) scse_bwd_apply_kernel(const T* __restrict__ gout, const T* __restrict__ raw, BNRef bn, SERef se,
                                       T* __restrict__ gbn, unsigned npix, int HW, int C) {
     constexpr int N = 8;
     __shared__ float red[N * EW_THREADS];
@@ -818,6 +853,7 @@ __global__ void scse_bwd_apply_kernel(const T* __restrict__ gout, const T* __res
     }
     block_reduce_slot<N>(sg, cg, bn.bsums + (size_t)blockIdx.x * 2 * C, red);
     block_reduce_slot<N>(sgx, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + C, red);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *bn.bslots = (int)gridDim.x;
     block_reduce_add<N, float>(sws, cg, se.dws, red);
     red[threadIdx.x] = sbs;
     __syncthreads();
@@ -828,6 +864,7 @@ __global__ void scse_bwd_apply_kernel(const T* __restrict__ gout, const T* __res
     }
 }
 void k_scse_bwd(cudaStream_t st, const Tensor& gout, const Tensor& raw, const BNRef& bn, const SERef& se, const Tensor& gbn) {
+    SaltProfScope prof_scope(SALT_PROF_SCSE, 5.0 * (double)raw.bytes(), st);
     SALT_COUNT(4);
     const int HW = raw.H * raw.W, C = raw.C;
     const unsigned npix = (unsigned)raw.B * HW;
@@ -861,6 +898,7 @@ __global__ void final_fwd_kernel(const T* __restrict__ raw, const float* __restr
 }
 void k_final_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const float* w, const float* b,
                  int K, float* logits) {
+    SaltProfScope prof_scope(SALT_PROF_OTHER, (double)raw.bytes(), st);
     SALT_COUNT(1);
     const unsigned npix = (unsigned)raw.B * raw.H * raw.W;
     const int cg = raw.C / 8;
@@ -911,6 +949,7 @@ __global__ void final_bwd_kernel(const float* __restrict__ dlogits, const T* __r
     }
     block_reduce_slot<N>(sg, cg, bn.bsums + (size_t)blockIdx.x * 2 * C, red);
     block_reduce_slot<N>(sgx, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + C, red);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *bn.bslots = (int)gridDim.x;
     for (int k = 0; k < K; ++k) block_reduce_add<N, float>(sdw[k], cg, dw + k * C, red);
     for (int k = 0; k < K; ++k) {
         red[threadIdx.x] = sdb[k];
@@ -925,6 +964,7 @@ __global__ void final_bwd_kernel(const float* __restrict__ dlogits, const T* __r
 }
 void k_final_bwd(cudaStream_t st, const float* dlogits, const Tensor& raw, const BNRef& bn, const float* w, int K,
                  float* dw, float* db, const Tensor& gbn) {
+    SaltProfScope prof_scope(SALT_PROF_OTHER, 2.0 * (double)raw.bytes(), st);
     SALT_COUNT(1);
     const unsigned npix = (unsigned)raw.B * raw.H * raw.W;
     const int HW = raw.H * raw.W;
@@ -947,6 +987,7 @@ __global__ void relu_mask_inplace_kernel(T* __restrict__ g, const T* __restrict_
     stv(g + (size_t)idx * N, vmaskpos(ldv(g + (size_t)idx * N), ldv(mask + (size_t)idx * N)));
 }
 void k_relu_mask_inplace(cudaStream_t st, const Tensor& g, const Tensor& mask) {
+    SaltProfScope prof_scope(SALT_PROF_OTHER, 3.0 * (double)g.bytes(), st);
     SALT_COUNT(1);
     SALT_DISPATCH(g.dt, T, {
         const unsigned nvec = (unsigned)(g.numel() / VW<T>::N);
@@ -956,7 +997,7 @@ void k_relu_mask_inplace(cudaStream_t st, const Tensor& g, const Tensor& mask) {
 // upstream gradient seen by a BN layer: g, optionally gated per (image, channel): g*gate[n][c] + addc[n][c] (encoder SE),
 // optionally masked by the layer's own ReLU.  grid = (pixel blocks, channel slabs)
 template <typename T>
-__global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ raw, BNRef bn, int self_mask,
+__global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restrict__ raw, BNRef bn, int self_mask,
                                      const float* __restrict__ gate, const float* __restrict__ addc, unsigned npix, int HW, int C) {
     constexpr int N = VW<T>::N;
     __shared__ float red[N * EW_THREADS];
@@ -973,24 +1014,26 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ g, const T* __restric
         sg = vadd(sg, gv);
         sgx = vfma(gv, vxhat(x, mu, is), sgx);
     };
-    // 4 pixels = 8 independent 16-byte loads in flight per thread: with <= 2 blocks per SM (one partial-sum slot per block) a
-    // one-pixel loop left the kernel latency-bound at 1.9 TB/s (profiles/r1_launches_f_final.md)
+    // 2 pixels = 4 independent 16-byte loads in flight per thread, 3 blocks per SM (a 4-pixel version needed 149 registers: one
+    // block per SM, no faster; the one-pixel loop with <= 2 blocks per SM ran at 1.9 TB/s - profiles/r2_notes.md)
     const unsigned step = gridDim.x * lanes;
     unsigned pix = blockIdx.x * lanes + lane;
-    for (; pix + 3 * step < npix; pix += 4 * step) {
-        Vf<N> xs[4], gs[4];
+    for (; pix + step < npix; pix += 2 * step) {
+        Vf<N> xs[2], gs[2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { xs[u] = ldv(raw + (size_t)(pix + u * step) * C + c); gs[u] = ldv(g + (size_t)(pix + u * step) * C + c); }
+        for (int u = 0; u < 2; ++u) { xs[u] = ldv(raw + (size_t)(pix + u * step) * C + c); gs[u] = ldv(g + (size_t)(pix + u * step) * C + c); }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) accumulate(pix + u * step, xs[u], gs[u]);
+        for (int u = 0; u < 2; ++u) accumulate(pix + u * step, xs[u], gs[u]);
     }
     for (; pix < npix; pix += step) accumulate(pix, ldv(raw + (size_t)pix * C + c), ldv(g + (size_t)pix * C + c));
     const int coff = blockIdx.y * cg * N;
     block_reduce_slot<N>(sg, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + coff, red);
     block_reduce_slot<N>(sgx, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + C + coff, red);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *bn.bslots = (int)gridDim.x;
 }
 void k_bn_bwd_reduce(cudaStream_t st, const Tensor& g, const Tensor& raw, const BNRef& bn, bool self_mask, const float* gate,
                      const float* addc) {
+    SaltProfScope prof_scope(SALT_PROF_BN_BWD_REDUCE, 2.0 * (double)raw.bytes(), st);
     SALT_COUNT(1);
     const unsigned npix = (unsigned)raw.B * raw.H * raw.W;
     SALT_DISPATCH(raw.dt, T, {
@@ -1001,7 +1044,7 @@ void k_bn_bwd_reduce(cudaStream_t st, const Tensor& g, const Tensor& raw, const 
     });
 }
 template <typename T>
-__global__ void bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict__ raw, BNRef bn, int self_mask,
+__global__ void __launch_bounds__(EW_THREADS, 2) bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict__ raw, BNRef bn, int self_mask,
                                     const float* __restrict__ gate, const float* __restrict__ addc, T* __restrict__ graw,
                                     unsigned npix, int HW, int C) {
     // a thread keeps ONE channel group (5 per-channel coefficient vectors in registers) and strides over pixels
@@ -1023,17 +1066,18 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, const T* __restrict
     };
     const unsigned step = gridDim.x * lanes;
     unsigned pix = blockIdx.x * lanes + lane;
-    for (; pix + 3 * step < npix; pix += 4 * step) {           // 8 independent 16-byte loads in flight per thread
-        Vf<N> xs[4], gs[4];
+    for (; pix + step < npix; pix += 2 * step) {           // 4 independent 16-byte loads in flight per thread, 3 blocks per SM
+        Vf<N> xs[2], gs[2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { xs[u] = ldv(raw + (size_t)(pix + u * step) * C + c); gs[u] = ldv(g + (size_t)(pix + u * step) * C + c); }
+        for (int u = 0; u < 2; ++u) { xs[u] = ldv(raw + (size_t)(pix + u * step) * C + c); gs[u] = ldv(g + (size_t)(pix + u * step) * C + c); }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) finish(pix + u * step, xs[u], gs[u]);
+        for (int u = 0; u < 2; ++u) finish(pix + u * step, xs[u], gs[u]);
     }
     for (; pix < npix; pix += step) finish(pix, ldv(raw + (size_t)pix * C + c), ldv(g + (size_t)pix * C + c));
 }
 void k_bn_bwd_apply(cudaStream_t st, const Tensor& g, const Tensor& raw, const BNRef& bn, bool self_mask, const Tensor& graw,
                     const float* gate, const float* addc) {
+    SaltProfScope prof_scope(SALT_PROF_BN_BWD_APPLY, 3.0 * (double)raw.bytes(), st);
     SALT_COUNT(1);
     SALT_DISPATCH(raw.dt, T, {
         const unsigned npix = (unsigned)raw.B * raw.H * raw.W;

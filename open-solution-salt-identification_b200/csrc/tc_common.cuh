@@ -159,23 +159,31 @@ __device__ __forceinline__ void epi_pack32(const float* v, uint4* pk) {
         pk[q].z = *reinterpret_cast<uint32_t*>(&b2); pk[q].w = *reinterpret_cast<uint32_t*>(&b3);
     }
 }
+// 256-bit global store (sm_100: STG.256): a thread's 32 bf16 channels leave in two full 32-byte sectors instead of four half
+// sectors - the epilogue's scattered 16-byte stores were what bounded the K = 576 layers (profiles/r2_notes.md).  32-byte aligned.
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* r) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 // store 32 channels of one pixel to every physical position it owns: rows py0..py1, columns px0..px1 (one position unless on a border)
 __device__ __forceinline__ void epi_store32(const float* v, bf16* obase, int py0, int py1, int px0, int px1, int Wp, int Co) {
     uint4 pk[4];
     epi_pack32(v, pk);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(pk);
     for (int yy = py0; yy <= py1; ++yy)
         for (int xx = px0; xx <= px1; ++xx) {
-            uint4* o4 = reinterpret_cast<uint4*>(obase + ((size_t)yy * Wp + xx) * Co);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) o4[q] = pk[q];
+            bf16* o = obase + ((size_t)yy * Wp + xx) * Co;
+            st_global_256(o, w);
+            st_global_256(o + 16, w + 8);
         }
 }
 __device__ __forceinline__ void epi_store32(const float* v, float* obase, int py0, int py1, int px0, int px1, int Wp, int Co) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(v);
     for (int yy = py0; yy <= py1; ++yy)
         for (int xx = px0; xx <= px1; ++xx) {
-            float4* o4 = reinterpret_cast<float4*>(obase + ((size_t)yy * Wp + xx) * Co);
+            float* o = obase + ((size_t)yy * Wp + xx) * Co;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) o4[q] = make_float4(v[q * 4 + 0], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            for (int q = 0; q < 4; ++q) st_global_256(o + 8 * q, w + 8 * q);
         }
 }
 

@@ -51,6 +51,8 @@ PROTOTYPES = {
     'salt_loss_bce_dice_reduce': (_i, [_vp, _fp, _fp, _i, _dp, _vp]),
     'salt_loss_bce_dice_finish': (_i, [_vp, _fp, _fp, _i, _dp, C.c_double, _f, _fp, _fp, _vp]),
     'salt_backward': (_i, [_vp, _fp, _vp]),
+    'salt_backward_segment': (_i, [_vp, _fp, _i, _vp]),
+    'salt_grad_segment': (_i, [_vp, _i, C.POINTER(_sz), C.POINTER(_sz)]),
     'salt_adam_step': (_i, [_vp, _f, _f, _f, _f, _f, _i, _f, _vp]),
     'salt_predict': (_i, [_vp, _fp, _fp, _i, _i, _f, _fp, _vp, _vp]),
     'salt_adapt_tiles': (_i, [_vp, _i, _i, _i, _i, _f, _f, _i, _fp, _vp]),

@@ -61,6 +61,15 @@ class DataParallelContext:
         dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=self.group)
         return 1.0 / self.world
 
+    def allreduce_async(self, tensor):
+        """Start an in-place SUM all-reduce of one gradient bucket and return its handle (``.wait()`` makes the current stream wait).
+        NCCL runs it on the process group's own stream, ordered after the work already queued on the current stream, so the
+        kernels launched next (the following backward segment) overlap it."""
+        if self.world == 1:
+            return None
+        import torch.distributed as dist
+        return dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
     def gather_rows(self, *arrays):
         """Concatenate per-rank numpy arrays along axis 0 in rank order on every rank (validation counts: the images of a
         validation epoch are sharded across ranks, the threshold sweep needs all of them; a few KB, once per epoch)."""

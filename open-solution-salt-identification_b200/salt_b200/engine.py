@@ -165,6 +165,19 @@ class UNetEngine:
     def backward(self, dlogits):
         _lib.check(self.lib.salt_backward(self.h, _ptr(dlogits), self._stream()))
 
+    N_SEGMENTS = 3
+
+    def backward_segment(self, dlogits, segment):
+        """One of the three consecutive segments of the backward pass (0: final + decoder + center, 1: layer4 + layer3,
+        2: layer2 + layer1 + stem); afterwards ``grad_segment(segment)`` of the flat gradient buffer is final."""
+        _lib.check(self.lib.salt_backward_segment(self.h, _ptr(dlogits), int(segment), self._stream()))
+
+    def grad_segment(self, segment):
+        """Flat view of the gradients that ``backward_segment(segment)`` completes (a contiguous range of ``self.grads``)."""
+        off, n = C.c_size_t(), C.c_size_t()
+        _lib.check(self.lib.salt_grad_segment(self.h, int(segment), C.byref(off), C.byref(n)))
+        return self.grads[off.value:off.value + n.value]
+
     def adam_step(self, lr=1e-4, weight_decay=1e-4, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
         self.step_count += 1
         _lib.check(self.lib.salt_adam_step(self.h, lr, weight_decay, betas[0], betas[1], eps, self.step_count,
@@ -189,6 +202,17 @@ class UNetEngine:
             ms, fl, n = C.c_double(), C.c_double(), C.c_longlong()
             _lib.check(self.lib.salt_profile_read(self.h, cls, C.byref(ms), C.byref(fl), C.byref(n)))
             out[name] = (ms.value, fl.value, n.value)
+        return out
+
+    PASS_CLASSES = ('bn_apply', 'bn_bwd_reduce', 'bn_bwd_apply', 'bn_finalize', 'gather_fwd', 'gather_bwd', 'scse', 'other')
+
+    def profile_read_passes(self):
+        """{class: (ms, algorithmic bytes, launches)} for the memory-bound passes since profile(True)."""
+        out = {}
+        for i, name in enumerate(self.PASS_CLASSES):
+            ms, by, n = C.c_double(), C.c_double(), C.c_longlong()
+            _lib.check(self.lib.salt_profile_read(self.h, 3 + i, C.byref(ms), C.byref(by), C.byref(n)))
+            out[name] = (ms.value, by.value, n.value)
         return out
 
     PROFILE_GROUPS = ('stem', 'layer1', 'layer2', 'layer3', 'layer4', 'center', 'dec5', 'dec4', 'dec3', 'dec2', 'dec1', 'final')

@@ -448,9 +448,19 @@ class SegmentationModel(Model):
             with torch.cuda.graph(gf, capture_error_mode=mode):
                 eng.forward(st['x'][:b], train=True, out=st['logits'][:b])
             n1 = _lib.launch_count()
-            gb = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gb, capture_error_mode=mode):
-                eng.backward(st['dlogits'][:b])
+            if self.dp.world > 1:
+                # data parallel: one graph per backward segment, so that each segment's gradient bucket can be all-reduced
+                # (NCCL, side stream) while the next segment computes - SURVEY.md 8(e)
+                gb = []
+                for seg in range(eng.N_SEGMENTS):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, capture_error_mode=mode):
+                        eng.backward_segment(st['dlogits'][:b], seg)
+                    gb.append(g)
+            else:
+                gb = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gb, capture_error_mode=mode):
+                    eng.backward(st['dlogits'][:b])
             n2 = _lib.launch_count()
         except Exception as exc:                  # pragma: no cover - depends on driver / NCCL state
             import warnings
@@ -479,9 +489,18 @@ class SegmentationModel(Model):
         if weight != 1.0:
             batch_loss = batch_loss * weight
             st['dlogits'][:b].mul_(weight)
-        gb.replay()
+        if isinstance(gb, list):
+            works = []
+            for seg, g in enumerate(gb):
+                g.replay()
+                works.append(self.dp.allreduce_async(eng.grad_segment(seg)))       # overlaps the next segment's kernels
+            for w in works:
+                w.wait()
+            scale = 1.0 / self.dp.world
+        else:
+            gb.replay()
+            scale = self.dp.allreduce_grads(eng.grads)
         _lib.count_replayed(nf + nb)
-        scale = self.dp.allreduce_grads(eng.grads)
         self.optimizer.step(grad_scale=scale)
         return {'sum': batch_loss}
 
@@ -508,8 +527,17 @@ class SegmentationModel(Model):
         batch_loss = loss_function(outputs_batch, target) * weight
         partial_batch_losses['sum'] = batch_loss
         dlogits = loss_function.dlogits if weight == 1.0 else loss_function.dlogits * weight
-        self.engine.backward(dlogits)
-        scale = self.dp.allreduce_grads(self.engine.grads)
+        if self.dp.world > 1:
+            works = []
+            for seg in range(self.engine.N_SEGMENTS):
+                self.engine.backward_segment(dlogits, seg)
+                works.append(self.dp.allreduce_async(self.engine.grad_segment(seg)))
+            for w in works:
+                w.wait()
+            scale = 1.0 / self.dp.world
+        else:
+            self.engine.backward(dlogits)
+            scale = 1.0
         self.optimizer.step(grad_scale=scale)
         return partial_batch_losses
 

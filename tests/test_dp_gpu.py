@@ -1,0 +1,155 @@
+"""GPU: data-parallel training semantics of the engine.
+
+* the segmented backward pass (salt_backward_segment: 3 consecutive segments, each completing a contiguous bucket of the flat gradient
+  buffer so that its all-reduce can overlap the next segment) gives the gradients of the one-call backward;
+* 2 ranks x 64 images == what nn.DataParallel computes for a 128-image batch on 2 devices (reference models.py:81-85): per-replica
+  BatchNorm statistics, gradients summed over replicas, loss = mean over all images, running statistics of replica 0.  Needs 2 GPUs
+  (`gpurun --gpus 2`); skipped on a single-GPU box.
+"""
+import json
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+from oracle import synth            # noqa: E402
+
+
+def _engine(*a, **k):
+    from salt_b200.engine import UNetEngine
+    return UNetEngine(*a, **k)
+
+
+@pytest.mark.parametrize('depth,prec', [(34, 'bf16'), (18, 'fp32'), (50, 'bf16')])
+def test_segmented_backward_equals_backward(depth, prec):
+    b, s = 4, 128
+    sd_np = synth.synth_state_dict(depth, 2, 0)
+    x = torch.from_numpy(synth.synth_inputs(b, s, 5)).cuda()
+    t = torch.from_numpy(synth.synth_targets(b, s, 5)).cuda()
+    eng = _engine(depth, 2, b, s, precision=prec)
+    eng.load_state(sd_np)
+    logits = eng.forward(x, train=True)
+    _, dl = eng.loss_lovasz(logits, t)
+    eng.backward(dl)
+    torch.cuda.synchronize()
+    whole = eng.grads.clone()
+    eng.grads.fill_(float('nan'))
+    covered = torch.zeros_like(whole, dtype=torch.bool)
+    for seg in range(eng.N_SEGMENTS):
+        eng.backward_segment(dl, seg)
+        torch.cuda.synchronize()
+        gs = eng.grad_segment(seg)
+        lo = gs.data_ptr() - eng.grads.data_ptr()
+        assert lo % 4 == 0
+        lo //= 4
+        assert not covered[lo:lo + gs.numel()].any(), 'segments overlap'
+        covered[lo:lo + gs.numel()] = True
+        # the bucket is final as soon as its segment returns
+        ref = whole[lo:lo + gs.numel()]
+        err = (gs - ref).abs().max().item() / (ref.abs().max().item() + 1e-30)
+        print('segment %d: %d floats, max deviation from the one-call backward %.3e of the largest gradient' % (seg, gs.numel(), err))
+        assert torch.isfinite(gs).all() and err <= 1e-5
+    assert covered.all(), 'the three segments must cover the whole flat gradient buffer'
+
+
+WORKER = textwrap.dedent('''
+    import os, sys, json
+    ROOT = %r
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'open-solution-salt-identification_b200'))
+    import numpy as np, torch
+    os.environ['SALT_ENGINE_PRECISION'] = 'bf16'; os.environ['SALT_ENGINE_MAX_BATCH'] = '64'; os.environ['SALT_ENGINE_SIZE'] = '128'
+    os.environ['SALT_ENGINE_LOSS'] = 'lovasz'
+    from salt_b200 import synthetic as synth
+    from salt_b200.models import SegmentationModel
+    arch = {'model_params': {'architecture': 'UNetResNet', 'encoder_depth': 34, 'in_channels': 3, 'out_channels': 2, 'activation': 'sigmoid'},
+            'optimizer_params': {'lr': 1e-4}, 'regularizer_params': {'regularize': True, 'weight_decay_conv2d': 1e-4}}
+    model = SegmentationModel(arch, {'epochs': 1}, {})
+    ctx, eng = model.dp, model.engine
+    assert ctx.world == 2
+    eng.load_state(synth.synth_state_dict(34, 2, 0))
+    losses = []
+    for step in range(4):                      # steps 0-1 eager, 2-3 through the captured graphs
+        x = torch.from_numpy(synth.synth_inputs(128, 128, 100 + step)); t = torch.from_numpy(synth.synth_targets(128, 128, 100 + step))
+        lo, hi = ctx.shard(128)
+        out = model.train_step_device(x[lo:hi].to(eng.device), [t[lo:hi].to(eng.device)])
+        losses.append(float(out['sum'].cpu()[0]))
+    torch.cuda.synchronize()
+    np.save(os.path.join(sys.argv[1], 'params_rank%%d.npy' %% ctx.rank), eng.params.cpu().numpy())
+    np.save(os.path.join(sys.argv[1], 'buffers_rank%%d.npy' %% ctx.rank), eng.buffers.cpu().numpy())
+    print(json.dumps(dict(rank=ctx.rank, losses=losses, graphs=sorted(model._graph_state()['graphs']))))
+    torch.distributed.destroy_process_group()
+''') % ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (gpurun --gpus 2)')
+def test_two_ranks_equal_dataparallel_semantics(tmp_path):
+    script = tmp_path / 'worker.py'
+    script.write_text(WORKER)
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
+                        '--master-port', str(_free_port()), str(script), str(tmp_path)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    outs = [json.loads(l) for l in r.stdout.splitlines() if l.startswith('{')]
+    assert len(outs) == 2 and outs[0]['graphs'] == [64], outs
+    p0, p1 = np.load(tmp_path / 'params_rank0.npy'), np.load(tmp_path / 'params_rank1.npy')
+    assert np.array_equal(p0, p1), 'replicas diverged'
+    # single-GPU emulation of nn.DataParallel: the two shards go through the SAME engine one after the other (per-replica BatchNorm
+    # statistics), their gradients are added, Adam sees the mean
+    eng = _engine(34, 2, 64, 128, precision='bf16')
+    eng.load_state(synth.synth_state_dict(34, 2, 0))
+    ref_losses = []
+    for step in range(4):
+        x = torch.from_numpy(synth.synth_inputs(128, 128, 100 + step)).cuda()
+        t = torch.from_numpy(synth.synth_targets(128, 128, 100 + step)).cuda()
+        acc, ls, bufs0 = None, [], None
+        start_buffers = eng.buffers.clone()
+        for sh in range(2):
+            eng.buffers.copy_(start_buffers)                    # every replica starts from the same running statistics
+            logits = eng.forward(x[sh * 64:(sh + 1) * 64].contiguous(), train=True)
+            loss, dl = eng.loss_lovasz(logits, t[sh * 64:(sh + 1) * 64].contiguous())
+            eng.backward(dl)
+            ls.append(loss.item())
+            acc = eng.grads.clone() if acc is None else acc + eng.grads
+            if sh == 0:
+                bufs0 = eng.buffers.clone()                     # DataParallel keeps replica 0's running statistics
+        eng.grads.copy_(acc)
+        eng.buffers.copy_(bufs0)
+        eng.adam_step(grad_scale=0.5)
+        ref_losses.append(ls)
+    torch.cuda.synchronize()
+    ref = eng.params.cpu().numpy()
+    init = np.zeros_like(ref)
+    e0 = _engine(34, 2, 1, 128, precision='bf16', training=False)
+    e0.load_state(synth.synth_state_dict(34, 2, 0))
+    init = e0.params.cpu().numpy()
+    moved = np.abs(ref - init)
+    err = np.abs(p0 - ref)
+    sel = moved > 1e-6
+    frac = float((err[sel] > 0.3 * moved[sel]).mean())
+    print('2-rank vs sequential-shard emulation: max |dp| %.3e, max err %.3e, parameters off by > 30 %% of their own movement: %.4f %%'
+          % (moved.max(), err.max(), 100 * frac))
+    # per-rank losses are the shard losses of the emulation (rank r <-> shard r) up to the wgrad summation order of earlier steps
+    for r_ in outs:
+        got = r_['losses']
+        want = [l[r_['rank']] for l in ref_losses]
+        assert np.allclose(got, want, rtol=5e-3, atol=1e-4), (got, want)
+    # the first Adam steps are ~ lr * sign(g): elements whose tiny gradient changes sign with the fp32 summation order may differ by 2 lr
+    assert frac <= 0.02 and err.max() <= 4 * 4 * 1e-4
+    b0 = np.load(tmp_path / 'buffers_rank0.npy')
+    assert np.allclose(b0, eng.buffers.cpu().numpy(), rtol=2e-2, atol=2e-3)
