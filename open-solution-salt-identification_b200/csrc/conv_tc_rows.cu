@@ -63,6 +63,9 @@ struct RowsParams {
     int m_tiles, total_groups;  // cluster mode: a group = CL consecutive pixel tiles of one channel tile (one per CTA of the cluster)
     int B, Ho, Wo, Co, Ca, cblks, pad;
     int accumulate;
+    int ksteps;                // K = 16 steps per tap and 64-channel block that carry data: 4, or 2 for a 32-channel input (the TMA
+                               // box is still 64 channels wide - channels 32..63 are out of bounds and zero-filled - so the layout,
+                               // the descriptors and the byte counts are unchanged; the two all-zero K steps are simply not issued)
     int split_c;               // fp32-output instantiations: channels of ONE operand term (stages with cb*64 < split_c hold the h*h products)
     const float* bias;
     float* stats;              // [SALT_STAT_SLOTS_CONV][2*Co] partial slots, slot = blockIdx.x
@@ -456,7 +459,8 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         const uint64_t bdesc = bdesc0 + soff + (uint64_t)((r * Cfg::B_BYTES) >> 4);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            if (r == 2 && k == 2) {      // 10 of 12 issued: probe what the next iteration will need
+                            if (k >= p.ksteps) break;
+                            if (r == 2 && k == p.ksteps - 2) {      // all but the last two issued: probe what the next iteration will need
                                 if (!last || more) probe_stage = mbar_try_wait(full0 + 8 * nstage, nphase) ? 1u : 0u;
                                 if (last && more) probe_acc = mbar_try_wait(tempty0 + 8 * nacc, nacc_phase ^ 1) ? 1u : 0u;
                             }
@@ -633,7 +637,7 @@ conv_tc_rows_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 }
 
 bool tc_conv_rows_supported(int Ca, int Nout, int R, int S, int stride, int Ho, int Wo) {
-    return R == 3 && S == 3 && stride == 1 && Ca % 64 == 0 && Nout % 32 == 0 && Ho >= 16 && Wo >= 8;
+    return R == 3 && S == 3 && stride == 1 && (Ca % 64 == 0 || Ca == 32) && Nout % 32 == 0 && Ho >= 16 && Wo >= 8;
 }
 
 // largest number of 2-CTA clusters of this kernel that can be resident at once (persistent grid = that many clusters)
@@ -771,7 +775,8 @@ void k_conv_tc_rows(cudaStream_t st, const void* A, int B, int Ha, int Wa, int C
     if (!out_f32 && rows_wide_pref() && BN == 64) { if (Nout % 192 == 0) BN = 192; else if (Nout % 160 == 0) BN = 160; }
     p.tiles_co = Nout / BN;
     p.total_tiles = p.tiles_x * p.tiles_y * B * p.tiles_co;
-    p.B = B; p.Ho = Ho; p.Wo = Wo; p.Co = Nout; p.Ca = Ca; p.cblks = Ca / 64; p.pad = pad;
+    p.B = B; p.Ho = Ho; p.Wo = Wo; p.Co = Nout; p.Ca = Ca; p.cblks = cdiv(Ca, 64); p.pad = pad;
+    p.ksteps = Ca == 32 ? 2 : 4;
     p.accumulate = accumulate ? 1 : 0; p.bias = bias; p.stats = stats; p.out = out; p.split_c = split_c;
     CUtensorMap ma = make_map_nhwc(A, Ca, Wa, Ha, B, 64, RW_TW, RW_TH + 2, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B);
     p.m_tiles = p.tiles_x * p.tiles_y * B; p.total_groups = 0;
@@ -781,7 +786,7 @@ void k_conv_tc_rows(cudaStream_t st, const void* A, int B, int Ha, int Wa, int C
         else launch_rows_any<32, float>(st, ma, Wp, Ca, Nout, p);
         return;
     }
-    if (BN == 128 && rows_pair_pref()) {
+    if (BN == 128 && rows_pair_pref() && Ca % 64 == 0) {
         // >= 128 output channels: the CTA-pair kernel (half the weight bytes per SM; N = 256 tiles when the layer has them)
         if (Nout % 256 == 0) {
             RowsParams q = p; q.tiles_co = Nout / 256; q.total_tiles = q.tiles_x * q.tiles_y * B * q.tiles_co;

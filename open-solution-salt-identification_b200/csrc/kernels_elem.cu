@@ -115,40 +115,66 @@ template <int N> __device__ __forceinline__ Vf<N> vxhat(const Vf<N>& x, const Vf
     for (int i = 0; i < N; ++i) r.v[i] = (x.v[i] - mu.v[i]) * is.v[i];
     return r; }
 
-// Sum a per-thread vector over the threads that share a channel group (tid % cg) and add it to dst[c..].
-template <int N, typename D>
-__device__ __forceinline__ void block_reduce_add(const Vf<N>& v, int cg, D* dst, float* red) {
-    const int tid = threadIdx.x;
+// Block sum of a per-thread vector over the threads that share a channel group (tid % cg; cg a power of two).  Fixed order:
+// warp shuffles over the lanes of a warp that share the group (xor offsets cg, 2cg, ...), then the 8 warps through shared memory
+// in warp order - no atomics, bit-reproducible, and ~20 instructions instead of the 32-step serial shared-memory loop whose tail
+// made every extra block of the reduction passes expensive (profiles/r2_notes.md).  The result is valid in threads tid < cg.
+template <int N>
+__device__ __forceinline__ void block_sum(Vf<N>& v, int cg, float* red) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = EW_THREADS / 32;
+    if (cg < 32) {
+        for (int off = cg; off < 32; off <<= 1) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) red[i * EW_THREADS + tid] = v.v[i];
-    __syncthreads();
-    if (tid < cg) {
+            for (int i = 0; i < N; ++i) v.v[i] += __shfl_xor_sync(0xffffffffu, v.v[i], off);
+        }
+        if (lane < cg) {
 #pragma unroll
-        for (int i = 0; i < N; ++i) {
-            float s = 0.f;
-            for (int t = tid; t < EW_THREADS; t += cg) s += red[i * EW_THREADS + t];
-            atomicAdd(dst + tid * N + i, (D)s);
+            for (int i = 0; i < N; ++i) red[(i * NW + warp) * 32 + lane] = v.v[i];
+        }
+        __syncthreads();
+        if (tid < cg) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                float s = 0.f;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) s += red[(i * NW + w) * 32 + tid];
+                v.v[i] = s;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) red[i * EW_THREADS + tid] = v.v[i];
+        __syncthreads();
+        if (tid < cg) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                float s = 0.f;
+                for (int t = tid; t < EW_THREADS; t += cg) s += red[i * EW_THREADS + t];
+                v.v[i] = s;
+            }
         }
     }
     __syncthreads();
 }
-// Same reduction, but the block's sum is STORED into the block's own partial slot (dst already points at the slot): the
-// finalize kernel adds the slots in a fixed order, so the result does not depend on block scheduling.
-template <int N>
-__device__ __forceinline__ void block_reduce_slot(const Vf<N>& v, int cg, float* dst, float* red) {
-    const int tid = threadIdx.x;
+// ... added to dst[c..] with atomics (parameter gradients that several blocks contribute to)
+template <int N, typename D>
+__device__ __forceinline__ void block_reduce_add(Vf<N> v, int cg, D* dst, float* red) {
+    block_sum<N>(v, cg, red);
+    if ((int)threadIdx.x < cg) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) red[i * EW_THREADS + tid] = v.v[i];
-    __syncthreads();
-    if (tid < cg) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            float s = 0.f;
-            for (int t = tid; t < EW_THREADS; t += cg) s += red[i * EW_THREADS + t];
-            dst[tid * N + i] = s;
-        }
+        for (int i = 0; i < N; ++i) atomicAdd(dst + threadIdx.x * N + i, (D)v.v[i]);
     }
-    __syncthreads();
+}
+// ... STORED into the block's own partial slot (dst already points at the slot): the finalize kernel adds the slots in a fixed
+// order, so the result does not depend on block scheduling.
+template <int N>
+__device__ __forceinline__ void block_reduce_slot(Vf<N> v, int cg, float* dst, float* red) {
+    block_sum<N>(v, cg, red);
+    if ((int)threadIdx.x < cg) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) dst[threadIdx.x * N + i] = v.v[i];
+    }
 }
 static inline int reduce_blocks(long long npix, int cg) {
     int lanes = EW_THREADS / cg;
