@@ -428,6 +428,11 @@ class SegmentationModel(Model):
                              'seen': {}, 'graphs': {}}
         return st
 
+    def _bucketed(self):
+        """Data parallel: all-reduce the gradient in three buckets overlapped with the backward segments (SALT_DP_BUCKETS=0: one
+        all-reduce after the whole backward pass, as round 1 did)."""
+        return self.dp.world > 1 and os.environ.get('SALT_DP_BUCKETS', '1') != '0'
+
     def _graph_enabled(self):
         return (os.environ.get('SALT_ENGINE_GRAPH', '1') != '0' and not self.engine.profiling
                 and not getattr(self, '_gs', {}).get('disabled', False))
@@ -448,7 +453,7 @@ class SegmentationModel(Model):
             with torch.cuda.graph(gf, capture_error_mode=mode):
                 eng.forward(st['x'][:b], train=True, out=st['logits'][:b])
             n1 = _lib.launch_count()
-            if self.dp.world > 1:
+            if self._bucketed():
                 # data parallel: one graph per backward segment, so that each segment's gradient bucket can be all-reduced
                 # (NCCL, side stream) while the next segment computes - SURVEY.md 8(e)
                 gb = []
@@ -527,7 +532,7 @@ class SegmentationModel(Model):
         batch_loss = loss_function(outputs_batch, target) * weight
         partial_batch_losses['sum'] = batch_loss
         dlogits = loss_function.dlogits if weight == 1.0 else loss_function.dlogits * weight
-        if self.dp.world > 1:
+        if self._bucketed():
             works = []
             for seg in range(self.engine.N_SEGMENTS):
                 self.engine.backward_segment(dlogits, seg)
@@ -537,7 +542,7 @@ class SegmentationModel(Model):
             scale = 1.0 / self.dp.world
         else:
             self.engine.backward(dlogits)
-            scale = 1.0
+            scale = self.dp.allreduce_grads(self.engine.grads)
         self.optimizer.step(grad_scale=scale)
         return partial_batch_losses
 

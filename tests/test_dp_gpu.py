@@ -82,6 +82,10 @@ WORKER = textwrap.dedent('''
         lo, hi = ctx.shard(128)
         out = model.train_step_device(x[lo:hi].to(eng.device), [t[lo:hi].to(eng.device)])
         losses.append(float(out['sum'].cpu()[0]))
+        if step == 0:
+            torch.cuda.synchronize()
+            np.save(os.path.join(sys.argv[1], 'grads0_rank%%d.npy' %% ctx.rank), eng.grads.cpu().numpy())      # all-reduced SUM
+            np.save(os.path.join(sys.argv[1], 'params1_rank%%d.npy' %% ctx.rank), eng.params.cpu().numpy())   # after one Adam step
     torch.cuda.synchronize()
     np.save(os.path.join(sys.argv[1], 'params_rank%%d.npy' %% ctx.rank), eng.params.cpu().numpy())
     np.save(os.path.join(sys.argv[1], 'buffers_rank%%d.npy' %% ctx.rank), eng.buffers.cpu().numpy())
@@ -113,7 +117,10 @@ def test_two_ranks_equal_dataparallel_semantics(tmp_path):
     # statistics), their gradients are added, Adam sees the mean
     eng = _engine(34, 2, 64, 128, precision='bf16')
     eng.load_state(synth.synth_state_dict(34, 2, 0))
-    ref_losses = []
+    e0 = _engine(34, 2, 1, 128, precision='bf16', training=False)
+    e0.load_state(synth.synth_state_dict(34, 2, 0))
+    init = e0.params.cpu().numpy()
+    ref_losses, g0, ref1 = [], None, None
     for step in range(4):
         x = torch.from_numpy(synth.synth_inputs(128, 128, 100 + step)).cuda()
         t = torch.from_numpy(synth.synth_targets(128, 128, 100 + step)).cuda()
@@ -132,24 +139,32 @@ def test_two_ranks_equal_dataparallel_semantics(tmp_path):
         eng.buffers.copy_(bufs0)
         eng.adam_step(grad_scale=0.5)
         ref_losses.append(ls)
+        if step == 0:
+            torch.cuda.synchronize()
+            g0, ref1 = acc.cpu().numpy(), eng.params.cpu().numpy()
     torch.cuda.synchronize()
-    ref = eng.params.cpu().numpy()
-    init = np.zeros_like(ref)
-    e0 = _engine(34, 2, 1, 128, precision='bf16', training=False)
-    e0.load_state(synth.synth_state_dict(34, 2, 0))
-    init = e0.params.cpu().numpy()
-    moved = np.abs(ref - init)
-    err = np.abs(p0 - ref)
-    sel = moved > 1e-6
-    frac = float((err[sel] > 0.3 * moved[sel]).mean())
-    print('2-rank vs sequential-shard emulation: max |dp| %.3e, max err %.3e, parameters off by > 30 %% of their own movement: %.4f %%'
-          % (moved.max(), err.max(), 100 * frac))
-    # per-rank losses are the shard losses of the emulation (rank r <-> shard r) up to the wgrad summation order of earlier steps
+    # (1) the all-reduced gradient of the first step IS the sum of the two shard gradients (fp32 summation order aside)
+    gd = np.load(tmp_path / 'grads0_rank0.npy')
+    gerr = np.abs(gd - g0).max() / np.abs(g0).max()
+    print('step 0: all-reduced gradient vs sum of the shard gradients: max deviation %.3e of the largest gradient' % gerr)
+    assert gerr <= 1e-5
+    # (2) one Adam step: ~ lr * sign(g) per element, so compare where the gradient is above the summation-order noise
+    p1 = np.load(tmp_path / 'params1_rank0.npy')
+    moved = np.abs(ref1 - init)
+    sel = (np.abs(g0) > 1e-4 * np.abs(g0).max()) & (moved > 0)
+    frac1 = float((np.abs(p1 - ref1)[sel] > 0.3 * moved[sel]).mean())
+    print('step 0: parameters (|g| above the noise floor: %d of %d) off by > 30 %% of their own movement: %.4f %%' % (sel.sum(), sel.size, 100 * frac1))
+    assert frac1 <= 0.01
+    # (3) four steps (the last two replayed from the captured forward / 3 segment graphs): per-rank losses follow the emulation
     for r_ in outs:
         got = r_['losses']
         want = [l[r_['rank']] for l in ref_losses]
+        print('rank %d losses' % r_['rank'], got, 'emulation', want)
         assert np.allclose(got, want, rtol=5e-3, atol=1e-4), (got, want)
-    # the first Adam steps are ~ lr * sign(g): elements whose tiny gradient changes sign with the fp32 summation order may differ by 2 lr
-    assert frac <= 0.02 and err.max() <= 4 * 4 * 1e-4
+    ref = eng.params.cpu().numpy()
+    err = np.abs(p0 - ref)
+    print('after 4 steps: max |dp| %.3e, max deviation from the emulation %.3e (each Adam step moves an element by <= ~lr = 1e-4; elements '
+          'whose gradient is at the fp32 summation-noise level take lr * sign(noise))' % (np.abs(ref - init).max(), err.max()))
+    assert err.max() <= 2 * 4 * 1e-4 * 1.05
     b0 = np.load(tmp_path / 'buffers_rank0.npy')
     assert np.allclose(b0, eng.buffers.cpu().numpy(), rtol=2e-2, atol=2e-3)
