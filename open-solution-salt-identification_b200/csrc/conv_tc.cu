@@ -42,6 +42,7 @@ __device__ __forceinline__ float butterfly_reduce32(float* v, int lane) {
 struct TcTap { short dy, dx; int kofs; };
 struct TcPhase { int ntaps, oy, ox; TcTap taps[9]; };
 struct TcParams {
+    FastDiv d_tpp, d_co, d_x, d_y;     // tiles_per_phase, tiles_co, tiles_x, tiles_y
     int tw, th, tn;
     int tiles_x, tiles_y, tiles_b, tiles_co, tiles_per_phase;
     int m_tiles;
@@ -61,9 +62,9 @@ struct TcTile { int pi, nt, mt; bool live; };
 __device__ __forceinline__ bool tc_tile(const TcParams& p, int k, TcTile& t) {
     const int tile = blockIdx.x + k * gridDim.x;
     if (tile >= p.nphases * p.tiles_per_phase) return false;
-    t.pi = tile / p.tiles_per_phase;
+    t.pi = (int)p.d_tpp.div((uint32_t)tile);
     const int r = tile - t.pi * p.tiles_per_phase;
-    t.nt = r % p.tiles_co; t.mt = r / p.tiles_co; t.live = true;
+    t.mt = (int)p.d_co.div((uint32_t)r); t.nt = r - t.mt * p.tiles_co; t.live = true;
     return true;
 }
 
@@ -125,7 +126,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int k = 0; tc_tile(p, k, tt); ++k) {
                 const TcPhase& ph = p.ph[tt.pi];
                 const int nt = tt.nt, mt = tt.mt;
-                const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
+                const int trow = (int)p.d_x.div((uint32_t)mt), tx = mt - trow * p.tiles_x, tb = (int)p.d_y.div((uint32_t)trow), ty = trow - tb * p.tiles_y;
                 const int w0 = tx * p.tw * p.a_stride, h0 = ty * p.th * p.a_stride, n0 = tb * p.tn;
                 for (int tap = 0; tap < ph.ntaps; ++tap) {
                     const int dy = ph.taps[tap].dy, dx = ph.taps[tap].dx, kofs = ph.taps[tap].kofs;
@@ -201,7 +202,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         TcTile tt;
         for (int kk = 0; tc_tile(p, kk, tt); ++kk) {
             const int pi = tt.pi, nt = tt.nt, mt = tt.mt;
-            const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, tb = mt / (p.tiles_x * p.tiles_y);
+            const int trow = (int)p.d_x.div((uint32_t)mt), tx = mt - trow * p.tiles_x, tb = (int)p.d_y.div((uint32_t)trow), ty = trow - tb * p.tiles_y;
             const int x = tx * p.tw + lx, y = ty * p.th + ly, n = tb * p.tn + ln;
             const bool valid = tt.live && (n < p.B) && (y < p.Ho) && (x < p.Wo);
             const int oy = y * p.osy + p.ph[pi].oy, ox = x * p.osx + p.ph[pi].ox;
@@ -345,6 +346,7 @@ static void run_tc(cudaStream_t st, const void* A, int B, int Ha, int Wa, int Ca
     while (BN > 64 && (long long)p.nphases * p.tiles_x * p.tiles_y * p.tiles_b * (Nout / BN) < num_sms()) BN >>= 1;
     p.tiles_co = Nout / BN;
     p.tiles_per_phase = p.tiles_x * p.tiles_y * p.tiles_b * p.tiles_co;
+    p.d_tpp = make_fastdiv(p.tiles_per_phase); p.d_co = make_fastdiv(p.tiles_co); p.d_x = make_fastdiv(p.tiles_x); p.d_y = make_fastdiv(p.tiles_y);
     p.B = B; p.Co = Nout; p.cblks = Ca / BK;
     const bool sw64 = BK == 32;
     CUtensorMap ma = make_map_nhwc(A, Ca, Wa, Ha, B, BK, p.tw, p.th, p.tn, p.a_stride,

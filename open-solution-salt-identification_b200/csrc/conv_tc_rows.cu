@@ -59,6 +59,7 @@ extern "C" int salt_debug_rows_timing(unsigned long long* out, int reset) {
 #endif
 
 struct RowsParams {
+    FastDiv d_co, d_x, d_y;    // tiles_co, tiles_x, tiles_y
     int tiles_x, tiles_y, tiles_co, total_tiles;
     int m_tiles, total_groups;  // cluster mode: a group = CL consecutive pixel tiles of one channel tile (one per CTA of the cluster)
     int B, Ho, Wo, Co, Ca, cblks, pad;
@@ -90,7 +91,7 @@ template <int BN> struct RowsCfg {
     static constexpr int ACC_STRIDE_SPLIT = 2 * BN;
     static constexpr int TMEM_COLS_SPLIT = 2 * ACC_STRIDE_SPLIT < 32 ? 32 : 2 * ACC_STRIDE_SPLIT;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256 + 8 * 2 * BN * 4;      // + per-epilogue-warp BN statistics
+    static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256 + 8 * 2 * BN * 4 + BN * 4;      // + per-epilogue-warp BN statistics + the bias
 };
 
 // ---- thread-block-cluster helpers (weight multicast)
@@ -182,18 +183,25 @@ __device__ __forceinline__ bool rows_tile(const RowsParams& p, int k, uint32_t r
     if constexpr (CL == 1) {
         const int tile = blockIdx.x + k * gridDim.x;
         if (tile >= p.total_tiles) return false;
-        t.nt = tile % p.tiles_co; mt = tile / p.tiles_co; t.live = true;
+        mt = (int)p.d_co.div((uint32_t)tile); t.nt = tile - mt * p.tiles_co; t.live = true;
     } else {
-        const int g = blockIdx.x / CL + k * (gridDim.x / CL);
+        const int g = (int)(blockIdx.x / CL) + k * (int)(gridDim.x / CL);
         if (g >= p.total_groups) return false;
-        t.nt = g % p.tiles_co; mt = (g / p.tiles_co) * CL + (int)rank;
+        const int q = (int)p.d_co.div((uint32_t)g);
+        t.nt = g - q * p.tiles_co; mt = q * CL + (int)rank;
         t.live = mt < p.m_tiles;
         if (!t.live) mt = p.m_tiles - 1;
     }
-    t.tx = mt % p.tiles_x; t.ty = (mt / p.tiles_x) % p.tiles_y; t.n = mt / (p.tiles_x * p.tiles_y);
+    const int row = (int)p.d_x.div((uint32_t)mt);          // (image, tile row)
+    t.tx = mt - row * p.tiles_x;
+    t.n = (int)p.d_y.div((uint32_t)row);
+    t.ty = row - t.n * p.tiles_y;
     return true;
 }
 
+// accumulator buffers per CTA: 2, or 4 for the narrow (<= 64 column) bf16 tiles - their tiles are short (36 MMAs for K = 576), so the
+// MMA -> epilogue -> MMA hand-off latencies were exposed with only two buffers (profiles/r2_notes.md)
+template <int BN, typename OutT, bool PAIR> struct RowsAcc { static constexpr int N = (!PAIR && sizeof(OutT) == 2 && BN <= 64) ? 4 : 2; };
 template <int BN, typename OutT, bool NARROW, int CL, bool PAIR = false>
 __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int warp, const int lane, const uint32_t tmem_base,
                                       const uint32_t tfull0, const uint32_t tempty0, float* s_stats, const uint32_t rank) {
@@ -210,13 +218,11 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
     // the CTA; the cross-lane butterfly runs once per kernel instead of once per tile.  For K = 576 layers the per-tile
     // butterflies (62 shuffles per chunk) made the epilogue longer than the MMA phase (profiles/r1_notes.md).
     const bool own_chunk = half < BN / 32;
-    float rs1[32], rs2[32], rbias[32];
+    float rs1[32], rs2[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { rs1[i] = 0.f; rs2[i] = 0.f; rbias[i] = 0.f; }
-    if (NARROW && own_chunk && p.bias) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) rbias[i] = __ldg(p.bias + half * 32 + i);
-    }
+    for (int i = 0; i < 32; ++i) { rs1[i] = 0.f; rs2[i] = 0.f; }
+    // the bias of the narrow layers sits in shared memory behind the statistics (32 more live registers spilled the sums above)
+    const float4* s_bias4 = reinterpret_cast<const float4*>(s_stats + 8 * 2 * BN + (own_chunk ? half * 32 : 0));
     RowsTile<CL> t;
     for (int k = 0; rows_tile<CL>(p, k, rank, t); ++k) {
         const int nt = t.nt, n = t.n;
@@ -246,6 +252,14 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
         mbar_wait(tfull0 + 8 * acc, acc_phase);
         TCT(if (warp == 2 && lane == 0) g_rows_timing[blockIdx.x][6] += (unsigned long long)(clock64() - te0);)
         fence_after();
+        constexpr bool SPLIT = sizeof(OutT) == 4;
+        constexpr int ACC_STRIDE = SPLIT ? RowsCfg<BN>::ACC_STRIDE_SPLIT : (PAIR ? BN : RowsCfg<BN>::ACC_STRIDE);
+        // tiles with several 32-column chunks per warp (BN >= 128, wide dgrad tiles): the TMEM load of chunk c+1 is in flight while
+        // chunk c is converted and stored (the wide dgrads were epilogue-bound at 3x the MMA time, profiles/r2_notes.md)
+        constexpr bool PREFETCH = !NARROW && !SPLIT && BN > 64;
+        const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * ACC_STRIDE;
+        float vnext[PREFETCH ? 32 : 1];
+        if constexpr (PREFETCH) { if (half < BN / 32) tmem_ld32_issue(tacc + half * 32, vnext); }
 #pragma unroll 1
         for (int ch = half; ch < BN / 32; ch += 2) {
             float v[32];
@@ -254,18 +268,26 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
 #pragma unroll
                 for (int q = 0; q < 4; ++q) old[q] = o4[q];
             }
-            constexpr bool SPLIT = sizeof(OutT) == 4;
-            constexpr int ACC_STRIDE = SPLIT ? RowsCfg<BN>::ACC_STRIDE_SPLIT : (PAIR ? BN : RowsCfg<BN>::ACC_STRIDE);
-            tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * ACC_STRIDE + ch * 32, v);
+            if constexpr (PREFETCH) {
+                tmem_ld_wait32(vnext);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = vnext[i];
+                if (ch + 2 < BN / 32) tmem_ld32_issue(tacc + (ch + 2) * 32, vnext);
+            } else {
+                tmem_ld32(tacc + ch * 32, v);
+            }
             if constexpr (SPLIT) {          // + the accumulator of the correction products
                 float v2[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * ACC_STRIDE + BN + ch * 32, v2);
+                tmem_ld32(tacc + BN + ch * 32, v2);
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] += v2[i];
             }
             if constexpr (NARROW) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] += rbias[i];
+                for (int i = 0; i < 8; ++i) {
+                    const float4 b4 = s_bias4[i];
+                    v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+                }
             } else {
                 if (p.bias) {
 #pragma unroll
@@ -305,7 +327,7 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
             if (PAIR && rank != 0) mbar_arrive_remote(tempty0 + 8 * acc, 0);       // the accumulator barrier lives in the leader CTA
             else mbar_arrive(tempty0 + 8 * acc);
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == RowsAcc<BN, OutT, PAIR>::N) { acc = 0; acc_phase ^= 1; }
         if (p.stats && p.tiles_co > 1) {
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const int tt = threadIdx.x - 64;
@@ -349,26 +371,29 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
-    // bars: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    // bars: full[STAGES], empty[STAGES], tmem_full[4], tmem_empty[4]
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
     float* s_stats = reinterpret_cast<float*>(smem + Cfg::BAR_OFF + 256);
+    constexpr int NACC = RowsAcc<BN, OutT, false>::N;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem0 = smem_u32(smem);
-    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES, tfull0 = empty0 + 8 * STAGES, tempty0 = tfull0 + 16;
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES, tfull0 = empty0 + 8 * STAGES, tempty0 = tfull0 + 32;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
         for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, CL); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 8); }
+        for (int i = 0; i < NACC; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     constexpr bool SPLIT = sizeof(OutT) == 4;
-    constexpr int TMEM_COLS = SPLIT ? Cfg::TMEM_COLS_SPLIT : Cfg::TMEM_COLS, ACC_STRIDE = SPLIT ? Cfg::ACC_STRIDE_SPLIT : Cfg::ACC_STRIDE;
+    constexpr int ACC_STRIDE = SPLIT ? Cfg::ACC_STRIDE_SPLIT : Cfg::ACC_STRIDE;
+    constexpr int TMEM_COLS = NACC * ACC_STRIDE < 32 ? 32 : NACC * ACC_STRIDE;
     static_assert(TMEM_COLS <= 512, "accumulators do not fit TMEM");
     if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), TMEM_COLS);
     for (int i = threadIdx.x; i < 8 * 2 * BN; i += RW_THREADS) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < BN; i += RW_THREADS) s_stats[8 * 2 * BN + i] = (p.bias && p.tiles_co == 1) ? __ldg(p.bias + i) : 0.f;
     fence_before();
     __syncthreads();
     uint32_t rank = 0;
@@ -435,8 +460,8 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 if (!acc_ready) mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
                 TCT(ti_tempty += clock64() - tw0;)
                 const uint32_t tmem_d0 = tmem_base + acc * ACC_STRIDE;
-                const int nacc = acc ^ 1;
-                const uint32_t nacc_phase = acc_phase ^ (uint32_t)acc;      // the phase flips when acc wraps from 1 to 0
+                const int nacc = acc + 1 == NACC ? 0 : acc + 1;
+                const uint32_t nacc_phase = acc + 1 == NACC ? acc_phase ^ 1u : acc_phase;      // the phase flips when acc wraps
                 uint32_t used = 0;          // bit 0 / 1: the main / correction accumulator of this tile has been written
                 for (int it = 0; it < stages_per_tile; ++it) {
                     const uint32_t sub = (SPLIT && (it / 3) * 64 >= p.split_c) ? 1u : 0u;
@@ -515,7 +540,7 @@ template <int BN> struct PairCfg {
     static constexpr int STAGES = BN == 256 ? 3 : (BN == 128 ? 4 : 6);
     static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
-    static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256 + 8 * 2 * BN * 4;
+    static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256 + 8 * 2 * BN * 4 + BN * 4;
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
     static_assert(TMEM_COLS <= 512, "accumulators do not fit TMEM");
 };
@@ -546,6 +571,7 @@ conv_tc_rows_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     }
     if (warp == 1) tmem_alloc_pair(smem_u32(tmem_ptr_smem), Cfg::TMEM_COLS);
     for (int i = threadIdx.x; i < 8 * 2 * BN; i += RW_THREADS) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < BN; i += RW_THREADS) s_stats[8 * 2 * BN + i] = (p.bias && p.tiles_co == 1) ? __ldg(p.bias + i) : 0.f;
     fence_before();
     __syncthreads();
     cluster_sync_all();                 // both CTAs' barriers and TMEM exist before any cross-CTA traffic
@@ -774,6 +800,7 @@ void k_conv_tc_rows(cudaStream_t st, const void* A, int B, int Ha, int Wa, int C
     // a 64-wide one in 1.5x the time.  SALT_TC_WIDE=0 turns it off.
     if (!out_f32 && rows_wide_pref() && BN == 64) { if (Nout % 192 == 0) BN = 192; else if (Nout % 160 == 0) BN = 160; }
     p.tiles_co = Nout / BN;
+    p.d_co = make_fastdiv(p.tiles_co); p.d_x = make_fastdiv(p.tiles_x); p.d_y = make_fastdiv(p.tiles_y);
     p.total_tiles = p.tiles_x * p.tiles_y * B * p.tiles_co;
     p.B = B; p.Ho = Ho; p.Wo = Wo; p.Co = Nout; p.Ca = Ca; p.cblks = cdiv(Ca, 64); p.pad = pad;
     p.ksteps = Ca == 32 ? 2 : 4;
@@ -789,7 +816,7 @@ void k_conv_tc_rows(cudaStream_t st, const void* A, int B, int Ha, int Wa, int C
     if (BN == 128 && rows_pair_pref() && Ca % 64 == 0) {
         // >= 128 output channels: the CTA-pair kernel (half the weight bytes per SM; N = 256 tiles when the layer has them)
         if (Nout % 256 == 0) {
-            RowsParams q = p; q.tiles_co = Nout / 256; q.total_tiles = q.tiles_x * q.tiles_y * B * q.tiles_co;
+            RowsParams q = p; q.tiles_co = Nout / 256; q.d_co = make_fastdiv(q.tiles_co); q.total_tiles = q.tiles_x * q.tiles_y * B * q.tiles_co;
             if (launch_rows_pair<256>(st, ma, Wp, Ca, Nout, q)) return;
         }
         if (launch_rows_pair<128>(st, ma, Wp, Ca, Nout, p)) return;

@@ -81,6 +81,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// the same load without the wait: the registers must not be read before tmem_ld_wait32(v), which carries them as in/out operands
+// so that the compiler cannot move a use above the wait
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait32(float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+          "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+          "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+          "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+        :: "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(
@@ -116,6 +138,25 @@ __device__ __forceinline__ uint32_t instr_desc_bf16(int n, bool a_mn, bool b_mn)
     d |= (uint32_t)(n >> 3) << 17;
     d |= (uint32_t)(128 >> 4) << 24;
     return d;
+}
+
+// n / d for n < 2^31 with a precomputed multiplier: one __umulhi + shift instead of a ~25-instruction division sequence.  The
+// tile -> (channel tile, x, y, image) map is evaluated per tile by every thread of the CTA; its five divisions were 17 % of the
+// stall samples of a layer1 launch (profiles/r2_notes.md).
+struct FastDiv {
+    uint32_t d, mul, shr;
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : __umulhi(n, mul) >> shr; }
+};
+static inline FastDiv make_fastdiv(int d) {
+    FastDiv f; f.d = (uint32_t)d; f.mul = 0; f.shr = 0;
+    if (d > 1) {
+        int lg = 0;
+        while ((1u << lg) < (uint32_t)d) ++lg;
+        const unsigned p = 31 + lg;
+        f.mul = (uint32_t)(((1ull << p) + (uint32_t)d - 1) / (uint32_t)d);
+        f.shr = p - 32;
+    }
+    return f;
 }
 
 // ------------------------------------------------------------------------------------------------ fused epilogue tail

@@ -86,6 +86,7 @@ WORKER = textwrap.dedent('''
             torch.cuda.synchronize()
             np.save(os.path.join(sys.argv[1], 'grads0_rank%%d.npy' %% ctx.rank), eng.grads.cpu().numpy())      # all-reduced SUM
             np.save(os.path.join(sys.argv[1], 'params1_rank%%d.npy' %% ctx.rank), eng.params.cpu().numpy())   # after one Adam step
+            np.save(os.path.join(sys.argv[1], 'buffers1_rank%%d.npy' %% ctx.rank), eng.buffers.cpu().numpy())
     torch.cuda.synchronize()
     np.save(os.path.join(sys.argv[1], 'params_rank%%d.npy' %% ctx.rank), eng.params.cpu().numpy())
     np.save(os.path.join(sys.argv[1], 'buffers_rank%%d.npy' %% ctx.rank), eng.buffers.cpu().numpy())
@@ -120,7 +121,7 @@ def test_two_ranks_equal_dataparallel_semantics(tmp_path):
     e0 = _engine(34, 2, 1, 128, precision='bf16', training=False)
     e0.load_state(synth.synth_state_dict(34, 2, 0))
     init = e0.params.cpu().numpy()
-    ref_losses, g0, ref1 = [], None, None
+    ref_losses, g0, ref1, refb1 = [], None, None, None
     for step in range(4):
         x = torch.from_numpy(synth.synth_inputs(128, 128, 100 + step)).cuda()
         t = torch.from_numpy(synth.synth_targets(128, 128, 100 + step)).cuda()
@@ -141,7 +142,7 @@ def test_two_ranks_equal_dataparallel_semantics(tmp_path):
         ref_losses.append(ls)
         if step == 0:
             torch.cuda.synchronize()
-            g0, ref1 = acc.cpu().numpy(), eng.params.cpu().numpy()
+            g0, ref1, refb1 = acc.cpu().numpy(), eng.params.cpu().numpy(), eng.buffers.cpu().numpy()
     torch.cuda.synchronize()
     # (1) the all-reduced gradient of the first step IS the sum of the two shard gradients (fp32 summation order aside)
     gd = np.load(tmp_path / 'grads0_rank0.npy')
@@ -166,5 +167,13 @@ def test_two_ranks_equal_dataparallel_semantics(tmp_path):
     print('after 4 steps: max |dp| %.3e, max deviation from the emulation %.3e (each Adam step moves an element by <= ~lr = 1e-4; elements '
           'whose gradient is at the fp32 summation-noise level take lr * sign(noise))' % (np.abs(ref - init).max(), err.max()))
     assert err.max() <= 2 * 4 * 1e-4 * 1.05
-    b0 = np.load(tmp_path / 'buffers_rank0.npy')
-    assert np.allclose(b0, eng.buffers.cpu().numpy(), rtol=2e-2, atol=2e-3)
+    # (4) running BatchNorm statistics are replica 0's (models.py:81-85: nn.DataParallel keeps device 0's buffers).  After the first
+    # step rank 0 has run exactly the emulation's shard-0 forward on the same parameters - the train-mode forward is bit-reproducible
+    # - so the buffers agree to the last bit; after four steps the parameters differ by the lr * sign(noise) elements above, so the
+    # statistics are compared against their own scale per tensor
+    b1 = np.load(tmp_path / 'buffers1_rank0.npy')
+    assert np.array_equal(b1, refb1), 'running statistics after step 0: max |diff| %.3e' % np.abs(b1 - refb1).max()
+    b0, bref = np.load(tmp_path / 'buffers_rank0.npy'), eng.buffers.cpu().numpy()
+    berr = np.abs(b0 - bref) / (np.abs(bref) + 0.05 * np.abs(bref).max())
+    print('after 4 steps: running statistics max deviation %.3e (relative, floor 5 %% of the largest statistic)' % berr.max())
+    assert berr.max() <= 0.05
