@@ -143,6 +143,9 @@ int salt_profile_read(salt_engine* h, int kernel_class, double* ms, double* flop
 /* the same restricted to one layer group: 0 stem, 1-4 encoder layer1..layer4, 5 center, 6-10 dec5..dec1, 11 hypercolumn + final;
  * -1 = all groups (bench.py: roofline.per_group) */
 int salt_profile_read_group(salt_engine* h, int kernel_class, int layer_group, double* ms, double* flops, long long* launches);
+/* every bracketed launch since salt_profile_enable(h, 1), in launch order: class, layer group, algorithmic work (FLOPs for classes
+ * 0-2, bytes for the memory-bound classes) and device milliseconds; writes at most max_records entries, returns the total number. */
+long long salt_profile_records(salt_engine* h, int* kernel_class, int* layer_group, double* work, double* ms, long long max_records);
 
 /* ---- single-operator entry points (unit tests; tensors NHWC in the given precision) ------------------ */
 typedef struct salt_conv_desc {

@@ -160,6 +160,9 @@ int salt_profile_enable(salt_engine* h, int on) { h->e->profile_enable(on != 0);
 int salt_profile_read(salt_engine* h, int kernel_class, double* ms, double* flops, long long* launches) {
     return salt_profile_read_group(h, kernel_class, -1, ms, flops, launches);
 }
+long long salt_profile_records(salt_engine* h, int* kernel_class, int* layer_group, double* work, double* ms, long long max_records) {
+    return h->e->profile_records(kernel_class, layer_group, work, ms, max_records);
+}
 int salt_profile_read_group(salt_engine* h, int kernel_class, int layer_group, double* ms, double* flops, long long* launches) {
     if (kernel_class < 0 || kernel_class >= Engine::PROF_NCLASS) return fail("salt_profile_read: unknown kernel class");
     if (layer_group < -1 || layer_group >= Engine::PROF_NGROUPS) return fail("salt_profile_read: unknown layer group");

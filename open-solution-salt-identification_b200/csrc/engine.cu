@@ -418,6 +418,18 @@ void Engine::profile_read(int cls, double* ms, double* flops, long long* launche
         *ms += t; *flops += r.flops; *launches += 1;
     }
 }
+long long Engine::profile_records(int* cls, int* group, double* work, double* ms, long long max_records) {
+    cudaDeviceSynchronize();
+    long long n = 0;
+    for (auto& r : prof_) {
+        if (n >= max_records) break;
+        float t = 0.f;
+        cudaEventElapsedTime(&t, r.a, r.b);
+        cls[n] = r.cls; group[n] = r.group; work[n] = r.flops; ms[n] = t;
+        ++n;
+    }
+    return (long long)prof_.size();
+}
 void Engine::conv_fwd(const ConvLayer& c, const Tensor& in, const Tensor& out, BNLayer* bn, bool train, cudaStream_t st) {
     ConvGeom g = geom(c, in, out);
     const float* bias = c.o_b >= 0 ? params_ + c.o_b : nullptr;

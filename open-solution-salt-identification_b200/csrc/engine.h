@@ -120,6 +120,7 @@ public:
     void prof_end(cudaStream_t st);
     // synchronises, then returns accumulated device time / algorithmic flops / launches since enable
     void profile_read(int cls, double* ms, double* flops, long long* launches, int group = -1);
+    long long profile_records(int* cls, int* group, double* work, double* ms, long long max_records);
     // layer groups of the profile records: 0 stem, 1-4 encoder layer1..layer4, 5 center, 6-10 dec5..dec1, 11 final
     enum { PROF_NGROUPS = 12 };
 

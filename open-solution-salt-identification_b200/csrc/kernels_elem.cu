@@ -7,187 +7,8 @@
 #include <algorithm>
 #include <stdexcept>
 
-#define EW_THREADS 256
-
-// ------------------------------------------------------------------------------------------------
-// 16-byte channel vectors
-// ------------------------------------------------------------------------------------------------
-template <typename T> struct VW;
-template <> struct VW<float> { static constexpr int N = 4; };
-template <> struct VW<bf16> { static constexpr int N = 8; };
-template <int N> struct Vf { float v[N]; };
-
-__device__ __forceinline__ Vf<4> ldv(const float* p) {
-    float4 a = *reinterpret_cast<const float4*>(p);
-    Vf<4> r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
-    return r;
-}
-__device__ __forceinline__ Vf<8> ldv(const bf16* p) {
-    uint4 u = *reinterpret_cast<const uint4*>(p);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-    Vf<8> r;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y; }
-    return r;
-}
-__device__ __forceinline__ void stv(float* p, const Vf<4>& a) { *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]); }
-__device__ __forceinline__ void stv(bf16* p, const Vf<8>& a) {
-    uint4 u;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(a.v[2 * i], a.v[2 * i + 1]);
-    *reinterpret_cast<uint4*>(p) = u;
-}
-// streaming (evict-first) stores for write-once outputs that must not push re-used inputs out of L2
-__device__ __forceinline__ void stv_stream(float* p, const Vf<4>& a) { __stcs(reinterpret_cast<float4*>(p), make_float4(a.v[0], a.v[1], a.v[2], a.v[3])); }
-__device__ __forceinline__ void stv_stream(bf16* p, const Vf<8>& a) {
-    uint4 u;
-    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(a.v[2 * i], a.v[2 * i + 1]);
-    __stcs(reinterpret_cast<uint4*>(p), u);
-}
-// The per-pixel kernels (scSE, final 1x1) reduce over the channel groups of ONE pixel with warp shuffles (<= 32 lanes); they use
-// 8-channel vectors for both storage types so that C <= 256 fits a warp.
-__device__ __forceinline__ Vf<8> ldv8(const bf16* p) { return ldv(p); }
-__device__ __forceinline__ Vf<8> ldv8(const float* p) {
-    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-    Vf<8> r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
-    return r;
-}
-__device__ __forceinline__ void stv8(bf16* p, const Vf<8>& a) { stv(p, a); }
-__device__ __forceinline__ void stv8(float* p, const Vf<8>& a) {
-    *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
-    *reinterpret_cast<float4*>(p + 4) = make_float4(a.v[4], a.v[5], a.v[6], a.v[7]);
-}
-template <int N> __device__ __forceinline__ Vf<N> ldp(const float* p) {      // N fp32 per-channel parameters
-    Vf<N> r;
-#pragma unroll
-    for (int i = 0; i < N; i += 4) {
-        float4 a = *reinterpret_cast<const float4*>(p + i);
-        r.v[i] = a.x; r.v[i + 1] = a.y; r.v[i + 2] = a.z; r.v[i + 3] = a.w;
-    }
-    return r;
-}
-template <int N> __device__ __forceinline__ void stp(float* p, const Vf<N>& a) {
-#pragma unroll
-    for (int i = 0; i < N; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(a.v[i], a.v[i + 1], a.v[i + 2], a.v[i + 3]);
-}
-template <int N> __device__ __forceinline__ Vf<N> vzero() { Vf<N> r;
-#pragma unroll
-    for (int i = 0; i < N; ++i) r.v[i] = 0.f;
-    return r; }
-template <int N> __device__ __forceinline__ Vf<N> vfma(const Vf<N>& a, const Vf<N>& b, const Vf<N>& c) { Vf<N> r;
-#pragma unroll
-    for (int i = 0; i < N; ++i) r.v[i] = fmaf(a.v[i], b.v[i], c.v[i]);
-    return r; }
-template <int N> __device__ __forceinline__ Vf<N> vadd(const Vf<N>& a, const Vf<N>& b) { Vf<N> r;
-#pragma unroll
-    for (int i = 0; i < N; ++i) r.v[i] = a.v[i] + b.v[i];
-    return r; }
-template <int N> __device__ __forceinline__ Vf<N> vmul(const Vf<N>& a, const Vf<N>& b) { Vf<N> r;
-#pragma unroll
-    for (int i = 0; i < N; ++i) r.v[i] = a.v[i] * b.v[i];
-    return r; }
-template <int N> __device__ __forceinline__ Vf<N> vaxpy(const Vf<N>& a, float s, const Vf<N>& c) { Vf<N> r;   // a*s + c
-#pragma unroll
-    for (int i = 0; i < N; ++i) r.v[i] = fmaf(a.v[i], s, c.v[i]);
-    return r; }
-template <int N> __device__ __forceinline__ Vf<N> vscale(const Vf<N>& a, float s) { Vf<N> r;
-#pragma unroll
-    for (int i = 0; i < N; ++i) r.v[i] = a.v[i] * s;
-    return r; }
-template <int N> __device__ __forceinline__ Vf<N> vrelu(const Vf<N>& a) { Vf<N> r;
-#pragma unroll
-    for (int i = 0; i < N; ++i) r.v[i] = fmaxf(a.v[i], 0.f);
-    return r; }
-template <int N> __device__ __forceinline__ Vf<N> vmaskpos(const Vf<N>& g, const Vf<N>& m) { Vf<N> r;       // g where m > 0
-#pragma unroll
-    for (int i = 0; i < N; ++i) r.v[i] = m.v[i] > 0.f ? g.v[i] : 0.f;
-    return r; }
-template <int N> __device__ __forceinline__ float vdot(const Vf<N>& a, const Vf<N>& b) { float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < N; ++i) s = fmaf(a.v[i], b.v[i], s);
-    return s; }
-// xhat = (x - mean) * invstd
-template <int N> __device__ __forceinline__ Vf<N> vxhat(const Vf<N>& x, const Vf<N>& mu, const Vf<N>& is) { Vf<N> r;
-#pragma unroll
-    for (int i = 0; i < N; ++i) r.v[i] = (x.v[i] - mu.v[i]) * is.v[i];
-    return r; }
-
-// Block sum of a per-thread vector over the threads that share a channel group (tid % cg; cg a power of two).  Fixed order:
-// warp shuffles over the lanes of a warp that share the group (xor offsets cg, 2cg, ...), then the 8 warps through shared memory
-// in warp order - no atomics, bit-reproducible, and ~20 instructions instead of the 32-step serial shared-memory loop whose tail
-// made every extra block of the reduction passes expensive (profiles/r2_notes.md).  The result is valid in threads tid < cg.
-template <int N>
-__device__ __forceinline__ void block_sum(Vf<N>& v, int cg, float* red) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = EW_THREADS / 32;
-    if (cg < 32) {
-        for (int off = cg; off < 32; off <<= 1) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) v.v[i] += __shfl_xor_sync(0xffffffffu, v.v[i], off);
-        }
-        if (lane < cg) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) red[(i * NW + warp) * 32 + lane] = v.v[i];
-        }
-        __syncthreads();
-        if (tid < cg) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                float s = 0.f;
-#pragma unroll
-                for (int w = 0; w < NW; ++w) s += red[(i * NW + w) * 32 + tid];
-                v.v[i] = s;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < N; ++i) red[i * EW_THREADS + tid] = v.v[i];
-        __syncthreads();
-        if (tid < cg) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                float s = 0.f;
-                for (int t = tid; t < EW_THREADS; t += cg) s += red[i * EW_THREADS + t];
-                v.v[i] = s;
-            }
-        }
-    }
-    __syncthreads();
-}
-// ... added to dst[c..] with atomics (parameter gradients that several blocks contribute to)
-template <int N, typename D>
-__device__ __forceinline__ void block_reduce_add(Vf<N> v, int cg, D* dst, float* red) {
-    block_sum<N>(v, cg, red);
-    if ((int)threadIdx.x < cg) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) atomicAdd(dst + threadIdx.x * N + i, (D)v.v[i]);
-    }
-}
-// ... STORED into the block's own partial slot (dst already points at the slot): the finalize kernel adds the slots in a fixed
-// order, so the result does not depend on block scheduling.
-template <int N>
-__device__ __forceinline__ void block_reduce_slot(Vf<N> v, int cg, float* dst, float* red) {
-    block_sum<N>(v, cg, red);
-    if ((int)threadIdx.x < cg) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) dst[threadIdx.x * N + i] = v.v[i];
-    }
-}
-static inline int reduce_blocks(long long npix, int cg) {
-    int lanes = EW_THREADS / cg;
-    long long b = (npix + (long long)lanes * 8 - 1) / ((long long)lanes * 8);
-    if (b > SALT_STAT_SLOTS_BWD) b = SALT_STAT_SLOTS_BWD;      // one partial slot per block (kernels.h); up to 8 blocks per SM
-    if (b < 1) b = 1;
-    return (int)b;
-}
-// sum over the cg (power of two, <= 32) lanes that share one pixel
-__device__ __forceinline__ float group_sum(float v, int cg) {
-    for (int o = cg >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
+#include "elem_vec.cuh"
+#include "kernels_stream.h"
 
 // ------------------------------------------------------------------------------------------------
 // input adapter: fp32 NCHW [B,3,H,W] -> NHWC with C padded to 4
@@ -402,6 +223,7 @@ void k_bn_apply(cudaStream_t st, const Tensor& raw, const float* scale, const fl
                 const float* rscale, const float* rshift, bool relu, const Tensor& out, const float* gate) {
     SaltProfScope prof_scope(SALT_PROF_BN_APPLY, (double)raw.bytes() * (res ? 2 : 1) + (double)out.bytes(), st);
     SALT_COUNT(1);
+    if (k_ring_bn_apply(st, raw, scale, shift, res, rscale, rshift, relu, out, gate)) return;
     SALT_DISPATCH(raw.dt, T, {
         const int nrows = raw.B * raw.H;
         const long long row_bytes = (long long)raw.W * raw.C * sizeof(T);
@@ -820,7 +642,8 @@ void k_scse_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const fl
     SALT_DISPATCH(raw.dt, T, {
         launch_se_pool<T, false, true>(st, raw, nullptr, scale, shift, se);
         launch_se_fc(st, se, raw.B, HW);
-        scse_apply_kernel<T><<<cdiv((long long)npix * (C / 8), EW_THREADS), EW_THREADS, 0, st>>>((const T*)raw.p, scale, shift, se, (T*)out.p, npix, HW, C);
+        if (!k_ring_scse_apply(st, raw, scale, shift, se, out))
+            scse_apply_kernel<T><<<cdiv((long long)npix * (C / 8), EW_THREADS), EW_THREADS, 0, st>>>((const T*)raw.p, scale, shift, se, (T*)out.p, npix, HW, C);
     });
 }
 
@@ -897,7 +720,8 @@ void k_scse_bwd(cudaStream_t st, const Tensor& gout, const Tensor& raw, const BN
     SALT_DISPATCH(raw.dt, T, {
         launch_se_pool<T, true, true>(st, raw, gout.p, bn.scale, bn.shift, se);
         launch_se_fc_bwd(st, se, raw.B, HW);
-        scse_bwd_apply_kernel<T><<<reduce_blocks(npix, C / 8), EW_THREADS, 0, st>>>((const T*)gout.p, (const T*)raw.p, bn, se, (T*)gbn.p, npix, HW, C);
+        if (!k_ring_scse_bwd_apply(st, gout, raw, bn, se, gbn))
+            scse_bwd_apply_kernel<T><<<reduce_blocks(npix, C / 8), EW_THREADS, 0, st>>>((const T*)gout.p, (const T*)raw.p, bn, se, (T*)gbn.p, npix, HW, C);
     });
 }
 
@@ -929,6 +753,7 @@ void k_final_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const f
     const unsigned npix = (unsigned)raw.B * raw.H * raw.W;
     const int cg = raw.C / 8;
     if (raw.C % 8 || cg > 32 || (cg & (cg - 1))) throw std::runtime_error("final 1x1 conv: channel count must be 8 * 2^k <= 256");
+    if (k_ring_final_fwd(st, raw, scale, shift, w, b, K, logits)) return;
     SALT_DISPATCH(raw.dt, T, {
         final_fwd_kernel<T><<<cdiv((long long)npix * cg, EW_THREADS), EW_THREADS, 0, st>>>((const T*)raw.p, scale, shift, w, b, K, logits,
                                                                                        npix, raw.H * raw.W, raw.C);
@@ -994,6 +819,7 @@ void k_final_bwd(cudaStream_t st, const float* dlogits, const Tensor& raw, const
     SALT_COUNT(1);
     const unsigned npix = (unsigned)raw.B * raw.H * raw.W;
     const int HW = raw.H * raw.W;
+    if (k_ring_final_bwd(st, dlogits, raw, bn, w, K, dw, db, gbn)) return;
 #define LAUNCH_FB(KK) final_bwd_kernel<T, KK><<<blocks, EW_THREADS, 0, st>>>(dlogits, (const T*)raw.p, bn, w, dw, db, (T*)gbn.p, npix, HW, raw.C)
     SALT_DISPATCH(raw.dt, T, {
         const int blocks = reduce_blocks(npix, raw.C / 8);
@@ -1015,6 +841,7 @@ __global__ void relu_mask_inplace_kernel(T* __restrict__ g, const T* __restrict_
 void k_relu_mask_inplace(cudaStream_t st, const Tensor& g, const Tensor& mask) {
     SaltProfScope prof_scope(SALT_PROF_OTHER, 3.0 * (double)g.bytes(), st);
     SALT_COUNT(1);
+    if (k_ring_relu_mask(st, g, mask)) return;
     SALT_DISPATCH(g.dt, T, {
         const unsigned nvec = (unsigned)(g.numel() / VW<T>::N);
         relu_mask_inplace_kernel<T><<<cdiv(nvec, EW_THREADS), EW_THREADS, 0, st>>>((T*)g.p, (const T*)mask.p, nvec);
@@ -1061,6 +888,7 @@ void k_bn_bwd_reduce(cudaStream_t st, const Tensor& g, const Tensor& raw, const 
                      const float* addc) {
     SaltProfScope prof_scope(SALT_PROF_BN_BWD_REDUCE, 2.0 * (double)raw.bytes(), st);
     SALT_COUNT(1);
+    if (k_ring_bn_bwd_reduce(st, g, raw, bn, self_mask, gate, addc)) return;
     const unsigned npix = (unsigned)raw.B * raw.H * raw.W;
     SALT_DISPATCH(raw.dt, T, {
         const int cgt = raw.C / VW<T>::N, cg = std::min(cgt, EW_THREADS);
@@ -1105,6 +933,7 @@ void k_bn_bwd_apply(cudaStream_t st, const Tensor& g, const Tensor& raw, const B
                     const float* gate, const float* addc) {
     SaltProfScope prof_scope(SALT_PROF_BN_BWD_APPLY, 3.0 * (double)raw.bytes(), st);
     SALT_COUNT(1);
+    if (k_ring_bn_bwd_apply(st, g, raw, bn, self_mask, graw, gate, addc)) return;
     SALT_DISPATCH(raw.dt, T, {
         const unsigned npix = (unsigned)raw.B * raw.H * raw.W;
         const int cgt = raw.C / VW<T>::N, cg = std::min(cgt, EW_THREADS), lanes = EW_THREADS / cg;

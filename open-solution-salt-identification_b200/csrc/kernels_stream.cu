@@ -1,0 +1,441 @@
+// The BatchNorm passes of the engine on the stream ring (stream_ring.cuh): same arithmetic, same fixed-order partial-slot
+// reductions as kernels_elem.cu - only the way the bytes reach the SM differs.  Each launcher returns false when the tensors do
+// not fit the ring's geometry (row bytes not a power of two <= 4096, bordered input); the caller then takes the direct-load kernel.
+#include "kernels_stream.h"
+#include "stream_ring.cuh"
+#include <algorithm>
+
+namespace {
+
+__device__ __forceinline__ int ilog2(unsigned v) { return 31 - __clz(v); }
+
+// ------------------------------------------------------------------------------------------------ BN apply (+ residual, ReLU)
+template <typename T, bool RES>
+struct BnApplyOp {
+    static constexpr int N = VW<T>::N;
+    static constexpr bool FULL_WARPS = false;
+    const float *scale, *shift, *rscale, *rshift, *gate;
+    T* out;
+    int relu, C, H, W, pt, pb, pl, pr;
+    // per thread
+    Vf<N> sc, sh, rsc, rsh;
+    int c, rshift_bits;
+    __device__ void begin(int tid) {
+        const int rb = C * (int)sizeof(T);
+        rshift_bits = ilog2((unsigned)rb);
+        c = ((tid * 16) & (rb - 1)) / (int)sizeof(T);
+        sc = ldp<N>(scale + c); sh = ldp<N>(shift + c);
+        rsc = vzero<N>(); rsh = vzero<N>();
+        if (RES && rscale) { rsc = ldp<N>(rscale + c); rsh = ldp<N>(rshift + c); }
+    }
+    __device__ void vec(size_t off, const uint4 (&in)[RES ? 2 : 1]) {
+        Vf<N> v = vfma(vfrom<T>(in[0]), sc, sh);
+        const unsigned pix = (unsigned)(off >> rshift_bits);
+        if (gate) v = vmul(v, ldp<N>(gate + (size_t)(pix / (unsigned)(H * W)) * C + c));
+        if constexpr (RES) {
+            Vf<N> r = vfrom<T>(in[1]);
+            if (rscale) r = vfma(r, rsc, rsh);
+            v = vadd(v, r);
+        }
+        if (relu) v = vrelu(v);
+        const uint4 o = vto<T>(v);
+        if ((pt | pb | pl | pr) == 0) {
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) + off) = o;
+        } else {
+            const unsigned row = pix / (unsigned)W, x = pix - row * W, n = row / (unsigned)H, y = row - n * H;
+            const int Hp = H + pt + pb, Wp = W + pl + pr;
+            const int y0 = (y == 0) ? 0 : (int)y + pt, y1 = ((int)y == H - 1) ? Hp - 1 : (int)y + pt;
+            const int x0 = (x == 0) ? 0 : (int)x + pl, x1 = ((int)x == W - 1) ? Wp - 1 : (int)x + pl;
+            for (int yy = y0; yy <= y1; ++yy)
+                for (int xx = x0; xx <= x1; ++xx) *reinterpret_cast<uint4*>(out + (((size_t)n * Hp + yy) * Wp + xx) * C + c) = o;
+        }
+    }
+    __device__ void end(int, float*) {}
+};
+
+// ------------------------------------------------------------------------------------------------ BN backward: reduce, apply
+// upstream gradient seen by the layer: g, optionally gated per (image, channel) (encoder SE), optionally masked by its own ReLU
+template <typename T>
+struct BnBwdReduceOp {
+    static constexpr int N = VW<T>::N;
+    static constexpr bool FULL_WARPS = false;
+    BNRef bn;
+    const float *gate, *addc;
+    int self_mask, HW, C;
+    Vf<N> sc, sh, mu, is, sg, sgx;
+    int c, rshift_bits;
+    __device__ void begin(int tid) {
+        const int rb = C * (int)sizeof(T);
+        rshift_bits = ilog2((unsigned)rb);
+        c = ((tid * 16) & (rb - 1)) / (int)sizeof(T);
+        sc = ldp<N>(bn.scale + c); sh = ldp<N>(bn.shift + c); mu = ldp<N>(bn.mean + c); is = ldp<N>(bn.invstd + c);
+        sg = vzero<N>(); sgx = vzero<N>();
+    }
+    __device__ void vec(size_t off, const uint4 (&in)[2]) {
+        Vf<N> gv = vfrom<T>(in[0]);
+        const Vf<N> x = vfrom<T>(in[1]);
+        if (gate) {
+            const size_t o = (size_t)((unsigned)(off >> rshift_bits) / (unsigned)HW) * C + c;
+            gv = vfma(gv, ldp<N>(gate + o), ldp<N>(addc + o));
+        }
+        if (self_mask) gv = vmaskpos(gv, vfma(x, sc, sh));
+        sg = vadd(sg, gv);
+        sgx = vfma(gv, vxhat(x, mu, is), sgx);
+    }
+    __device__ void end(int tid, float* red) {
+        const int cg = C / N;
+        block_reduce_slot<N, true>(sg, cg, bn.bsums + (size_t)blockIdx.x * 2 * C, red);
+        block_reduce_slot<N, true>(sgx, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + C, red);
+        if (blockIdx.x == 0 && tid == 0) *bn.bslots = (int)gridDim.x;
+    }
+};
+
+template <typename T>
+struct BnBwdApplyOp {
+    static constexpr int N = VW<T>::N;
+    static constexpr bool FULL_WARPS = false;
+    BNRef bn;
+    const float *gate, *addc;
+    T* graw;
+    int self_mask, HW, C;
+    Vf<N> sc, sh, mu, cb, cc;
+    int c, rshift_bits;
+    __device__ void begin(int tid) {
+        const int rb = C * (int)sizeof(T);
+        rshift_bits = ilog2((unsigned)rb);
+        c = ((tid * 16) & (rb - 1)) / (int)sizeof(T);
+        sc = ldp<N>(bn.scale + c); sh = ldp<N>(bn.shift + c); mu = ldp<N>(bn.mean + c); cb = ldp<N>(bn.cb + c); cc = ldp<N>(bn.cc + c);
+    }
+    __device__ void vec(size_t off, const uint4 (&in)[2]) {
+        Vf<N> gv = vfrom<T>(in[0]);
+        const Vf<N> x = vfrom<T>(in[1]);
+        if (gate) {
+            const size_t o = (size_t)((unsigned)(off >> rshift_bits) / (unsigned)HW) * C + c;
+            gv = vfma(gv, ldp<N>(gate + o), ldp<N>(addc + o));
+        }
+        if (self_mask) gv = vmaskpos(gv, vfma(x, sc, sh));
+        Vf<N> r;
+#pragma unroll
+        for (int i = 0; i < N; ++i) r.v[i] = sc.v[i] * (gv.v[i] - cb.v[i] - cc.v[i] * (x.v[i] - mu.v[i]));
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(graw) + off) = vto<T>(r);
+    }
+    __device__ void end(int, float*) {}
+};
+
+// g <- g where mask > 0 (the ReLU that closes a residual block), in place
+template <typename T>
+struct ReluMaskOp {
+    static constexpr int N = VW<T>::N;
+    static constexpr bool FULL_WARPS = false;
+    T* g;
+    __device__ void begin(int) {}
+    __device__ void vec(size_t off, const uint4 (&in)[2]) {
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(g) + off) = vto<T>(vmaskpos(vfrom<T>(in[0]), vfrom<T>(in[1])));
+    }
+    __device__ void end(int, float*) {}
+};
+
+// ------------------------------------------------------------------------------------------------ per-pixel passes (bf16)
+// scSE gate, final 1x1 convolution: the C/8 consecutive threads that hold one pixel reduce over its channels with warp shuffles
+// (C <= 256), so every thread runs every pass of a chunk (FULL_WARPS).
+__device__ __forceinline__ uint4 lds16(const uint8_t* p) { return *reinterpret_cast<const uint4*>(p); }
+
+// out = z * (cse[n][c] + sigmoid(<z, ws> + bs)),  z = relu(raw*scale+shift)      (base.py:82-117)
+struct ScseApplyOp {
+    static constexpr int N = 8;
+    static constexpr bool FULL_WARPS = true;
+    const float *scale, *shift;
+    SERef se;
+    bf16* out;
+    int HW, C;
+    Vf<N> sc, sh, w;
+    float bs;
+    int c, cg, rshift_bits;
+    __device__ void begin(int tid) {
+        const int rb = C * 2;
+        rshift_bits = ilog2((unsigned)rb); cg = C / N;
+        c = ((tid * 16) & (rb - 1)) / 2;
+        sc = ldp<N>(scale + c); sh = ldp<N>(shift + c); w = ldp<N>(se.ws + c); bs = se.bs[0];
+    }
+    __device__ void vec(size_t off, const uint8_t* stage, int o, bool valid) {
+        const Vf<N> z = vrelu(vfma(vfrom<bf16>(lds16(stage + o)), sc, sh));
+        const float dot = group_sum(vdot(z, w), cg);
+        const float sg = 1.f / (1.f + expf(-(dot + bs)));
+        const unsigned n = (unsigned)(off >> rshift_bits) / (unsigned)HW;
+        Vf<N> gate = ldp<N>(se.cse + (size_t)n * C + c);
+#pragma unroll
+        for (int i = 0; i < N; ++i) gate.v[i] += sg;
+        if (valid) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) + off) = vto<bf16>(vrelu(vmul(z, gate)));
+    }
+    __device__ void end(int, float*) {}
+};
+
+// scSE backward through out = z*(cse + s): gradient w.r.t. the BatchNorm output (ReLU-masked), BatchNorm backward sums in the
+// block's slot, spatial-gate parameter gradients
+struct ScseBwdOp {
+    static constexpr int N = 8;
+    static constexpr bool FULL_WARPS = true;
+    BNRef bn;
+    SERef se;
+    bf16* gbn;
+    int HW, C;
+    Vf<N> sc, sh, mu, is, w, sg, sgx, sws;
+    float bs, sbs;
+    int c, cg, rshift_bits;
+    __device__ void begin(int tid) {
+        const int rb = C * 2;
+        rshift_bits = ilog2((unsigned)rb); cg = C / N;
+        c = ((tid * 16) & (rb - 1)) / 2;
+        sc = ldp<N>(bn.scale + c); sh = ldp<N>(bn.shift + c); mu = ldp<N>(bn.mean + c); is = ldp<N>(bn.invstd + c);
+        w = ldp<N>(se.ws + c); bs = se.bs[0];
+        sg = vzero<N>(); sgx = vzero<N>(); sws = vzero<N>(); sbs = 0.f;
+    }
+    __device__ void vec(size_t off, const uint8_t* stage, int o, bool valid) {
+        const Vf<N> g = vfrom<bf16>(lds16(stage + o)), x = vfrom<bf16>(lds16(stage + ring::CHUNK + o));
+        const Vf<N> z = vrelu(vfma(x, sc, sh));
+        const float dot = group_sum(vdot(z, w), cg);
+        const float s = 1.f / (1.f + expf(-(dot + bs)));
+        const float D = group_sum(vdot(g, z), cg);
+        const float dsp = D * s * (1.f - s);
+        const size_t no = (size_t)((unsigned)(off >> rshift_bits) / (unsigned)HW) * C + c;
+        const Vf<N> cse = ldp<N>(se.cse + no), G = ldp<N>(se.G + no);
+        Vf<N> dz;
+#pragma unroll
+        for (int i = 0; i < N; ++i) dz.v[i] = z.v[i] > 0.f ? g.v[i] * (cse.v[i] + s) + dsp * w.v[i] + G.v[i] : 0.f;
+        if (valid) {
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(gbn) + off) = vto<bf16>(dz);
+            sg = vadd(sg, dz);
+            sgx = vfma(dz, vxhat(x, mu, is), sgx);
+            sws = vaxpy(z, dsp, sws);
+            if (c == 0) sbs += dsp;
+        }
+    }
+    __device__ void end(int tid, float* red) {
+        block_reduce_slot<N, true>(sg, cg, bn.bsums + (size_t)blockIdx.x * 2 * C, red);
+        block_reduce_slot<N, true>(sgx, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + C, red);
+        if (blockIdx.x == 0 && tid == 0) *bn.bslots = (int)gridDim.x;
+        block_reduce_add<N, float, true>(sws, cg, se.dws, red);
+        red[tid] = sbs;
+        ring::consumer_sync();
+        if (tid == 0) {
+            float t = 0.f;
+            for (int i = 0; i < EW_THREADS; ++i) t += red[i];
+            atomicAdd(se.dbs, t);
+        }
+    }
+};
+
+// logits[n][k][p] = <relu(raw*scale+shift), w[k]> + b[k]      (fp32 NCHW, the reference layout)
+struct FinalFwdOp {
+    static constexpr int N = 8;
+    static constexpr bool FULL_WARPS = true;
+    const float *scale, *shift, *w, *b;
+    float* logits;
+    int K, HW, C;
+    Vf<N> sc, sh;
+    int c, cg, rshift_bits;
+    __device__ void begin(int tid) {
+        const int rb = C * 2;
+        rshift_bits = ilog2((unsigned)rb); cg = C / N;
+        c = ((tid * 16) & (rb - 1)) / 2;
+        sc = ldp<N>(scale + c); sh = ldp<N>(shift + c);
+    }
+    __device__ void vec(size_t off, const uint8_t* stage, int o, bool valid) {
+        const Vf<N> z = vrelu(vfma(vfrom<bf16>(lds16(stage + o)), sc, sh));
+        const unsigned pix = (unsigned)(off >> rshift_bits), n = pix / (unsigned)HW, p = pix - n * HW;
+        for (int k = 0; k < K; ++k) {
+            const float d = group_sum(vdot(z, ldp<N>(w + k * C + c)), cg);
+            if (valid && c == 0) logits[((size_t)n * K + k) * HW + p] = d + b[k];
+        }
+    }
+    __device__ void end(int, float*) {}
+};
+
+// backward of the final 1x1 convolution + the ReLU / BatchNorm sums of final.0: streams 1..K are the dlogits planes of the image
+template <int K>
+struct FinalBwdOp {
+    static constexpr int N = 8;
+    static constexpr bool FULL_WARPS = true;
+    BNRef bn;
+    const float* w;
+    float *dw, *db;
+    bf16* gbn;
+    int C;
+    Vf<N> sc, sh, mu, is, sg, sgx, wk[K], sdw[K];
+    float sdb[K];
+    int c, cg, rshift_bits;
+    __device__ void begin(int tid) {
+        const int rb = C * 2;
+        cg = C / N; rshift_bits = ilog2((unsigned)rb);
+        c = ((tid * 16) & (rb - 1)) / 2;
+        sc = ldp<N>(bn.scale + c); sh = ldp<N>(bn.shift + c); mu = ldp<N>(bn.mean + c); is = ldp<N>(bn.invstd + c);
+        sg = vzero<N>(); sgx = vzero<N>();
+#pragma unroll
+        for (int k = 0; k < K; ++k) { wk[k] = ldp<N>(w + k * C + c); sdw[k] = vzero<N>(); sdb[k] = 0.f; }
+    }
+    __device__ void end(int tid, float* red) {
+        block_reduce_slot<N, true>(sg, cg, bn.bsums + (size_t)blockIdx.x * 2 * C, red);
+        block_reduce_slot<N, true>(sgx, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + C, red);
+        if (blockIdx.x == 0 && tid == 0) *bn.bslots = (int)gridDim.x;
+#pragma unroll
+        for (int k = 0; k < K; ++k) block_reduce_add<N, float, true>(sdw[k], cg, dw + k * C, red);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            red[tid] = sdb[k];
+            ring::consumer_sync();
+            if (tid == 0) {
+                float t = 0.f;
+                for (int i = 0; i < EW_THREADS; ++i) t += red[i];
+                atomicAdd(db + k, t);
+            }
+            ring::consumer_sync();
+        }
+    }
+    // the dlogits planes are 1/(C/2) as dense as the activation stream, so the op addresses the stage itself (no shuffles here:
+    // the tail of a short chunk simply returns)
+    __device__ void vec(size_t off, const uint8_t* stage, int o, bool valid) {
+        if (!valid) return;
+        const Vf<N> x = vfrom<bf16>(lds16(stage + o));
+        const Vf<N> z = vrelu(vfma(x, sc, sh));
+        const int pl = o >> rshift_bits;                  // pixel within the chunk
+        Vf<N> gz = vzero<N>();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float dl = *reinterpret_cast<const float*>(stage + (size_t)(k + 1) * ring::CHUNK + pl * 4);
+            gz = vaxpy(wk[k], dl, gz);
+            sdw[k] = vaxpy(z, dl, sdw[k]);
+            if (c == 0) sdb[k] += dl;
+        }
+        gz = vmaskpos(gz, z);
+        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(gbn) + off) = vto<bf16>(gz);
+        sg = vadd(sg, gz);
+        sgx = vfma(gz, vxhat(x, mu, is), sgx);
+    }
+};
+
+bool same_shape(const Tensor& a, const Tensor& b) { return a.B == b.B && a.H == b.H && a.W == b.W && a.C == b.C && a.dt == b.dt; }
+size_t flat_bytes(const Tensor& t) { return (size_t)t.B * t.H * t.W * t.C * dtype_size(t.dt); }
+
+}  // namespace
+
+bool ring_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SALT_EW_RING"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+
+bool k_ring_bn_apply(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const Tensor* res, const float* rscale,
+                     const float* rshift, bool relu, const Tensor& out, const float* gate) {
+    if (!ring_enabled() || !ring::row_ok(raw) || (res && (!ring::row_ok(*res) || !same_shape(raw, *res)))) return false;
+    if (out.B != raw.B || out.H != raw.H || out.W != raw.W || out.C != raw.C || out.dt != raw.dt) return false;
+    SALT_DISPATCH(raw.dt, T, {
+        if (res) {
+            BnApplyOp<T, true> op;
+            op.scale = scale; op.shift = shift; op.rscale = rscale; op.rshift = rshift; op.gate = gate; op.out = (T*)out.p;
+            op.relu = relu ? 1 : 0; op.C = raw.C; op.H = raw.H; op.W = raw.W; op.pt = out.pt; op.pb = out.pb; op.pl = out.pl; op.pr = out.pr;
+            ring::Streams<2> s; s.p[0] = (const uint8_t*)raw.p; s.p[1] = (const uint8_t*)res->p; s.nbytes = flat_bytes(raw);
+            ring::launch<2>(st, s, op);
+        } else {
+            BnApplyOp<T, false> op;
+            op.scale = scale; op.shift = shift; op.rscale = nullptr; op.rshift = nullptr; op.gate = gate; op.out = (T*)out.p;
+            op.relu = relu ? 1 : 0; op.C = raw.C; op.H = raw.H; op.W = raw.W; op.pt = out.pt; op.pb = out.pb; op.pl = out.pl; op.pr = out.pr;
+            ring::Streams<1> s; s.p[0] = (const uint8_t*)raw.p; s.nbytes = flat_bytes(raw);
+            ring::launch<1>(st, s, op);
+        }
+    });
+    return true;
+}
+
+bool k_ring_bn_bwd_reduce(cudaStream_t st, const Tensor& g, const Tensor& raw, const BNRef& bn, bool self_mask, const float* gate,
+                          const float* addc) {
+    if (!ring_enabled() || !ring::row_ok(raw) || !ring::row_ok(g) || !same_shape(raw, g)) return false;
+    SALT_DISPATCH(raw.dt, T, {
+        BnBwdReduceOp<T> op;
+        op.bn = bn; op.gate = gate; op.addc = addc; op.self_mask = self_mask ? 1 : 0; op.HW = raw.H * raw.W; op.C = raw.C;
+        ring::Streams<2> s; s.p[0] = (const uint8_t*)g.p; s.p[1] = (const uint8_t*)raw.p; s.nbytes = flat_bytes(raw);
+        ring::launch<2>(st, s, op);
+    });
+    return true;
+}
+
+bool k_ring_bn_bwd_apply(cudaStream_t st, const Tensor& g, const Tensor& raw, const BNRef& bn, bool self_mask, const Tensor& graw,
+                         const float* gate, const float* addc) {
+    if (!ring_enabled() || !ring::row_ok(raw) || !ring::row_ok(g) || !ring::row_ok(graw) || !same_shape(raw, g) || !same_shape(raw, graw))
+        return false;
+    SALT_DISPATCH(raw.dt, T, {
+        BnBwdApplyOp<T> op;
+        op.bn = bn; op.gate = gate; op.addc = addc; op.graw = (T*)graw.p; op.self_mask = self_mask ? 1 : 0; op.HW = raw.H * raw.W;
+        op.C = raw.C;
+        ring::Streams<2> s; s.p[0] = (const uint8_t*)g.p; s.p[1] = (const uint8_t*)raw.p; s.nbytes = flat_bytes(raw);
+        ring::launch<2>(st, s, op);
+    });
+    return true;
+}
+
+bool k_ring_relu_mask(cudaStream_t st, const Tensor& g, const Tensor& mask) {
+    if (!ring_enabled() || !ring::row_ok(g) || !ring::row_ok(mask) || !same_shape(g, mask)) return false;
+    SALT_DISPATCH(g.dt, T, {
+        ReluMaskOp<T> op; op.g = (T*)g.p;
+        ring::Streams<2> s; s.p[0] = (const uint8_t*)g.p; s.p[1] = (const uint8_t*)mask.p; s.nbytes = flat_bytes(g);
+        ring::launch<2>(st, s, op);
+    });
+    return true;
+}
+
+static bool pixel_group_ok(const Tensor& t) {       // bf16, one pixel's channel groups inside a warp
+    const int cg = t.C / 8;
+    return t.dt == DT_BF16 && t.C % 8 == 0 && cg <= 32 && (cg & (cg - 1)) == 0 && ring::row_ok(t);
+}
+bool k_ring_scse_apply(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const SERef& se, const Tensor& out) {
+    if (!ring_enabled() || !pixel_group_ok(raw) || !ring::row_ok(out) || !same_shape(raw, out)) return false;
+    ScseApplyOp op;
+    op.scale = scale; op.shift = shift; op.se = se; op.out = (bf16*)out.p; op.HW = raw.H * raw.W; op.C = raw.C;
+    ring::Streams<1> s; s.p[0] = (const uint8_t*)raw.p; s.nbytes = flat_bytes(raw);
+    ring::launch<1>(st, s, op);
+    return true;
+}
+bool k_ring_scse_bwd_apply(cudaStream_t st, const Tensor& gout, const Tensor& raw, const BNRef& bn, const SERef& se, const Tensor& gbn) {
+    if (!ring_enabled() || !pixel_group_ok(raw) || !ring::row_ok(gout) || !ring::row_ok(gbn) || !same_shape(raw, gout) ||
+        !same_shape(raw, gbn))
+        return false;
+    ScseBwdOp op;
+    op.bn = bn; op.se = se; op.gbn = (bf16*)gbn.p; op.HW = raw.H * raw.W; op.C = raw.C;
+    ring::Streams<2> s; s.p[0] = (const uint8_t*)gout.p; s.p[1] = (const uint8_t*)raw.p; s.nbytes = flat_bytes(raw);
+    ring::launch<2>(st, s, op);
+    return true;
+}
+bool k_ring_final_fwd(cudaStream_t st, const Tensor& raw, const float* scale, const float* shift, const float* w, const float* b, int K,
+                      float* logits) {
+    if (!ring_enabled() || !pixel_group_ok(raw)) return false;
+    FinalFwdOp op;
+    op.scale = scale; op.shift = shift; op.w = w; op.b = b; op.logits = logits; op.K = K; op.HW = raw.H * raw.W; op.C = raw.C;
+    ring::Streams<1> s; s.p[0] = (const uint8_t*)raw.p; s.nbytes = flat_bytes(raw);
+    ring::launch<1>(st, s, op);
+    return true;
+}
+template <int K>
+static void launch_final_bwd(cudaStream_t st, const float* dlogits, const Tensor& raw, const BNRef& bn, const float* w, float* dw, float* db,
+                             const Tensor& gbn) {
+    FinalBwdOp<K> op;
+    op.bn = bn; op.w = w; op.dw = dw; op.db = db; op.gbn = (bf16*)gbn.p; op.C = raw.C;
+    const size_t HW = (size_t)raw.H * raw.W;
+    int shift = 0;
+    while ((1 << shift) < raw.C / 2) ++shift;            // activation bytes per pixel (2C) / dlogits bytes per pixel and plane (4)
+    ring::Streams<K + 1> s;
+    s.p[0] = (const uint8_t*)raw.p; s.nbytes = flat_bytes(raw); s.img_bytes = HW * raw.C * 2;
+    for (int k = 0; k < K; ++k) {
+        s.p[k + 1] = (const uint8_t*)(dlogits + (size_t)k * HW);
+        s.shift[k + 1] = shift; s.img_stride[k + 1] = (size_t)K * HW * sizeof(float);
+    }
+    ring::launch<K + 1>(st, s, op);
+}
+bool k_ring_final_bwd(cudaStream_t st, const float* dlogits, const Tensor& raw, const BNRef& bn, const float* w, int K, float* dw, float* db,
+                      const Tensor& gbn) {
+    if (!ring_enabled() || !pixel_group_ok(raw) || !ring::row_ok(gbn) || !same_shape(raw, gbn) || K < 1 || K > 3) return false;
+    const size_t img_bytes = (size_t)raw.H * raw.W * raw.C * 2;
+    if (img_bytes % ring::CHUNK || (ring::CHUNK / (raw.C / 2)) % 16 || (reinterpret_cast<uintptr_t>(dlogits) & 15)) return false;
+    if (K == 1) launch_final_bwd<1>(st, dlogits, raw, bn, w, dw, db, gbn);
+    else if (K == 2) launch_final_bwd<2>(st, dlogits, raw, bn, w, dw, db, gbn);
+    else launch_final_bwd<3>(st, dlogits, raw, bn, w, dw, db, gbn);
+    return true;
+}

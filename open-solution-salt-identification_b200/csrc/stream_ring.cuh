@@ -1,0 +1,167 @@
+// Stream ring: the pipeline every HBM-bound elementwise / reduction pass of the engine runs on.
+//
+// The passes read one to three equally shaped NHWC tensors front to back.  With plain global loads the bytes in flight per SM are
+// (resident threads) x (loads a thread can keep in registers); the register-heavy passes (five per-channel coefficient vectors,
+// reduction accumulators) sat at 2 blocks per SM and 16-32 KB in flight, i.e. 2.4-3.5 TB/s of the 6.4 TB/s copy peak
+// (profiles/r2_notes.md section 4).  Here ONE elected thread of a producer warp streams CHUNK-byte pieces of every input into a
+// shared-memory ring with cp.async.bulk (completion on an mbarrier), so 96-128 KB per SM are in flight whatever the consumers'
+// register budget is; 8 consumer warps read 16-byte vectors from the ring (conflict-free: consecutive threads, consecutive
+// vectors), keep their per-channel coefficients in registers and store results straight to global memory.
+//
+// Geometry: a chunk is a whole number of pixels and 256 threads x 16 bytes is a whole number of pixels (row bytes = C * sizeof(T)
+// is a power of two <= 4096), so a consumer thread serves ONE channel group for the whole kernel.  Grid = min(#SMs, chunks)
+// persistent CTAs, chunk i of CTA b = b + i * grid.  Reductions end in the block's own partial slot (fixed-order finalize).
+#pragma once
+#include "elem_vec.cuh"
+
+namespace ring {
+
+constexpr int CONSUMERS = EW_THREADS;        // 8 warps
+constexpr int THREADS = CONSUMERS + 32;      // + the producer warp
+constexpr int CHUNK = 16384;                 // bytes per input per stage
+template <int NS> struct Cfg {
+    static constexpr int STAGES = NS == 1 ? 6 : (NS == 2 ? 4 : 3);
+    static constexpr int RING_BYTES = STAGES * NS * CHUNK;
+    static constexpr int SMEM = RING_BYTES + 128;
+};
+// Stream 0 is the primary tensor (nbytes, byte offsets `off` refer to it).  A secondary stream may be narrower per pixel
+// (shift[i]: its bytes = primary bytes >> shift[i]) and may be laid out per image with its own image stride (planes of an NCHW
+// tensor): source offset = (off / img_bytes) * img_stride[i] + ((off % img_bytes) >> shift[i]); img_stride[i] == 0 = flat.
+template <int NS> struct Streams {
+    const uint8_t* p[NS]; size_t nbytes;
+    int shift[NS] = {}; size_t img_stride[NS] = {}; size_t img_bytes = 0;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+// bounded: a mis-programmed pipeline traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) break;
+        if (++spins > (1u << 24)) { printf("ring: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// Op interface (all members __device__):
+//   void begin(int tid)                                   per-thread set-up (coefficients of the thread's channel group)
+//   static constexpr bool FULL_WARPS
+//   void vec(size_t off, const uint4 (&in)[NS])           FULL_WARPS = false: one 16-byte vector of every input at byte offset
+//                                                         `off` of the tensors
+//   void vec(size_t off, const uint8_t* stage, int o, bool valid)
+//                                                         FULL_WARPS = true (ops with warp shuffles): the op reads its inputs from
+//                                                         the stage itself (stream i at stage + i*CHUNK, primary offset o)
+//   void end(int tid, float* red)                         after the last chunk; `red` = EW_THREADS * 8 floats of shared memory,
+//                                                         consumers synchronise with consumer_sync() / the NAMED block sums
+template <int NS, class Op>
+__global__ void __launch_bounds__(THREADS, 1) ring_kernel(Streams<NS> s, Op op) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int STAGES = Cfg<NS>::STAGES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg<NS>::RING_BYTES);
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const size_t nchunks = (s.nbytes + CHUNK - 1) / CHUNK;
+    if (warp == CONSUMERS / 32) {
+        if (lane == 0) {
+            int st = 0; uint32_t ph = 0;
+            for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+                mbar_wait(empty0 + 8 * st, ph ^ 1);
+                const size_t off = ch * CHUNK;
+                const uint32_t bytes = (uint32_t)min((size_t)CHUNK, s.nbytes - off);
+                uint32_t total = 0;
+#pragma unroll
+                for (int i = 0; i < NS; ++i) total += bytes >> s.shift[i];
+                mbar_expect_tx(full0 + 8 * st, total);
+#pragma unroll
+                for (int i = 0; i < NS; ++i) {
+                    const size_t so = s.img_stride[i] ? (off / s.img_bytes) * s.img_stride[i] + ((off % s.img_bytes) >> s.shift[i])
+                                                      : (off >> s.shift[i]);
+                    bulk_load(smem_u32(smem + (size_t)(st * NS + i) * CHUNK), s.p[i] + so, bytes >> s.shift[i], full0 + 8 * st);
+                }
+                if (++st == STAGES) { st = 0; ph ^= 1; }
+            }
+        }
+        return;
+    }
+    op.begin(threadIdx.x);
+    int st = 0; uint32_t ph = 0;
+    for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+        const size_t off = ch * CHUNK;
+        const int bytes = (int)min((size_t)CHUNK, s.nbytes - off);
+        mbar_wait(full0 + 8 * st, ph);
+        const uint8_t* base = smem + (size_t)st * NS * CHUNK;
+        if constexpr (Op::FULL_WARPS) {
+            // ops with warp shuffles: every thread runs every pass of a (possibly short) chunk, `valid` masks the tail
+#pragma unroll 2
+            for (int o = threadIdx.x * 16; o - (int)threadIdx.x * 16 < bytes; o += CONSUMERS * 16) {
+                const bool valid = o < bytes;
+                const int oc = valid ? o : (int)threadIdx.x * 16;
+                op.vec(off + oc, base, oc, valid);
+            }
+        } else {
+#pragma unroll 2
+            for (int o = threadIdx.x * 16; o < bytes; o += CONSUMERS * 16) {
+                uint4 in[NS];
+#pragma unroll
+                for (int i = 0; i < NS; ++i) in[i] = *reinterpret_cast<const uint4*>(base + (size_t)i * CHUNK + o);
+                op.vec(off + o, in);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * st);
+        if (++st == STAGES) { st = 0; ph ^= 1; }
+    }
+    consumer_sync();          // every stage has been consumed: the ring is free to serve as reduction scratch
+    op.end(threadIdx.x, reinterpret_cast<float*>(smem));
+}
+
+static inline int num_sms_cached() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
+    return n;
+}
+// a tensor can ride the ring if its row (C elements) is a power of two of 16..4096 bytes and it has no border
+static inline bool row_ok(const Tensor& t) {
+    const size_t rb = (size_t)t.C * dtype_size(t.dt);
+    return t.pt == 0 && t.pb == 0 && t.pl == 0 && t.pr == 0 && rb >= 16 && rb <= 4096 && (rb & (rb - 1)) == 0 &&
+           (reinterpret_cast<uintptr_t>(t.p) & 15) == 0;
+}
+template <int NS, class Op>
+static void launch(cudaStream_t st, const Streams<NS>& s, const Op& op) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(ring_kernel<NS, Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<NS>::SMEM);
+        attr_set = true;
+    }
+    const size_t nchunks = (s.nbytes + CHUNK - 1) / CHUNK;
+    const int grid = (int)std::min<size_t>((size_t)num_sms_cached(), nchunks);
+    ring_kernel<NS, Op><<<grid, THREADS, Cfg<NS>::SMEM, st>>>(s, op);
+}
+static inline int grid_for(size_t nbytes) {
+    const size_t nchunks = (nbytes + CHUNK - 1) / CHUNK;
+    return (int)std::min<size_t>((size_t)num_sms_cached(), nchunks);
+}
+
+}  // namespace ring

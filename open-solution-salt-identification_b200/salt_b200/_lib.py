@@ -65,6 +65,7 @@ PROTOTYPES = {
     'salt_profile_enable': (_i, [_vp, _i]),
     'salt_profile_read': (_i, [_vp, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     'salt_profile_read_group': (_i, [_vp, _i, _i, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
+    'salt_profile_records': (C.c_longlong, [_vp, C.POINTER(_i), C.POINTER(_i), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_longlong]),
     'salt_op_conv_forward': (_i, [C.POINTER(SaltConvDesc), _vp, _fp, _fp, _vp, _dp, _vp]),
     'salt_op_conv_dgrad': (_i, [C.POINTER(SaltConvDesc), _vp, _fp, _vp, _i, _vp]),
     'salt_op_conv_wgrad': (_i, [C.POINTER(SaltConvDesc), _vp, _vp, _fp, _vp]),

@@ -229,6 +229,15 @@ class UNetEngine:
             out[gname] = d
         return out
 
+    def profile_records(self):
+        """[(class name, group name, work, ms)] for every bracketed launch since profile(True), in launch order."""
+        n = self.lib.salt_profile_records(self.h, None, None, None, None, 0)
+        cls, grp = (C.c_int * n)(), (C.c_int * n)()
+        work, ms = (C.c_double * n)(), (C.c_double * n)()
+        self.lib.salt_profile_records(self.h, cls, grp, work, ms, n)
+        names = ('conv_fwd', 'conv_dgrad', 'conv_wgrad') + self.PASS_CLASSES
+        return [(names[cls[i]], self.PROFILE_GROUPS[grp[i]], work[i], ms[i]) for i in range(n)]
+
     def activation(self, name):
         shape = (C.c_int * 4)()
         _lib.check(self.lib.salt_get_activation(self.h, name.encode(), C.c_void_p(0), shape, self._stream()))
