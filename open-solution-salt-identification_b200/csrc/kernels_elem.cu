@@ -30,34 +30,38 @@ void k_zero(cudaStream_t st, void* p, size_t bytes) { cudaMemsetAsync(p, 0, byte
 #define STEM_PATCH_C 160
 template <typename T>
 __global__ void stem_im2col_kernel(const float* __restrict__ x, T* __restrict__ out, int H, int W) {
-    constexpr int N = VW<T>::N, CG = STEM_PATCH_C / N;
+    // one block per output row; a thread owns ONE channel vector of the patch (its (c, r, s) decomposition and row validity are
+    // computed once) and walks over the row's pixels - the per-element div/mod of the one-pixel-per-thread version made this pass
+    // integer-ALU bound at 0.9 TB/s (profiles/r2_notes.md)
+    constexpr int N = VW<T>::N, CG = STEM_PATCH_C / N, LANES = EW_THREADS / CG;
     const int Ho = H / 2, Wo = W / 2;
-    const int j = blockIdx.y * EW_THREADS + threadIdx.x;
-    if (j >= Wo * CG) return;
-    const int xo = j / CG, cv = j - xo * CG;
+    const int cv = threadIdx.x % CG, lane = threadIdx.x / CG;
+    if (lane >= LANES) return;
     const int row = blockIdx.x, n = row / Ho, yo = row - n * Ho;
     const float* xn = x + (size_t)n * 3 * H * W;
-    Vf<N> v;
+    int base[N], sx[N];                 // offset of (c, yi, -3 + s) in the image; column shift; base < 0: the whole tap row is outside
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         const int ch = cv * N + i;                       // c*49 + r*7 + s
-        float val = 0.f;
-        if (ch < 147) {
-            const int c = ch / 49, rs = ch - c * 49, r = rs / 7, s = rs - r * 7;
-            const int yi = 2 * yo + r - 3, xi = 2 * xo + s - 3;
-            if (yi >= 0 && yi < H && xi >= 0 && xi < W) val = __ldg(xn + ((size_t)c * H + yi) * W + xi);
-        }
-        v.v[i] = val;
+        const int c = ch / 49, rs = ch - c * 49, r = rs / 7, s = rs - r * 7;
+        const int yi = 2 * yo + r - 3;
+        sx[i] = s - 3;
+        base[i] = (ch < 147 && yi >= 0 && yi < H) ? (c * H + yi) * W : -1;
     }
-    stv(out + ((size_t)row * Wo + xo) * STEM_PATCH_C + cv * N, v);
+    for (int xo = lane; xo < Wo; xo += LANES) {
+        Vf<N> v;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int xi = 2 * xo + sx[i];
+            v.v[i] = (base[i] >= 0 && xi >= 0 && xi < W) ? __ldg(xn + base[i] + xi) : 0.f;
+        }
+        stv(out + ((size_t)row * Wo + xo) * STEM_PATCH_C + cv * N, v);
+    }
 }
 void k_stem_im2col(cudaStream_t st, DType dt, const float* x, void* patches, int B, int H, int W) {
-    SaltProfScope prof_scope(SALT_PROF_OTHER, 0.0, st);
+    SaltProfScope prof_scope(SALT_PROF_OTHER, (double)B * 3 * H * W * 4 + (double)B * (H / 2) * (W / 2) * STEM_PATCH_C * dtype_size(dt), st);
     SALT_COUNT(1);
-    SALT_DISPATCH(dt, T, {
-        dim3 grid(B * (H / 2), cdiv((W / 2) * (STEM_PATCH_C / VW<T>::N), EW_THREADS));
-        stem_im2col_kernel<T><<<grid, EW_THREADS, 0, st>>>(x, (T*)patches, H, W);
-    });
+    SALT_DISPATCH(dt, T, (stem_im2col_kernel<T><<<B * (H / 2), EW_THREADS, 0, st>>>(x, (T*)patches, H, W)));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -364,6 +368,8 @@ void k_gather_fwd(cudaStream_t st, const Tensor& out, const GatherSrc* srcs, int
 template <typename T>
 __global__ void fold_bwd_kernel(const T* __restrict__ gP, int c0, T* __restrict__ gsrc, int accumulate,
                                 int H, int W, int Cp, int Cs, int pt, int pb, int pl, int pr) {
+    // one (pixel, channel vector) item per thread; a four-items-per-thread version with the centre loads issued up front measured
+    // 2x SLOWER (110 registers, profiles/r2_notes.md)
     constexpr int N = VW<T>::N;
     const int cg = Cs / N, Hp = H + pt + pb, Wp = W + pl + pr;
     const int j = blockIdx.y * EW_THREADS + threadIdx.x;
@@ -402,56 +408,76 @@ __device__ __forceinline__ void adj_range(int j, int f, int pad, int ndst, int n
     lo = dlo <= 0 ? 0 : dlo + pad;
     hi = dhi >= ndst ? nphys : dhi + pad;
 }
+// One block per (image, source row jy).  Phase A reduces along y straight from global memory: item = (physical column xp, channel
+// vector), all threads walk the SAME 2f destination rows with non-zero weight (uniform weights, unconditional independent loads, four
+// rows in flight), the fp32 row of partial sums stays in shared memory.  Phase B reduces along x out of shared memory and writes the
+// source-row gradient.  Nothing but the gradient slice is read and nothing but the source gradient is written: the two-kernel
+// version went through an fp32 temporary in global memory that is as large as the slice itself for f = 2 (profiles/r2_notes.md).
 template <typename T>
-__global__ void upsample_bwd_x_kernel(const T* __restrict__ gP, int c0, float* __restrict__ tmp, int W, int Cp, int Cs,
-                                      int pl, int pr, int f) {
+__global__ void __launch_bounds__(EW_THREADS) upsample_bwd_kernel(const T* __restrict__ gP, int c0, T* __restrict__ gsrc, int accumulate,
+                                                                  int H, int W, int Cp, int Cs, int pt, int pb, int pl, int pr, int f,
+                                                                  int Cslab) {
     constexpr int N = VW<T>::N;
-    const int cg = Cs / N, Wp = W + pl + pr, Ws = W / f;
-    const int j = blockIdx.y * EW_THREADS + threadIdx.x;
-    if (j >= Ws * cg) return;
-    const int jx = j / cg, c = (j - jx * cg) * N;
-    const int row = blockIdx.x;                            // n*Hp + yp
-    int lo, hi;
-    adj_range(jx, f, pl, W, Wp, lo, hi);
-    Vf<N> acc = vzero<N>();
-    for (int xp = lo; xp < hi; ++xp) {
-        float w = bilin_adj_w(xp, pl, W, f, Ws, jx);
-        if (w != 0.f) acc = vaxpy(ldv(gP + ((size_t)row * Wp + xp) * Cp + c0 + c), w, acc);
-    }
-    stp<N>(tmp + ((size_t)row * Ws + jx) * Cs + c, acc);
-}
-template <typename T>
-__global__ void upsample_bwd_y_kernel(const float* __restrict__ tmp, T* __restrict__ gsrc, int accumulate, int H,
-                                      int W, int Cs, int pt, int pb, int f) {
-    constexpr int N = VW<T>::N;
-    const int cg = Cs / N, Hp = H + pt + pb, Ws = W / f, Hs = H / f;
-    const int j = blockIdx.y * EW_THREADS + threadIdx.x;
-    if (j >= Ws * cg) return;
-    const int jx = j / cg, c = (j - jx * cg) * N;
+    extern __shared__ __align__(16) float rowacc[];      // [Wp][Cslab]: blockIdx.y selects a slab of Cslab source channels
+    const int cg = Cslab / N, Hp = H + pt + pb, Wp = W + pl + pr, Hs = H / f, Ws = W / f;
+    c0 += blockIdx.y * Cslab;
+    gsrc += blockIdx.y * Cslab;
     const int row = blockIdx.x, n = row / Hs, jy = row - n * Hs;
     int lo, hi;
     adj_range(jy, f, pt, H, Hp, lo, hi);
-    Vf<N> acc = vzero<N>();
-    for (int yp = lo; yp < hi; ++yp) {
-        float w = bilin_adj_w(yp, pt, H, f, Hs, jy);
-        if (w != 0.f) acc = vaxpy(ldp<N>(tmp + (((size_t)n * Hp + yp) * Ws + jx) * Cs + c), w, acc);
+    while (lo < hi && bilin_adj_w(lo, pt, H, f, Hs, jy) == 0.f) ++lo;            // the rows with non-zero weight are contiguous
+    while (hi > lo && bilin_adj_w(hi - 1, pt, H, f, Hs, jy) == 0.f) --hi;
+    const T* base = gP + (size_t)n * Hp * Wp * Cp + c0;
+    for (int item = threadIdx.x; item < Wp * cg; item += EW_THREADS) {
+        const int xp = item / cg, c = (item - xp * cg) * N;
+        const T* col = base + (size_t)xp * Cp + c;
+        Vf<N> acc = vzero<N>();
+        int yp = lo;
+        for (; yp + 3 < hi; yp += 4) {
+            Vf<N> v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = ldv(col + (size_t)(yp + u) * Wp * Cp);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc = vaxpy(v[u], bilin_adj_w(yp + u, pt, H, f, Hs, jy), acc);
+        }
+        for (; yp < hi; ++yp) acc = vaxpy(ldv(col + (size_t)yp * Wp * Cp), bilin_adj_w(yp, pt, H, f, Hs, jy), acc);
+        stp<N>(rowacc + (size_t)xp * Cslab + c, acc);
     }
-    T* o = gsrc + ((size_t)row * Ws + jx) * Cs + c;
-    if (accumulate) acc = vadd(acc, ldv(o));
-    stv(o, acc);
+    __syncthreads();
+    for (int item = threadIdx.x; item < Ws * cg; item += EW_THREADS) {
+        const int jx = item / cg, c = (item - jx * cg) * N;
+        int xlo, xhi;
+        adj_range(jx, f, pl, W, Wp, xlo, xhi);
+        Vf<N> acc = vzero<N>();
+        for (int xp = xlo; xp < xhi; ++xp) {
+            const float w = bilin_adj_w(xp, pl, W, f, Ws, jx);
+            if (w != 0.f) acc = vaxpy(ldp<N>(rowacc + (size_t)xp * Cslab + c), w, acc);
+        }
+        T* o = gsrc + ((size_t)row * Ws + jx) * Cs + c;
+        if (accumulate) acc = vadd(acc, ldv(o));
+        stv(o, acc);
+    }
 }
 size_t upsample_bwd_tmp_floats(const Tensor& gP, int f, int Csrc) {
     return (size_t)gP.B * gP.Hp() * (gP.W / f) * Csrc;
 }
-void k_upsample_bwd(cudaStream_t st, const Tensor& gP, int c0, int f, const Tensor& gsrc, float* tmp, bool accumulate) {
+void k_upsample_bwd(cudaStream_t st, const Tensor& gP, int c0, int f, const Tensor& gsrc, float* /*tmp: unused since the fused kernel*/,
+                    bool accumulate) {
     SaltProfScope prof_scope(SALT_PROF_GATHER_BWD, (double)gP.bytes() * gsrc.C / gP.C + (double)gsrc.bytes(), st);
-    SALT_COUNT(2);
+    SALT_COUNT(1);
     SALT_DISPATCH(gP.dt, T, {
-        const int rowlen = (gP.W / f) * (gsrc.C / VW<T>::N);
-        upsample_bwd_x_kernel<T><<<dim3(gP.B * gP.Hp(), cdiv(rowlen, EW_THREADS)), EW_THREADS, 0, st>>>(
-            (const T*)gP.p, c0, tmp, gP.W, gP.C, gsrc.C, gP.pl, gP.pr, f);
-        upsample_bwd_y_kernel<T><<<dim3(gsrc.B * gsrc.H, cdiv(rowlen, EW_THREADS)), EW_THREADS, 0, st>>>(
-            tmp, (T*)gsrc.p, accumulate ? 1 : 0, gP.H, gP.W, gsrc.C, gP.pt, gP.pb, f);
+        int cslab = gsrc.C;                           // halve the channel slab until the fp32 row fits 64 KB
+        while (gP.Wp() * cslab * (int)sizeof(float) > 64 * 1024 && cslab % (2 * VW<T>::N) == 0) cslab >>= 1;
+        const int smem = gP.Wp() * cslab * (int)sizeof(float);
+        static int smem_set = 0;
+        if (smem > 48 * 1024 && smem > smem_set) {
+            if (smem > 200 * 1024) throw std::runtime_error("upsample backward: row of partial sums exceeds shared memory");
+            cudaFuncSetAttribute(upsample_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            smem_set = smem;
+        }
+        upsample_bwd_kernel<T><<<dim3(gsrc.B * gsrc.H, gsrc.C / cslab), EW_THREADS, smem, st>>>((const T*)gP.p, c0, (T*)gsrc.p,
+                                                                         accumulate ? 1 : 0, gP.H, gP.W,
+                                                                         gP.C, gsrc.C, gP.pt, gP.pb, gP.pl, gP.pr, f, cslab);
     });
 }
 
@@ -474,12 +500,24 @@ __global__ void se_pool_kernel(const T* __restrict__ raw, const T* __restrict__ 
     const int p0 = blockIdx.x * chunk, p1 = min(HW, p0 + chunk);
     const Vf<N> sc = ldp<N>(scale + cv * N), sh = ldp<N>(shift + cv * N);
     Vf<N> acc = vzero<N>();
-    for (int p = p0 + lane; p < p1; p += lanes) {
-        const size_t o = ((size_t)n * HW + p) * C + cv * N;
-        Vf<N> z = vfma(ldv(raw + o), sc, sh);
-        if (RELU) z = vrelu(z);
-        if (WITH_G) z = vmul(z, ldv(g + o));
-        acc = vadd(acc, z);
+    // four pixels per pass: all loads of a pass are issued before the first use (one load in flight per thread ran at 2 TB/s)
+    for (int p = p0 + lane; p < p1; p += 4 * lanes) {
+        Vf<N> xs[4], gs[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const size_t o = ((size_t)n * HW + min(p + u * lanes, p1 - 1)) * C + cv * N;
+            xs[u] = ldv(raw + o);
+            if (WITH_G) gs[u] = ldv(g + o);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (p + u * lanes < p1) {
+                Vf<N> z = vfma(xs[u], sc, sh);
+                if (RELU) z = vrelu(z);
+                if (WITH_G) z = vmul(z, gs[u]);
+                acc = vadd(acc, z);
+            }
+        }
     }
 #pragma unroll
     for (int i = 0; i < N; ++i) red[i * EW_THREADS + threadIdx.x] = acc.v[i];

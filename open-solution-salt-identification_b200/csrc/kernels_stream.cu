@@ -157,15 +157,27 @@ struct ScseApplyOp {
         c = ((tid * 16) & (rb - 1)) / 2;
         sc = ldp<N>(scale + c); sh = ldp<N>(shift + c); w = ldp<N>(se.ws + c); bs = se.bs[0];
     }
-    __device__ void vec(size_t off, const uint8_t* stage, int o, bool valid) {
-        const Vf<N> z = vrelu(vfma(vfrom<bf16>(lds16(stage + o)), sc, sh));
-        const float dot = group_sum(vdot(z, w), cg);
-        const float sg = 1.f / (1.f + expf(-(dot + bs)));
-        const unsigned n = (unsigned)(off >> rshift_bits) / (unsigned)HW;
-        Vf<N> gate = ldp<N>(se.cse + (size_t)n * C + c);
+    static constexpr int U = 4;
+    __device__ void vecs(size_t off, const uint8_t* stage, const int (&o)[U], const bool (&valid)[U]) {
+        Vf<N> z[U], gate[U];
+        float dot[U];
 #pragma unroll
-        for (int i = 0; i < N; ++i) gate.v[i] += sg;
-        if (valid) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) + off) = vto<bf16>(vrelu(vmul(z, gate)));
+        for (int u = 0; u < U; ++u) {
+            z[u] = vrelu(vfma(vfrom<bf16>(lds16(stage + o[u])), sc, sh));
+            gate[u] = ldp<N>(se.cse + (size_t)((unsigned)((off + o[u]) >> rshift_bits) / (unsigned)HW) * C + c);
+            dot[u] = vdot(z[u], w);
+        }
+        for (int m = cg >> 1; m > 0; m >>= 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], m);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float sg = 1.f / (1.f + expf(-(dot[u] + bs)));
+#pragma unroll
+            for (int i = 0; i < N; ++i) gate[u].v[i] += sg;
+            if (valid[u]) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) + off + o[u]) = vto<bf16>(vrelu(vmul(z[u], gate[u])));
+        }
     }
     __device__ void end(int, float*) {}
 };
@@ -190,24 +202,36 @@ struct ScseBwdOp {
         w = ldp<N>(se.ws + c); bs = se.bs[0];
         sg = vzero<N>(); sgx = vzero<N>(); sws = vzero<N>(); sbs = 0.f;
     }
-    __device__ void vec(size_t off, const uint8_t* stage, int o, bool valid) {
-        const Vf<N> g = vfrom<bf16>(lds16(stage + o)), x = vfrom<bf16>(lds16(stage + ring::CHUNK + o));
-        const Vf<N> z = vrelu(vfma(x, sc, sh));
-        const float dot = group_sum(vdot(z, w), cg);
-        const float s = 1.f / (1.f + expf(-(dot + bs)));
-        const float D = group_sum(vdot(g, z), cg);
-        const float dsp = D * s * (1.f - s);
-        const size_t no = (size_t)((unsigned)(off >> rshift_bits) / (unsigned)HW) * C + c;
-        const Vf<N> cse = ldp<N>(se.cse + no), G = ldp<N>(se.G + no);
-        Vf<N> dz;
+    static constexpr int U = 2;
+    __device__ void vecs(size_t off, const uint8_t* stage, const int (&o)[U], const bool (&valid)[U]) {
+        Vf<N> g[U], x[U], z[U];
+        float dot[U], D[U];
 #pragma unroll
-        for (int i = 0; i < N; ++i) dz.v[i] = z.v[i] > 0.f ? g.v[i] * (cse.v[i] + s) + dsp * w.v[i] + G.v[i] : 0.f;
-        if (valid) {
-            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(gbn) + off) = vto<bf16>(dz);
-            sg = vadd(sg, dz);
-            sgx = vfma(dz, vxhat(x, mu, is), sgx);
-            sws = vaxpy(z, dsp, sws);
-            if (c == 0) sbs += dsp;
+        for (int u = 0; u < U; ++u) {
+            g[u] = vfrom<bf16>(lds16(stage + o[u])); x[u] = vfrom<bf16>(lds16(stage + ring::CHUNK + o[u]));
+            z[u] = vrelu(vfma(x[u], sc, sh));
+            dot[u] = vdot(z[u], w); D[u] = vdot(g[u], z[u]);
+        }
+        for (int m = cg >> 1; m > 0; m >>= 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) { dot[u] += __shfl_xor_sync(0xffffffffu, dot[u], m); D[u] += __shfl_xor_sync(0xffffffffu, D[u], m); }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float s = 1.f / (1.f + expf(-(dot[u] + bs)));
+            const float dsp = D[u] * s * (1.f - s);
+            const size_t no = (size_t)((unsigned)((off + o[u]) >> rshift_bits) / (unsigned)HW) * C + c;
+            const Vf<N> cse = ldp<N>(se.cse + no), G = ldp<N>(se.G + no);
+            Vf<N> dz;
+#pragma unroll
+            for (int i = 0; i < N; ++i) dz.v[i] = z[u].v[i] > 0.f ? g[u].v[i] * (cse.v[i] + s) + dsp * w.v[i] + G.v[i] : 0.f;
+            if (valid[u]) {
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(gbn) + off + o[u]) = vto<bf16>(dz);
+                sg = vadd(sg, dz);
+                sgx = vfma(dz, vxhat(x[u], mu, is), sgx);
+                sws = vaxpy(z[u], dsp, sws);
+                if (c == 0) sbs += dsp;
+            }
         }
     }
     __device__ void end(int tid, float* red) {
@@ -240,12 +264,28 @@ struct FinalFwdOp {
         c = ((tid * 16) & (rb - 1)) / 2;
         sc = ldp<N>(scale + c); sh = ldp<N>(shift + c);
     }
-    __device__ void vec(size_t off, const uint8_t* stage, int o, bool valid) {
-        const Vf<N> z = vrelu(vfma(vfrom<bf16>(lds16(stage + o)), sc, sh));
-        const unsigned pix = (unsigned)(off >> rshift_bits), n = pix / (unsigned)HW, p = pix - n * HW;
+    static constexpr int U = 4;
+    __device__ void vecs(size_t off, const uint8_t* stage, const int (&o)[U], const bool (&valid)[U]) {
+        Vf<N> z[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) z[u] = vrelu(vfma(vfrom<bf16>(lds16(stage + o[u])), sc, sh));
         for (int k = 0; k < K; ++k) {
-            const float d = group_sum(vdot(z, ldp<N>(w + k * C + c)), cg);
-            if (valid && c == 0) logits[((size_t)n * K + k) * HW + p] = d + b[k];
+            const Vf<N> wk = ldp<N>(w + k * C + c);
+            float d[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) d[u] = vdot(z[u], wk);
+            for (int m = cg >> 1; m > 0; m >>= 1) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) d[u] += __shfl_xor_sync(0xffffffffu, d[u], m);
+            }
+            if (c == 0) {
+                const float bk = b[k];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const unsigned pix = (unsigned)((off + o[u]) >> rshift_bits), n = pix / (unsigned)HW, p = pix - n * HW;
+                    if (valid[u]) logits[((size_t)n * K + k) * HW + p] = d[u] + bk;
+                }
+            }
         }
     }
     __device__ void end(int, float*) {}
@@ -293,8 +333,13 @@ struct FinalBwdOp {
     }
     // the dlogits planes are 1/(C/2) as dense as the activation stream, so the op addresses the stage itself (no shuffles here:
     // the tail of a short chunk simply returns)
-    __device__ void vec(size_t off, const uint8_t* stage, int o, bool valid) {
-        if (!valid) return;
+    static constexpr int U = 2;
+    __device__ void vecs(size_t off, const uint8_t* stage, const int (&o)[U], const bool (&valid)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (valid[u]) one(off + o[u], stage, o[u]);
+    }
+    __device__ void one(size_t off, const uint8_t* stage, int o) {
         const Vf<N> x = vfrom<bf16>(lds16(stage + o));
         const Vf<N> z = vrelu(vfma(x, sc, sh));
         const int pl = o >> rshift_bits;                  // pixel within the chunk

@@ -65,9 +65,10 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;
 //   static constexpr bool FULL_WARPS
 //   void vec(size_t off, const uint4 (&in)[NS])           FULL_WARPS = false: one 16-byte vector of every input at byte offset
 //                                                         `off` of the tensors
-//   void vec(size_t off, const uint8_t* stage, int o, bool valid)
-//                                                         FULL_WARPS = true (ops with warp shuffles): the op reads its inputs from
-//                                                         the stage itself (stream i at stage + i*CHUNK, primary offset o)
+//   void vecs(size_t off, const uint8_t* stage, const int (&o)[U], const bool (&valid)[U])
+//                                                         FULL_WARPS = true (ops with warp shuffles): U vectors per call, the op
+//                                                         reads its inputs from the stage itself (stream i at stage + i*CHUNK +
+//                                                         o[u]; tensor byte offset off + o[u])
 //   void end(int tid, float* red)                         after the last chunk; `red` = EW_THREADS * 8 floats of shared memory,
 //                                                         consumers synchronise with consumer_sync() / the NAMED block sums
 template <int NS, class Op>
@@ -113,12 +114,18 @@ __global__ void __launch_bounds__(THREADS, 1) ring_kernel(Streams<NS> s, Op op) 
         mbar_wait(full0 + 8 * st, ph);
         const uint8_t* base = smem + (size_t)st * NS * CHUNK;
         if constexpr (Op::FULL_WARPS) {
-            // ops with warp shuffles: every thread runs every pass of a (possibly short) chunk, `valid` masks the tail
-#pragma unroll 2
-            for (int o = threadIdx.x * 16; o - (int)threadIdx.x * 16 < bytes; o += CONSUMERS * 16) {
-                const bool valid = o < bytes;
-                const int oc = valid ? o : (int)threadIdx.x * 16;
-                op.vec(off + oc, base, oc, valid);
+            // ops with warp shuffles: every thread runs every pass of a (possibly short) chunk, `valid` masks the tail; the op takes
+            // Op::U vectors (U consecutive passes) at once so that their shuffle / special-function chains overlap
+            constexpr int U = Op::U;
+            for (int o0 = threadIdx.x * 16; o0 - (int)threadIdx.x * 16 < bytes; o0 += U * CONSUMERS * 16) {
+                int oc[U]; bool valid[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int o = o0 + u * CONSUMERS * 16;
+                    valid[u] = o < bytes;
+                    oc[u] = valid[u] ? o : (int)threadIdx.x * 16;
+                }
+                op.vecs(off, base, oc, valid);
             }
         } else {
 #pragma unroll 2
