@@ -175,6 +175,177 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     if (warp == 1) { fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// ------------------------------------------------------------------------------------------------ halo-box variant (3x3, stride 1)
+// The kernel above loads one shifted [32 px][64 ch] input tile PER TAP: 9 x 4 KB + the gradient tile per 10 MMAs = 64-80 B/clk of
+// L2 -> SM traffic, above what the chip delivers to all SMs at once (~42 B/clk/SM) - the 3x3 weight gradients ran at 40-59 % of
+// the sustained tensor rate, ingest-bound.  Here ONE TMA box of (PW+2) x (PH+2) input pixels x 64 channels per stage serves all nine
+// taps: tap (r, s) of 16-pixel K-step kk is the same shared-memory tile entered at pixel row (kk + r) * (PW + 2) + s - the
+// descriptor start address may sit anywhere inside the 8-row swizzle atom because the tensor core applies the 128B swizzle to
+// absolute shared-memory address bits (known-answer test profiles/desc_offset_test.cu), and the leading-byte offset that stacks the
+// second tap of a pair into rows 64-127 of the M = 128 instruction is simply the byte distance between the two taps' entry points.
+// One CTA = one 64-channel input block x one 64-channel output tile, all nine taps (5 accumulators of 64 columns), a 64-pixel chunk
+// per stage (4 K-steps): 22 KB per 20 MMAs = 18 B/clk.  N = 64 caps an MMA at 64 clk (half the tensor peak), still above what
+// the ingest-bound N = 128 form reached.
+constexpr int WH_STAGES = 6;
+constexpr int WH_XBYTES = 14336;       // >= (PW+2)*(PH+2)*128: 18 x 6 (PW = 16, PH = 4) or 10 x 10 (PW = 8, PH = 8) pixel rows, 1024-aligned
+constexpr int WH_GBYTES = 8192;        // 64 pixels x 64 channels
+constexpr int WH_STAGE = WH_XBYTES + WH_GBYTES;
+constexpr int WH_SMEM = WH_STAGES * WH_STAGE + 1024 + 256;
+
+template <int PW>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, const WgParams p) {
+    constexpr int PH = 64 / PW, BW = PW + 2, STAGES = WH_STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * WH_STAGE);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
+    const int cb = blockIdx.y, k0 = blockIdx.z * 64;
+    const int chunk_begin = blockIdx.x * p.chunks_per_split;
+    const int chunk_end = min(p.total_chunks, chunk_begin + p.chunks_per_split);
+    const int nchunks = chunk_end - chunk_begin;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_g) : "memory");
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (nchunks > 0) {
+        if (warp == 0) {
+            if (elect_one()) {
+                int stage = 0; uint32_t phase = 0;
+                constexpr uint32_t tx_bytes = (uint32_t)(BW * (PH + 2) * 128 + WH_GBYTES);
+                int cx = chunk_begin % p.chunks_x, cy = (chunk_begin / p.chunks_x) % p.chunks_y, n = chunk_begin / (p.chunks_x * p.chunks_y);
+                for (int ck = chunk_begin; ck < chunk_end; ++ck) {
+                    const int x0 = cx * PW, y0 = cy * PH;
+                    const uint32_t st = smem_u32(smem + stage * WH_STAGE), fb = full0 + 8 * stage;
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(fb, tx_bytes);
+                    tma_load_4d(st, &map_x, fb, cb * 64, x0 - p.pad, y0 - p.pad, n);
+                    tma_load_4d(st + WH_XBYTES, &map_g, fb, k0, x0, y0, n);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++cx == p.chunks_x) { cx = 0; if (++cy == p.chunks_y) { cy = 0; ++n; } }
+                }
+            }
+        } else if (warp == 1) {
+            const uint32_t idesc = instr_desc_bf16(64, true, true);
+            const uint32_t smem0 = smem_u32(smem);
+            // pixel-row offset of tap t = (r, s) inside the box; a K-step is one 16-pixel image row (PW = 16: SBO 1024) or two
+            // 8-pixel rows (PW = 8: the second 8-row group starts one box row = BW * 128 B further)
+            constexpr uint32_t SBO = PW == 16 ? 1024 : BW * 128;
+            constexpr int KROWS = PW == 16 ? BW : 2 * BW;            // box rows (pixels) advanced per K-step
+            uint64_t adesc0[5];
+#pragma unroll
+            for (int g = 0; g < 5; ++g) {
+                const int ta = 2 * g, tb = 2 * g + 1 < 9 ? 2 * g + 1 : 2 * g;
+                const int ra = (ta / 3) * BW + ta % 3, rb = (tb / 3) * BW + tb % 3;
+                adesc0[g] = smem_desc(smem0 + ra * 128, (uint32_t)(rb - ra) * 128, SBO, 2);
+            }
+            const uint64_t bdesc0 = smem_desc(smem0 + WH_XBYTES, 0, 1024, 2);
+            if (elect_one()) {
+                int stage = 0; uint32_t phase = 0;
+                bool stage_ready = false;
+                for (int it = 0; it < nchunks; ++it) {
+                    if (!stage_ready) mbar_wait(full0 + 8 * stage, phase);
+                    fence_after();
+                    const int nstage = stage + 1 == STAGES ? 0 : stage + 1;
+                    const uint32_t nphase = stage + 1 == STAGES ? phase ^ 1 : phase;
+                    const uint64_t soff = (uint64_t)((stage * WH_STAGE) >> 4);
+                    uint32_t probe = 0;
+#pragma unroll
+                    for (int g = 0; g < 5; ++g) {
+                        if (g == 4 && it + 1 < nchunks) probe = mbar_try_wait(full0 + 8 * nstage, nphase) ? 1u : 0u;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16(tmem_base + g * 64, adesc0[g] + soff + (uint64_t)(kk * KROWS * 8), bdesc0 + soff + (uint64_t)(kk * 128),
+                                      idesc, (it | kk) != 0);
+                    }
+                    umma_commit(empty0 + 8 * stage);
+                    if (it == nchunks - 1) umma_commit(tfull);
+                    stage_ready = probe != 0;
+                    stage = nstage; phase = nphase;
+                }
+            }
+            __syncwarp();
+        } else {
+            // epilogue: TMEM -> red.global.add.v4.f32 into dwp[tap][c][k]
+            const int quarter = warp & 3;
+            const int m = quarter * 32 + lane;
+            mbar_wait(tfull, 0);
+            fence_after();
+            for (int g = 0; g < 5; ++g) {
+                const int tap = 2 * g + (m >> 6);
+                const bool row_ok = tap < 9 && cb * 64 + (m & 63) < p.Ci_pad;
+                float* drow = p.dwp + ((size_t)(tap < 9 ? tap : 8) * p.Ci_pad + cb * 64 + (m & 63)) * p.Co + k0;
+#pragma unroll 1
+                for (int ch = 0; ch < 2; ++ch) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + g * 64 + ch * 32, v);
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (k0 + ch * 32 + j < p.Co)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + ch * 32 + j), "f"(v[j]),
+                                             "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+                        }
+                    }
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) { fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+static bool wgrad_halo_pref() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SALT_WGRAD_HALO"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
+// 3x3 stride-1 weight gradients whose map tiles into 16 x 4 or 8 x 8 pixel chunks
+static bool wgrad_halo_ok(const ConvGeom& g) {
+    if (!wgrad_halo_pref() || g.R != 3 || g.S != 3 || g.stride != 1 || g.Ci % 8 || g.Co % 8) return false;
+    if (g.Wo >= 16) return g.Wo % 16 == 0 && g.Ho % 4 == 0;
+    return g.Wo == 8 && g.Ho % 8 == 0;
+}
+template <int PW>
+static void launch_wg_halo(cudaStream_t st, const void* in, const void* gout, float* dwp, const ConvGeom& g) {
+    constexpr int PH = 64 / PW;
+    WgParams p;
+    p.B = g.B; p.Ho = g.Ho; p.Wo = g.Wo; p.Ci_pad = cdiv(g.Ci, 64) * 64; p.Co = g.Co;
+    p.RS = 9; p.S = 3; p.stride = 1; p.pad = g.pad;
+    p.cblks = cdiv(g.Ci, 64); p.total_slots = 9 * p.cblks; p.slots_per_cta = 9;
+    p.pw = PW; p.ph = PH; p.chunks_x = g.Wo / PW; p.chunks_y = g.Ho / PH;
+    p.total_chunks = g.B * p.chunks_x * p.chunks_y;
+    const int k_tiles = cdiv(g.Co, 64);
+    int splits = num_sms() / (p.cblks * k_tiles);          // one wave of CTAs, as above
+    const int max_splits = cdiv(p.total_chunks, 4);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.chunks_per_split = cdiv(p.total_chunks, splits);
+    splits = cdiv(p.total_chunks, p.chunks_per_split);
+    p.dwp = dwp;
+    CUtensorMap mx = make_map_nhwc(in, g.Ci, g.Wi, g.Hi, g.B, 64, PW + 2, PH + 2, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+    CUtensorMap mg = make_map_nhwc(gout, g.Co, g.Wo, g.Ho, g.B, 64, PW, PH, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(conv_wgrad_halo_kernel<PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, WH_SMEM);
+        configured = true;
+    }
+    conv_wgrad_halo_kernel<PW><<<dim3(splits, p.cblks, k_tiles), WG_THREADS, WH_SMEM, st>>>(mx, mg, p);
+}
+
 bool tc_wgrad_supported(const ConvGeom& g) {
     if (g.Wo < 8 || g.Ho < 4) return false;
     const int pw = g.Wo >= 16 ? 16 : 8, ph = 32 / pw;
@@ -225,6 +396,11 @@ size_t tc_wgrad_scratch_floats(int Ci, int Co, int RS) { return (size_t)RS * (cd
 // in: [B,Hi,Wi,Ci] bf16 (physical dims); gout: [B,Ho,Wo,Co] bf16; dwp: zeroed fp32 scratch [RS][ceil64(Ci)][Co], accumulated into
 void k_conv_wgrad_tc(cudaStream_t st, const void* in, const void* gout, float* dwp, const ConvGeom& g) {
     SALT_COUNT(1);
+    if (wgrad_halo_ok(g)) {
+        if (g.Wo >= 16) launch_wg_halo<16>(st, in, gout, dwp, g);
+        else launch_wg_halo<8>(st, in, gout, dwp, g);
+        return;
+    }
     WgParams p;
     p.B = g.B; p.Ho = g.Ho; p.Wo = g.Wo; p.Ci_pad = cdiv(g.Ci, 64) * 64; p.Co = g.Co;
     p.RS = g.R * g.S; p.S = g.S; p.stride = g.stride; p.pad = g.pad;

@@ -7,6 +7,23 @@
 // ------------------------------------------------------------------------------------------------
 // 16-byte channel vectors
 // ------------------------------------------------------------------------------------------------
+// n / d for n < 2^31 by multiply-shift (the hardware has no integer divide: a 32-bit division is ~30 instructions through the
+// special-function unit, and the ring consumers are instruction-bound - profiles/r2_notes.md)
+struct FDiv {
+    uint32_t d, mul, shr;
+    __device__ __forceinline__ uint32_t div(uint32_t n) const { return d == 1 ? n : __umulhi(n, mul) >> shr; }
+};
+static inline FDiv make_fdiv(int d) {
+    FDiv f; f.d = (uint32_t)d; f.mul = 0; f.shr = 0;
+    if (d > 1) {
+        int lg = 0;
+        while ((1u << lg) < (uint32_t)d) ++lg;
+        const unsigned p = 31 + lg;
+        f.mul = (uint32_t)(((1ull << p) + (uint32_t)d - 1) / (uint32_t)d);
+        f.shr = p - 32;
+    }
+    return f;
+}
 template <typename T> struct VW;
 template <> struct VW<float> { static constexpr int N = 4; };
 template <> struct VW<bf16> { static constexpr int N = 8; };
@@ -140,14 +157,15 @@ template <int N> __device__ __forceinline__ Vf<N> vxhat(const Vf<N>& x, const Vf
 // made every extra block of the reduction passes expensive (profiles/r2_notes.md).  The result is valid in threads tid < cg.
 // NAMED: the block carries extra warps that do not take part (the producer warp of the stream-ring kernels): the EW_THREADS
 // reducing threads meet on named barrier 1 instead of __syncthreads().
-template <bool NAMED> __device__ __forceinline__ void ew_sync() {
-    if constexpr (NAMED) asm volatile("bar.sync 1, 256;" ::: "memory");
+// NT = number of reducing threads (a multiple of 32; the ring kernels run 8 or 16 consumer warps); red holds N * NT floats.
+template <bool NAMED, int NT> __device__ __forceinline__ void ew_sync() {
+    if constexpr (NAMED) asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
     else __syncthreads();
 }
-template <int N, bool NAMED = false>
+template <int N, bool NAMED = false, int NT = EW_THREADS>
 __device__ __forceinline__ void block_sum(Vf<N>& v, int cg, float* red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = EW_THREADS / 32;
+    constexpr int NW = NT / 32;
     if (cg < 32) {
         for (int off = cg; off < 32; off <<= 1) {
 #pragma unroll
@@ -157,7 +175,7 @@ __device__ __forceinline__ void block_sum(Vf<N>& v, int cg, float* red) {
 #pragma unroll
             for (int i = 0; i < N; ++i) red[(i * NW + warp) * 32 + lane] = v.v[i];
         }
-        ew_sync<NAMED>();
+        ew_sync<NAMED, NT>();
         if (tid < cg) {
 #pragma unroll
             for (int i = 0; i < N; ++i) {
@@ -169,23 +187,23 @@ __device__ __forceinline__ void block_sum(Vf<N>& v, int cg, float* red) {
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < N; ++i) red[i * EW_THREADS + tid] = v.v[i];
-        ew_sync<NAMED>();
+        for (int i = 0; i < N; ++i) red[i * NT + tid] = v.v[i];
+        ew_sync<NAMED, NT>();
         if (tid < cg) {
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 float s = 0.f;
-                for (int t = tid; t < EW_THREADS; t += cg) s += red[i * EW_THREADS + t];
+                for (int t = tid; t < NT; t += cg) s += red[i * NT + t];
                 v.v[i] = s;
             }
         }
     }
-    ew_sync<NAMED>();
+    ew_sync<NAMED, NT>();
 }
 // ... added to dst[c..] with atomics (parameter gradients that several blocks contribute to)
-template <int N, typename D, bool NAMED = false>
+template <int N, typename D, bool NAMED = false, int NT = EW_THREADS>
 __device__ __forceinline__ void block_reduce_add(Vf<N> v, int cg, D* dst, float* red) {
-    block_sum<N, NAMED>(v, cg, red);
+    block_sum<N, NAMED, NT>(v, cg, red);
     if ((int)threadIdx.x < cg) {
 #pragma unroll
         for (int i = 0; i < N; ++i) atomicAdd(dst + threadIdx.x * N + i, (D)v.v[i]);
@@ -193,9 +211,9 @@ __device__ __forceinline__ void block_reduce_add(Vf<N> v, int cg, D* dst, float*
 }
 // ... STORED into the block's own partial slot (dst already points at the slot): the finalize kernel adds the slots in a fixed
 // order, so the result does not depend on block scheduling.
-template <int N, bool NAMED = false>
+template <int N, bool NAMED = false, int NT = EW_THREADS>
 __device__ __forceinline__ void block_reduce_slot(Vf<N> v, int cg, float* dst, float* red) {
-    block_sum<N, NAMED>(v, cg, red);
+    block_sum<N, NAMED, NT>(v, cg, red);
     if ((int)threadIdx.x < cg) {
 #pragma unroll
         for (int i = 0; i < N; ++i) dst[threadIdx.x * N + i] = v.v[i];

@@ -367,21 +367,26 @@ void k_gather_fwd(cudaStream_t st, const Tensor& out, const GatherSrc* srcs, int
 // adjoint of the replicate border for a copied (f == 1) source: gsrc[y,x] (+)= sum of the border cells mapped to it
 template <typename T>
 __global__ void fold_bwd_kernel(const T* __restrict__ gP, int c0, T* __restrict__ gsrc, int accumulate,
-                                int H, int W, int Cp, int Cs, int pt, int pb, int pl, int pr) {
+                                int H, int W, int Cp, int Cs, int pt, int pb, int pl, int pr, int cgs) {
     // one (pixel, channel vector) item per thread; a four-items-per-thread version with the centre loads issued up front measured
     // 2x SLOWER (110 registers, profiles/r2_notes.md)
     constexpr int N = VW<T>::N;
     const int cg = Cs / N, Hp = H + pt + pb, Wp = W + pl + pr;
     const int j = blockIdx.y * EW_THREADS + threadIdx.x;
     if (j >= W * cg) return;
-    const int x = j / cg, c = (j - x * cg) * N;
+    // (the pass is instruction-bound - ncu: issue slots 61 % busy at 3.1 TB/s - so the index arithmetic is kept short)
+    const int x = cgs >= 0 ? (j >> cgs) : j / cg, c = (j - x * cg) * N;
     const int row = blockIdx.x, n = row / H, y = row - n * H;
-    const int y0 = (y == 0) ? 0 : y + pt, y1 = (y == H - 1) ? Hp - 1 : y + pt;
-    const int x0 = (x == 0) ? 0 : x + pl, x1 = (x == W - 1) ? Wp - 1 : x + pl;
-    Vf<N> acc = vzero<N>();
-    for (int yy = y0; yy <= y1; ++yy)
-        for (int xx = x0; xx <= x1; ++xx) acc = vadd(acc, ldv(gP + (((size_t)n * Hp + yy) * Wp + xx) * Cp + c0 + c));
+    const T* img = gP + (size_t)n * Hp * Wp * Cp + c0 + c;
     T* o = gsrc + ((size_t)row * W + x) * Cs + c;
+    Vf<N> acc = ldv(img + ((size_t)(y + pt) * Wp + x + pl) * Cp);
+    if (y == 0 || y == H - 1 || x == 0 || x == W - 1) {                        // replicated border cells fold onto the edge pixels
+        const int y0 = (y == 0) ? 0 : y + pt, y1 = (y == H - 1) ? Hp - 1 : y + pt;
+        const int x0 = (x == 0) ? 0 : x + pl, x1 = (x == W - 1) ? Wp - 1 : x + pl;
+        for (int yy = y0; yy <= y1; ++yy)
+            for (int xx = x0; xx <= x1; ++xx)
+                if (yy != y + pt || xx != x + pl) acc = vadd(acc, ldv(img + ((size_t)yy * Wp + xx) * Cp));
+    }
     if (accumulate) acc = vadd(acc, ldv(o));
     stv(o, acc);
 }
@@ -390,8 +395,11 @@ void k_fold_bwd(cudaStream_t st, const Tensor& gP, int c0, const Tensor& gsrc, b
     SALT_COUNT(1);
     SALT_DISPATCH(gP.dt, T, {
         dim3 grid(gsrc.B * gsrc.H, cdiv(gsrc.W * (gsrc.C / VW<T>::N), EW_THREADS));
+        const int cg = gsrc.C / VW<T>::N;
+        int cgs = -1;                                   // log2 of the channel-group count when it is a power of two
+        if ((cg & (cg - 1)) == 0) { cgs = 0; while ((1 << cgs) < cg) ++cgs; }
         fold_bwd_kernel<T><<<grid, EW_THREADS, 0, st>>>((const T*)gP.p, c0, (T*)gsrc.p, accumulate ? 1 : 0, gP.H, gP.W, gP.C,
-                                                        gsrc.C, gP.pt, gP.pb, gP.pl, gP.pr);
+                                                        gsrc.C, gP.pt, gP.pb, gP.pl, gP.pr, cgs);
     });
 }
 
@@ -416,42 +424,59 @@ __device__ __forceinline__ void adj_range(int j, int f, int pad, int ndst, int n
 template <typename T>
 __global__ void __launch_bounds__(EW_THREADS) upsample_bwd_kernel(const T* __restrict__ gP, int c0, T* __restrict__ gsrc, int accumulate,
                                                                   int H, int W, int Cp, int Cs, int pt, int pb, int pl, int pr, int f,
-                                                                  int Cslab) {
+                                                                  int Cslab, int cgs) {
     constexpr int N = VW<T>::N;
     extern __shared__ __align__(16) float rowacc[];      // [Wp][Cslab]: blockIdx.y selects a slab of Cslab source channels
     const int cg = Cslab / N, Hp = H + pt + pb, Wp = W + pl + pr, Hs = H / f, Ws = W / f;
     c0 += blockIdx.y * Cslab;
     gsrc += blockIdx.y * Cslab;
     const int row = blockIdx.x, n = row / Hs, jy = row - n * Hs;
+    // the pass was instruction-bound (ncu: issue slots 70 % busy at 2 TB/s): the bilinear weights are tabulated once per block
+    // instead of being recomputed per (item, row) and per (item, column)
+    // (source index 1 has 3f + border candidates: its range starts at physical 0, so the tables are 3f + 4 wide)
+    const int tw = 3 * f + 4;
+    float* wy = rowacc + (size_t)Wp * Cslab;             // [tw] weights of the candidate rows
+    float* wx = wy + tw;                                 // [Ws][tw] weights of the candidate columns of source column jx
     int lo, hi;
     adj_range(jy, f, pt, H, Hp, lo, hi);
-    while (lo < hi && bilin_adj_w(lo, pt, H, f, Hs, jy) == 0.f) ++lo;            // the rows with non-zero weight are contiguous
-    while (hi > lo && bilin_adj_w(hi - 1, pt, H, f, Hs, jy) == 0.f) --hi;
+    for (int i = threadIdx.x; i < hi - lo; i += EW_THREADS) wy[i] = bilin_adj_w(lo + i, pt, H, f, Hs, jy);
+    for (int i = threadIdx.x; i < Ws * tw; i += EW_THREADS) {
+        const int jx = i / tw, k = i - jx * tw;
+        int xlo, xhi;
+        adj_range(jx, f, pl, W, Wp, xlo, xhi);
+        wx[i] = xlo + k < xhi ? bilin_adj_w(xlo + k, pl, W, f, Ws, jx) : 0.f;
+    }
+    __syncthreads();
+    int lo2 = lo, hi2 = hi;                              // the rows with non-zero weight are contiguous
+    while (lo2 < hi2 && wy[lo2 - lo] == 0.f) ++lo2;
+    while (hi2 > lo2 && wy[hi2 - 1 - lo] == 0.f) --hi2;
     const T* base = gP + (size_t)n * Hp * Wp * Cp + c0;
+    const size_t rstride = (size_t)Wp * Cp;
     for (int item = threadIdx.x; item < Wp * cg; item += EW_THREADS) {
-        const int xp = item / cg, c = (item - xp * cg) * N;
-        const T* col = base + (size_t)xp * Cp + c;
+        const int xp = cgs >= 0 ? (item >> cgs) : item / cg, c = (item - xp * cg) * N;
+        const T* col = base + (size_t)xp * Cp + c + (size_t)lo2 * rstride;
+        const float* w = wy + (lo2 - lo);
         Vf<N> acc = vzero<N>();
-        int yp = lo;
-        for (; yp + 3 < hi; yp += 4) {
+        int k = 0;
+        for (; k + 3 < hi2 - lo2; k += 4) {
             Vf<N> v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = ldv(col + (size_t)(yp + u) * Wp * Cp);
+            for (int u = 0; u < 4; ++u) v[u] = ldv(col + (size_t)(k + u) * rstride);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) acc = vaxpy(v[u], bilin_adj_w(yp + u, pt, H, f, Hs, jy), acc);
+            for (int u = 0; u < 4; ++u) acc = vaxpy(v[u], w[k + u], acc);
         }
-        for (; yp < hi; ++yp) acc = vaxpy(ldv(col + (size_t)yp * Wp * Cp), bilin_adj_w(yp, pt, H, f, Hs, jy), acc);
+        for (; k < hi2 - lo2; ++k) acc = vaxpy(ldv(col + (size_t)k * rstride), w[k], acc);
         stp<N>(rowacc + (size_t)xp * Cslab + c, acc);
     }
     __syncthreads();
     for (int item = threadIdx.x; item < Ws * cg; item += EW_THREADS) {
-        const int jx = item / cg, c = (item - jx * cg) * N;
+        const int jx = cgs >= 0 ? (item >> cgs) : item / cg, c = (item - jx * cg) * N;
         int xlo, xhi;
         adj_range(jx, f, pl, W, Wp, xlo, xhi);
+        const float* w = wx + jx * tw;
         Vf<N> acc = vzero<N>();
-        for (int xp = xlo; xp < xhi; ++xp) {
-            const float w = bilin_adj_w(xp, pl, W, f, Ws, jx);
-            if (w != 0.f) acc = vaxpy(ldp<N>(rowacc + (size_t)xp * Cslab + c), w, acc);
+        for (int k = 0; k < xhi - xlo; ++k) {
+            if (w[k] != 0.f) acc = vaxpy(ldp<N>(rowacc + (size_t)(xlo + k) * Cslab + c), w[k], acc);
         }
         T* o = gsrc + ((size_t)row * Ws + jx) * Cs + c;
         if (accumulate) acc = vadd(acc, ldv(o));
@@ -468,7 +493,10 @@ void k_upsample_bwd(cudaStream_t st, const Tensor& gP, int c0, int f, const Tens
     SALT_DISPATCH(gP.dt, T, {
         int cslab = gsrc.C;                           // halve the channel slab until the fp32 row fits 64 KB
         while (gP.Wp() * cslab * (int)sizeof(float) > 64 * 1024 && cslab % (2 * VW<T>::N) == 0) cslab >>= 1;
-        const int smem = gP.Wp() * cslab * (int)sizeof(float);
+        const int smem = (gP.Wp() * cslab + (3 * f + 4) * (1 + gP.W / f)) * (int)sizeof(float);
+        const int cg = cslab / VW<T>::N;
+        int cgs = -1;
+        if ((cg & (cg - 1)) == 0) { cgs = 0; while ((1 << cgs) < cg) ++cgs; }
         static int smem_set = 0;
         if (smem > 48 * 1024 && smem > smem_set) {
             if (smem > 200 * 1024) throw std::runtime_error("upsample backward: row of partial sums exceeds shared memory");
@@ -477,7 +505,7 @@ void k_upsample_bwd(cudaStream_t st, const Tensor& gP, int c0, int f, const Tens
         }
         upsample_bwd_kernel<T><<<dim3(gsrc.B * gsrc.H, gsrc.C / cslab), EW_THREADS, smem, st>>>((const T*)gP.p, c0, (T*)gsrc.p,
                                                                          accumulate ? 1 : 0, gP.H, gP.W,
-                                                                         gP.C, gsrc.C, gP.pt, gP.pb, gP.pl, gP.pr, f, cslab);
+                                                                         gP.C, gsrc.C, gP.pt, gP.pb, gP.pl, gP.pr, f, cslab, cgs);
     });
 }
 

@@ -14,9 +14,11 @@ template <typename T, bool RES>
 struct BnApplyOp {
     static constexpr int N = VW<T>::N;
     static constexpr bool FULL_WARPS = false;
+    static constexpr int WARPS = 16, NT = WARPS * 32;
     const float *scale, *shift, *rscale, *rshift, *gate;
     T* out;
     int relu, C, H, W, pt, pb, pl, pr;
+    FDiv dHW, dW, dH;
     // per thread
     Vf<N> sc, sh, rsc, rsh;
     int c, rshift_bits;
@@ -31,7 +33,7 @@ struct BnApplyOp {
     __device__ void vec(size_t off, const uint4 (&in)[RES ? 2 : 1]) {
         Vf<N> v = vfma(vfrom<T>(in[0]), sc, sh);
         const unsigned pix = (unsigned)(off >> rshift_bits);
-        if (gate) v = vmul(v, ldp<N>(gate + (size_t)(pix / (unsigned)(H * W)) * C + c));
+        if (gate) v = vmul(v, ldp<N>(gate + (size_t)dHW.div(pix) * C + c));
         if constexpr (RES) {
             Vf<N> r = vfrom<T>(in[1]);
             if (rscale) r = vfma(r, rsc, rsh);
@@ -42,7 +44,7 @@ struct BnApplyOp {
         if ((pt | pb | pl | pr) == 0) {
             *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) + off) = o;
         } else {
-            const unsigned row = pix / (unsigned)W, x = pix - row * W, n = row / (unsigned)H, y = row - n * H;
+            const unsigned row = dW.div(pix), x = pix - row * W, n = dH.div(row), y = row - n * H;
             const int Hp = H + pt + pb, Wp = W + pl + pr;
             const int y0 = (y == 0) ? 0 : (int)y + pt, y1 = ((int)y == H - 1) ? Hp - 1 : (int)y + pt;
             const int x0 = (x == 0) ? 0 : (int)x + pl, x1 = ((int)x == W - 1) ? Wp - 1 : (int)x + pl;
@@ -59,9 +61,11 @@ template <typename T>
 struct BnBwdReduceOp {
     static constexpr int N = VW<T>::N;
     static constexpr bool FULL_WARPS = false;
+    static constexpr int WARPS = 16, NT = WARPS * 32;
     BNRef bn;
     const float *gate, *addc;
     int self_mask, HW, C;
+    FDiv dHW;
     Vf<N> sc, sh, mu, is, sg, sgx;
     int c, rshift_bits;
     __device__ void begin(int tid) {
@@ -75,7 +79,7 @@ struct BnBwdReduceOp {
         Vf<N> gv = vfrom<T>(in[0]);
         const Vf<N> x = vfrom<T>(in[1]);
         if (gate) {
-            const size_t o = (size_t)((unsigned)(off >> rshift_bits) / (unsigned)HW) * C + c;
+            const size_t o = (size_t)dHW.div((unsigned)(off >> rshift_bits)) * C + c;
             gv = vfma(gv, ldp<N>(gate + o), ldp<N>(addc + o));
         }
         if (self_mask) gv = vmaskpos(gv, vfma(x, sc, sh));
@@ -84,8 +88,8 @@ struct BnBwdReduceOp {
     }
     __device__ void end(int tid, float* red) {
         const int cg = C / N;
-        block_reduce_slot<N, true>(sg, cg, bn.bsums + (size_t)blockIdx.x * 2 * C, red);
-        block_reduce_slot<N, true>(sgx, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + C, red);
+        block_reduce_slot<N, true, NT>(sg, cg, bn.bsums + (size_t)blockIdx.x * 2 * C, red);
+        block_reduce_slot<N, true, NT>(sgx, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + C, red);
         if (blockIdx.x == 0 && tid == 0) *bn.bslots = (int)gridDim.x;
     }
 };
@@ -94,10 +98,12 @@ template <typename T>
 struct BnBwdApplyOp {
     static constexpr int N = VW<T>::N;
     static constexpr bool FULL_WARPS = false;
+    static constexpr int WARPS = 16, NT = WARPS * 32;
     BNRef bn;
     const float *gate, *addc;
     T* graw;
     int self_mask, HW, C;
+    FDiv dHW;
     Vf<N> sc, sh, mu, cb, cc;
     int c, rshift_bits;
     __device__ void begin(int tid) {
@@ -110,7 +116,7 @@ struct BnBwdApplyOp {
         Vf<N> gv = vfrom<T>(in[0]);
         const Vf<N> x = vfrom<T>(in[1]);
         if (gate) {
-            const size_t o = (size_t)((unsigned)(off >> rshift_bits) / (unsigned)HW) * C + c;
+            const size_t o = (size_t)dHW.div((unsigned)(off >> rshift_bits)) * C + c;
             gv = vfma(gv, ldp<N>(gate + o), ldp<N>(addc + o));
         }
         if (self_mask) gv = vmaskpos(gv, vfma(x, sc, sh));
@@ -127,6 +133,7 @@ template <typename T>
 struct ReluMaskOp {
     static constexpr int N = VW<T>::N;
     static constexpr bool FULL_WARPS = false;
+    static constexpr int WARPS = 16, NT = WARPS * 32;
     T* g;
     __device__ void begin(int) {}
     __device__ void vec(size_t off, const uint4 (&in)[2]) {
@@ -144,10 +151,12 @@ __device__ __forceinline__ uint4 lds16(const uint8_t* p) { return *reinterpret_c
 struct ScseApplyOp {
     static constexpr int N = 8;
     static constexpr bool FULL_WARPS = true;
+    static constexpr int WARPS = 8, NT = WARPS * 32;
     const float *scale, *shift;
     SERef se;
     bf16* out;
     int HW, C;
+    FDiv dHW;
     Vf<N> sc, sh, w;
     float bs;
     int c, cg, rshift_bits;
@@ -164,7 +173,7 @@ struct ScseApplyOp {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             z[u] = vrelu(vfma(vfrom<bf16>(lds16(stage + o[u])), sc, sh));
-            gate[u] = ldp<N>(se.cse + (size_t)((unsigned)((off + o[u]) >> rshift_bits) / (unsigned)HW) * C + c);
+            gate[u] = ldp<N>(se.cse + (size_t)dHW.div((unsigned)((off + o[u]) >> rshift_bits)) * C + c);
             dot[u] = vdot(z[u], w);
         }
         for (int m = cg >> 1; m > 0; m >>= 1) {
@@ -187,10 +196,12 @@ struct ScseApplyOp {
 struct ScseBwdOp {
     static constexpr int N = 8;
     static constexpr bool FULL_WARPS = true;
+    static constexpr int WARPS = 8, NT = WARPS * 32;
     BNRef bn;
     SERef se;
     bf16* gbn;
     int HW, C;
+    FDiv dHW;
     Vf<N> sc, sh, mu, is, w, sg, sgx, sws;
     float bs, sbs;
     int c, cg, rshift_bits;
@@ -220,7 +231,7 @@ struct ScseBwdOp {
         for (int u = 0; u < U; ++u) {
             const float s = 1.f / (1.f + expf(-(dot[u] + bs)));
             const float dsp = D[u] * s * (1.f - s);
-            const size_t no = (size_t)((unsigned)((off + o[u]) >> rshift_bits) / (unsigned)HW) * C + c;
+            const size_t no = (size_t)dHW.div((unsigned)((off + o[u]) >> rshift_bits)) * C + c;
             const Vf<N> cse = ldp<N>(se.cse + no), G = ldp<N>(se.G + no);
             Vf<N> dz;
 #pragma unroll
@@ -235,15 +246,15 @@ struct ScseBwdOp {
         }
     }
     __device__ void end(int tid, float* red) {
-        block_reduce_slot<N, true>(sg, cg, bn.bsums + (size_t)blockIdx.x * 2 * C, red);
-        block_reduce_slot<N, true>(sgx, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + C, red);
+        block_reduce_slot<N, true, NT>(sg, cg, bn.bsums + (size_t)blockIdx.x * 2 * C, red);
+        block_reduce_slot<N, true, NT>(sgx, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + C, red);
         if (blockIdx.x == 0 && tid == 0) *bn.bslots = (int)gridDim.x;
-        block_reduce_add<N, float, true>(sws, cg, se.dws, red);
+        block_reduce_add<N, float, true, NT>(sws, cg, se.dws, red);
         red[tid] = sbs;
-        ring::consumer_sync();
+        ring::consumer_sync<NT>();
         if (tid == 0) {
             float t = 0.f;
-            for (int i = 0; i < EW_THREADS; ++i) t += red[i];
+            for (int i = 0; i < NT; ++i) t += red[i];
             atomicAdd(se.dbs, t);
         }
     }
@@ -253,9 +264,11 @@ struct ScseBwdOp {
 struct FinalFwdOp {
     static constexpr int N = 8;
     static constexpr bool FULL_WARPS = true;
+    static constexpr int WARPS = 16, NT = WARPS * 32;
     const float *scale, *shift, *w, *b;
     float* logits;
     int K, HW, C;
+    FDiv dHW;
     Vf<N> sc, sh;
     int c, cg, rshift_bits;
     __device__ void begin(int tid) {
@@ -264,7 +277,7 @@ struct FinalFwdOp {
         c = ((tid * 16) & (rb - 1)) / 2;
         sc = ldp<N>(scale + c); sh = ldp<N>(shift + c);
     }
-    static constexpr int U = 4;
+    static constexpr int U = 2;
     __device__ void vecs(size_t off, const uint8_t* stage, const int (&o)[U], const bool (&valid)[U]) {
         Vf<N> z[U];
 #pragma unroll
@@ -282,7 +295,7 @@ struct FinalFwdOp {
                 const float bk = b[k];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const unsigned pix = (unsigned)((off + o[u]) >> rshift_bits), n = pix / (unsigned)HW, p = pix - n * HW;
+                    const unsigned pix = (unsigned)((off + o[u]) >> rshift_bits), n = dHW.div(pix), p = pix - n * HW;
                     if (valid[u]) logits[((size_t)n * K + k) * HW + p] = d[u] + bk;
                 }
             }
@@ -296,6 +309,7 @@ template <int K>
 struct FinalBwdOp {
     static constexpr int N = 8;
     static constexpr bool FULL_WARPS = true;
+    static constexpr int WARPS = 8, NT = WARPS * 32;
     BNRef bn;
     const float* w;
     float *dw, *db;
@@ -314,21 +328,21 @@ struct FinalBwdOp {
         for (int k = 0; k < K; ++k) { wk[k] = ldp<N>(w + k * C + c); sdw[k] = vzero<N>(); sdb[k] = 0.f; }
     }
     __device__ void end(int tid, float* red) {
-        block_reduce_slot<N, true>(sg, cg, bn.bsums + (size_t)blockIdx.x * 2 * C, red);
-        block_reduce_slot<N, true>(sgx, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + C, red);
+        block_reduce_slot<N, true, NT>(sg, cg, bn.bsums + (size_t)blockIdx.x * 2 * C, red);
+        block_reduce_slot<N, true, NT>(sgx, cg, bn.bsums + (size_t)blockIdx.x * 2 * C + C, red);
         if (blockIdx.x == 0 && tid == 0) *bn.bslots = (int)gridDim.x;
 #pragma unroll
-        for (int k = 0; k < K; ++k) block_reduce_add<N, float, true>(sdw[k], cg, dw + k * C, red);
+        for (int k = 0; k < K; ++k) block_reduce_add<N, float, true, NT>(sdw[k], cg, dw + k * C, red);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             red[tid] = sdb[k];
-            ring::consumer_sync();
+            ring::consumer_sync<NT>();
             if (tid == 0) {
                 float t = 0.f;
-                for (int i = 0; i < EW_THREADS; ++i) t += red[i];
+                for (int i = 0; i < NT; ++i) t += red[i];
                 atomicAdd(db + k, t);
             }
-            ring::consumer_sync();
+            ring::consumer_sync<NT>();
         }
     }
     // the dlogits planes are 1/(C/2) as dense as the activation stream, so the op addresses the stage itself (no shuffles here:
@@ -378,12 +392,14 @@ bool k_ring_bn_apply(cudaStream_t st, const Tensor& raw, const float* scale, con
             BnApplyOp<T, true> op;
             op.scale = scale; op.shift = shift; op.rscale = rscale; op.rshift = rshift; op.gate = gate; op.out = (T*)out.p;
             op.relu = relu ? 1 : 0; op.C = raw.C; op.H = raw.H; op.W = raw.W; op.pt = out.pt; op.pb = out.pb; op.pl = out.pl; op.pr = out.pr;
+            op.dHW = make_fdiv(raw.H * raw.W); op.dW = make_fdiv(raw.W); op.dH = make_fdiv(raw.H);
             ring::Streams<2> s; s.p[0] = (const uint8_t*)raw.p; s.p[1] = (const uint8_t*)res->p; s.nbytes = flat_bytes(raw);
             ring::launch<2>(st, s, op);
         } else {
             BnApplyOp<T, false> op;
             op.scale = scale; op.shift = shift; op.rscale = nullptr; op.rshift = nullptr; op.gate = gate; op.out = (T*)out.p;
             op.relu = relu ? 1 : 0; op.C = raw.C; op.H = raw.H; op.W = raw.W; op.pt = out.pt; op.pb = out.pb; op.pl = out.pl; op.pr = out.pr;
+            op.dHW = make_fdiv(raw.H * raw.W); op.dW = make_fdiv(raw.W); op.dH = make_fdiv(raw.H);
             ring::Streams<1> s; s.p[0] = (const uint8_t*)raw.p; s.nbytes = flat_bytes(raw);
             ring::launch<1>(st, s, op);
         }
@@ -397,6 +413,7 @@ bool k_ring_bn_bwd_reduce(cudaStream_t st, const Tensor& g, const Tensor& raw, c
     SALT_DISPATCH(raw.dt, T, {
         BnBwdReduceOp<T> op;
         op.bn = bn; op.gate = gate; op.addc = addc; op.self_mask = self_mask ? 1 : 0; op.HW = raw.H * raw.W; op.C = raw.C;
+        op.dHW = make_fdiv(raw.H * raw.W);
         ring::Streams<2> s; s.p[0] = (const uint8_t*)g.p; s.p[1] = (const uint8_t*)raw.p; s.nbytes = flat_bytes(raw);
         ring::launch<2>(st, s, op);
     });
@@ -410,7 +427,7 @@ bool k_ring_bn_bwd_apply(cudaStream_t st, const Tensor& g, const Tensor& raw, co
     SALT_DISPATCH(raw.dt, T, {
         BnBwdApplyOp<T> op;
         op.bn = bn; op.gate = gate; op.addc = addc; op.graw = (T*)graw.p; op.self_mask = self_mask ? 1 : 0; op.HW = raw.H * raw.W;
-        op.C = raw.C;
+        op.C = raw.C; op.dHW = make_fdiv(raw.H * raw.W);
         ring::Streams<2> s; s.p[0] = (const uint8_t*)g.p; s.p[1] = (const uint8_t*)raw.p; s.nbytes = flat_bytes(raw);
         ring::launch<2>(st, s, op);
     });
@@ -435,6 +452,7 @@ bool k_ring_scse_apply(cudaStream_t st, const Tensor& raw, const float* scale, c
     if (!ring_enabled() || !pixel_group_ok(raw) || !ring::row_ok(out) || !same_shape(raw, out)) return false;
     ScseApplyOp op;
     op.scale = scale; op.shift = shift; op.se = se; op.out = (bf16*)out.p; op.HW = raw.H * raw.W; op.C = raw.C;
+    op.dHW = make_fdiv(raw.H * raw.W);
     ring::Streams<1> s; s.p[0] = (const uint8_t*)raw.p; s.nbytes = flat_bytes(raw);
     ring::launch<1>(st, s, op);
     return true;
@@ -445,6 +463,7 @@ bool k_ring_scse_bwd_apply(cudaStream_t st, const Tensor& gout, const Tensor& ra
         return false;
     ScseBwdOp op;
     op.bn = bn; op.se = se; op.gbn = (bf16*)gbn.p; op.HW = raw.H * raw.W; op.C = raw.C;
+    op.dHW = make_fdiv(raw.H * raw.W);
     ring::Streams<2> s; s.p[0] = (const uint8_t*)gout.p; s.p[1] = (const uint8_t*)raw.p; s.nbytes = flat_bytes(raw);
     ring::launch<2>(st, s, op);
     return true;
@@ -454,6 +473,7 @@ bool k_ring_final_fwd(cudaStream_t st, const Tensor& raw, const float* scale, co
     if (!ring_enabled() || !pixel_group_ok(raw)) return false;
     FinalFwdOp op;
     op.scale = scale; op.shift = shift; op.w = w; op.b = b; op.logits = logits; op.K = K; op.HW = raw.H * raw.W; op.C = raw.C;
+    op.dHW = make_fdiv(raw.H * raw.W);
     ring::Streams<1> s; s.p[0] = (const uint8_t*)raw.p; s.nbytes = flat_bytes(raw);
     ring::launch<1>(st, s, op);
     return true;

@@ -9,16 +9,17 @@
 // vectors), keep their per-channel coefficients in registers and store results straight to global memory.
 //
 // Geometry: a chunk is a whole number of pixels and 256 threads x 16 bytes is a whole number of pixels (row bytes = C * sizeof(T)
-// is a power of two <= 4096), so a consumer thread serves ONE channel group for the whole kernel.  Grid = min(#SMs, chunks)
+// is a power of two <= 4096, and so is the consumers' pass of 4 or 8 KB), so a consumer thread serves ONE channel group for the whole kernel.  Grid = min(#SMs, chunks)
 // persistent CTAs, chunk i of CTA b = b + i * grid.  Reductions end in the block's own partial slot (fixed-order finalize).
 #pragma once
 #include "elem_vec.cuh"
 
 namespace ring {
 
-constexpr int CONSUMERS = EW_THREADS;        // 8 warps
-constexpr int THREADS = CONSUMERS + 32;      // + the producer warp
 constexpr int CHUNK = 16384;                 // bytes per input per stage
+// Op::WARPS consumer warps (8 or 16) + the producer warp.  The consumers need ~70-190 instructions per 16-byte vector (unpack,
+// fp32 arithmetic, pack, addressing); with 8 warps - two per scheduler - they issue ~1.5 instructions per clock and top out near
+// 4 TB/s (ncu: issue slots 43-52 % busy, 14 % of the warp slots occupied).  Ops that fit 120 registers run 16 warps.
 template <int NS> struct Cfg {
     static constexpr int STAGES = NS == 1 ? 6 : (NS == 2 ? 4 : 3);
     static constexpr int RING_BYTES = STAGES * NS * CHUNK;
@@ -58,7 +59,7 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int NT> __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 
 // Op interface (all members __device__):
 //   void begin(int tid)                                   per-thread set-up (coefficients of the thread's channel group)
@@ -69,10 +70,11 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, 256;
 //                                                         FULL_WARPS = true (ops with warp shuffles): U vectors per call, the op
 //                                                         reads its inputs from the stage itself (stream i at stage + i*CHUNK +
 //                                                         o[u]; tensor byte offset off + o[u])
-//   void end(int tid, float* red)                         after the last chunk; `red` = EW_THREADS * 8 floats of shared memory,
-//                                                         consumers synchronise with consumer_sync() / the NAMED block sums
+//   void end(int tid, float* red)                         after the last chunk; `red` = 8 floats per consumer thread of shared memory,
+//                                                         consumers synchronise with consumer_sync<NT>() / the NAMED block sums
 template <int NS, class Op>
-__global__ void __launch_bounds__(THREADS, 1) ring_kernel(Streams<NS> s, Op op) {
+__global__ void __launch_bounds__(Op::WARPS * 32 + 32, 1) ring_kernel(Streams<NS> s, Op op) {
+    constexpr int CONSUMERS = Op::WARPS * 32;
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int STAGES = Cfg<NS>::STAGES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg<NS>::RING_BYTES);
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(THREADS, 1) ring_kernel(Streams<NS> s, Op op) 
         if (lane == 0) mbar_arrive(empty0 + 8 * st);
         if (++st == STAGES) { st = 0; ph ^= 1; }
     }
-    consumer_sync();          // every stage has been consumed: the ring is free to serve as reduction scratch
+    consumer_sync<CONSUMERS>();          // every stage has been consumed: the ring is free to serve as reduction scratch
     op.end(threadIdx.x, reinterpret_cast<float*>(smem));
 }
 
@@ -164,7 +166,7 @@ static void launch(cudaStream_t st, const Streams<NS>& s, const Op& op) {
     }
     const size_t nchunks = (s.nbytes + CHUNK - 1) / CHUNK;
     const int grid = (int)std::min<size_t>((size_t)num_sms_cached(), nchunks);
-    ring_kernel<NS, Op><<<grid, THREADS, Cfg<NS>::SMEM, st>>>(s, op);
+    ring_kernel<NS, Op><<<grid, Op::WARPS * 32 + 32, Cfg<NS>::SMEM, st>>>(s, op);
 }
 static inline int grid_for(size_t nbytes) {
     const size_t nchunks = (nbytes + CHUNK - 1) / CHUNK;
