@@ -283,7 +283,10 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             const int m = quarter * 32 + lane;
             mbar_wait(tfull, 0);
             fence_after();
-            for (int g = 0; g < 5; ++g) {
+            // all CTAs of a layer add into the SAME few hundred KB at the same moment: each starts at a different accumulator so that
+            // the L2 atomic units do not serialise on one address
+            for (int gi = 0; gi < 5; ++gi) {
+                const int g = (gi + (int)blockIdx.x) % 5;
                 const int tap = 2 * g + (m >> 6);
                 const bool row_ok = tap < 9 && cb * 64 + (m & 63) < p.Ci_pad;
                 float* drow = p.dwp + ((size_t)(tap < 9 ? tap : 8) * p.Ci_pad + cb * 64 + (m & 63)) * p.Co + k0;
@@ -313,9 +316,11 @@ static bool wgrad_halo_pref() {
     if (v < 0) { const char* e = getenv("SALT_WGRAD_HALO"); v = (e && e[0] == '0') ? 0 : 1; }
     return v == 1;
 }
-// 3x3 stride-1 weight gradients whose map tiles into 16 x 4 or 8 x 8 pixel chunks
+// 3x3 stride-1 weight gradients with <= 64 output channels whose map tiles into 16 x 4 or 8 x 8 pixel chunks.  Measured per layer
+// group (profiles/r2_notes.md): final.0 796 -> 1045 TFLOP/s, layer1 553 -> 639, dec1 399 -> 480, dec2 656 -> 749; layers with >= 128
+// output channels LOSE 5-10 % against the N = 128 kernel above (N = 64 instructions cap at half the tensor rate), so they stay there.
 static bool wgrad_halo_ok(const ConvGeom& g) {
-    if (!wgrad_halo_pref() || g.R != 3 || g.S != 3 || g.stride != 1 || g.Ci % 8 || g.Co % 8) return false;
+    if (!wgrad_halo_pref() || g.R != 3 || g.S != 3 || g.stride != 1 || g.Ci % 8 || g.Co % 8 || g.Co > 64) return false;
     if (g.Wo >= 16) return g.Wo % 16 == 0 && g.Ho % 4 == 0;
     return g.Wo == 8 && g.Ho % 8 == 0;
 }
