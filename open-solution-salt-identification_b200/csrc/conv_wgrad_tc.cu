@@ -311,6 +311,129 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     if (warp == 1) { fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// ---- the same idea for layers with >= 128 output channels: N = 128 instructions (full tensor rate).  512 TMEM columns hold only
+// four such accumulators, so a CTA takes ONE kernel row (3 taps) of a PAIR of 64-channel input blocks - the pair is stacked into
+// M = 128 through the leading-byte offset (= the distance between the two blocks' boxes) - and one 128-channel output tile.  Per
+// 64-pixel stage: two (PW+2) x PH boxes (horizontal halo only) + the 64 x 128 gradient tile = 35-37 KB per 12 MMAs of 64 clk
+// = 46 B/clk, against 80 B/clk of the per-tap loads above.
+constexpr int WR_STAGES = 5;
+constexpr int WR_XBYTES = 10240;       // >= (PW+2)*PH*128: 18 x 4 (PW = 16) or 10 x 8 (PW = 8) pixel rows, 1024-aligned
+constexpr int WR_GBYTES = 16384;       // 64 pixels x 128 channels (two 64-channel tiles)
+constexpr int WR_STAGE = 2 * WR_XBYTES + WR_GBYTES;
+constexpr int WR_SMEM = WR_STAGES * WR_STAGE + 1024 + 256;
+
+template <int PW>
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv_wgrad_halo_rows_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g, const WgParams p) {
+    constexpr int PH = 64 / PW, BW = PW + 2, STAGES = WR_STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * WR_STAGE);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + STAGES), tfull = smem_u32(bars + 2 * STAGES);
+    const int pair = blockIdx.y / 3, r = blockIdx.y - pair * 3, k0 = blockIdx.z * 128;
+    const int nblk = min(2, p.cblks - 2 * pair);                 // 64-channel input blocks of this pair that exist
+    const int chunk_begin = blockIdx.x * p.chunks_per_split;
+    const int chunk_end = min(p.total_chunks, chunk_begin + p.chunks_per_split);
+    const int nchunks = chunk_end - chunk_begin;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_g) : "memory");
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(smem_u32(tmem_ptr_smem), 512);
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (nchunks > 0) {
+        if (warp == 0) {
+            if (elect_one()) {
+                int stage = 0; uint32_t phase = 0;
+                const uint32_t tx_bytes = (uint32_t)(nblk * BW * PH * 128 + WR_GBYTES);
+                int cx = chunk_begin % p.chunks_x, cy = (chunk_begin / p.chunks_x) % p.chunks_y, n = chunk_begin / (p.chunks_x * p.chunks_y);
+                for (int ck = chunk_begin; ck < chunk_end; ++ck) {
+                    const int x0 = cx * PW, y0 = cy * PH;
+                    const uint32_t st = smem_u32(smem + stage * WR_STAGE), fb = full0 + 8 * stage;
+                    mbar_wait(empty0 + 8 * stage, phase ^ 1);
+                    mbar_expect_tx(fb, tx_bytes);
+                    for (int i = 0; i < nblk; ++i) tma_load_4d(st + i * WR_XBYTES, &map_x, fb, (2 * pair + i) * 64, x0 - p.pad, y0 + r - p.pad, n);
+                    tma_load_4d(st + 2 * WR_XBYTES, &map_g, fb, k0, x0, y0, n);
+                    tma_load_4d(st + 2 * WR_XBYTES + WR_GBYTES / 2, &map_g, fb, k0 + 64, x0, y0, n);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++cx == p.chunks_x) { cx = 0; if (++cy == p.chunks_y) { cy = 0; ++n; } }
+                }
+            }
+        } else if (warp == 1) {
+            const uint32_t idesc = instr_desc_bf16(128, true, true);
+            const uint32_t smem0 = smem_u32(smem);
+            constexpr uint32_t SBO = PW == 16 ? 1024 : BW * 128;
+            constexpr int KROWS = PW == 16 ? BW : 2 * BW;
+            uint64_t adesc0[3];
+#pragma unroll
+            for (int s = 0; s < 3; ++s) adesc0[s] = smem_desc(smem0 + s * 128, nblk == 2 ? WR_XBYTES : 0, SBO, 2);
+            const uint64_t bdesc0 = smem_desc(smem0 + 2 * WR_XBYTES, WR_GBYTES / 2, 1024, 2);
+            if (elect_one()) {
+                int stage = 0; uint32_t phase = 0;
+                bool stage_ready = false;
+                for (int it = 0; it < nchunks; ++it) {
+                    if (!stage_ready) mbar_wait(full0 + 8 * stage, phase);
+                    fence_after();
+                    const int nstage = stage + 1 == STAGES ? 0 : stage + 1;
+                    const uint32_t nphase = stage + 1 == STAGES ? phase ^ 1 : phase;
+                    const uint64_t soff = (uint64_t)((stage * WR_STAGE) >> 4);
+                    uint32_t probe = 0;
+#pragma unroll
+                    for (int s = 0; s < 3; ++s) {
+                        if (s == 2 && it + 1 < nchunks) probe = mbar_try_wait(full0 + 8 * nstage, nphase) ? 1u : 0u;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16(tmem_base + s * 128, adesc0[s] + soff + (uint64_t)(kk * KROWS * 8), bdesc0 + soff + (uint64_t)(kk * 128),
+                                      idesc, (it | kk) != 0);
+                    }
+                    umma_commit(empty0 + 8 * stage);
+                    if (it == nchunks - 1) umma_commit(tfull);
+                    stage_ready = probe != 0;
+                    stage = nstage; phase = nphase;
+                }
+            }
+            __syncwarp();
+        } else {
+            const int quarter = warp & 3;
+            const int m = quarter * 32 + lane;
+            mbar_wait(tfull, 0);
+            fence_after();
+            for (int si = 0; si < 3; ++si) {
+                const int s = (si + (int)blockIdx.x) % 3;                   // staggered start, see the kernel above
+                const int tap = r * 3 + s, c = (2 * pair + (m >> 6)) * 64 + (m & 63);
+                const bool row_ok = (m >> 6) < nblk;
+                float* drow = p.dwp + ((size_t)tap * p.Ci_pad + (row_ok ? c : 0)) * p.Co + k0;
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ++ch) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + s * 128 + ch * 32, v);
+                    if (row_ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (k0 + ch * 32 + j < p.Co)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + ch * 32 + j), "f"(v[j]),
+                                             "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+                        }
+                    }
+                }
+            }
+        }
+    }
+    fence_before();
+    __syncthreads();
+    if (warp == 1) { fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 static bool wgrad_halo_pref() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("SALT_WGRAD_HALO"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -319,10 +442,42 @@ static bool wgrad_halo_pref() {
 // 3x3 stride-1 weight gradients with <= 64 output channels whose map tiles into 16 x 4 or 8 x 8 pixel chunks.  Measured per layer
 // group (profiles/r2_notes.md): final.0 796 -> 1045 TFLOP/s, layer1 553 -> 639, dec1 399 -> 480, dec2 656 -> 749; layers with >= 128
 // output channels LOSE 5-10 % against the N = 128 kernel above (N = 64 instructions cap at half the tensor rate), so they stay there.
+static bool wgrad_halo_rows_pref() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SALT_WGRAD_HALO_ROWS"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
 static bool wgrad_halo_ok(const ConvGeom& g) {
-    if (!wgrad_halo_pref() || g.R != 3 || g.S != 3 || g.stride != 1 || g.Ci % 8 || g.Co % 8 || g.Co > 64) return false;
+    if (!wgrad_halo_pref() || g.R != 3 || g.S != 3 || g.stride != 1 || g.Ci % 8 || g.Co % 8) return false;
+    if (g.Co > 64 && (!wgrad_halo_rows_pref() || g.Ci < 128)) return false;
     if (g.Wo >= 16) return g.Wo % 16 == 0 && g.Ho % 4 == 0;
     return g.Wo == 8 && g.Ho % 8 == 0;
+}
+template <int PW>
+static void launch_wg_halo_rows(cudaStream_t st, const void* in, const void* gout, float* dwp, const ConvGeom& g) {
+    constexpr int PH = 64 / PW;
+    WgParams p;
+    p.B = g.B; p.Ho = g.Ho; p.Wo = g.Wo; p.Ci_pad = cdiv(g.Ci, 64) * 64; p.Co = g.Co;
+    p.RS = 9; p.S = 3; p.stride = 1; p.pad = g.pad;
+    p.cblks = cdiv(g.Ci, 64); p.total_slots = 9 * p.cblks; p.slots_per_cta = 6;
+    p.pw = PW; p.ph = PH; p.chunks_x = g.Wo / PW; p.chunks_y = g.Ho / PH;
+    p.total_chunks = g.B * p.chunks_x * p.chunks_y;
+    const int pairs = cdiv(p.cblks, 2), k_tiles = cdiv(g.Co, 128);
+    int splits = num_sms() / (pairs * 3 * k_tiles);
+    const int max_splits = cdiv(p.total_chunks, 4);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    p.chunks_per_split = cdiv(p.total_chunks, splits);
+    splits = cdiv(p.total_chunks, p.chunks_per_split);
+    p.dwp = dwp;
+    CUtensorMap mx = make_map_nhwc(in, g.Ci, g.Wi, g.Hi, g.B, 64, PW + 2, PH, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+    CUtensorMap mg = make_map_nhwc(gout, g.Co, g.Wo, g.Ho, g.B, 64, PW, PH, 1, 1, CU_TENSOR_MAP_SWIZZLE_128B);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(conv_wgrad_halo_rows_kernel<PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, WR_SMEM);
+        configured = true;
+    }
+    conv_wgrad_halo_rows_kernel<PW><<<dim3(splits, pairs * 3, k_tiles), WG_THREADS, WR_SMEM, st>>>(mx, mg, p);
 }
 template <int PW>
 static void launch_wg_halo(cudaStream_t st, const void* in, const void* gout, float* dwp, const ConvGeom& g) {
@@ -402,8 +557,13 @@ size_t tc_wgrad_scratch_floats(int Ci, int Co, int RS) { return (size_t)RS * (cd
 void k_conv_wgrad_tc(cudaStream_t st, const void* in, const void* gout, float* dwp, const ConvGeom& g) {
     SALT_COUNT(1);
     if (wgrad_halo_ok(g)) {
-        if (g.Wo >= 16) launch_wg_halo<16>(st, in, gout, dwp, g);
-        else launch_wg_halo<8>(st, in, gout, dwp, g);
+        if (g.Co > 64) {
+            if (g.Wo >= 16) launch_wg_halo_rows<16>(st, in, gout, dwp, g);
+            else launch_wg_halo_rows<8>(st, in, gout, dwp, g);
+        } else {
+            if (g.Wo >= 16) launch_wg_halo<16>(st, in, gout, dwp, g);
+            else launch_wg_halo<8>(st, in, gout, dwp, g);
+        }
         return;
     }
     WgParams p;

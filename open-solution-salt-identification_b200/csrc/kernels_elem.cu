@@ -424,63 +424,66 @@ __device__ __forceinline__ void adj_range(int j, int f, int pad, int ndst, int n
 template <typename T>
 __global__ void __launch_bounds__(EW_THREADS) upsample_bwd_kernel(const T* __restrict__ gP, int c0, T* __restrict__ gsrc, int accumulate,
                                                                   int H, int W, int Cp, int Cs, int pt, int pb, int pl, int pr, int f,
-                                                                  int Cslab, int cgs) {
+                                                                  int Cslab, int cgs, int rpb) {
     constexpr int N = VW<T>::N;
     extern __shared__ __align__(16) float rowacc[];      // [Wp][Cslab]: blockIdx.y selects a slab of Cslab source channels
     const int cg = Cslab / N, Hp = H + pt + pb, Wp = W + pl + pr, Hs = H / f, Ws = W / f;
     c0 += blockIdx.y * Cslab;
     gsrc += blockIdx.y * Cslab;
-    const int row = blockIdx.x, n = row / Hs, jy = row - n * Hs;
-    // the pass was instruction-bound (ncu: issue slots 70 % busy at 2 TB/s): the bilinear weights are tabulated once per block
-    // instead of being recomputed per (item, row) and per (item, column)
+    // the pass was instruction-bound (ncu: issue slots 70 % busy at 2 TB/s): the bilinear weights are tabulated instead of being
+    // recomputed per (item, row) and per (item, column); the column table is shared by the `rpb` source rows a block walks over
     // (source index 1 has 3f + border candidates: its range starts at physical 0, so the tables are 3f + 4 wide)
     const int tw = 3 * f + 4;
     float* wy = rowacc + (size_t)Wp * Cslab;             // [tw] weights of the candidate rows
     float* wx = wy + tw;                                 // [Ws][tw] weights of the candidate columns of source column jx
-    int lo, hi;
-    adj_range(jy, f, pt, H, Hp, lo, hi);
-    for (int i = threadIdx.x; i < hi - lo; i += EW_THREADS) wy[i] = bilin_adj_w(lo + i, pt, H, f, Hs, jy);
     for (int i = threadIdx.x; i < Ws * tw; i += EW_THREADS) {
         const int jx = i / tw, k = i - jx * tw;
         int xlo, xhi;
         adj_range(jx, f, pl, W, Wp, xlo, xhi);
         wx[i] = xlo + k < xhi ? bilin_adj_w(xlo + k, pl, W, f, Ws, jx) : 0.f;
     }
-    __syncthreads();
-    int lo2 = lo, hi2 = hi;                              // the rows with non-zero weight are contiguous
-    while (lo2 < hi2 && wy[lo2 - lo] == 0.f) ++lo2;
-    while (hi2 > lo2 && wy[hi2 - 1 - lo] == 0.f) --hi2;
-    const T* base = gP + (size_t)n * Hp * Wp * Cp + c0;
-    const size_t rstride = (size_t)Wp * Cp;
-    for (int item = threadIdx.x; item < Wp * cg; item += EW_THREADS) {
-        const int xp = cgs >= 0 ? (item >> cgs) : item / cg, c = (item - xp * cg) * N;
-        const T* col = base + (size_t)xp * Cp + c + (size_t)lo2 * rstride;
-        const float* w = wy + (lo2 - lo);
-        Vf<N> acc = vzero<N>();
-        int k = 0;
-        for (; k + 3 < hi2 - lo2; k += 4) {
-            Vf<N> v[4];
+    for (int row = blockIdx.x * rpb; row < (int)(blockIdx.x + 1) * rpb; ++row) {
+        const int n = row / Hs, jy = row - n * Hs;
+        int lo, hi;
+        adj_range(jy, f, pt, H, Hp, lo, hi);
+        __syncthreads();                                 // previous row's phase B is done with rowacc / wy
+        for (int i = threadIdx.x; i < hi - lo; i += EW_THREADS) wy[i] = bilin_adj_w(lo + i, pt, H, f, Hs, jy);
+        __syncthreads();
+        int lo2 = lo, hi2 = hi;                          // the rows with non-zero weight are contiguous
+        while (lo2 < hi2 && wy[lo2 - lo] == 0.f) ++lo2;
+        while (hi2 > lo2 && wy[hi2 - 1 - lo] == 0.f) --hi2;
+        const T* base = gP + (size_t)n * Hp * Wp * Cp + c0;
+        const size_t rstride = (size_t)Wp * Cp;
+        for (int item = threadIdx.x; item < Wp * cg; item += EW_THREADS) {
+            const int xp = cgs >= 0 ? (item >> cgs) : item / cg, c = (item - xp * cg) * N;
+            const T* col = base + (size_t)xp * Cp + c + (size_t)lo2 * rstride;
+            const float* w = wy + (lo2 - lo);
+            Vf<N> acc = vzero<N>();
+            int k = 0;
+            for (; k + 3 < hi2 - lo2; k += 4) {
+                Vf<N> v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = ldv(col + (size_t)(k + u) * rstride);
+                for (int u = 0; u < 4; ++u) v[u] = ldv(col + (size_t)(k + u) * rstride);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) acc = vaxpy(v[u], w[k + u], acc);
+                for (int u = 0; u < 4; ++u) acc = vaxpy(v[u], w[k + u], acc);
+            }
+            for (; k < hi2 - lo2; ++k) acc = vaxpy(ldv(col + (size_t)k * rstride), w[k], acc);
+            stp<N>(rowacc + (size_t)xp * Cslab + c, acc);
         }
-        for (; k < hi2 - lo2; ++k) acc = vaxpy(ldv(col + (size_t)k * rstride), w[k], acc);
-        stp<N>(rowacc + (size_t)xp * Cslab + c, acc);
-    }
-    __syncthreads();
-    for (int item = threadIdx.x; item < Ws * cg; item += EW_THREADS) {
-        const int jx = cgs >= 0 ? (item >> cgs) : item / cg, c = (item - jx * cg) * N;
-        int xlo, xhi;
-        adj_range(jx, f, pl, W, Wp, xlo, xhi);
-        const float* w = wx + jx * tw;
-        Vf<N> acc = vzero<N>();
-        for (int k = 0; k < xhi - xlo; ++k) {
-            if (w[k] != 0.f) acc = vaxpy(ldp<N>(rowacc + (size_t)(xlo + k) * Cslab + c), w[k], acc);
+        __syncthreads();
+        for (int item = threadIdx.x; item < Ws * cg; item += EW_THREADS) {
+            const int jx = cgs >= 0 ? (item >> cgs) : item / cg, c = (item - jx * cg) * N;
+            int xlo, xhi;
+            adj_range(jx, f, pl, W, Wp, xlo, xhi);
+            const float* w = wx + jx * tw;
+            Vf<N> acc = vzero<N>();
+            for (int k = 0; k < xhi - xlo; ++k) {
+                if (w[k] != 0.f) acc = vaxpy(ldp<N>(rowacc + (size_t)(xlo + k) * Cslab + c), w[k], acc);
+            }
+            T* o = gsrc + ((size_t)row * Ws + jx) * Cs + c;
+            if (accumulate) acc = vadd(acc, ldv(o));
+            stv(o, acc);
         }
-        T* o = gsrc + ((size_t)row * Ws + jx) * Cs + c;
-        if (accumulate) acc = vadd(acc, ldv(o));
-        stv(o, acc);
     }
 }
 size_t upsample_bwd_tmp_floats(const Tensor& gP, int f, int Csrc) {
@@ -503,9 +506,12 @@ void k_upsample_bwd(cudaStream_t st, const Tensor& gP, int c0, int f, const Tens
             cudaFuncSetAttribute(upsample_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             smem_set = smem;
         }
-        upsample_bwd_kernel<T><<<dim3(gsrc.B * gsrc.H, gsrc.C / cslab), EW_THREADS, smem, st>>>((const T*)gP.p, c0, (T*)gsrc.p,
+        const int rows = gsrc.B * gsrc.H;
+        int rpb = 1;                                    // source rows per block: amortises the column-weight table
+        while (rpb < 4 && rows % (2 * rpb) == 0 && rows / (2 * rpb) >= 148 * 16) rpb *= 2;   // (fewer, longer blocks lost 30 % at f = 4, 8)
+        upsample_bwd_kernel<T><<<dim3(rows / rpb, gsrc.C / cslab), EW_THREADS, smem, st>>>((const T*)gP.p, c0, (T*)gsrc.p,
                                                                          accumulate ? 1 : 0, gP.H, gP.W,
-                                                                         gP.C, gsrc.C, gP.pt, gP.pb, gP.pl, gP.pr, f, cslab, cgs);
+                                                                         gP.C, gsrc.C, gP.pt, gP.pb, gP.pl, gP.pr, f, cslab, cgs, rpb);
     });
 }
 

@@ -151,7 +151,7 @@ __device__ __forceinline__ uint4 lds16(const uint8_t* p) { return *reinterpret_c
 struct ScseApplyOp {
     static constexpr int N = 8;
     static constexpr bool FULL_WARPS = true;
-    static constexpr int WARPS = 8, NT = WARPS * 32;
+    static constexpr int WARPS = 16, NT = WARPS * 32;
     const float *scale, *shift;
     SERef se;
     bf16* out;
@@ -166,7 +166,7 @@ struct ScseApplyOp {
         c = ((tid * 16) & (rb - 1)) / 2;
         sc = ldp<N>(scale + c); sh = ldp<N>(shift + c); w = ldp<N>(se.ws + c); bs = se.bs[0];
     }
-    static constexpr int U = 4;
+    static constexpr int U = 2;
     __device__ void vecs(size_t off, const uint8_t* stage, const int (&o)[U], const bool (&valid)[U]) {
         Vf<N> z[U], gate[U];
         float dot[U];
@@ -182,7 +182,7 @@ struct ScseApplyOp {
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const float sg = 1.f / (1.f + expf(-(dot[u] + bs)));
+            const float sg = __fdividef(1.f, 1.f + __expf(-(dot[u] + bs)));
 #pragma unroll
             for (int i = 0; i < N; ++i) gate[u].v[i] += sg;
             if (valid[u]) *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) + off + o[u]) = vto<bf16>(vrelu(vmul(z[u], gate[u])));
@@ -229,7 +229,7 @@ struct ScseBwdOp {
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const float s = 1.f / (1.f + expf(-(dot[u] + bs)));
+            const float s = __fdividef(1.f, 1.f + __expf(-(dot[u] + bs)));
             const float dsp = D[u] * s * (1.f - s);
             const size_t no = (size_t)dHW.div((unsigned)((off + o[u]) >> rshift_bits)) * C + c;
             const Vf<N> cse = ldp<N>(se.cse + no), G = ldp<N>(se.G + no);
