@@ -78,10 +78,15 @@ constexpr int RW_THREADS = 320;                              // warp 0 TMA, warp
 constexpr int RW_EPI_THREADS = 256;
 constexpr int RW_TH = 16, RW_TW = 8;
 constexpr int RW_A_BYTES = (RW_TH + 2) * RW_TW * 128;        // 18 pixel rows x 8 pixels x 64 channels bf16 = 18 KB
-template <int BN> struct RowsCfg {
+// RESW (resident weights): layers with <= 64 input channels and ONE output-channel tile keep all nine weight slabs in shared memory
+// for the life of the persistent CTA (72 KB at BN = 64); a stage is then the activation box alone.  With the weights in the ring such
+// a layer pulled 42 KB per stage into the SM for 12 MMAs (6 for 32-channel inputs) = 55-109 B/clk, above what L2 and the shared-memory
+// fill path deliver (profiles/r2_notes.md section 7).
+template <int BN, bool RESW = false> struct RowsCfg {
     static constexpr int B_BYTES = BN * 128;                 // one tap: [BN][64] bf16
-    static constexpr int STAGE_BYTES = RW_A_BYTES + 3 * B_BYTES;
-    static constexpr int STAGES = BN == 128 ? 3 : (BN == 64 ? 4 : (BN == 32 ? 6 : 2));    // wide tiles (160 / 192): 78 / 90 KB stages
+    static constexpr int W_BYTES = RESW ? 9 * B_BYTES : 0;   // resident weight slabs, in front of the ring
+    static constexpr int STAGE_BYTES = RESW ? RW_A_BYTES : RW_A_BYTES + 3 * B_BYTES;
+    static constexpr int STAGES = RESW ? 6 : (BN == 128 ? 3 : (BN == 64 ? 4 : (BN == 32 ? 6 : 2)));    // wide tiles (160 / 192): 78 / 90 KB stages
     // column distance of the two accumulators: BN for the power-of-two tiles, 256 for the wide ones (tcgen05.alloc wants 2^k columns)
     static constexpr int ACC_STRIDE = (BN & (BN - 1)) == 0 ? BN : 256;
     static constexpr int TMEM_COLS = 2 * ACC_STRIDE < 32 ? 32 : 2 * ACC_STRIDE;
@@ -90,7 +95,7 @@ template <int BN> struct RowsCfg {
     // makes their share of that error negligible (measured: 3e-5 -> relative error per convolution, see profiles/r2_notes.md)
     static constexpr int ACC_STRIDE_SPLIT = 2 * BN;
     static constexpr int TMEM_COLS_SPLIT = 2 * ACC_STRIDE_SPLIT < 32 ? 32 : 2 * ACC_STRIDE_SPLIT;
-    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFF = W_BYTES + STAGES * STAGE_BYTES;
     static constexpr int SMEM_BYTES = BAR_OFF + 1024 + 256 + 8 * 2 * BN * 4 + BN * 4;      // + per-epilogue-warp BN statistics + the bias
 };
 
@@ -363,28 +368,31 @@ __device__ __forceinline__ void rows_epilogue(const RowsParams& p, const int war
 // CL CTAs (map_b then has a [64 c][BN/CL n] box).  Weights are 60-75 % of the bytes a stage pulls through L2, and the L2 -> SM
 // path (~42 B/clk/SM chip-wide), not the tensor pipe, bounds these kernels (profiles/r1_notes.md).  A stage may be overwritten only
 // when ALL CTAs of the cluster have consumed it: the MMA issuer's tcgen05.commit arrives on the `empty` barrier of every CTA.
-template <int BN, typename OutT, int CL>
+template <int BN, typename OutT, int CL, bool RESW = false>
 __global__ void __launch_bounds__(RW_THREADS, 1)
 conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const RowsParams p) {
-    using Cfg = RowsCfg<BN>;
+    static_assert(!RESW || CL == 1, "resident weights: one CTA per tile");
+    using Cfg = RowsCfg<BN, RESW>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::BAR_OFF);
-    // bars: full[STAGES], empty[STAGES], tmem_full[4], tmem_empty[4]
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
+    // bars: full[STAGES], empty[STAGES], tmem_full[4], tmem_empty[4], weights_full
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 9);
     float* s_stats = reinterpret_cast<float*>(smem + Cfg::BAR_OFF + 256);
     constexpr int NACC = RowsAcc<BN, OutT, false>::N;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t smem0 = smem_u32(smem);
-    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES, tfull0 = empty0 + 8 * STAGES, tempty0 = tfull0 + 32;
+    const uint32_t wsm0 = smem_u32(smem);                    // resident weight slabs (RESW), then the ring
+    const uint32_t smem0 = wsm0 + Cfg::W_BYTES;
+    const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * STAGES, tfull0 = empty0 + 8 * STAGES, tempty0 = tfull0 + 32, wfull = tempty0 + 32;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
         for (int i = 0; i < STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, CL); }
         for (int i = 0; i < NACC; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 8); }
+        mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     constexpr bool SPLIT = sizeof(OutT) == 4;
@@ -409,6 +417,11 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             int stage = 0; uint32_t phase = 0;
             RowsTile<CL> t;
             TCT(long long tp0 = clock64(); long long tp_wait = 0;)
+            if constexpr (RESW) {                        // all nine slabs once: box s = [3 taps r][BN][64 c] of kernel column s
+                mbar_expect_tx(wfull, Cfg::W_BYTES);
+#pragma unroll
+                for (int s = 0; s < 3; ++s) tma_load_4d(wsm0 + s * 3 * Cfg::B_BYTES, &map_b, wfull, 0, 0, 0, s);
+            }
             for (int k = 0; rows_tile<CL>(p, k, rank, t); ++k) {
                 const int nt = t.nt, n = t.n;
                 const int w0 = t.tx * RW_TW - p.pad, h0 = t.ty * RW_TH - p.pad;
@@ -421,7 +434,9 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                         {
                             mbar_expect_tx(fb, Cfg::STAGE_BYTES);
                             tma_load_4d(st, &map_a, fb, cb * 64, w0 + s, h0, n);
-                            if constexpr (CL == 1) {
+                            if constexpr (RESW) {
+                                // the weights are resident
+                            } else if constexpr (CL == 1) {
                                 tma_load_4d(st + RW_A_BYTES, &map_b, fb, cb * 64, nt * BN, 0, s);     // (c, n, r = 0..2, s)
                             } else {
                                 constexpr int PART = BN / CL;                                         // my rows of every weight slab
@@ -441,7 +456,7 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // ===================================================== MMA issuer: 12 MMAs per barrier wait
         const uint32_t idesc = instr_desc_bf16(BN, false, false);
         const uint64_t adesc0 = smem_desc(smem0, 16, 1024, 2);
-        const uint64_t bdesc0 = smem_desc(smem0 + RW_A_BYTES, 16, 1024, 2);
+        const uint64_t bdesc0 = smem_desc(RESW ? wsm0 : smem0 + RW_A_BYTES, 16, 1024, 2);
         // ONE elected thread runs the whole issue loop.  tcgen05.mma issue is throttled to the execution rate (the hardware
         // queue is shallow: profiles/r2_notes.md, rows_timing), so every cycle this thread spends between two MMAs idles the tensor
         // pipe - and a barrier probe has ~90 cycles of latency even when the barrier completed long ago.  The probe of the NEXT
@@ -453,6 +468,7 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             bool stage_ready = false, acc_ready = false;
             RowsTile<CL> t, tn;
             TCT(long long ti0 = clock64(); long long ti_full = 0, ti_tempty = 0, ti_stages = 0;)
+            if constexpr (RESW) mbar_wait(wfull, 0);
             bool more = rows_tile<CL>(p, 0, rank, t);
             for (int kk = 0; more; ++kk) {
                 more = rows_tile<CL>(p, kk + 1, rank, tn);
@@ -481,7 +497,9 @@ conv_tc_rows_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     for (int r = 0; r < 3; ++r) {
                         // vertical tap r = the same A buffer, r pixel-rows (r * 1024 bytes) further down
                         const uint64_t adesc = adesc0 + soff + (uint64_t)((r * 1024) >> 4);
-                        const uint64_t bdesc = bdesc0 + soff + (uint64_t)((r * Cfg::B_BYTES) >> 4);
+                        // resident weights: one 64-channel block, so stage `it` of a tile is kernel column s = it
+                        const uint64_t bdesc = RESW ? bdesc0 + (uint64_t)(((it * 3 + r) * Cfg::B_BYTES) >> 4)
+                                                    : bdesc0 + soff + (uint64_t)((r * Cfg::B_BYTES) >> 4);
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             if (k >= p.ksteps) break;
@@ -685,17 +703,17 @@ static int rows_max_clusters() {
     }
     return cached;
 }
-template <int BN, typename OutT, int CL>
+template <int BN, typename OutT, int CL, bool RESW = false>
 static void launch_rows(cudaStream_t st, const CUtensorMap& ma, const CUtensorMap& mb, RowsParams p) {
-    using Cfg = RowsCfg<BN>;
+    using Cfg = RowsCfg<BN, RESW>;
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(conv_tc_rows_kernel<BN, OutT, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaFuncSetAttribute(conv_tc_rows_kernel<BN, OutT, CL, RESW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         configured = true;
     }
     if constexpr (CL == 1) {
         const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-        conv_tc_rows_kernel<BN, OutT, 1><<<grid, RW_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
+        conv_tc_rows_kernel<BN, OutT, 1, RESW><<<grid, RW_THREADS, Cfg::SMEM_BYTES, st>>>(ma, mb, p);
     } else {
         const int clusters = std::min(rows_max_clusters<BN, OutT>(), p.total_groups);
         cudaLaunchConfig_t cfg = {};
@@ -761,9 +779,19 @@ static bool launch_rows_pair(cudaStream_t st, const CUtensorMap& ma, const void*
     ++g_salt_cluster_launches;
     return true;
 }
+// resident weights: env SALT_TC_RESW = 0 turns them off (read once)
+static int rows_resw_pref() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SALT_TC_RESW"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
 template <int BN, typename OutT>
 static void launch_rows_any(cudaStream_t st, const CUtensorMap& ma, const void* Wp, int Ca, int Nout, RowsParams p) {
     int cl = rows_cluster_pref();
+    // <= 64 input channels, one output-channel tile, bf16: the nine weight slabs stay in shared memory (one CTA per tile)
+    bool resw = false;
+    if constexpr (sizeof(OutT) == 2 && BN <= 64) resw = rows_resw_pref() && p.cblks == 1 && p.tiles_co == 1 && p.m_tiles >= 16;
+    if (resw) cl = 1;
     // a cluster only pays when there are enough pixel tiles to fill it and the machine with whole groups
     if (cl == 2 && (p.m_tiles < 16 || rows_max_clusters<BN, OutT>() * 2 < num_sms() * 3 / 4)) cl = 1;
     p.total_groups = cdiv(p.m_tiles, cl) * p.tiles_co;
@@ -779,6 +807,9 @@ static void launch_rows_any(cudaStream_t st, const CUtensorMap& ma, const void* 
                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(weights 4d) failed with code " + std::to_string((int)r));
+    }
+    if constexpr (sizeof(OutT) == 2 && BN <= 64) {
+        if (resw) { launch_rows<BN, OutT, 1, true>(st, ma, mb, p); return; }
     }
     if (cl == 2) launch_rows<BN, OutT, 2>(st, ma, mb, p);
     else launch_rows<BN, OutT, 1>(st, ma, mb, p);

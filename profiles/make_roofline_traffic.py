@@ -1,5 +1,7 @@
 """profiles/roofline_traffic.json (read by bench.py: roofline.traffic) from an ncu launch list that carries
 dram__bytes_read.sum / dram__bytes_write.sum per launch.
+The file is stamped with the sha of the convolution sources (bench.conv_source_sha): bench.py reports the traffic only while the
+sources it runs are the ones the capture was taken on - run this script on the SAME tree that produced the launch list.
 usage: python profiles/make_roofline_traffic.py <launches.csv> <steps_in_capture> <source note>"""
 import collections
 import csv
@@ -21,7 +23,10 @@ def main(path, steps, note):
             byt[name] += float(row['Metric Value'].replace(',', '')) * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[u]
         elif m == 'gpu__time_duration.sum':
             cnt[name] += 1
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
     out = {'traffic': sum(byt.values()) / steps,
+           'conv_source_sha': bench.conv_source_sha(),
            'unit': 'bytes per step (all tensor-core convolution launches of one training step: forward + dgrad + wgrad)',
            'launches_per_step': sum(cnt.values()) / steps,
            'per_kernel_bytes_per_step': {k: v / steps for k, v in sorted(byt.items(), key=lambda kv: -kv[1])},

@@ -59,7 +59,9 @@ def test_conv_tc_forward_and_dgrad(case):
     torch.cuda.synchronize()
     import os
     m_tiles = B * ((Ho + 15) // 16) * ((Wo + 7) // 8)
-    if k == 3 and s == 1 and Ci % 64 == 0 and Co % 32 == 0 and Ho >= 16 and m_tiles >= 32 and os.environ.get('SALT_TC_CLUSTER', '2') != '1':
+    resident = Ci <= 64 and Co <= 64 and os.environ.get('SALT_TC_RESW', '1') != '0'      # weights stay in shared memory: one CTA per tile
+    if (k == 3 and s == 1 and Ci % 64 == 0 and Co % 32 == 0 and Ho >= 16 and m_tiles >= 32 and not resident
+            and os.environ.get('SALT_TC_CLUSTER', '2') != '1'):
         # large enough for the thread-block-cluster variant: make sure THAT kernel (TMA-multicast weights) produced `out`
         assert lib.salt_cluster_launch_count() > cl0, 'cluster variant of the row-halo convolution was not launched'
     oks = [report('tc conv fwd %s' % (case,), _from_nhwc(out), y_ref, atol=2e-2, rtol=1e-2)[0]]
