@@ -429,9 +429,11 @@ class SegmentationModel(Model):
         return st
 
     def _bucketed(self):
-        """Data parallel: all-reduce the gradient in three buckets overlapped with the backward segments (SALT_DP_BUCKETS=0: one
-        all-reduce after the whole backward pass, as round 1 did)."""
-        return self.dp.world > 1 and os.environ.get('SALT_DP_BUCKETS', '1') != '0'
+        """Data parallel: SALT_DP_BUCKETS=1 all-reduces the gradient in three buckets overlapped with the backward segments.  Default
+        off: measured on B200 (profiles/r2_notes.md section 8) the overlapped form is SLOWER at 2 and at 8 GPUs (14.95 vs 14.84 ms,
+        15.45 vs 15.34 ms per step) - the NCCL kernels take whole SMs away from the persistent one-CTA-per-SM convolutions, whose
+        static tile schedule then runs a second wave - so one all-reduce after the backward pass (0.12 ms at 2 GPUs) is the default."""
+        return self.dp.world > 1 and os.environ.get('SALT_DP_BUCKETS', '0') == '1'
 
     def _graph_enabled(self):
         return (os.environ.get('SALT_ENGINE_GRAPH', '1') != '0' and not self.engine.profiling
