@@ -58,43 +58,62 @@ def _peaks():
 
 # ------------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+    """nvidia-smi in a side process, one line every 20 ms with a timestamp; started BEFORE the warm-up (the process needs ~100 ms to
+    deliver its first line, a 20-step timed region is only ~0.3 s long), the samples are then cut to the timed region [t0, t1]."""
+    Q = 'timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
 
     def __init__(self, gpu_index):
         self.path = tempfile.mktemp(suffix='.csv')
         self.proc = None
+        self.t0 = self.t1 = None
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(gpu_index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+                                          '-lms', '20'], stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def begin(self):
+        self.t0 = time.time()
+
+    def end(self):
+        self.t1 = time.time()
+
     def stop(self):
+        import datetime
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
         if self.proc is None:
             return out
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         try:
             for line in open(self.path):
-                f = [s.strip() for s in line.split(',')]
+                f = [x.strip() for x in line.split(',')]
                 if len(f) < 9:
                     continue
                 try:
-                    sm.append(float(f[1])); mx.append(float(f[2]))
+                    ts = datetime.datetime.strptime(f[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                    rows.append((ts, float(f[1]), float(f[2]), f[5:9]))
                 except ValueError:
                     continue
-                for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
-                    if v.lower().startswith('active'):
-                        reasons.add(name)
             os.unlink(self.path)
         except Exception:
             pass
+        inside = [r for r in rows if self.t0 is not None and self.t0 <= r[0] <= self.t1]
+        if len(inside) < 2 and self.t0 is not None:          # clock skew between time.time() and the tool's timestamps: widen
+            inside = [r for r in rows if self.t0 - 0.1 <= r[0] <= self.t1 + 0.1]
+        if not inside:
+            inside = rows
+        sm, mx, reasons = [r[1] for r in inside], [r[2] for r in inside], set()
+        for r in inside:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
         if sm:
             out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
         return out
@@ -262,11 +281,13 @@ def run_ours(args):
         model.callbacks = LossReader()
         model.fit(datagen=([[x_h, t_h]] * k, k))
 
+    sampler = ClockSampler(ctx.local_rank) if ctx.rank == 0 else None
     for _ in range(args.warmup):
         step_device()
-    sampler = ClockSampler(ctx.local_rank) if ctx.rank == 0 else None
     l0 = _lib.launch_count()
+    if sampler: sampler.begin()
     ms = timed(step_device, args.steps)
+    if sampler: sampler.end()
     launches = _lib.launch_count() - l0
     clocks = sampler.stop() if sampler else None
     run_e2e(3)

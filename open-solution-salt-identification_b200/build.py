@@ -54,7 +54,7 @@ def build(force=False, verbose=False, timing=False):
         f.write(log)
     if verbose:
         print(log)
-    cmd = [NVCC] + ARCH + ['-shared', '-o', LIB] + [o for o, _ in results] + ['-lcuda']
+    cmd = [NVCC] + ARCH + ['-shared', '-o', LIB] + [o for o, _ in results] + ['-lcuda', '-ldl']
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError('link failed:\n%s\n%s' % (r.stdout, r.stderr))

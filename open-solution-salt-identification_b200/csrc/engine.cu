@@ -1,4 +1,5 @@
 #include "engine.h"
+#include <nvtx3/nvToolsExt.h>
 #include <stdexcept>
 #include <cstring>
 #include <algorithm>
@@ -395,6 +396,20 @@ void Engine::profile_enable(bool on) {
     g_salt_prof_begin = on ? +[](int cls, double work, cudaStream_t st) { if (g_prof_engine) g_prof_engine->prof_begin(cls, work, st); } : nullptr;
     g_salt_prof_end = on ? +[](cudaStream_t st) { if (g_prof_engine) g_prof_engine->prof_end(st); } : nullptr;
 }
+// NVTX: one range per pass ("salt.forward" / "salt.backward") and one per layer group inside it, so a timeline tool (nsys, ncu
+// --nvtx) attributes the ~480 launches of a step to stem / layer1..4 / center / dec5..1 / final.  Host-side only: free when no
+// tool is attached, invisible to CUDA-graph capture.
+static const char* const kGroupNames[Engine::PROF_NGROUPS] = {"stem", "layer1", "layer2", "layer3", "layer4", "center",
+                                                              "dec5", "dec4", "dec3", "dec2", "dec1", "final"};
+void Engine::set_group(int g) {
+    prof_group_ = g;
+    if (nvtx_group_open_) nvtxRangePop();
+    nvtxRangePushA(kGroupNames[g]);
+    nvtx_group_open_ = true;
+}
+void Engine::close_group() {
+    if (nvtx_group_open_) { nvtxRangePop(); nvtx_group_open_ = false; }
+}
 void Engine::prof_begin(int cls, double flops, cudaStream_t st) {
     if (!prof_on_) return;
     if (prof_depth_++ > 0) return;
@@ -629,21 +644,22 @@ void Engine::forward_tiles(const uint8_t* tiles, int B, const TileGeom& g, float
     forward_body(B, logits_nchw, train, st);
 }
 void Engine::forward_body(int B, float* logits_nchw, bool train, cudaStream_t st) {
+    nvtxRangePushA(train ? "salt.forward(train)" : "salt.forward(eval)");
     if (packed_dirty_) pack_all(st);
     if (train) { k_zero(st, stats_arena_, sizeof(float) * stats_floats_); eval_coef_dirty_ = true; }
     else if (eval_coef_dirty_ && fuse_eval_) finalize_eval_all(st);
     Tensor x4 = view(x4_), sraw = view(stem_raw_);
-    prof_group_ = 0;
+    set_group(0);
     if (!train && fusable(stem_, x4, sraw)) {
         conv_bn_fused(stem_, x4, view(stem_out_.t), stem_bn_, nullptr, true, st);
     } else {
         conv_fwd(stem_, x4, sraw, &stem_bn_, train, st);
         k_bn_apply(st, sraw, stem_bn_.scale, stem_bn_.shift, nullptr, nullptr, nullptr, true, view(stem_out_.t));
     }
-    for (auto& b : blocks_) { prof_group_ = b->group; block_fwd(*b, train, st); }
-    for (auto& b : bnecks_) { prof_group_ = b->group; bneck_fwd(*b, train, st); }
+    for (auto& b : blocks_) { set_group(b->group); block_fwd(*b, train, st); }
+    for (auto& b : bnecks_) { set_group(b->group); bneck_fwd(*b, train, st); }
     // center
-    prof_group_ = 5;
+    set_group(5);
     gather_fwd(center_src_, view(center0_.P), st);
     if (!train && fusable(center0_.c, view(center0_.P), view(center0_.raw)) && fusable(center1_.c, view(center1_.P), view(center1_.raw))) {
         conv_bn_fused(center0_.c, view(center0_.P), view(center1_.P), center0_.bn, nullptr, true, st);
@@ -655,8 +671,8 @@ void Engine::forward_body(int B, float* logits_nchw, bool train, cudaStream_t st
         cbr_fwd(center1_, train, st);
         k_bn_relu_avgpool(st, view(center1_.raw), center1_.bn.scale, center1_.bn.shift, view(center_out_.t));
     }
-    for (int i = 0; i < 5; ++i) { prof_group_ = 6 + i; decoder_fwd(dec_[i], train, st); }
-    prof_group_ = 11;
+    for (int i = 0; i < 5; ++i) { set_group(6 + i); decoder_fwd(dec_[i], train, st); }
+    set_group(11);
     gather_fwd(final_src_, view(final0_.P), st);
     if (!train && fusable(final0_.c, view(final0_.P), view(final0_.raw))) {
         conv_bn_fused(final0_.c, view(final0_.P), view(final0_.raw), final0_.bn, nullptr, true, st);
@@ -667,6 +683,8 @@ void Engine::forward_body(int B, float* logits_nchw, bool train, cudaStream_t st
                     cfg_.num_classes, logits_nchw);
     }
     trained_forward_ = train;
+    close_group();
+    nvtxRangePop();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -780,13 +798,14 @@ void Engine::backward(const float* dlogits, cudaStream_t st, int seg) {
     if (!trained_forward_) throw std::runtime_error("backward() requires a preceding forward(train=1)");
     if (seg < -1 || seg > 2) throw std::runtime_error("backward: segment must be -1 (all), 0, 1 or 2");
     const bool all = seg < 0;
+    nvtxRangePushA("salt.backward");
     if (all || seg == 0) {
     k_zero(st, grads_, sizeof(float) * n_params_);
     // (the backward BatchNorm partial-sum slots need no clearing: every producing block stores its slot and records the slot count)
     if (cfg_.dt == DT_BF16 && cfg_.use_tc) k_zero(st, dwp_arena_, sizeof(float) * dwp_floats_);
     for (auto& g : gradbufs_) g->fresh = true;
     // ---- final
-    prof_group_ = 11;
+    set_group(11);
     {
         const Tensor raw = view(final0_.raw), P = view(final0_.P);
         BNRef bn = bn_ref(final0_.bn);
@@ -799,9 +818,9 @@ void Engine::backward(const float* dlogits, cudaStream_t st, int seg) {
         conv_dgrad(final0_.c, graw, gP, false, st);
         gather_bwd(final_src_, gP, st);
     }
-    for (int i = 4; i >= 0; --i) { prof_group_ = 6 + i; decoder_bwd(dec_[i], st); }
+    for (int i = 4; i >= 0; --i) { set_group(6 + i); decoder_bwd(dec_[i], st); }
     // ---- center
-    prof_group_ = 5;
+    set_group(5);
     {
         const Tensor raw1 = view(center1_.raw), raw0 = view(center0_.raw), P1 = view(center1_.P), P0 = view(center0_.P);
         const double cnt = (double)B_ * raw1.H * raw1.W;
@@ -829,16 +848,16 @@ void Engine::backward(const float* dlogits, cudaStream_t st, int seg) {
     // encoder blocks in reverse order; segment 1 = layer4 + layer3 (groups 4, 3), segment 2 = layer2 + layer1 (+ stem)
     for (int i = (int)blocks_.size() - 1; i >= 0; --i) {
         const int g = blocks_[i]->group;
-        if (all || (seg == 1 && g >= 3) || (seg == 2 && g <= 2)) { prof_group_ = g; block_bwd(*blocks_[i], st); }
+        if (all || (seg == 1 && g >= 3) || (seg == 2 && g <= 2)) { set_group(g); block_bwd(*blocks_[i], st); }
     }
     for (int i = (int)bnecks_.size() - 1; i >= 0; --i) {
         const int g = bnecks_[i]->group;
-        if (all || (seg == 1 && g >= 3) || (seg == 2 && g <= 2)) { prof_group_ = g; bneck_bwd(*bnecks_[i], st); }
+        if (all || (seg == 1 && g >= 3) || (seg == 2 && g <= 2)) { set_group(g); bneck_bwd(*bnecks_[i], st); }
     }
     if (seg == 1) unpack_all(st, 1);
     if (all || seg == 2) {
     // ---- stem (no input gradient)
-    prof_group_ = 0;
+    set_group(0);
     {
         const Tensor raw = view(stem_raw_);
         BNRef bn = bn_ref(stem_bn_);
@@ -850,6 +869,8 @@ void Engine::backward(const float* dlogits, cudaStream_t st, int seg) {
     }
     unpack_all(st, all ? 3 : 2);
     }
+    close_group();
+    nvtxRangePop();
 }
 void Engine::adam(float lr, float wd, float b1, float b2, float eps, int step, float grad_scale, cudaStream_t st) {
     if (!adam_m_ || !adam_v_ || !grads_) throw std::runtime_error("engine bound without optimiser state");

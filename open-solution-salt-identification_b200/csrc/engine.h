@@ -119,6 +119,9 @@ public:
     void prof_begin(int cls, double work, cudaStream_t st);       // (public: called through the g_salt_prof_* hooks)
     void prof_end(cudaStream_t st);
     // synchronises, then returns accumulated device time / algorithmic flops / launches since enable
+    void set_group(int g);          // layer group of the launches that follow (profile records, NVTX range)
+    void close_group();
+    bool nvtx_group_open_ = false;
     void profile_read(int cls, double* ms, double* flops, long long* launches, int group = -1);
     long long profile_records(int* cls, int* group, double* work, double* ms, long long max_records);
     // layer groups of the profile records: 0 stem, 1-4 encoder layer1..layer4, 5 center, 6-10 dec5..dec1, 11 final

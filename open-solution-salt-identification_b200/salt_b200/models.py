@@ -391,6 +391,13 @@ class SegmentationModel(Model):
 
     # models.py:105-136
     def _fit_loop(self, data):
+        torch.cuda.nvtx.range_push('salt.fit.step')          # host-side marker: one range per optimisation step
+        try:
+            return self._fit_loop_impl(data)
+        finally:
+            torch.cuda.nvtx.range_pop()
+
+    def _fit_loop_impl(self, data):
         if isinstance(data, self._Staged):
             return self._fit_staged(data)
         dev = self.engine.device
