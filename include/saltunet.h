@@ -23,12 +23,15 @@ extern "C" {
 typedef struct salt_engine salt_engine;
 
 enum { SALT_PREC_FP32 = 0, SALT_PREC_BF16 = 1 };
-enum { SALT_ARCH_UNET_RESNET = 0, SALT_ARCH_UNET_SERESNET = 1 };
+enum { SALT_ARCH_UNET_RESNET = 0, SALT_ARCH_UNET_SERESNET = 1, SALT_ARCH_UNET_SERESNEXT = 2 };
 
 typedef struct salt_config {
     int arch;            /* SALT_ARCH_UNET_RESNET   <- models.py:15-18 ARCHITECTURES['UNetResNet']   (unet.py:22-109)
-                            SALT_ARCH_UNET_SERESNET <- models.py:19-24 ARCHITECTURES['UNetSeResNet'] (unet.py:112-172)    */
-    int encoder_depth;   /* UNetResNet: 18 or 34 (encoders.py:10-13); UNetSeResNet: 50, 101 or 152 (encoders.py:52-57) */
+                            SALT_ARCH_UNET_SERESNET <- models.py:19-24 ARCHITECTURES['UNetSeResNet'] (unet.py:112-172)
+                            SALT_ARCH_UNET_SERESNEXT <- models.py:25-30 ARCHITECTURES['UNetSeResNetXt'] (unet.py:175-236,
+                                                        encoders.py:86-118: se_resnext50_32x4d / se_resnext101_32x4d)     */
+    int encoder_depth;   /* UNetResNet: 18 or 34 (encoders.py:10-13); UNetSeResNet: 50, 101 or 152 (encoders.py:52-57);
+                            UNetSeResNetXt: 50 or 101 (encoders.py:90-95)                                           */
     int num_classes;     /* out_channels           <- models.py:182                                             */
     int max_batch;       /* largest batch any call will pass                                                    */
     int height, width;   /* network input size, multiples of 32 (128 for the 101x101 tiles, loaders.py)         */

@@ -31,12 +31,12 @@ const char* salt_version(void) { return "saltunet-b200 0.1 (sm_100a)"; }
 
 int salt_create(const salt_config* cfg, salt_engine** out) {
     if (!cfg || !out) return fail("salt_create: null argument");
-    if (cfg->arch != SALT_ARCH_UNET_RESNET && cfg->arch != SALT_ARCH_UNET_SERESNET)
-        return fail("salt_create: unknown architecture (UNetResNet and UNetSeResNet are implemented)");
+    if (cfg->arch != SALT_ARCH_UNET_RESNET && cfg->arch != SALT_ARCH_UNET_SERESNET && cfg->arch != SALT_ARCH_UNET_SERESNEXT)
+        return fail("salt_create: unknown architecture (UNetResNet, UNetSeResNet and UNetSeResNetXt are implemented)");
     if (cfg->precision != SALT_PREC_FP32 && cfg->precision != SALT_PREC_BF16) return fail("salt_create: unknown precision");
     try {
         EngineConfig c;
-        c.arch = cfg->arch == SALT_ARCH_UNET_SERESNET ? 1 : 0;
+        c.arch = cfg->arch == SALT_ARCH_UNET_SERESNEXT ? 2 : (cfg->arch == SALT_ARCH_UNET_SERESNET ? 1 : 0);
         c.depth = cfg->encoder_depth; c.num_classes = cfg->num_classes; c.max_batch = cfg->max_batch;
         c.H = cfg->height; c.W = cfg->width; c.dt = cfg->precision == SALT_PREC_FP32 ? DT_F32 : DT_BF16;
         c.use_tc = cfg->use_tensor_cores;

@@ -22,7 +22,9 @@ Engine::Engine(const EngineConfig& cfg) : cfg_(cfg) {
         throw std::runtime_error("UNetResNet: only encoder_depth 18 and 34 are implemented in this engine");
     if (cfg.arch == 1 && cfg.depth != 50 && cfg.depth != 101 && cfg.depth != 152)
         throw std::runtime_error("UNetSeResNet: encoder_depth must be 50, 101 or 152 (reference encoders.py:52-59)");
-    if (cfg.arch != 0 && cfg.arch != 1) throw std::runtime_error("unknown architecture id");
+    if (cfg.arch == 2 && cfg.depth != 50 && cfg.depth != 101)
+        throw std::runtime_error("UNetSeResNetXt: encoder_depth must be 50 or 101 (reference encoders.py:90-95)");
+    if (cfg.arch < 0 || cfg.arch > 2) throw std::runtime_error("unknown architecture id");
     if (cfg.H % 32 || cfg.W % 32) throw std::runtime_error("input height/width must be multiples of 32");
     if (cfg.num_classes < 1 || cfg.num_classes > 4) throw std::runtime_error("num_classes must be 1..4");
     counting_ = true;
@@ -67,9 +69,12 @@ GradBuf* Engine::make_gradbuf(const Tensor& like) {
     g->g = make_tensor(like.H, like.W, like.C);
     return g;
 }
-ConvLayer Engine::make_conv(const std::string& wname, const std::string& bname, int ci, int co, int k, int stride, int pad, int ci_mem) {
+ConvLayer Engine::make_conv(const std::string& wname, const std::string& bname, int ci, int co, int k, int stride, int pad, int ci_mem,
+                            int groups) {
     ConvLayer c; c.Ci_real = ci; c.Ci = ci_mem > 0 ? ci_mem : ci; c.Co = co; c.R = c.S = k; c.stride = stride; c.pad = pad;
-    c.o_w = add_param(wname, {co, ci, k, k});
+    c.groups = groups;
+    if (ci % groups || co % groups) throw std::runtime_error("grouped convolution: channel counts must be multiples of the group count");
+    c.o_w = add_param(wname, {co, ci / groups, k, k});
     c.o_b = bname.empty() ? -1 : (long long)add_param(bname, {co});
     size_t wb = (size_t)co * k * k * c.Ci * dtype_size(cfg_.dt);
     c.wp = ws_alloc(wb);
@@ -150,7 +155,8 @@ void Engine::build() {
     // ---- encoder, parameter order = state_dict order
     //   arch 0: reference encoders.py:10-45, torchvision ResNet-18/34 (BasicBlock)
     //   arch 1: reference encoders.py:48-83, pretrainedmodels se_resnet50 (layer0 = conv7x7/2 + BN + ReLU, SEResNetBottleneck x [3,4,6,3])
-    const bool se50 = cfg_.arch == 1;
+    const bool se50 = cfg_.arch >= 1;           // bottleneck encoders: SE-ResNet (arch 1) and SE-ResNeXt 32x4d (arch 2)
+    const bool resnext = cfg_.arch == 2;
     const std::string e = "encoders.encoder.";
     // the 7x7 stride-2 stem runs as a 1x1 convolution over im2col patches (160 channels, 147 real): see k_stem_im2col
     x4_ = make_tensor(H / 2, W / 2, 160);
@@ -203,26 +209,32 @@ void Engine::build() {
                 const int pl = chans[li], co = 4 * pl;
                 b.down = (bi == 0);
                 b.x = cur;
-                b.c1 = make_conv(p + "conv1.weight", "", cin, pl, 1, stride, 0);      // Caffe-style: the stride sits on conv1
-                b.b1 = make_bn(p + "bn1", pl);
-                b.c2 = make_conv(p + "conv2.weight", "", pl, pl, 3, 1, 1);
-                b.b2 = make_bn(p + "bn2", pl);
-                b.c3 = make_conv(p + "conv3.weight", "", pl, co, 1, 1, 0);
-                b.b3 = make_bn(p + "bn3", co);
+                // SE-ResNet (senet.py SEResNetBottleneck): 1x1 stride s -> 3x3 -> 1x1, width = planes.
+                // SE-ResNeXt 32x4d (SEResNeXtBottleneck, base_width 4): 1x1 -> 3x3 stride s, 32 groups -> 1x1, width = planes * 2.
+                const int wd = resnext ? 2 * pl : pl;
+                const int hin = h, win = w;
                 h /= stride; w /= stride;
+                const int h1 = resnext ? hin : h, w1 = resnext ? win : w;       // resolution of conv1's output
+                b.c1 = make_conv(p + "conv1.weight", "", cin, wd, 1, resnext ? 1 : stride, 0);
+                b.b1 = make_bn(p + "bn1", wd);
+                b.c2 = make_conv(p + "conv2.weight", "", wd, wd, 3, resnext ? stride : 1, 1, -1, resnext ? 32 : 1);
+                b.b2 = make_bn(p + "bn2", wd);
+                b.c3 = make_conv(p + "conv3.weight", "", wd, co, 1, 1, 0);
+                b.b3 = make_bn(p + "bn3", co);
                 b.se = make_se(p + "se_module.fc1.weight", p + "se_module.fc1.bias", p + "se_module.fc2.weight", p + "se_module.fc2.bias",
                                co, h * w, true);
                 if (b.down) {
                     b.cd = make_conv(p + "downsample.0.weight", "", cin, co, 1, stride, 0);
                     b.bd = make_bn(p + "downsample.1", co);
                 }
-                b.raw1 = make_tensor(h, w, pl); b.a1 = make_tensor(h, w, pl);
-                b.raw2 = make_tensor(h, w, pl); b.a2 = make_tensor(h, w, pl);
+                b.raw1 = make_tensor(h1, w1, wd); b.a1 = make_tensor(h1, w1, wd);
+                b.raw2 = make_tensor(h, w, wd); b.a2 = make_tensor(h, w, wd);
                 b.raw3 = make_tensor(h, w, co);
                 if (b.down) b.rawd = make_tensor(h, w, co);
                 b.out.t = make_tensor(h, w, co);
                 b.out.gb = b.down ? make_gradbuf(b.out.t) : cur->gb;
                 need_scratch(0, b.raw3.bytes()); need_scratch(1, b.raw3.bytes()); need_scratch(2, b.raw3.bytes());
+                need_scratch(0, b.raw1.bytes()); need_scratch(1, b.raw1.bytes());
                 cur = &b.out; cin = co;
             }
         }
@@ -335,7 +347,7 @@ std::vector<ConvLayer*> Engine::all_convs() {
 void Engine::build_pack_table() {
     std::vector<PackDesc> descs; std::vector<int> start(1, 0);
     for (ConvLayer* c : all_convs()) {
-        PackDesc d; d.w = params_ + c->o_w; d.wp = c->wp; d.wpd = c->wpd; d.Co = c->Co; d.Ci_real = c->Ci_real; d.Ci = c->Ci; d.RS = c->R * c->S;
+        PackDesc d; d.w = params_ + c->o_w; d.wp = c->wp; d.wpd = c->wpd; d.Co = c->Co; d.Ci_real = c->Ci_real; d.Ci = c->Ci; d.RS = c->R * c->S; d.groups = c->groups;
         descs.push_back(d);
         start.push_back(start.back() + pack_blocks(c->Co, c->Ci, c->R * c->S));
         pack_max_rs_ = std::max(pack_max_rs_, c->R * c->S);
@@ -363,7 +375,7 @@ void Engine::unpack_all(cudaStream_t st, int table) {
                 if (!c->in_unpack_table) continue;
                 const int seg = c->o_w >= seg_bound_[2] ? 0 : (c->o_w >= seg_bound_[1] ? 1 : 2);
                 if (tb < 3 && seg != tb) continue;
-                UnpackDesc d; d.dwp = c->dwp; d.dw = grads_ + c->o_w; d.Co = c->Co; d.Ci_real = c->Ci_real; d.Ci_pad = cdiv(c->Ci, 64) * 64; d.RS = c->R * c->S;
+                UnpackDesc d; d.dwp = c->dwp; d.dw = grads_ + c->o_w; d.Co = c->Co; d.Ci_real = c->Ci_real; d.Ci_pad = cdiv(c->Ci, 64) * 64; d.RS = c->R * c->S; d.groups = c->groups;
                 descs.push_back(d);
                 start.push_back(start.back() + cdiv(c->Co, 32) * cdiv(c->Ci_real, 32));
                 unpack_max_rs_[tb] = std::max(unpack_max_rs_[tb], d.RS);
@@ -448,7 +460,7 @@ long long Engine::profile_records(int* cls, int* group, double* work, double* ms
 void Engine::conv_fwd(const ConvLayer& c, const Tensor& in, const Tensor& out, BNLayer* bn, bool train, cudaStream_t st) {
     ConvGeom g = geom(c, in, out);
     const float* bias = c.o_b >= 0 ? params_ + c.o_b : nullptr;
-    prof_begin(PROF_CONV_FWD, conv_flops(g, c.Ci_real), st);
+    prof_begin(PROF_CONV_FWD, conv_flops(g, c.Ci_real / c.groups), st);
     float* stats = (bn && train) ? bn->sums : nullptr;
     ConvGeom g6 = g; g6.Ci = 6 * g.Ci;
     const bool tc_split = split_tc() && tc_conv_supported(g6, false);
@@ -496,7 +508,7 @@ void Engine::conv_bn_fused(const ConvLayer& c, const Tensor& in, const Tensor& d
     EpiParams ep;
     ep.scale = bn.scale; ep.shift = bn.shift; ep.res = res ? res->p : nullptr; ep.relu = relu ? 1 : 0;
     ep.Hp = dst.Hp(); ep.Wp = dst.Wp(); ep.pt = dst.pt; ep.pl = dst.pl;
-    prof_begin(PROF_CONV_FWD, conv_flops(g, c.Ci_real), st);
+    prof_begin(PROF_CONV_FWD, conv_flops(g, c.Ci_real / c.groups), st);
     if (cfg_.dt == DT_F32) {
         k_split6_act(st, (const float*)in.p, split_scratch_, (size_t)g.B * g.Hi * g.Wi, g.Ci);
         k_conv_tc(st, split_scratch_, g.B, g.Hi, g.Wi, 6 * g.Ci, c.wp6, g.Co, g.R, g.S, g.stride, g.pad, dst.p, g.Ho, g.Wo, bias, nullptr,
@@ -508,7 +520,7 @@ void Engine::conv_bn_fused(const ConvLayer& c, const Tensor& in, const Tensor& d
 }
 void Engine::conv_dgrad(const ConvLayer& c, const Tensor& gout, const Tensor& gin, bool accumulate, cudaStream_t st) {
     ConvGeom g = geom(c, gin, gout);
-    prof_begin(PROF_CONV_DGRAD, conv_flops(g, c.Ci_real), st);
+    prof_begin(PROF_CONV_DGRAD, conv_flops(g, c.Ci_real / c.groups), st);
     const bool tc_ok = cfg_.dt == DT_BF16 && cfg_.use_tc && tc_conv_supported(g, true);
     if (tc_ok && g.stride == 1)
         // dgrad = correlation of the output gradient with the tap-flipped, transposed weights, zero padding R-1-pad
@@ -521,12 +533,12 @@ void Engine::conv_dgrad(const ConvLayer& c, const Tensor& gout, const Tensor& gi
 }
 void Engine::conv_wgrad(ConvLayer& c, const Tensor& in, const Tensor& gout, cudaStream_t st) {
     ConvGeom g = geom(c, in, gout);
-    prof_begin(PROF_CONV_WGRAD, conv_flops(g, c.Ci_real), st);
+    prof_begin(PROF_CONV_WGRAD, conv_flops(g, c.Ci_real / c.groups), st);
     if (cfg_.dt == DT_BF16 && cfg_.use_tc && tc_wgrad_supported(g)) {
         k_conv_wgrad_tc(st, in.p, gout.p, c.dwp, g);      // partial sums land in c.dwp; unpack_all() transposes them at the end of backward()
         if (!c.in_unpack_table) { c.in_unpack_table = true; unpack_table_dirty_ = true; }
     } else
-        k_conv_wgrad_simt(st, cfg_.dt, in.p, gout.p, grads_ + c.o_w, c.Ci_real, g);
+        k_conv_wgrad_simt(st, cfg_.dt, in.p, gout.p, grads_ + c.o_w, c.Ci_real, g, c.groups);
     prof_end(st);
 }
 void Engine::gather_fwd(const std::vector<Source>& srcs, const Tensor& P, cudaStream_t st) {
@@ -775,14 +787,14 @@ void Engine::bneck_bwd(Bottleneck& b, cudaStream_t st) {
     conv_dgrad(b.c3, graw3, ga2, false, st);
     Tensor graw2 = scratch(0, raw2.H, raw2.W, raw2.C);
     k_bn_bwd_reduce(st, ga2, raw2, bn2, true);
-    k_bn_bwd_finalize(st, bn2, cnt);
+    k_bn_bwd_finalize(st, bn2, (double)B_ * raw2.H * raw2.W);
     k_bn_bwd_apply(st, ga2, raw2, bn2, true, graw2);
     conv_wgrad(b.c2, a1, graw2, st);
     Tensor ga1 = scratch(1, raw1.H, raw1.W, raw1.C);
     conv_dgrad(b.c2, graw2, ga1, false, st);
     Tensor graw1 = scratch(0, raw1.H, raw1.W, raw1.C);
     k_bn_bwd_reduce(st, ga1, raw1, bn1, true);
-    k_bn_bwd_finalize(st, bn1, cnt);
+    k_bn_bwd_finalize(st, bn1, (double)B_ * raw1.H * raw1.W);      // SE-ResNeXt: conv1 runs at the block's INPUT resolution
     k_bn_bwd_apply(st, ga1, raw1, bn1, true, graw1);
     conv_wgrad(b.c1, x, graw1, st);
     // identity blocks: Gx aliases G and already holds the shortcut gradient -> accumulate.  A stride-2 1x1 convolution only

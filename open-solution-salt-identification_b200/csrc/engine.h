@@ -20,6 +20,7 @@ struct TensorInfo {            // one named entry of the reference state_dict
 
 struct ConvLayer {
     int Ci = 0, Ci_real = 0, Co = 0, R = 1, S = 1, stride = 1, pad = 0;
+    int groups = 1;            // > 1: grouped convolution run densely over block-diagonal packed weights (kernels_batched.h)
     size_t o_w = 0;
     long long o_b = -1;        // bias offset or -1
     void* wp = nullptr;        // packed fwd weights   [Co][R*S][Ci]
@@ -136,7 +137,8 @@ private:
     // ---- plan construction
     size_t add_param(const std::string& name, std::vector<int> shape);
     size_t add_buffer(const std::string& name, std::vector<int> shape);
-    ConvLayer make_conv(const std::string& wname, const std::string& bname, int ci, int co, int k, int stride, int pad, int ci_mem = -1);
+    ConvLayer make_conv(const std::string& wname, const std::string& bname, int ci, int co, int k, int stride, int pad, int ci_mem = -1,
+                        int groups = 1);
     BNLayer make_bn(const std::string& prefix, int c);
     Tensor make_tensor(int H, int W, int C, int pt = 0, int pb = 0, int pl = 0, int pr = 0);
     size_t make_tensor_bytes(int H, int W, int C) const;

@@ -26,7 +26,7 @@ void k_stats_reduce(cudaStream_t st, const float* stats, int nslots, int C, doub
 void k_conv_dgrad_simt(cudaStream_t st, DType dt, const void* gout, const void* wpd, void* gin, bool accumulate,
                        const ConvGeom& g);
 void k_conv_wgrad_simt(cudaStream_t st, DType dt, const void* in, const void* gout, float* dw, int Ci_real,
-                       const ConvGeom& g);
+                       const ConvGeom& g, int groups = 1);
 
 // -------------------------------------------------------------------- fp32 parity mode on the tensor cores (split-bf16 operands)
 // x = h + m + l with h = bf16(x), m = bf16(x - h), l = bf16(x - h - m): three bf16 terms carry 24 mantissa bits.  A convolution

@@ -29,9 +29,21 @@ __global__ void __launch_bounds__(256) pack_all_kernel(const PackDesc* __restric
     const int creal = max(0, min(CT, d.Ci_real - c0));         // channels of this tile that exist in the master weights
     const int cmem = min(CT, d.Ci - c0);                       // channels of this tile that exist in the packed copies (zero pad)
     const int ncols = creal * RS;
-    for (int k = ty; k < 32; k += 8) {
-        const float* src = d.w + ((size_t)(k0 + k) * d.Ci_real + c0) * RS;
-        for (int j = tx; j < CT * RS; j += 32) tile[k * pitch + j] = (k0 + k < d.Co && j < ncols) ? src[j] : 0.f;
+    if (d.groups == 1) {
+        for (int k = ty; k < 32; k += 8) {
+            const float* src = d.w + ((size_t)(k0 + k) * d.Ci_real + c0) * RS;
+            for (int j = tx; j < CT * RS; j += 32) tile[k * pitch + j] = (k0 + k < d.Co && j < ncols) ? src[j] : 0.f;
+        }
+    } else {                                           // block-diagonal: zero outside the output channel's own group
+        const int cpg = d.Ci_real / d.groups, kpg = d.Co / d.groups;
+        for (int k = ty; k < 32; k += 8) {
+            const int kk = k0 + k, cg0 = kk < d.Co ? (kk / kpg) * cpg : 0;
+            const float* src = d.w + (size_t)kk * cpg * RS;
+            for (int j = tx; j < CT * RS; j += 32) {
+                const int c = c0 + j / RS, t = j - (j / RS) * RS;
+                tile[k * pitch + j] = (kk < d.Co && j < ncols && c >= cg0 && c < cg0 + cpg) ? src[(c - cg0) * RS + t] : 0.f;
+            }
+        }
     }
     __syncthreads();
     T* wp = (T*)d.wp;
@@ -83,10 +95,23 @@ __global__ void __launch_bounds__(256) unpack_all_kernel(const UnpackDesc* __res
         }
     __syncthreads();
     const int ncols = min(32, d.Ci_real - c0) * RS;  // contiguous run in dw for one k
-    for (int k = ty; k < 32; k += 8) {
-        if (k0 + k >= d.Co) continue;
-        float* o = d.dw + ((size_t)(k0 + k) * d.Ci_real + c0) * RS;
-        for (int j = tx; j < ncols; j += 32) o[j] = tile[k * pitch + j];
+    if (d.groups == 1) {
+        for (int k = ty; k < 32; k += 8) {
+            if (k0 + k >= d.Co) continue;
+            float* o = d.dw + ((size_t)(k0 + k) * d.Ci_real + c0) * RS;
+            for (int j = tx; j < ncols; j += 32) o[j] = tile[k * pitch + j];
+        }
+    } else {                                           // keep the diagonal blocks only
+        const int cpg = d.Ci_real / d.groups, kpg = d.Co / d.groups;
+        for (int k = ty; k < 32; k += 8) {
+            const int kk = k0 + k;
+            if (kk >= d.Co) continue;
+            const int cg0 = (kk / kpg) * cpg;
+            for (int j = tx; j < ncols; j += 32) {
+                const int c = c0 + j / RS, t = j - (j / RS) * RS;
+                if (c >= cg0 && c < cg0 + cpg) d.dw[((size_t)kk * cpg + (c - cg0)) * RS + t] = tile[k * pitch + j];
+            }
+        }
     }
 }
 void k_unpack_all(cudaStream_t st, const UnpackDesc* descs, const int* blk_start, int nlayers, int total_blocks, int max_rs) {

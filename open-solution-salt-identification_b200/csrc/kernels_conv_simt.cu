@@ -191,6 +191,7 @@ struct WGradArgs {
     int P, Co, Ci, Ci_real, NC;     // pixels, channels, NC = R*S*Ci
     int Hi, Wi, Ho, Wo, R, S, stride, pad;
     int chunk;                       // pixels per z-slice (multiple of TK)
+    int groups;
 };
 template <typename T>
 __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(const T* __restrict__ in, const T* __restrict__ gout,
@@ -261,13 +262,19 @@ __global__ void __launch_bounds__(256) conv_wgrad_simt_kernel(const T* __restric
             int cl = n0 + tx * 4 + j;
             if (cl >= a.NC) continue;
             int t = cl / a.Ci, c = cl - t * a.Ci;
-            if (c < a.Ci_real) atomicAdd(dw + ((size_t)k * a.Ci_real + c) * RS + t, acc[i][j]);
+            if (c < a.Ci_real) {
+                // grouped convolution computed densely (block-diagonal packed weights): only the group's own input channels exist in
+                // the reference-layout gradient [Co][Ci/groups][R][S]
+                const int cpg = a.Ci_real / a.groups, cg0 = (k / (a.Co / a.groups)) * cpg;
+                if (c >= cg0 && c < cg0 + cpg) atomicAdd(dw + ((size_t)k * cpg + (c - cg0)) * RS + t, acc[i][j]);
+            }
         }
     }
 }
-void k_conv_wgrad_simt(cudaStream_t st, DType dt, const void* in, const void* gout, float* dw, int Ci_real, const ConvGeom& g) {
+void k_conv_wgrad_simt(cudaStream_t st, DType dt, const void* in, const void* gout, float* dw, int Ci_real, const ConvGeom& g, int groups) {
     SALT_COUNT(1);
     WGradArgs a;
+    a.groups = groups;
     a.P = g.B * g.Ho * g.Wo; a.Co = g.Co; a.Ci = g.Ci; a.Ci_real = Ci_real; a.NC = g.R * g.S * g.Ci;
     a.Hi = g.Hi; a.Wi = g.Wi; a.Ho = g.Ho; a.Wo = g.Wo; a.R = g.R; a.S = g.S; a.stride = g.stride; a.pad = g.pad;
     int tiles = cdiv(a.Co, TM) * cdiv(a.NC, TN);

@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get('SALT_LIB_PATH') or os.path.join(os.path.dirname(_HERE
 PREC_FP32, PREC_BF16 = 0, 1
 ARCH_UNET_RESNET = 0
 ARCH_UNET_SERESNET = 1
+ARCH_UNET_SERESNEXT = 2
 
 
 class SaltEngineError(RuntimeError):

@@ -19,8 +19,10 @@ def _ptr(t):
 
 
 class UNetEngine:
-    """UNetResNet (reference architectures/unet.py:22-109; encoder_depth 18/34) or UNetSeResNet (unet.py:112-172;
-    encoder_depth 50/101/152, architecture='UNetSeResNet') on the CUDA engine.
+    """UNetResNet (reference architectures/unet.py:22-109; encoder_depth 18/34), UNetSeResNet (unet.py:112-172;
+    encoder_depth 50/101/152, architecture='UNetSeResNet') or UNetSeResNetXt (unet.py:175-236; SE-ResNeXt 32x4d encoder of depth
+    50/101, architecture='UNetSeResNetXt' - its grouped 3x3 convolutions run densely over block-diagonal packed weights) on the
+    CUDA engine.
 
     precision: 'fp32' (parity mode: fp32 storage, fp32 FMA) or 'bf16' (bf16 activations / weights copies,
     fp32 accumulation, fp32 master weights and optimiser state).
@@ -37,7 +39,8 @@ class UNetEngine:
         if architecture is None:
             architecture = 'UNetSeResNet' if encoder_depth >= 50 else 'UNetResNet'
         self.architecture = architecture
-        arch_id = {'UNetResNet': _lib.ARCH_UNET_RESNET, 'UNetSeResNet': _lib.ARCH_UNET_SERESNET}[architecture]
+        arch_id = {'UNetResNet': _lib.ARCH_UNET_RESNET, 'UNetSeResNet': _lib.ARCH_UNET_SERESNET,
+                   'UNetSeResNetXt': _lib.ARCH_UNET_SERESNEXT}[architecture]
         cfg = _lib.SaltConfig(arch_id, encoder_depth, num_classes, max_batch, size, size,
                               {'fp32': _lib.PREC_FP32, 'bf16': _lib.PREC_BF16}[precision], int(bool(use_tensor_cores)))
         h = C.c_void_p()

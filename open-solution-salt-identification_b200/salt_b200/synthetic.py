@@ -13,7 +13,7 @@ def resnet_block_counts(depth):
     return {18: (2, 2, 2, 2), 34: (3, 4, 6, 3), 50: (3, 4, 6, 3), 101: (3, 4, 23, 3), 152: (3, 8, 36, 3)}[depth]
 
 
-def param_specs(depth=34, num_classes=2):
+def param_specs(depth=34, num_classes=2, arch=None):
     """Canonical (name, shape, kind) list of every tensor the network owns.
 
     depth 18/34 -> UNetResNet (unet.py:22-109), depth 50/101/152 -> UNetSeResNet
@@ -32,6 +32,7 @@ def param_specs(depth=34, num_classes=2):
 
     e = 'encoders.encoder.'
     se50 = depth >= 50          # SE-ResNet-50 / 101 / 152 (reference encoders.py:52-57)
+    resnext = arch == 'UNetSeResNetXt'      # SE-ResNeXt 32x4d (encoders.py:90-95): width = 2 * planes, conv2 has 32 groups
     specs.append((e + ('layer0.conv1.weight' if se50 else 'conv1.weight'), (64, 3, 7, 7), 'conv_w'))
     bn(e + ('layer0.bn1' if se50 else 'bn1'), 64)
     cin = 64
@@ -40,11 +41,12 @@ def param_specs(depth=34, num_classes=2):
             p = '%slayer%d.%d.' % (e, li, b)
             if se50:        # pretrainedmodels SEResNetBottleneck: registration order conv1..bn3, se_module, downsample
                 co = 4 * cout
-                specs.append((p + 'conv1.weight', (cout, cin, 1, 1), 'conv_w'))
-                bn(p + 'bn1', cout)
-                specs.append((p + 'conv2.weight', (cout, cout, 3, 3), 'conv_w'))
-                bn(p + 'bn2', cout)
-                specs.append((p + 'conv3.weight', (co, cout, 1, 1), 'conv_w'))
+                wd = 2 * cout if resnext else cout
+                specs.append((p + 'conv1.weight', (wd, cin, 1, 1), 'conv_w'))
+                bn(p + 'bn1', wd)
+                specs.append((p + 'conv2.weight', (wd, wd // 32 if resnext else wd, 3, 3), 'conv_w'))
+                bn(p + 'bn2', wd)
+                specs.append((p + 'conv3.weight', (co, wd, 1, 1), 'conv_w'))
                 bn(p + 'bn3', co)
                 specs.append((p + 'se_module.fc1.weight', (co // 16, co, 1, 1), 'conv_w'))
                 specs.append((p + 'se_module.fc1.bias', (co // 16,), 'bias'))
@@ -91,11 +93,11 @@ def param_specs(depth=34, num_classes=2):
     return specs
 
 
-def synth_state_dict(depth=34, num_classes=2, seed=0):
+def synth_state_dict(depth=34, num_classes=2, seed=0, arch=None):
     """name -> float32 ndarray; He-scaled conv weights, non-trivial BN statistics."""
     rng = np.random.default_rng(seed)
     sd = {}
-    for name, shape, kind in param_specs(depth, num_classes):
+    for name, shape, kind in param_specs(depth, num_classes, arch):
         if kind in ('conv_w', 'lin_w'):
             fan_in = int(np.prod(shape[1:]))
             a = rng.standard_normal(shape) * np.sqrt(2.0 / fan_in)

@@ -30,7 +30,11 @@ CASES = [
     # on top of oracle/senet_restated.py (pretrainedmodels is absent - see that file's header)
     ('se50_b2_s64', 50, 2, 64, 2, 777),
     ('se101_b2_s64', 101, 2, 64, 4, 555),     # depth variant of the same class (encoders.py:54-55: se_resnet101, layers [3,4,23,3])
+    # UNetSeResNetXt: the reference's UNetSeResNetXt / SeResNetXtEncoders on the restated se_resnext50_32x4d
+    ('sex50_b2_s64', 50, 2, 64, 6, 999, 'UNetSeResNetXt'),
 ]
+ARCH_IDS = {None: 0, 'UNetSeResNetXt': 2}
+ARCH_NAMES = {0: None, 2: 'UNetSeResNetXt'}
 
 GRAD_KEYS = ['encoders.encoder.conv1.weight', 'encoders.encoder.layer1.0.conv1.weight',
              'encoders.encoder.layer2.0.downsample.0.weight', 'encoders.encoder.layer4.1.bn2.weight',
@@ -75,16 +79,16 @@ def _ref_losses():
     return ref_models.lovasz_loss, ref_models.mixed_dice_bce_loss
 
 
-def run_case(tag, depth, batch, size, wseed, dseed):
+def run_case(tag, depth, batch, size, wseed, dseed, arch=None):
     torch.manual_seed(0)
     torch.set_num_threads(8)
-    sd_np = synth.synth_state_dict(depth, 2, wseed)
+    sd_np = synth.synth_state_dict(depth, 2, wseed, arch)
     x = torch.from_numpy(synth.synth_inputs(batch, size, dseed))
     t = torch.from_numpy(synth.synth_targets(batch, size, dseed))
     lovasz_ref, bcedice_ref = _ref_losses()
 
     out = {}
-    net = ref_shims.load_numpy_state(ref_shims.reference_unet(depth), sd_np, depth)
+    net = ref_shims.load_numpy_state(ref_shims.reference_unet(depth, 2, arch), sd_np, depth)
 
     # ---- eval-mode forward (running statistics)
     net.eval()
@@ -95,14 +99,14 @@ def run_case(tag, depth, batch, size, wseed, dseed):
         logits_eval_flip = net(torch.flip(x, dims=[3])).numpy()     # h-flip TTA copy, same (pristine) weights
     sd_t = unet_oracle.to_torch_state(sd_np)
     with torch.no_grad():
-        mine = unet_oracle.unet_resnet_forward(sd_t, x, depth, train=False)
+        mine = unet_oracle.unet_resnet_forward(sd_t, x, depth, train=False, arch=arch)
     d = (mine - logits_eval).abs().max().item()
     assert d <= 1e-5, 'oracle eval forward differs from reference: %g' % d
 
     # ---- train-mode forward + both losses + backward (batch statistics)
     for loss_name, loss_fn, mine_fn in (('lovasz', lovasz_ref, losses_oracle.lovasz_hinge_per_image),
                                         ('bcedice', bcedice_ref, losses_oracle.bce_dice)):
-        net = ref_shims.load_numpy_state(ref_shims.reference_unet(depth), sd_np, depth)
+        net = ref_shims.load_numpy_state(ref_shims.reference_unet(depth, 2, arch), sd_np, depth)
         net.train()
         logits = net(x)
         logits.retain_grad()
@@ -121,7 +125,7 @@ def run_case(tag, depth, batch, size, wseed, dseed):
         out['running_var_final0_' + loss_name] = net.state_dict()['final.0.batch_norm.running_var'].numpy()
 
         sd_t = unet_oracle.to_torch_state(sd_np, requires_grad=True)
-        lg = unet_oracle.unet_resnet_forward(sd_t, x, depth, train=True)
+        lg = unet_oracle.unet_resnet_forward(sd_t, x, depth, train=True, arch=arch)
         lg.retain_grad()
         ls = mine_fn(lg, t)
         ls.backward()
@@ -162,6 +166,8 @@ def run_case(tag, depth, batch, size, wseed, dseed):
         assert (m_mine == out['tta_masks']).all()
 
     meta = dict(depth=depth, batch=batch, size=size, wseed=wseed, dseed=dseed)
+    if arch is not None:
+        meta['arch'] = ARCH_IDS[arch]
     np.savez_compressed(os.path.join(GOLDEN_DIR, tag + '.npz'), **out,
                         **{'meta_' + k: np.int64(v) for k, v in meta.items()})
     print('wrote', tag, {k: getattr(v, 'shape', None) for k, v in out.items() if k.startswith('lo')})

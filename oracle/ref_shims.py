@@ -166,7 +166,7 @@ def install():
     if isinstance(sys.modules['pretrainedmodels'], _StubModule):
         # encoders.py:52-53 looks the constructor up in the package __dict__; the package is absent, use the restatement
         from . import senet_restated
-        for fn in ('se_resnet50', 'se_resnet101', 'se_resnet152'):
+        for fn in ('se_resnet50', 'se_resnet101', 'se_resnet152', 'se_resnext50_32x4d', 'se_resnext101_32x4d'):
             sys.modules['pretrainedmodels'].__dict__[fn] = getattr(senet_restated, fn)
     _install_cocomask_stub()
     sys.modules['steppy.base'].BaseTransformer = BaseTransformer
@@ -183,14 +183,18 @@ def install():
     _installed = True
 
 
-def reference_unet(depth, num_classes=2):
+def reference_unet(depth, num_classes=2, arch=None):
     """common_blocks.architectures.unet.UNetResNet(pretrained=False, hypercolumn, pool0=False); depth 50 builds
-    unet.UNetSeResNet on top of oracle/senet_restated.py (the reference's own wrapper classes, unmodified)."""
+    unet.UNetSeResNet - or, arch='UNetSeResNetXt', unet.UNetSeResNetXt - on top of oracle/senet_restated.py (the reference's own
+    wrapper classes, unmodified)."""
     install()
     import warnings
     from common_blocks.architectures import unet
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
+        if arch == 'UNetSeResNetXt':
+            return unet.UNetSeResNetXt(encoder_depth=depth, num_classes=num_classes, dropout_2d=0.0, pretrained=None,
+                                       use_hypercolumn=True, pool0=False)
         if depth >= 50:
             return unet.UNetSeResNet(encoder_depth=depth, num_classes=num_classes, dropout_2d=0.0, pretrained=None,
                                      use_hypercolumn=True, pool0=False)

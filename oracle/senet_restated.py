@@ -13,7 +13,11 @@ own ``SeResNetEncoders`` / ``UNetSeResNet`` wrap it unchanged and produce the re
   se_module = global average pool - fc1 (1x1 conv C -> C/16, bias) - relu - fc2 (1x1 conv C/16 -> C, bias) - sigmoid - scale
   blocks per layer [3, 4, 6, 3], planes [64, 128, 256, 512], avg_pool 7, last_linear 2048 -> num_classes
 
-PARITY UNPINNED for this encoder: there is no copy of the original to run against; what IS pinned by
+SE-ResNeXt 32x4d (``se_resnext50_32x4d`` / ``se_resnext101_32x4d``, reference encoders.py:90-95; Xie et al., "Aggregated Residual
+Transformations"): the same SENet skeleton with SEResNeXtBottleneck - conv1 1x1 (stride 1) to width = floor(planes * 4 / 64) * 32
+= 2 * planes, conv2 3x3 pad 1 with the STRIDE and 32 groups, conv3 1x1 to 4 * planes, then bn3, se_module, shortcut, relu.
+
+PARITY UNPINNED for these encoders: there is no copy of the original to run against; what IS pinned by
 oracle/make_golden.py is everything the reference owns on top of it (UNetSeResNet wiring, decoder, key aliasing).
 """
 from collections import OrderedDict
@@ -59,9 +63,30 @@ class SEResNetBottleneck(nn.Module):
         return self.relu(self.se_module(y) + shortcut)
 
 
-class SENet(nn.Module):
-    def __init__(self, layers=(3, 4, 6, 3), reduction=16, num_classes=1000):
+class SEResNeXtBottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, groups, reduction, stride=1, downsample=None, base_width=4):
         super().__init__()
+        width = (planes * base_width // 64) * groups
+        self.conv1 = nn.Conv2d(inplanes, width, kernel_size=1, bias=False, stride=1)
+        self.bn1 = nn.BatchNorm2d(width)
+        self.conv2 = nn.Conv2d(width, width, kernel_size=3, stride=stride, padding=1, groups=groups, bias=False)
+        self.bn2 = nn.BatchNorm2d(width)
+        self.conv3 = nn.Conv2d(width, planes * 4, kernel_size=1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.relu = nn.ReLU(inplace=True)
+        self.se_module = SEModule(planes * 4, reduction=reduction)
+        self.downsample = downsample
+        self.stride = stride
+
+    forward = SEResNetBottleneck.forward
+
+
+class SENet(nn.Module):
+    def __init__(self, layers=(3, 4, 6, 3), reduction=16, num_classes=1000, block=SEResNetBottleneck, groups=1):
+        super().__init__()
+        self.block, self.groups = block, groups
         self.inplanes = 64
         self.layer0 = nn.Sequential(OrderedDict([
             ('conv1', nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)),
@@ -83,10 +108,10 @@ class SENet(nn.Module):
         if stride != 1 or self.inplanes != out_planes:
             downsample = nn.Sequential(nn.Conv2d(self.inplanes, out_planes, kernel_size=1, stride=stride, padding=0, bias=False),
                                        nn.BatchNorm2d(out_planes))
-        mods = [SEResNetBottleneck(self.inplanes, planes, 1, reduction, stride, downsample)]
+        mods = [self.block(self.inplanes, planes, self.groups, reduction, stride, downsample)]
         self.inplanes = out_planes
         for _ in range(1, blocks):
-            mods.append(SEResNetBottleneck(self.inplanes, planes, 1, reduction))
+            mods.append(self.block(self.inplanes, planes, self.groups, reduction))
         return nn.Sequential(*mods)
 
     def forward(self, x):
@@ -108,3 +133,13 @@ def se_resnet101(num_classes=1000, pretrained=None):
 def se_resnet152(num_classes=1000, pretrained=None):
     """pretrainedmodels se_resnet152: layers [3, 8, 36, 3] (reference encoders.py:56-57)."""
     return SENet((3, 8, 36, 3), reduction=16, num_classes=num_classes)
+
+
+def se_resnext50_32x4d(num_classes=1000, pretrained=None):
+    """pretrainedmodels se_resnext50_32x4d: SEResNeXtBottleneck, layers [3, 4, 6, 3], 32 groups (reference encoders.py:90-91)."""
+    return SENet((3, 4, 6, 3), reduction=16, num_classes=num_classes, block=SEResNeXtBottleneck, groups=32)
+
+
+def se_resnext101_32x4d(num_classes=1000, pretrained=None):
+    """pretrainedmodels se_resnext101_32x4d: layers [3, 4, 23, 3] (reference encoders.py:92-93)."""
+    return SENet((3, 4, 23, 3), reduction=16, num_classes=num_classes, block=SEResNeXtBottleneck, groups=32)

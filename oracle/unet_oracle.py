@@ -12,6 +12,8 @@ Reference followed:
   torchvision/models/resnet.py:59-105            BasicBlock
   common_blocks/architectures/unet.py:112-172    UNetSeResNet (depth 50; bottom_channel_nr 2048)
   common_blocks/architectures/encoders.py:48-83  SeResNetEncoders (pretrainedmodels se_resnet50, see senet_restated.py)
+  common_blocks/architectures/unet.py:175-236    UNetSeResNetXt (same decoder; arch='UNetSeResNetXt')
+  common_blocks/architectures/encoders.py:86-118 SeResNetXtEncoders (pretrainedmodels se_resnext50_32x4d, see senet_restated.py)
 """
 import numpy as np
 import torch
@@ -34,7 +36,7 @@ def to_torch_state(sd_np, requires_grad=False):
     return out
 
 
-def alias_keys(depth=34):
+def alias_keys(depth=34, arch=None):
     """alias key -> canonical key, for the duplicated registrations the reference
     creates in ResNetEncoders (encoders.py:21-36)."""
     amap = {}
@@ -43,7 +45,7 @@ def alias_keys(depth=34):
         amap['encoders.conv1.0.' + s] = stem + 'conv1.' + s
     for s in ('weight', 'bias', 'running_mean', 'running_var', 'num_batches_tracked'):
         amap['encoders.conv1.1.' + s] = stem + 'bn1.' + s
-    for name, _, _ in param_specs(depth):
+    for name, _, _ in param_specs(depth, 2, arch):
         for li in (1, 2, 3, 4):
             pre = 'encoders.encoder.layer%d.' % li
             if name.startswith(pre):
@@ -92,11 +94,30 @@ def _se_bottleneck(sd, p, x, stride, train):
     return F.relu(out * g + idn)
 
 
-def encoder_forward(sd, x, depth, train):
+def _sex_bottleneck(sd, p, x, stride, train):
+    # pretrainedmodels senet.py SEResNeXtBottleneck (restated: oracle/senet_restated.py): 1x1 -> 3x3 (stride, 32 groups) -> 1x1 + SE
+    out = F.conv2d(x, sd[p + 'conv1.weight'], None)
+    out = F.relu(_bn(sd, p + 'bn1', out, train))
+    out = F.conv2d(out, sd[p + 'conv2.weight'], None, stride=stride, padding=1, groups=32)
+    out = F.relu(_bn(sd, p + 'bn2', out, train))
+    out = F.conv2d(out, sd[p + 'conv3.weight'], None)
+    out = _bn(sd, p + 'bn3', out, train)
+    if (p + 'downsample.0.weight') in sd:
+        idn = F.conv2d(x, sd[p + 'downsample.0.weight'], None, stride=stride)
+        idn = _bn(sd, p + 'downsample.1', idn, train)
+    else:
+        idn = x
+    g = out.mean(dim=(2, 3), keepdim=True)
+    g = F.relu(F.conv2d(g, sd[p + 'se_module.fc1.weight'], sd[p + 'se_module.fc1.bias']))
+    g = torch.sigmoid(F.conv2d(g, sd[p + 'se_module.fc2.weight'], sd[p + 'se_module.fc2.bias']))
+    return F.relu(out * g + idn)
+
+
+def encoder_forward(sd, x, depth, train, arch=None):
     # encoders.py:38-45 / :76-83 with pool0=False (no maxpool)
     e = 'encoders.encoder.'
     stem = e + ('layer0.' if depth >= 50 else '')
-    block = _se_bottleneck if depth >= 50 else _basic_block
+    block = _sex_bottleneck if arch == 'UNetSeResNetXt' else (_se_bottleneck if depth >= 50 else _basic_block)
     y = F.conv2d(x, sd[stem + 'conv1.weight'], None, stride=2, padding=3)
     y = F.relu(_bn(sd, stem + 'bn1', y, train))
     feats = []
@@ -137,11 +158,11 @@ def decoder_block(sd, name, x, skip, train):
     return F.relu(cse + sse)
 
 
-def unet_resnet_forward(sd, x, depth=34, train=False, return_stages=False):
+def unet_resnet_forward(sd, x, depth=34, train=False, return_stages=False, arch=None):
     """[B,3,H,W] fp32 -> logits [B,num_classes,H,W] (unet.py:89-109, hypercolumn on,
     dropout_2d p=0 is the identity).  depth 50 = UNetSeResNet (unet.py:152-172): same graph, SE-ResNet-50 encoder,
     decoder widths derived from the state (bottom_channel_nr 2048)."""
-    e2, e3, e4, e5 = encoder_forward(sd, x, depth, train)
+    e2, e3, e4, e5 = encoder_forward(sd, x, depth, train, arch)
     c = conv_bn_relu(sd, 'center.0', e5, train)
     c = conv_bn_relu(sd, 'center.1', c, train)
     c = F.avg_pool2d(c, 2, 2)

@@ -15,7 +15,7 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 from oracle import synth, unet_oracle, losses_oracle            # noqa: E402
-from oracle.make_golden import sample, GRAD_KEYS, grad_keys                 # noqa: E402
+from oracle.make_golden import sample, GRAD_KEYS, grad_keys, ARCH_NAMES     # noqa: E402
 
 
 def _engine(*a, **k):
@@ -133,8 +133,8 @@ def test_adam_matches_torch():
 STAGES = ['e2', 'e3', 'e4', 'e5', 'center', 'd5', 'd4', 'd3', 'd2', 'd1']
 
 
-def _setup(depth, b, s, wseed=0, dseed=1234):
-    sd_np = synth.synth_state_dict(depth, 2, wseed)
+def _setup(depth, b, s, wseed=0, dseed=1234, arch=None):
+    sd_np = synth.synth_state_dict(depth, 2, wseed, arch)
     x = torch.from_numpy(synth.synth_inputs(b, s, dseed))
     t = torch.from_numpy(synth.synth_targets(b, s, dseed))
     return sd_np, x, t
@@ -219,14 +219,16 @@ def test_train_step_fp32(depth, b, s, loss_name):
 
 
 @pytest.mark.parametrize('tag,tc', [('r18_b2_s64', True), ('r34_b2_s64', True), ('r18_b8_s128', True), ('se50_b2_s64', True),
-                                    ('se101_b2_s64', True), ('r18_b8_s128', False), ('r34_b2_s64', False)])
+                                    ('se101_b2_s64', True), ('r18_b8_s128', False), ('r34_b2_s64', False),
+                                    ('sex50_b2_s64', True), ('sex50_b2_s64', False)])
 def test_golden_fixtures_fp32(golden_dir, tag, tc):
     """Engine vs vectors produced by the unmodified reference modules (tests/golden, oracle/make_golden.py).  tc: forward
     convolutions on tcgen05 with split-bf16 operands (the default fp32 mode) or the fp32-FMA kernels (use_tensor_cores=False)."""
     g = np.load(os.path.join(golden_dir, tag + '.npz'))
     m = {k[5:]: int(g[k]) for k in g.files if k.startswith('meta_')}
-    sd_np, x, t = _setup(m['depth'], m['batch'], m['size'], m['wseed'], m['dseed'])
-    eng = _engine(m['depth'], 2, m['batch'], m['size'], precision='fp32', use_tensor_cores=tc)
+    arch = ARCH_NAMES[m.get('arch', 0)]              # 'UNetSeResNetXt' for the sex50 fixture (grouped convolutions run densely)
+    sd_np, x, t = _setup(m['depth'], m['batch'], m['size'], m['wseed'], m['dseed'], arch)
+    eng = _engine(m['depth'], 2, m['batch'], m['size'], precision='fp32', use_tensor_cores=tc, architecture=arch)
     eng.load_state(sd_np)
     xd, td = x.cuda(), t.cuda()
     oks = [report('golden eval logits', eng.forward(xd, train=False), g['logits_eval'], atol=1e-3)[0]]
@@ -264,21 +266,21 @@ def test_golden_fixtures_fp32(golden_dir, tag, tc):
     assert all(oks)
 
 
-@pytest.mark.parametrize('depth,b,s', [(18, 8, 128), (34, 4, 128), (50, 4, 128)])
-def test_bf16_mode(depth, b, s):
+@pytest.mark.parametrize('depth,b,s,arch', [(18, 8, 128, None), (34, 4, 128, None), (50, 4, 128, None), (50, 4, 128, 'UNetSeResNetXt')])
+def test_bf16_mode(depth, b, s, arch):
     """bf16 precision mode (configs 2-5): bounded deviation from the fp32 oracle.  bf16 storage rounds every
     activation to 8 mantissa bits (2^-9 relative) ~50 times along the deepest path, so the stated tolerances are:
     logits max-abs <= 3 % of the logit range + 0.05, mean-abs <= 0.03; thresholded masks identical except where
     the oracle's logit is within that max-abs bound of 0; train-mode (small-batch BatchNorm) logits <= 8 % of the range
     + 0.05; Lovasz loss within 2 %; gradient cosine >= 0.90 (the stem, behind the longest bf16 chain, is the worst)."""
-    sd_np, x, t = _setup(depth, b, s)
+    sd_np, x, t = _setup(depth, b, s, arch=arch)
     sd = unet_oracle.to_torch_state(sd_np, requires_grad=True)
     with torch.no_grad():
-        ref_eval = unet_oracle.unet_resnet_forward(sd, x, depth, False)
-    ref = unet_oracle.unet_resnet_forward(sd, x, depth, True)
+        ref_eval = unet_oracle.unet_resnet_forward(sd, x, depth, False, arch=arch)
+    ref = unet_oracle.unet_resnet_forward(sd, x, depth, True, arch=arch)
     loss_ref = losses_oracle.lovasz_hinge_per_image(ref, t)
     loss_ref.backward()
-    eng = _engine(depth, 2, b, s, precision='bf16')
+    eng = _engine(depth, 2, b, s, precision='bf16', architecture=arch)
     eng.load_state(sd_np)
     xd, td = x.cuda(), t.cuda()
     le = eng.forward(xd, train=False)

@@ -7,24 +7,25 @@ import pytest
 import torch
 
 from oracle import synth, unet_oracle, losses_oracle
-from oracle.make_golden import sample, grad_keys, stem_bn
+from oracle.make_golden import sample, grad_keys, stem_bn, ARCH_NAMES
 
-CASES = ['r18_b2_s64', 'r34_b2_s64', 'se50_b2_s64', 'se101_b2_s64']
+CASES = ['r18_b2_s64', 'r34_b2_s64', 'se50_b2_s64', 'se101_b2_s64', 'sex50_b2_s64']
 
 
 def _load(golden_dir, tag):
     g = np.load(os.path.join(golden_dir, tag + '.npz'))
     meta = {k[5:]: int(g[k]) for k in g.files if k.startswith('meta_')}
+    meta['arch'] = ARCH_NAMES[meta.get('arch', 0)]          # None, or 'UNetSeResNetXt' 
     return g, meta
 
 
 @pytest.mark.parametrize('tag', CASES)
 def test_eval_forward_matches_reference(golden_dir, tag):
     g, m = _load(golden_dir, tag)
-    sd = unet_oracle.to_torch_state(synth.synth_state_dict(m['depth'], 2, m['wseed']))
+    sd = unet_oracle.to_torch_state(synth.synth_state_dict(m['depth'], 2, m['wseed'], m['arch']))
     x = torch.from_numpy(synth.synth_inputs(m['batch'], m['size'], m['dseed']))
     with torch.no_grad():
-        logits = unet_oracle.unet_resnet_forward(sd, x, m['depth'], train=False)
+        logits = unet_oracle.unet_resnet_forward(sd, x, m['depth'], train=False, arch=m['arch'])
     assert np.abs(logits.numpy() - g['logits_eval']).max() <= 1e-5
 
 
@@ -32,10 +33,10 @@ def test_eval_forward_matches_reference(golden_dir, tag):
 @pytest.mark.parametrize('loss_name', ['lovasz', 'bcedice'])
 def test_train_step_matches_reference(golden_dir, tag, loss_name):
     g, m = _load(golden_dir, tag)
-    sd = unet_oracle.to_torch_state(synth.synth_state_dict(m['depth'], 2, m['wseed']), requires_grad=True)
+    sd = unet_oracle.to_torch_state(synth.synth_state_dict(m['depth'], 2, m['wseed'], m['arch']), requires_grad=True)
     x = torch.from_numpy(synth.synth_inputs(m['batch'], m['size'], m['dseed']))
     t = torch.from_numpy(synth.synth_targets(m['batch'], m['size'], m['dseed']))
-    logits = unet_oracle.unet_resnet_forward(sd, x, m['depth'], train=True)
+    logits = unet_oracle.unet_resnet_forward(sd, x, m['depth'], train=True, arch=m['arch'])
     logits.retain_grad()
     fn = losses_oracle.lovasz_hinge_per_image if loss_name == 'lovasz' else losses_oracle.bce_dice
     loss = fn(logits, t)
