@@ -259,3 +259,32 @@ def test_loss_wrapper_never_reuses_a_buffer_of_another_batch_size(patched):
     assert l1.data_ptr() != l2.data_ptr() and tuple(l1.shape) == (1,)
     with pytest.raises(ValueError):
         fn(torch.randn(3, 2, S, S, generator=g), torch.zeros(3, 2, S, S))       # > max_batch
+
+
+def test_architecture_names_of_the_reference(patched):
+    """`model_params['architecture']` selects among the reference's ARCHITECTURES entries this engine implements (models.py:15-30):
+    the engine receives the name and the entry's default encoder_depth; every other name - implemented by the reference or not -
+    raises NotImplementedError like the reference does for an unknown one (models.py:188)."""
+    import copy
+    seen = []
+    orig_init = StubEngine.__init__
+
+    def spy(self, architecture=None, encoder_depth=34, **kw):
+        seen.append((architecture, encoder_depth))
+        orig_init(self, architecture=architecture, encoder_depth=encoder_depth, **kw)
+
+    StubEngine.__init__ = spy
+    try:
+        for name, depth in (('UNetResNet', 34), ('UNetSeResNet', 50), ('UNetSeResNetXt', 50)):
+            arch = copy.deepcopy(ARCH)
+            arch['model_params']['architecture'] = name
+            arch['model_params'].pop('encoder_depth', None)
+            patched.SegmentationModel(arch, {'epochs': 1}, {})
+            assert seen[-1] == (name, depth)
+        for name in ('PSPNet', 'LargeKernelMatters', 'UNetDenseNet', 'NoSuchNet'):
+            arch = copy.deepcopy(ARCH)
+            arch['model_params']['architecture'] = name
+            with pytest.raises(NotImplementedError):
+                patched.SegmentationModel(arch, {'epochs': 1}, {})
+    finally:
+        StubEngine.__init__ = orig_init
