@@ -30,3 +30,25 @@ def test_bench_final_line_has_the_contract_keys():
     assert abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
     assert d['e2e']['h2d_bytes_per_step'] > 0 and d['gpu_launches'] > 0 and d['clocks']['samples'] >= 2
     assert d['cpu_baseline']['kind'] in ('port', 'reference') and d['cpu_baseline']['cores'] >= 1
+
+
+def test_clock_sampler_cuts_samples_to_the_timed_region(tmp_path):
+    """bench.ClockSampler: nvidia-smi lines carry a timestamp; only the samples inside [begin(), end()] count."""
+    import datetime
+    import time
+    import bench
+
+    class _Proc:
+        def terminate(self): pass
+        def wait(self, timeout=None): pass
+
+    cs = bench.ClockSampler.__new__(bench.ClockSampler)
+    cs.path, cs.proc = str(tmp_path / 'smi.csv'), _Proc()
+    now = time.time()
+    with open(cs.path, 'w') as f:
+        for i in range(10):
+            ts = datetime.datetime.fromtimestamp(now + 0.02 * i).strftime('%Y/%m/%d %H:%M:%S.%f')[:-3]
+            f.write('%s, %d, 1965, 900.1, 0x4, Not Active, Not Active, Not Active, %s\n' % (ts, 1900 + i, 'Active' if i == 4 else 'Not Active'))
+    cs.t0, cs.t1 = now + 0.05, now + 0.15
+    out = cs.stop()
+    assert out['samples'] == 5 and out['sm_mhz'] == 1905.0 and out['sm_max_mhz'] == 1965.0 and out['reasons'] == ['sw_power_cap']
