@@ -568,6 +568,7 @@ __global__ void se_pool_kernel(const T* __restrict__ raw, const T* __restrict__ 
 }
 template <typename T, bool WITH_G, bool RELU>
 static void launch_se_pool(cudaStream_t st, const Tensor& raw, const void* g, const float* scale, const float* shift, const SERef& se) {
+    if (k_ring_se_pool(st, raw, WITH_G ? g : nullptr, RELU, scale, shift, se)) return;
     dim3 grid(se.chunks, raw.B, cdiv(raw.C / VW<T>::N, EW_THREADS));
     se_pool_kernel<T, WITH_G, RELU><<<grid, EW_THREADS, 0, st>>>((const T*)raw.p, (const T*)g, scale, shift, se.part, raw.H * raw.W, raw.C);
 }

@@ -372,6 +372,40 @@ struct FinalBwdOp {
     }
 };
 
+// ------------------------------------------------------------------------------------------------ squeeze (per-image channel sums)
+// part[n][slice][c] = sum over the slice's pixels of  [g *] [relu](raw*scale+shift): the pooling pass of both squeeze-and-excitation
+// kinds (decoder scSE: RELU; encoder SE module: plain; WITH_G: the backward pass).  One CTA = one slice of one image
+// (Streams::group_chunks), so the partial belongs to one image; the FC kernels add the `chunks` partial slots in slot order.
+template <typename T, bool WITH_G, bool RELU>
+struct SePoolOp {
+    static constexpr int N = VW<T>::N;
+    static constexpr bool FULL_WARPS = false;
+    static constexpr int WARPS = 8, NT = WARPS * 32;
+    const float *scale, *shift;
+    float* part;
+    int C, slices, chunks;
+    Vf<N> sc, sh, acc;
+    int c;
+    __device__ void begin(int tid) {
+        const int rb = C * (int)sizeof(T);
+        c = ((tid * 16) & (rb - 1)) / (int)sizeof(T);
+        sc = ldp<N>(scale + c); sh = ldp<N>(shift + c);
+        acc = vzero<N>();
+    }
+    __device__ void vec(size_t, const uint4 (&in)[WITH_G ? 2 : 1]) {
+        Vf<N> z = vfma(vfrom<T>(in[0]), sc, sh);
+        if (RELU) z = vrelu(z);
+        if constexpr (WITH_G) z = vmul(z, vfrom<T>(in[1]));
+        acc = vadd(acc, z);
+    }
+    __device__ void end(int tid, float* red) {
+        const int n = blockIdx.x / slices, slice = blockIdx.x - n * slices;
+        block_reduce_slot<N, true, NT>(acc, C / N, part + ((size_t)n * chunks + slice) * C, red);
+        if (slice == 0)                                   // the slots this launch does not use must read as zero
+            for (int i = tid; i < (chunks - slices) * C; i += NT) part[((size_t)n * chunks + slices) * C + i] = 0.f;
+    }
+};
+
 bool same_shape(const Tensor& a, const Tensor& b) { return a.B == b.B && a.H == b.H && a.W == b.W && a.C == b.C && a.dt == b.dt; }
 size_t flat_bytes(const Tensor& t) { return (size_t)t.B * t.H * t.W * t.C * dtype_size(t.dt); }
 
@@ -503,4 +537,31 @@ bool k_ring_final_bwd(cudaStream_t st, const float* dlogits, const Tensor& raw, 
     else if (K == 2) launch_final_bwd<2>(st, dlogits, raw, bn, w, dw, db, gbn);
     else launch_final_bwd<3>(st, dlogits, raw, bn, w, dw, db, gbn);
     return true;
+}
+
+template <typename T, bool WITH_G, bool RELU>
+static bool ring_se_pool_t(cudaStream_t st, const Tensor& raw, const void* g, const float* scale, const float* shift, const SERef& se) {
+    const size_t img_bytes = (size_t)raw.H * raw.W * raw.C * sizeof(T);
+    if (img_bytes % ring::CHUNK) return false;           // an image must be a whole number of chunks
+    const int cpi = (int)(img_bytes / ring::CHUNK);
+    // Slices per image are a property of the LAYER, never of the batch size: the summation order of an image's partial sums must
+    // not depend on how many other images ride along (tests/test_engine_gpu.py::test_batch_independence_full_size).  At the
+    // benchmark batch (128) two slices of the single-stream ring (two CTAs per SM) / one of the two-stream ring fill one wave.
+    const int slices = std::min(WITH_G ? 1 : 2, std::min(cpi, se.chunks));
+    SePoolOp<T, WITH_G, RELU> op;
+    op.scale = scale; op.shift = shift; op.part = se.part; op.C = raw.C; op.slices = slices; op.chunks = se.chunks;
+    ring::Streams<WITH_G ? 2 : 1> s;
+    s.p[0] = (const uint8_t*)raw.p; s.nbytes = flat_bytes(raw); s.group_chunks = cpi; s.slices = slices;
+    if constexpr (WITH_G) s.p[1] = (const uint8_t*)g;
+    ring::launch<WITH_G ? 2 : 1>(st, s, op);
+    return true;
+}
+bool k_ring_se_pool(cudaStream_t st, const Tensor& raw, const void* g, bool relu, const float* scale, const float* shift, const SERef& se) {
+    if (!ring_enabled() || !ring::row_ok(raw) || (g && (reinterpret_cast<uintptr_t>(g) & 15))) return false;
+    bool ok = false;
+    SALT_DISPATCH(raw.dt, T, {
+        if (g) ok = relu ? ring_se_pool_t<T, true, true>(st, raw, g, scale, shift, se) : ring_se_pool_t<T, true, false>(st, raw, g, scale, shift, se);
+        else ok = relu ? ring_se_pool_t<T, false, true>(st, raw, g, scale, shift, se) : ring_se_pool_t<T, false, false>(st, raw, g, scale, shift, se);
+    });
+    return ok;
 }

@@ -18,3 +18,5 @@ bool k_ring_final_fwd(cudaStream_t st, const Tensor& raw, const float* scale, co
                       float* logits);
 bool k_ring_final_bwd(cudaStream_t st, const float* dlogits, const Tensor& raw, const BNRef& bn, const float* w, int K, float* dw, float* db,
                       const Tensor& gbn);
+// squeeze pass of both SE kinds: part[n][slot][c] partial channel sums per image (g != NULL: the backward pre-pass, sum of g*z)
+bool k_ring_se_pool(cudaStream_t st, const Tensor& raw, const void* g, bool relu, const float* scale, const float* shift, const SERef& se);

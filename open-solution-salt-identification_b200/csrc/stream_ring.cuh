@@ -28,9 +28,12 @@ template <int NS> struct Cfg {
 // Stream 0 is the primary tensor (nbytes, byte offsets `off` refer to it).  A secondary stream may be narrower per pixel
 // (shift[i]: its bytes = primary bytes >> shift[i]) and may be laid out per image with its own image stride (planes of an NCHW
 // tensor): source offset = (off / img_bytes) * img_stride[i] + ((off % img_bytes) >> shift[i]); img_stride[i] == 0 = flat.
+// group_chunks > 0 (per-image reductions): the grid is (images x slices) CTAs, CTA b walks the chunks slice, slice + slices, ...
+// of image b / slices only (an image is a whole number of chunks), so that its partial result belongs to ONE image.
 template <int NS> struct Streams {
     const uint8_t* p[NS]; size_t nbytes;
     int shift[NS] = {}; size_t img_stride[NS] = {}; size_t img_bytes = 0;
+    int group_chunks = 0, slices = 1;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -86,10 +89,15 @@ __global__ void __launch_bounds__(Op::WARPS * 32 + 32, 1) ring_kernel(Streams<NS
     }
     __syncthreads();
     const size_t nchunks = (s.nbytes + CHUNK - 1) / CHUNK;
+    size_t ch_first = blockIdx.x, ch_last = nchunks, ch_step = gridDim.x;
+    if (s.group_chunks > 0) {
+        const size_t g = blockIdx.x / s.slices;
+        ch_first = g * s.group_chunks + (blockIdx.x - g * s.slices); ch_last = (g + 1) * s.group_chunks; ch_step = s.slices;
+    }
     if (warp == CONSUMERS / 32) {
         if (lane == 0) {
             int st = 0; uint32_t ph = 0;
-            for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+            for (size_t ch = ch_first; ch < ch_last; ch += ch_step) {
                 mbar_wait(empty0 + 8 * st, ph ^ 1);
                 const size_t off = ch * CHUNK;
                 const uint32_t bytes = (uint32_t)min((size_t)CHUNK, s.nbytes - off);
@@ -110,7 +118,7 @@ __global__ void __launch_bounds__(Op::WARPS * 32 + 32, 1) ring_kernel(Streams<NS
     }
     op.begin(threadIdx.x);
     int st = 0; uint32_t ph = 0;
-    for (size_t ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    for (size_t ch = ch_first; ch < ch_last; ch += ch_step) {
         const size_t off = ch * CHUNK;
         const int bytes = (int)min((size_t)CHUNK, s.nbytes - off);
         mbar_wait(full0 + 8 * st, ph);
@@ -165,7 +173,8 @@ static void launch(cudaStream_t st, const Streams<NS>& s, const Op& op) {
         attr_set = true;
     }
     const size_t nchunks = (s.nbytes + CHUNK - 1) / CHUNK;
-    const int grid = (int)std::min<size_t>((size_t)num_sms_cached(), nchunks);
+    const int grid = s.group_chunks > 0 ? (int)(nchunks / s.group_chunks) * s.slices
+                                        : (int)std::min<size_t>((size_t)num_sms_cached(), nchunks);
     ring_kernel<NS, Op><<<grid, Op::WARPS * 32 + 32, Cfg<NS>::SMEM, st>>>(s, op);
 }
 static inline int grid_for(size_t nbytes) {
